@@ -1,0 +1,173 @@
+/*
+ * perfb200.h -- C-ABI of libperfb200.so: the B200-native (sm_100a) implementation of PeRF's
+ * per-ray hot path (equirect ray-gen -> fixed-S sampling -> hash-grid encode + 64-wide MLP ->
+ * alpha composite, forward and backward, + fused Adam).
+ *
+ * Boundary rules:
+ *   - extern "C", plain C types; no torch / pybind types cross this boundary.
+ *   - Every pointer named d_* is a DEVICE pointer owned by the caller; h_* is a host pointer.
+ *   - Every entry point enqueues work on `stream` (a cudaStream_t passed as void*) of the
+ *     CURRENT device and returns without synchronising.  The library never allocates.
+ *   - Return value: PERF_OK (0) or a negative PERF_E* code; perf_last_error() returns a
+ *     thread-local human-readable message for the last failure.
+ *   - Re-entrant across distinct streams / devices.
+ *
+ * Each function cites the reference interface it replaces (paths relative to the PeRF
+ * repository, perf-project/PeRF @ 1431a35a).  The third-party modules the reference calls on
+ * this path (tinycudann 1.7, nerfacc 0.5.3, torch_efficient_distloss 0.1.3) are not vendored;
+ * the call sites are cited instead.
+ */
+#ifndef PERFB200_H
+#define PERFB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PERF_ABI_VERSION 1
+
+#define PERF_OK            0
+#define PERF_EINVAL       -1   /* bad argument (null pointer, unsupported size, misaligned) */
+#define PERF_EUNSUPPORTED -2   /* configuration outside what the kernels implement          */
+#define PERF_ECUDA        -3   /* a CUDA runtime call failed (launch error, wrong arch ...)  */
+
+#define PERF_MAX_LEVELS 16
+
+/* encoding_config of tcnn.NetworkWithInputEncoding / tcnn.Encoding as the reference passes it
+ * (modules/fields/ngp_nerf.py:99-106,119-126; modules/geo_predictors/pano_joint_predictor.py:30). */
+typedef struct perf_grid_cfg {
+    uint32_t n_levels;              /* <= PERF_MAX_LEVELS                       */
+    uint32_t n_features_per_level;  /* must be 2                                */
+    uint32_t log2_hashmap_size;
+    uint32_t base_resolution;
+    float    per_level_scale;
+    uint32_t interpolation;         /* 0 = Linear, 1 = Smoothstep               */
+} perf_grid_cfg;
+
+typedef struct perf_level {
+    float    scale;        /* exp2f(l*log2f(s))*base - 1                       */
+    uint32_t resolution;   /* ceilf(scale) + 1                                 */
+    uint32_t size;         /* entries in the level                             */
+    uint32_t offset;       /* first entry of the level in the flat table       */
+    uint32_t hashed;       /* 1: xor-prime hash, 0: dense x-fastest indexing   */
+} perf_level;
+
+/* network_config of tcnn FullyFusedMLP (ngp_nerf.py:107-113,127-133): bias-free, ReLU hidden. */
+typedef struct perf_mlp_cfg {
+    uint32_t n_in;               /* must be 32 (= 16 levels x 2 features)       */
+    uint32_t n_out;              /* 1..16; last matrix is stored padded to 16 rows */
+    uint32_t n_neurons;          /* must be 64                                  */
+    uint32_t n_hidden_layers;    /* 1 or 2                                      */
+    uint32_t output_activation;  /* 0 = None, 1 = Sigmoid                       */
+} perf_mlp_cfg;
+
+/* flags of the render / field entry points */
+#define PERF_FLAG_TRAINING   1u   /* stratified jitter + training background rule        */
+#define PERF_FLAG_SIMT_MLP   2u   /* debug only: MLP on CUDA cores instead of tcgen05     */
+
+int         perf_abi_version(void);
+const char* perf_last_error(void);
+/* compute capability of the current device as major*10+minor (100 on B200), or <0 */
+int         perf_device_arch(void);
+
+/* Level/offset table of a grid config (tcnn GridEncodingTemplated ctor).
+ * h_levels: n_levels entries (may be NULL); h_n_entries: total table entries (may be NULL). */
+int perf_grid_describe(const perf_grid_cfg* cfg, perf_level* h_levels, uint64_t* h_n_entries);
+/* Length of the flat `params` vector of a network (MLP matrices, then the grid). */
+int perf_network_param_count(const perf_grid_cfg* grid, const perf_mlp_cfg* mlp, uint64_t* h_count);
+
+/* fp32 master params -> fp16 shadow, n elements (replaces the per-forward `params.to(half)` of
+ * the tcnn torch binding; ngp_nerf.py:142,158 call sites). */
+int perf_params_to_half(const float* d_params, void* d_params_half, uint64_t n, void* stream);
+
+/* Interleave the two fp16 grid tables into one {geo.f0,geo.f1,app.f0,app.f1} table so one
+ * 8-byte gather serves both fields.  d_*_params_half: full fp16 params of each network. */
+int perf_pack_tables(const perf_grid_cfg* grid, const perf_mlp_cfg* geo_mlp, const perf_mlp_cfg* app_mlp,
+                     const void* d_geo_params_half, const void* d_app_params_half,
+                     void* d_packed /* n_entries * 8 bytes */, void* stream);
+
+/* Equirect rays for image rows [row0,row0+rows) of an H x W panorama; h_pose: row-major 4x4
+ * camera-to-world.  d_rays_o/d_rays_d: [rows*W,3] fp32.
+ * Replaces utils/camera_utils.py:229-234 gen_pano_rays (+ :113-155). */
+int perf_raygen_pano(const float* h_pose, int H, int W, int row0, int rows,
+                     float* d_rays_o, float* d_rays_d, void* stream);
+
+/* Hash-grid encode forward: d_x01 [N,3] fp32 in [0,1] -> d_feat [N, L*2] fp16.
+ * d_table: fp16 [n_entries,2].  Replaces tcnn kernel_grid (Encoding.forward). */
+int perf_hashgrid_fwd(const perf_grid_cfg* cfg, const void* d_table, const float* d_x01,
+                      uint64_t N, void* d_feat, void* stream);
+/* Hash-grid backward w.r.t. the table: d_dtable [n_entries,2] fp32 += scatter(w * dfeat)
+ * (caller zeroes it).  d_dfeat [N, L*2] fp32.  Replaces tcnn kernel_grid_backward. */
+int perf_hashgrid_bwd(const perf_grid_cfg* cfg, const float* d_x01, const float* d_dfeat,
+                      uint64_t N, float* d_dtable, void* stream);
+
+/* Network forward = encode + MLP fused (tcnn NetworkWithInputEncoding.forward;
+ * ngp_nerf.py:142,158).  d_x01 [N,3] fp32; d_params_half: fp16 flat params (MLP | grid);
+ * d_out [N, n_out] fp16.  Optional saves for the backward pass (NULL to skip):
+ * d_feat [N,32] fp16, d_h1 [N,64] fp16, d_h2 [N,64] fp16 (2-hidden-layer nets only). */
+int perf_network_fwd(const perf_grid_cfg* grid, const perf_mlp_cfg* mlp, const void* d_params_half,
+                     const float* d_x01, uint64_t N, void* d_out,
+                     void* d_feat, void* d_h1, void* d_h2, uint32_t flags, void* stream);
+
+/* MLP forward alone on the tensor cores: d_in [N,32] fp16 -> d_out [N,n_out] fp16
+ * (tcnn kernel_mlp_fused).  d_weights_half: the MLP part of the fp16 flat params. */
+int perf_mlp_fwd(const perf_mlp_cfg* mlp, const void* d_weights_half, const void* d_in,
+                 uint64_t N, void* d_out, void* d_h1, void* d_h2, uint32_t flags, void* stream);
+
+/* Packed transmittance scan (nerfacc render_weight_from_density; nerf_renderer.py:170-171).
+ * Samples sorted by ray; d_ray_indices int64 [N].  Outputs fp32 [N] (any may be NULL). */
+int perf_weights_from_density(const float* d_t_starts, const float* d_t_ends, const float* d_sigmas,
+                              const int64_t* d_ray_indices, uint64_t N, uint64_t n_rays,
+                              float* d_weights, float* d_trans, float* d_alphas, void* stream);
+/* Backward of the above w.r.t. sigmas given dL/dweights (and optional dL/dtrans). */
+int perf_weights_from_density_bwd(const float* d_t_starts, const float* d_t_ends, const float* d_sigmas,
+                                  const int64_t* d_ray_indices, uint64_t N, uint64_t n_rays,
+                                  const float* d_weights, const float* d_trans,
+                                  const float* d_grad_weights, const float* d_grad_trans /*nullable*/,
+                                  float* d_grad_sigmas, void* stream);
+/* out[r, :] = sum_{i in ray r} w_i * v_i[:]  (nerfacc accumulate_along_rays;
+ * nerf_renderer.py:173,175,183).  d_values [N,D] fp32 or NULL (D=1, v=1).  d_out [n_rays,D]
+ * is overwritten.  Deterministic (no atomics). */
+int perf_accumulate_along_rays(const float* d_weights, const float* d_values, int D,
+                               const int64_t* d_ray_indices, uint64_t N, uint64_t n_rays,
+                               float* d_out, void* stream);
+
+/* Arguments of the fused renderer (NeRFOCCRenderer.render, nerf_renderer.py:112-209, with the
+ * fixed-S sampler; NeRFScene.render, nerf.py:74-99). */
+typedef struct perf_render_args {
+    perf_grid_cfg grid;           /* both fields use the same grid config (ngp_nerf.py:96-134) */
+    const void*   d_packed_table; /* from perf_pack_tables                                      */
+    const void*   d_geo_mlp_half; /* fp16 MLP matrices of the density net (3072 values)         */
+    const void*   d_app_mlp_half; /* fp16 MLP matrices of the colour net  (7168 values)         */
+    float         aabb[6];        /* min xyz, max xyz (nerf.py:35)                              */
+    uint32_t      n_samples;      /* S                                                          */
+    float         near, far;      /* nerf.py:317-318: 1e-2, 1.0                                 */
+    uint32_t      flags;          /* PERF_FLAG_*                                                */
+    const float*  d_jitter;       /* [R] U[0,1) per-ray offset (training) or NULL               */
+    const float*  d_bg_noise;     /* [R,4] training background rgb + distance noise or NULL     */
+    float*        d_rgb;          /* [R,3]                                                      */
+    float*        d_distance;     /* [R]                                                        */
+    float*        d_opacity;      /* [R] or NULL                                                */
+} perf_render_args;
+
+/* Render explicit rays: d_rays_o / d_rays_d [R,3] fp32. */
+int perf_render_rays(const perf_render_args* args, const float* d_rays_o, const float* d_rays_d,
+                     uint64_t R, void* stream);
+/* Render rows [row0,row0+rows) of an H x W equirect panorama with ray generation fused in
+ * (core_exp_runner.py:229-238 render_dense inner loop).  Outputs are [rows*W, .]. */
+int perf_render_pano(const perf_render_args* args, const float* h_pose, int H, int W,
+                     int row0, int rows, void* stream);
+
+/* Fused Adam on a flat fp32 parameter vector + refresh of its fp16 shadow
+ * (torch.optim.Adam at nerf.py:171,180,253,293; betas/eps defaults).  grad_scale multiplies
+ * the gradient first (the reference never unscales its 128x GradScaler; pass 1 to keep that). */
+int perf_adam_step(float* d_params, const float* d_grads, float* d_exp_avg, float* d_exp_avg_sq,
+                   void* d_params_half /*nullable*/, uint64_t n, float lr, float beta1, float beta2,
+                   float eps, uint32_t step /*1-based*/, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PERFB200_H */

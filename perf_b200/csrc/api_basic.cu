@@ -1,0 +1,487 @@
+// api_basic.cu -- C-ABI entry points that are not the tensor-core paths:
+// error state, level table, params cast / table packing, ray generation, stand-alone hash-grid
+// encode forward / backward, packed composite (nerfacc-style) kernels, fused Adam.
+#include "common.cuh"
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace perf {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...)
+{
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+}
+
+int num_sms()
+{
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    static int cache[64] = {0};
+    if (dev >= 0 && dev < 64 && cache[dev]) return cache[dev];
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    if (dev >= 0 && dev < 64) cache[dev] = n;
+    return n;
+}
+
+// tcnn GridEncodingTemplated constructor + grid_scale/grid_resolution;
+// mirrored by oracle/hashgrid.py::level_table and asserted equal in tests/test_abi.py.
+int build_level_table(const perf_grid_cfg* cfg, LevelTable* out, uint64_t* n_entries)
+{
+    PERF_CHECK_ARG(cfg != nullptr, "grid cfg is NULL");
+    PERF_CHECK_SUP(cfg->n_levels >= 1 && cfg->n_levels <= PERF_MAX_LEVELS, "n_levels=%u not in [1,%d]", cfg->n_levels, PERF_MAX_LEVELS);
+    PERF_CHECK_SUP(cfg->n_features_per_level == 2, "n_features_per_level=%u (only 2 is implemented)", cfg->n_features_per_level);
+    PERF_CHECK_SUP(cfg->log2_hashmap_size >= 4 && cfg->log2_hashmap_size <= 28, "log2_hashmap_size=%u out of range", cfg->log2_hashmap_size);
+    PERF_CHECK_SUP(cfg->interpolation <= 1, "interpolation=%u (0 Linear, 1 Smoothstep)", cfg->interpolation);
+    PERF_CHECK_ARG(cfg->base_resolution >= 1 && cfg->per_level_scale >= 1.0f, "bad base_resolution / per_level_scale");
+    LevelTable lt; memset(&lt, 0, sizeof(lt));
+    lt.n_levels = cfg->n_levels; lt.smoothstep = cfg->interpolation;
+    const float log2s = log2f(cfg->per_level_scale);
+    uint64_t offset = 0;
+    for (uint32_t l = 0; l < cfg->n_levels; ++l) {
+        volatile float x = (float)l * log2s;
+        volatile float e = exp2f(x);
+        volatile float m = e * (float)cfg->base_resolution;
+        const float scale = m - 1.0f;
+        const uint32_t res = (uint32_t)ceilf(scale) + 1u;
+        const uint64_t max_params = 0xFFFFFFFFull / 2;
+        uint64_t dense = ((double)res * res * res > (double)max_params) ? max_params : (uint64_t)res * res * res;
+        dense = (dense + 7) / 8 * 8;
+        uint64_t size = dense < (1ull << cfg->log2_hashmap_size) ? dense : (1ull << cfg->log2_hashmap_size);
+        uint64_t stride = 1; int dims = 0;
+        while (dims < 3 && stride <= size) { stride *= res; ++dims; }
+        const bool hashed = size < stride;
+        PERF_CHECK_SUP(hashed || dims == 3, "level %u: dense level with fewer than 3 strided dims", l);
+        lt.scale[l] = scale; lt.res[l] = res; lt.size[l] = (uint32_t)size; lt.offset[l] = (uint32_t)offset;
+        if (hashed) lt.hashed_mask |= 1u << l;
+        if ((size & (size - 1)) == 0) lt.pow2_mask |= 1u << l;
+        offset += size;
+        PERF_CHECK_SUP(offset < (1ull << 31), "grid too large");
+    }
+    if (out) *out = lt;
+    if (n_entries) *n_entries = offset;
+    return PERF_OK;
+}
+
+int check_mlp(const perf_mlp_cfg* mlp)
+{
+    PERF_CHECK_ARG(mlp != nullptr, "mlp cfg is NULL");
+    PERF_CHECK_SUP(mlp->n_in == 32, "mlp n_in=%u (only 32 = 16 levels x 2 features is implemented)", mlp->n_in);
+    PERF_CHECK_SUP(mlp->n_neurons == 64, "mlp n_neurons=%u (only 64)", mlp->n_neurons);
+    PERF_CHECK_SUP(mlp->n_hidden_layers == 1 || mlp->n_hidden_layers == 2, "mlp n_hidden_layers=%u (1 or 2)", mlp->n_hidden_layers);
+    PERF_CHECK_SUP(mlp->n_out >= 1 && mlp->n_out <= 16, "mlp n_out=%u (1..16)", mlp->n_out);
+    PERF_CHECK_SUP(mlp->output_activation <= 1, "mlp output_activation=%u (0 None, 1 Sigmoid)", mlp->output_activation);
+    return PERF_OK;
+}
+
+int mlp_param_count(const perf_mlp_cfg* mlp, uint64_t* count)
+{
+    int rc = check_mlp(mlp); if (rc) return rc;
+    const uint64_t padded_out = (mlp->n_out + 15) / 16 * 16;
+    *count = (uint64_t)mlp->n_neurons * mlp->n_in + (uint64_t)(mlp->n_hidden_layers - 1) * mlp->n_neurons * mlp->n_neurons
+           + padded_out * mlp->n_neurons;
+    return PERF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void params_to_half_kernel(const float* __restrict__ p, __half* __restrict__ h, uint64_t n)
+{
+    uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n) {
+        float4 v = *reinterpret_cast<const float4*>(p + i);
+        uint2 o; o.x = pack_half2(v.x, v.y); o.y = pack_half2(v.z, v.w);
+        *reinterpret_cast<uint2*>(h + i) = o;
+    } else {
+        for (; i < n; ++i) h[i] = __float2half_rn(p[i]);
+    }
+}
+
+__global__ void pack_tables_kernel(const uint32_t* __restrict__ geo, const uint32_t* __restrict__ app,
+                                   uint2* __restrict__ out, uint64_t n)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_uint2(geo[i], app[i]);
+}
+
+// torch.linspace(start, end, steps)[i] in fp32 (ATen's symmetric formula), so that pixel centres
+// match utils/camera_utils.py:113-117 to the ulp.
+__device__ __forceinline__ float linspace_val(int i, int n)
+{
+    const float start = (float)(0.5 / (double)n), end = (float)(1.0 - 0.5 / (double)n);
+    if (n == 1) return start;
+    const float step = (end - start) / (float)(n - 1);
+    return (i < n / 2) ? __fadd_rn(start, __fmul_rn(step, (float)i)) : __fsub_rn(end, __fmul_rn(step, (float)(n - i - 1)));
+}
+
+// camera-space equirect direction of pixel (row, col): camera_utils.py:120-126,142-147
+__device__ __forceinline__ void pano_dir(int row, int col, int H, int W, float& dx, float& dy, float& dz)
+{
+    const float y = linspace_val(row, H), x = linspace_val(col, W);
+    const float beta = -(y - 0.5f) * 3.14159274101257324f;            // float32(np.pi)
+    const float alpha = -(x - 0.5f) * 6.28318548202514648f;           // float32(2 np.pi)
+    float sa, ca, sb, cb;
+    sincosf(alpha, &sa, &ca); sincosf(beta, &sb, &cb);
+    dx = ca * cb; dy = sa * cb; dz = sb;
+}
+
+struct Pose { float r[9]; float t[3]; };
+
+__global__ void raygen_pano_kernel(Pose pose, int H, int W, int row0, int rows, float* __restrict__ o, float* __restrict__ d)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (uint64_t)rows * W) return;
+    int row = row0 + (int)(i / W), col = (int)(i % W);
+    float cx, cy, cz; pano_dir(row, col, H, W, cx, cy, cz);
+    // apply_rot (camera_utils.py:44-46): d_world = R d
+    d[3 * i + 0] = pose.r[0] * cx + pose.r[1] * cy + pose.r[2] * cz;
+    d[3 * i + 1] = pose.r[3] * cx + pose.r[4] * cy + pose.r[5] * cz;
+    d[3 * i + 2] = pose.r[6] * cx + pose.r[7] * cy + pose.r[8] * cz;
+    o[3 * i + 0] = pose.t[0]; o[3 * i + 1] = pose.t[1]; o[3 * i + 2] = pose.t[2];
+}
+
+// ---- stand-alone hash-grid encode (tcnn kernel_grid): one thread per sample, all levels.
+__global__ void __launch_bounds__(256)
+hashgrid_fwd_kernel(LevelTable lt, const uint32_t* __restrict__ table, const float* __restrict__ x01,
+                    uint64_t N, uint32_t* __restrict__ feat)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const float x = x01[3 * i], y = x01[3 * i + 1], z = x01[3 * i + 2];
+    uint32_t packed[PERF_MAX_LEVELS];
+#pragma unroll
+    for (int l = 0; l < PERF_MAX_LEVELS; ++l) {
+        if (l < (int)lt.n_levels) {
+            Corner8 c; level_corners(lt, l, x, y, z, c);
+            uint32_t v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = __ldg(table + c.idx[k]);
+            float f0 = 0.f, f1 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { float2 t = unpack_half2(v[k]); f0 = fmaf(c.w[k], t.x, f0); f1 = fmaf(c.w[k], t.y, f1); }
+            packed[l] = pack_half2(f0, f1);
+        }
+    }
+    uint32_t* dst = feat + i * lt.n_levels;
+    if (lt.n_levels == 16) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            reinterpret_cast<uint4*>(dst)[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+    } else {
+#pragma unroll
+        for (int l = 0; l < PERF_MAX_LEVELS; ++l) if (l < (int)lt.n_levels) dst[l] = packed[l];
+    }
+}
+
+// ---- hash-grid backward (tcnn kernel_grid_backward): dtable[idx] += w * dfeat, float2 atomics.
+// One thread per (sample, level): neighbouring threads of a warp work on the same level of
+// neighbouring samples, which keeps the atomics of a warp inside one level's table.
+__global__ void __launch_bounds__(256)
+hashgrid_bwd_kernel(LevelTable lt, const float* __restrict__ x01, const float* __restrict__ dfeat,
+                    uint64_t N, float2* __restrict__ dtable)
+{
+    const int l = blockIdx.y;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const float2 g = *reinterpret_cast<const float2*>(dfeat + i * (2 * lt.n_levels) + 2 * l);
+    if (g.x == 0.f && g.y == 0.f) return;
+    const float x = x01[3 * i], y = x01[3 * i + 1], z = x01[3 * i + 2];
+    // level index must be a compile-time-like constant for the by-value table: copy the fields
+    LevelTable const& t = lt;
+    Corner8 c;
+    {
+        // dynamic l: index the parameter arrays directly (constant bank, dynamic index is fine)
+        const float scale = t.scale[l];
+        const uint32_t res = t.res[l], size = t.size[l], off = t.offset[l];
+        const bool hashed = (t.hashed_mask >> l) & 1u, pow2 = (t.pow2_mask >> l) & 1u;
+        float px = fmaf(scale, x, 0.5f), py = fmaf(scale, y, 0.5f), pz = fmaf(scale, z, 0.5f);
+        float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+        uint32_t gx = (uint32_t)(int)fx, gy = (uint32_t)(int)fy, gz = (uint32_t)(int)fz;
+        float wx = px - fx, wy = py - fy, wz = pz - fz;
+        if (t.smoothstep) { wx = wx * wx * (3.f - 2.f * wx); wy = wy * wy * (3.f - 2.f * wy); wz = wz * wz * (3.f - 2.f * wz); }
+        const float ox = 1.f - wx, oy = 1.f - wy, oz = 1.f - wz;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            c.w[k] = __fmul_rn(__fmul_rn((k & 1) ? wx : ox, (k & 2) ? wy : oy), (k & 4) ? wz : oz);
+            c.idx[k] = off + level_index(gx + (k & 1), gy + ((k >> 1) & 1), gz + ((k >> 2) & 1), hashed, pow2, res, size);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        atomicAdd(dtable + c.idx[k], make_float2(c.w[k] * g.x, c.w[k] * g.y));
+}
+
+// ---- packed composite kernels (nerfacc semantics): one warp per ray, lanes over its samples.
+__device__ __forceinline__ uint64_t lower_bound_i64(const int64_t* a, uint64_t n, int64_t key)
+{
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (a[mid] < key) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+__device__ __forceinline__ float warp_incl_scan(float v, int lane)
+{
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { float t = __shfl_up_sync(0xffffffffu, v, off); if (lane >= off) v += t; }
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+__global__ void __launch_bounds__(256)
+weights_from_density_kernel(const float* __restrict__ ts, const float* __restrict__ te, const float* __restrict__ sig,
+                            const int64_t* __restrict__ ri, uint64_t N, uint64_t n_rays,
+                            float* __restrict__ w_out, float* __restrict__ T_out, float* __restrict__ a_out)
+{
+    const int lane = threadIdx.x & 31;
+    const uint64_t ray = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (ray >= n_rays) return;
+    const uint64_t s = lower_bound_i64(ri, N, (int64_t)ray), e = lower_bound_i64(ri, N, (int64_t)ray + 1);
+    float carry = 0.f;
+    for (uint64_t b = s; b < e; b += 32) {
+        const uint64_t i = b + lane;
+        const bool ok = i < e;
+        const float sd = ok ? sig[i] * (te[i] - ts[i]) : 0.f;
+        const float inc = warp_incl_scan(sd, lane);
+        float exc = __shfl_up_sync(0xffffffffu, inc, 1); if (lane == 0) exc = 0.f;
+        if (ok) {
+            const float Tq = expf(-(carry + exc));
+            const float a = 1.f - expf(-sd);
+            if (w_out) w_out[i] = Tq * a;
+            if (T_out) T_out[i] = Tq;
+            if (a_out) a_out[i] = a;
+        }
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+}
+
+// dL/dsigma_i = dt_i * [ (T_i - w_i) gw_i - sum_{j>i} (w_j gw_j + T_j gT_j) ]      
+__global__ void __launch_bounds__(256)
+weights_from_density_bwd_kernel(const float* __restrict__ ts, const float* __restrict__ te,
+                                const int64_t* __restrict__ ri, uint64_t N, uint64_t n_rays,
+                                const float* __restrict__ w, const float* __restrict__ T,
+                                const float* __restrict__ gw, const float* __restrict__ gT, float* __restrict__ gsig)
+{
+    const int lane = threadIdx.x & 31;
+    const uint64_t ray = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (ray >= n_rays) return;
+    const uint64_t s = lower_bound_i64(ri, N, (int64_t)ray), e = lower_bound_i64(ri, N, (int64_t)ray + 1);
+    if (e == s) return;
+    float carry = 0.f;                                   // sum over samples after the current chunk
+    const uint64_t n = e - s, nchunks = (n + 31) / 32;
+    for (uint64_t cidx = nchunks; cidx-- > 0;) {
+        // reversed lane order inside the chunk: lane 0 holds the LAST sample of the chunk
+        const uint64_t i = s + cidx * 32 + (31 - lane);
+        const bool ok = i < e;
+        const float wi = ok ? w[i] : 0.f, Ti = ok ? T[i] : 0.f;
+        const float gwi = ok ? gw[i] : 0.f, gTi = (ok && gT) ? gT[i] : 0.f;
+        const float term = wi * gwi + Ti * gTi;
+        const float inc = warp_incl_scan(term, lane);
+        float exc = __shfl_up_sync(0xffffffffu, inc, 1); if (lane == 0) exc = 0.f;
+        if (ok) gsig[i] = (te[i] - ts[i]) * ((Ti - wi) * gwi - (carry + exc));
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+accumulate_along_rays_kernel(const float* __restrict__ w, const float* __restrict__ v, int D,
+                             const int64_t* __restrict__ ri, uint64_t N, uint64_t n_rays, float* __restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const uint64_t ray = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (ray >= n_rays) return;
+    const uint64_t s = lower_bound_i64(ri, N, (int64_t)ray), e = lower_bound_i64(ri, N, (int64_t)ray + 1);
+    for (int d = 0; d < D; ++d) {
+        float acc = 0.f;
+        for (uint64_t i = s + lane; i < e; i += 32) acc += v ? w[i] * v[i * D + d] : w[i];
+        acc = warp_sum(acc);
+        if (lane == 0) out[ray * D + d] = acc;
+    }
+}
+
+// ---- fused Adam (torch.optim.Adam semantics, amsgrad=False, weight_decay=0) + fp16 shadow.
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+            __half* __restrict__ ph, uint64_t n, float lr, float b1, float b2, float eps,
+            float bc1, float bc2_sqrt, float gscale)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float gi = g[i] * gscale;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;          // exp_avg.lerp_(grad, 1-beta1)
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;     // exp_avg_sq.mul_(b2).addcmul_(g, g, 1-b2)
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    const float pi = p[i] - (lr / bc1) * (mi / denom);
+    p[i] = pi;
+    if (ph) ph[i] = __float2half_rn(pi);
+}
+
+}  // namespace perf
+
+// ------------------------------------------------------------------------------------------------
+// C-ABI
+// ------------------------------------------------------------------------------------------------
+using namespace perf;
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline unsigned blocks_for(uint64_t n, unsigned per) { return (unsigned)((n + per - 1) / per); }
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int perf_abi_version(void) { return PERF_ABI_VERSION; }
+const char* perf_last_error(void) { return perf::g_err; }
+
+int perf_device_arch(void)
+{
+    int dev = 0, major = 0, minor = 0;
+    PERF_CUDA(cudaGetDevice(&dev));
+    PERF_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    PERF_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+    return major * 10 + minor;
+}
+
+int perf_grid_describe(const perf_grid_cfg* cfg, perf_level* h_levels, uint64_t* h_n_entries)
+{
+    LevelTable lt; uint64_t n = 0;
+    int rc = build_level_table(cfg, &lt, &n); if (rc) return rc;
+    if (h_levels)
+        for (uint32_t l = 0; l < lt.n_levels; ++l) {
+            h_levels[l].scale = lt.scale[l]; h_levels[l].resolution = lt.res[l]; h_levels[l].size = lt.size[l];
+            h_levels[l].offset = lt.offset[l]; h_levels[l].hashed = (lt.hashed_mask >> l) & 1u;
+        }
+    if (h_n_entries) *h_n_entries = n;
+    return PERF_OK;
+}
+
+int perf_network_param_count(const perf_grid_cfg* grid, const perf_mlp_cfg* mlp, uint64_t* h_count)
+{
+    PERF_CHECK_ARG(h_count != nullptr, "h_count is NULL");
+    uint64_t ne = 0, nm = 0;
+    int rc = build_level_table(grid, nullptr, &ne); if (rc) return rc;
+    rc = mlp_param_count(mlp, &nm); if (rc) return rc;
+    *h_count = nm + ne * grid->n_features_per_level;
+    return PERF_OK;
+}
+
+int perf_params_to_half(const float* d_params, void* d_params_half, uint64_t n, void* stream)
+{
+    PERF_CHECK_ARG(d_params && d_params_half, "NULL pointer");
+    PERF_CHECK_ARG(((uintptr_t)d_params % 16 == 0) && ((uintptr_t)d_params_half % 8 == 0), "params must be 16-byte aligned");
+    if (n == 0) return PERF_OK;
+    params_to_half_kernel<<<blocks_for((n + 3) / 4, 256), 256, 0, S(stream)>>>(d_params, (__half*)d_params_half, n);
+    PERF_LAUNCH_CHECK();
+    return PERF_OK;
+}
+
+int perf_pack_tables(const perf_grid_cfg* grid, const perf_mlp_cfg* geo_mlp, const perf_mlp_cfg* app_mlp,
+                     const void* d_geo_params_half, const void* d_app_params_half, void* d_packed, void* stream)
+{
+    PERF_CHECK_ARG(d_geo_params_half && d_app_params_half && d_packed, "NULL pointer");
+    uint64_t ne = 0, ng = 0, na = 0;
+    int rc = build_level_table(grid, nullptr, &ne); if (rc) return rc;
+    rc = mlp_param_count(geo_mlp, &ng); if (rc) return rc;
+    rc = mlp_param_count(app_mlp, &na); if (rc) return rc;
+    const uint32_t* geo = reinterpret_cast<const uint32_t*>((const __half*)d_geo_params_half + ng);
+    const uint32_t* app = reinterpret_cast<const uint32_t*>((const __half*)d_app_params_half + na);
+    PERF_CHECK_ARG(((uintptr_t)geo % 4 == 0) && ((uintptr_t)app % 4 == 0) && ((uintptr_t)d_packed % 8 == 0), "misaligned tables");
+    pack_tables_kernel<<<blocks_for(ne, 256), 256, 0, S(stream)>>>(geo, app, (uint2*)d_packed, ne);
+    PERF_LAUNCH_CHECK();
+    return PERF_OK;
+}
+
+int perf_raygen_pano(const float* h_pose, int H, int W, int row0, int rows, float* d_rays_o, float* d_rays_d, void* stream)
+{
+    PERF_CHECK_ARG(h_pose && d_rays_o && d_rays_d, "NULL pointer");
+    PERF_CHECK_ARG(H > 0 && W > 0 && row0 >= 0 && rows >= 0 && row0 + rows <= H, "bad panorama window H=%d W=%d row0=%d rows=%d", H, W, row0, rows);
+    if (rows == 0) return PERF_OK;
+    Pose p;
+    for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) p.r[3 * r + c] = h_pose[4 * r + c]; p.t[r] = h_pose[4 * r + 3]; }
+    raygen_pano_kernel<<<blocks_for((uint64_t)rows * W, 256), 256, 0, S(stream)>>>(p, H, W, row0, rows, d_rays_o, d_rays_d);
+    PERF_LAUNCH_CHECK();
+    return PERF_OK;
+}
+
+int perf_hashgrid_fwd(const perf_grid_cfg* cfg, const void* d_table, const float* d_x01, uint64_t N, void* d_feat, void* stream)
+{
+    PERF_CHECK_ARG(d_table && d_x01 && d_feat, "NULL pointer");
+    LevelTable lt; int rc = build_level_table(cfg, &lt, nullptr); if (rc) return rc;
+    PERF_CHECK_ARG((uintptr_t)d_table % 4 == 0 && (uintptr_t)d_feat % 16 == 0, "misaligned table/feat");
+    if (N == 0) return PERF_OK;
+    hashgrid_fwd_kernel<<<blocks_for(N, 256), 256, 0, S(stream)>>>(lt, (const uint32_t*)d_table, d_x01, N, (uint32_t*)d_feat);
+    PERF_LAUNCH_CHECK();
+    return PERF_OK;
+}
+
+int perf_hashgrid_bwd(const perf_grid_cfg* cfg, const float* d_x01, const float* d_dfeat, uint64_t N, float* d_dtable, void* stream)
+{
+    PERF_CHECK_ARG(d_x01 && d_dfeat && d_dtable, "NULL pointer");
+    LevelTable lt; int rc = build_level_table(cfg, &lt, nullptr); if (rc) return rc;
+    PERF_CHECK_ARG((uintptr_t)d_dtable % 8 == 0 && (uintptr_t)d_dfeat % 8 == 0, "misaligned dtable/dfeat");
+    if (N == 0) return PERF_OK;
+    dim3 grid(blocks_for(N, 256), lt.n_levels);
+    hashgrid_bwd_kernel<<<grid, 256, 0, S(stream)>>>(lt, d_x01, d_dfeat, N, (float2*)d_dtable);
+    PERF_LAUNCH_CHECK();
+    return PERF_OK;
+}
+
+int perf_weights_from_density(const float* d_t_starts, const float* d_t_ends, const float* d_sigmas,
+                              const int64_t* d_ray_indices, uint64_t N, uint64_t n_rays,
+                              float* d_weights, float* d_trans, float* d_alphas, void* stream)
+{
+    PERF_CHECK_ARG(d_t_starts && d_t_ends && d_sigmas && d_ray_indices, "NULL pointer");
+    if (N == 0 || n_rays == 0) return PERF_OK;
+    weights_from_density_kernel<<<blocks_for(n_rays * 32, 256), 256, 0, S(stream)>>>(
+        d_t_starts, d_t_ends, d_sigmas, d_ray_indices, N, n_rays, d_weights, d_trans, d_alphas);
+    PERF_LAUNCH_CHECK();
+    return PERF_OK;
+}
+
+int perf_weights_from_density_bwd(const float* d_t_starts, const float* d_t_ends, const float* d_sigmas,
+                                  const int64_t* d_ray_indices, uint64_t N, uint64_t n_rays,
+                                  const float* d_weights, const float* d_trans,
+                                  const float* d_grad_weights, const float* d_grad_trans, float* d_grad_sigmas, void* stream)
+{
+    (void)d_sigmas;
+    PERF_CHECK_ARG(d_t_starts && d_t_ends && d_ray_indices && d_weights && d_trans && d_grad_weights && d_grad_sigmas, "NULL pointer");
+    if (N == 0 || n_rays == 0) return PERF_OK;
+    weights_from_density_bwd_kernel<<<blocks_for(n_rays * 32, 256), 256, 0, S(stream)>>>(
+        d_t_starts, d_t_ends, d_ray_indices, N, n_rays, d_weights, d_trans, d_grad_weights, d_grad_trans, d_grad_sigmas);
+    PERF_LAUNCH_CHECK();
+    return PERF_OK;
+}
+
+int perf_accumulate_along_rays(const float* d_weights, const float* d_values, int D, const int64_t* d_ray_indices,
+                               uint64_t N, uint64_t n_rays, float* d_out, void* stream)
+{
+    PERF_CHECK_ARG(d_weights && d_ray_indices && d_out, "NULL pointer");
+    PERF_CHECK_ARG(D >= 1 && D <= 64 && (d_values || D == 1), "bad D=%d", D);
+    if (n_rays == 0) return PERF_OK;
+    accumulate_along_rays_kernel<<<blocks_for(n_rays * 32, 256), 256, 0, S(stream)>>>(
+        d_weights, d_values, D, d_ray_indices, N, n_rays, d_out);
+    PERF_LAUNCH_CHECK();
+    return PERF_OK;
+}
+
+int perf_adam_step(float* d_params, const float* d_grads, float* d_exp_avg, float* d_exp_avg_sq, void* d_params_half,
+                   uint64_t n, float lr, float beta1, float beta2, float eps, uint32_t step, float grad_scale, void* stream)
+{
+    PERF_CHECK_ARG(d_params && d_grads && d_exp_avg && d_exp_avg_sq, "NULL pointer");
+    PERF_CHECK_ARG(step >= 1, "step is 1-based");
+    if (n == 0) return PERF_OK;
+    const float bc1 = 1.0f - powf(beta1, (float)step);
+    const float bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
+    adam_kernel<<<blocks_for(n, 256), 256, 0, S(stream)>>>(d_params, d_grads, d_exp_avg, d_exp_avg_sq, (__half*)d_params_half,
+                                                           n, lr, beta1, beta2, eps, bc1, bc2_sqrt, grad_scale);
+    PERF_LAUNCH_CHECK();
+    return PERF_OK;
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

@@ -1,0 +1,186 @@
+// common.cuh -- shared host/device helpers of libperfb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <math.h>
+#include "../../include/perfb200.h"
+
+namespace perf {
+
+// ---------------------------------------------------------------- errors
+void set_error(const char* fmt, ...);
+#define PERF_CHECK_ARG(cond, ...)  do { if (!(cond)) { perf::set_error(__VA_ARGS__); return PERF_EINVAL; } } while (0)
+#define PERF_CHECK_SUP(cond, ...)  do { if (!(cond)) { perf::set_error(__VA_ARGS__); return PERF_EUNSUPPORTED; } } while (0)
+#define PERF_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { \
+    perf::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); return PERF_ECUDA; } } while (0)
+#define PERF_LAUNCH_CHECK() PERF_CUDA(cudaGetLastError())
+
+int num_sms();   // cached multiprocessor count of the current device
+
+// ---------------------------------------------------------------- grid level table
+// Passed BY VALUE as a kernel parameter (272 bytes) -> lives in the constant bank.
+struct LevelTable {
+    float    scale[PERF_MAX_LEVELS];
+    uint32_t res[PERF_MAX_LEVELS];
+    uint32_t size[PERF_MAX_LEVELS];
+    uint32_t offset[PERF_MAX_LEVELS];
+    uint32_t n_levels;
+    uint32_t hashed_mask;      // bit l set: level l is hashed
+    uint32_t pow2_mask;        // bit l set: size[l] is a power of two (mod == and)
+    uint32_t smoothstep;
+};
+int build_level_table(const perf_grid_cfg* cfg, LevelTable* out, uint64_t* n_entries);
+int mlp_param_count(const perf_mlp_cfg* mlp, uint64_t* count);
+int check_mlp(const perf_mlp_cfg* mlp);
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------- device: hash-grid addressing
+// tcnn pos_fract / grid_index / coherent-prime hash; mirrored 1:1 by
+// oracle/hashgrid.py so that indices are bit-identical and the fp32 blend matches to the ulp.
+struct Corner8 {
+    uint32_t idx[8];     // absolute entry index (level offset included)
+    float    w[8];       // trilinear weight, corner c: bit0=x, bit1=y, bit2=z
+};
+
+__device__ __forceinline__ uint32_t level_index(uint32_t gx, uint32_t gy, uint32_t gz,
+                                                bool hashed, bool pow2, uint32_t res, uint32_t size)
+{
+    uint32_t idx;
+    if (hashed) {
+        idx = gx ^ (gy * 2654435761u) ^ (gz * 805459861u);
+        idx = pow2 ? (idx & (size - 1u)) : (idx % size);
+    } else {
+        // dense stride walk; for these levels res^3 (rounded up to 8) == size so all three
+        // dims participate.  (tcnn stops early only when stride > size, which implies hashed.)
+        idx = gx + gy * res + gz * res * res;
+        if (idx >= size) idx %= size;
+    }
+    return idx;
+}
+
+__device__ __forceinline__ void level_corners(const LevelTable& lt, int l, float x, float y, float z, Corner8& c)
+{
+    const float scale = lt.scale[l];
+    const uint32_t res = lt.res[l], size = lt.size[l], off = lt.offset[l];
+    const bool hashed = (lt.hashed_mask >> l) & 1u, pow2 = (lt.pow2_mask >> l) & 1u;
+    float px = fmaf(scale, x, 0.5f), py = fmaf(scale, y, 0.5f), pz = fmaf(scale, z, 0.5f);
+    float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+    uint32_t gx = (uint32_t)(int)fx, gy = (uint32_t)(int)fy, gz = (uint32_t)(int)fz;
+    float wx = px - fx, wy = py - fy, wz = pz - fz;
+    if (lt.smoothstep) {
+        wx = wx * wx * (3.0f - 2.0f * wx); wy = wy * wy * (3.0f - 2.0f * wy); wz = wz * wz * (3.0f - 2.0f * wz);
+    }
+    const float ox = 1.0f - wx, oy = 1.0f - wy, oz = 1.0f - wz;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        // weight = ((1 * ax) * ay) * az in this order (oracle/hashgrid.py::_corner_weights_indices)
+        float w = __fmul_rn(__fmul_rn((k & 1) ? wx : ox, (k & 2) ? wy : oy), (k & 4) ? wz : oz);
+        c.w[k] = w;
+        c.idx[k] = off + level_index(gx + (k & 1), gy + ((k >> 1) & 1), gz + ((k >> 2) & 1), hashed, pow2, res, size);
+    }
+}
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b)
+{
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_half2(uint32_t u)
+{
+    return __half22float2(*reinterpret_cast<__half2*>(&u));
+}
+__device__ __forceinline__ float round_half(float v) { return __half2float(__float2half_rn(v)); }
+
+// ---------------------------------------------------------------- device: tcgen05 / mbarrier PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after()  { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// Spin on an mbarrier phase with a bounded number of polls; a kernel that would hang traps
+// instead (so a descriptor bug surfaces as a CUDA error, not a wedged GPU).
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst)   // one full warp
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 :: "r"(smem_u32(smem_dst)), "r"(COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr)     // same warp that allocated
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(COLS) : "memory");
+}
+
+// Shared-memory matrix descriptor, K-major, no swizzle ("interleave"): 8x16-byte core
+// matrices; LBO = byte distance between the two core matrices of one K=16 step,
+// SBO = byte distance between 8-row groups.  (cute::UMMA::SmemDescriptor, version_=1.)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
+    return d;                                     // base_offset 0, lbo_mode 0, layout SWIZZLE_NONE
+}
+// Instruction descriptor: fp16 x fp16 -> fp32, both operands K-major, M x N tile.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N)
+{
+    return (1u << 4)                 // D format  = F32
+         | (0u << 7) | (0u << 10)    // A, B format = F16
+         | (0u << 15) | (0u << 16)   // A, B K-major
+         | ((uint32_t)(N >> 3) << 17)
+         | ((uint32_t)(M >> 4) << 24);
+}
+// D[tmem] (+)= A[smem] * B[smem]^T ; one thread issues.
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "setp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                 :: "r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread i of warp w reads TMEM lane 32*(w%4)+i.
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
+{
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+#endif  // __CUDACC__
+
+}  // namespace perf

@@ -1,0 +1,399 @@
+// render.cu -- the fused per-ray megakernel: ray-gen -> fixed-S sampling -> hash-grid encode of
+// BOTH fields (one 8-byte gather per corner from the interleaved table) -> density MLP and
+// colour MLP on tcgen05 -> alpha composite with warp-shuffle segmented scans along the ray.
+// Nothing per-sample ever touches HBM: inputs are the pose (or [R,3] rays) and the tables,
+// outputs are 16-20 B per ray.
+//
+// Replaces the whole inner stack of SURVEY.md section 3.1:
+//   NeRFScene.render / render_once      modules/scene/nerf.py:74-123
+//   NeRFOCCRenderer.render              modules/scene/nerf_renderer.py:112-209 (fixed-S sampler)
+//   NGPNeRF.query_density / query_rgb   modules/fields/ngp_nerf.py:136-162
+//   gen_pano_rays                       utils/camera_utils.py:229-234
+// Arithmetic contract: oracle/render.py::render_rays(mixed=True).
+#include "mlp_tc.cuh"
+
+namespace perf {
+
+struct RenderArgs {
+    LevelTable    lt;
+    const uint2*  table;        // {geo half2, app half2} per entry
+    const __half* geo_w;        // W1 [64,32] | Wout [16,64]
+    const __half* app_w;        // W1 [64,32] | W2 [64,64] | Wout [16,64]
+    float         aabb_min[3], aabb_ext[3];
+    uint32_t      S;            // samples per ray
+    uint32_t      rays_per_unit, tiles_per_unit;
+    float         near, far;
+    uint32_t      training;
+    const float*  jitter;       // [R] or null
+    const float*  bg_noise;     // [R,4] or null
+    float*        rgb;          // [R,3]
+    float*        distance;     // [R]
+    float*        opacity;      // [R] or null
+    uint64_t      R;
+    // ray source
+    const float*  rays_o;       // [R,3]  (PANO == false)
+    const float*  rays_d;
+    float         pose_r[9], pose_t[3];
+    int           H, W, row0;   // (PANO == true): ray r is pixel (row0 + r / W, r % W)
+};
+
+constexpr int RS_A     = 0;                         // 16 KB: A_geo | A_app, later H (K=64)
+constexpr int RS_W1G   = RS_A + A64_BYTES;
+constexpr int RS_W1A   = RS_W1G + W32_BYTES;
+constexpr int RS_W2A   = RS_W1A + W32_BYTES;
+constexpr int RS_WOUT  = RS_W2A + W64_BYTES;        // fp32: geo [64] then app [3][64]
+constexpr int RS_TAILS = RS_WOUT + 4 * HID * 4;     // [2 scans][4 warps][8] floats
+constexpr int RS_CARRY = RS_TAILS + 2 * 4 * 8 * 4;  // [2 parities][8] floats
+constexpr int RS_BAR   = RS_CARRY + 2 * 8 * 4;
+constexpr int RS_TOTAL = RS_BAR + 16;
+
+__device__ __forceinline__ float linspace_val_r(int i, int n)
+{
+    const float start = (float)(0.5 / (double)n), end = (float)(1.0 - 0.5 / (double)n);
+    if (n == 1) return start;
+    const float step = (end - start) / (float)(n - 1);
+    return (i < n / 2) ? __fadd_rn(start, __fmul_rn(step, (float)i)) : __fsub_rn(end, __fmul_rn(step, (float)(n - i - 1)));
+}
+
+// Inclusive scan of NV values along the ray across the whole CTA tile (and across the tiles of
+// a unit through `carry`).  Lanes are consecutive samples; a ray may start anywhere.
+//   k        : index of this sample inside its ray
+//   k0_tile  : in-ray index of the tile's first sample (sample of thread 0)
+// Deterministic: tree inside a warp, then warps in order, then tiles in order.
+template <int NV>
+__device__ __forceinline__ void ray_scan(float (&val)[NV], float (&excl)[NV], uint32_t k, uint32_t k0_tile, uint32_t S, int tid,
+                                         float* tails /*[4][8]*/, const float* carry_in /*[8] or null*/, float* carry_out /*[8]*/)
+{
+    const int lane = tid & 31, warp = tid >> 5;
+    const int seg_start = (k >= (uint32_t)lane) ? 0 : lane - (int)k;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const float t = __shfl_up_sync(0xffffffffu, val[j], off);
+            if (lane - off >= seg_start) val[j] += t;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {               // exclusive prefix inside the warp (no inf - inf)
+        const float t = __shfl_up_sync(0xffffffffu, val[j], 1);
+        excl[j] = (lane - 1 >= seg_start) ? t : 0.f;
+    }
+    if (lane == 31) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) tails[warp * 8 + j] = val[j];
+    }
+    __syncthreads();
+    // carry into the ray of lane 0 of warp w:  c[0] = carry_in;  c[w+1] = k0(w+1)==0 ? 0 : (one_seg(w) ? c[w] : 0) + tail[w]
+    float c[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) c[j] = (carry_in != nullptr && k0_tile != 0) ? carry_in[j] : 0.f;
+    const int upto = (carry_out != nullptr && tid == 0) ? 4 : warp;     // thread 0 also produces the tile's carry-out
+    float cw[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) cw[j] = c[j];
+#pragma unroll 1
+    for (int w = 0; w < upto; ++w) {
+        const uint32_t k0w = (k0_tile + 32u * w) % S;            // in-ray index of lane 0 of warp w
+        const uint32_t k0n = (k0_tile + 32u * (w + 1)) % S;      // ... of lane 0 of warp w+1
+        const bool one_seg = (k0w + 31u) < S;                    // warp w lies inside one ray
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const float prev = one_seg ? c[j] : 0.f;
+            c[j] = (k0n == 0) ? 0.f : prev + tails[w * 8 + j];
+        }
+        if (w + 1 == warp) {
+#pragma unroll
+            for (int j = 0; j < NV; ++j) cw[j] = c[j];
+        }
+    }
+    if (carry_out != nullptr && tid == 0) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) carry_out[j] = c[j];
+    }
+    if (k >= (uint32_t)lane) {               // same ray as lane 0 of my warp
+#pragma unroll
+        for (int j = 0; j < NV; ++j) { val[j] += cw[j]; excl[j] += cw[j]; }
+    }
+}
+
+template <bool PANO, bool SIMT>
+__global__ void __launch_bounds__(TILE, 4) render_kernel(const __grid_constant__ RenderArgs a)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sA   = smem + RS_A;
+    uint8_t* sAg  = sA;                     // geo features, K=32
+    uint8_t* sAa  = sA + A32_BYTES;         // app features, K=32
+    uint8_t* sW1g = smem + RS_W1G;
+    uint8_t* sW1a = smem + RS_W1A;
+    uint8_t* sW2a = smem + RS_W2A;
+    float*   sWoutG = reinterpret_cast<float*>(smem + RS_WOUT);
+    float*   sWoutA = sWoutG + HID;
+    float*   sTails = reinterpret_cast<float*>(smem + RS_TAILS);
+    float*   sCarry = reinterpret_cast<float*>(smem + RS_CARRY);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + RS_BAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + RS_BAR + 8);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+
+    load_weight_canonical(a.geo_w, 32, sW1g, tid, TILE);
+    load_wout(a.geo_w + HID * 32, 1, sWoutG, tid, TILE);
+    load_weight_canonical(a.app_w, 32, sW1a, tid, TILE);
+    load_weight_canonical(a.app_w + HID * 32, 64, sW2a, tid, TILE);
+    load_wout(a.app_w + HID * 32 + HID * HID, 3, sWoutA, tid, TILE);
+    uint32_t tmem_base = 0;
+    if (!SIMT) {
+        if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+        __syncwarp();
+        if (warp == 0) tmem_alloc<128>(tmem_slot);
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        tmem_base = *tmem_slot;
+    } else {
+        __syncthreads();
+    }
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    uint32_t parity = 0;
+
+    const uint32_t S = a.S;
+    const float step = __fdiv_rn(__fsub_rn(a.far, a.near), (float)S);
+    const uint64_t n_units = (a.R + a.rays_per_unit - 1) / a.rays_per_unit;
+    uint32_t tile_counter = 0;
+
+    for (uint64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        for (uint32_t t = 0; t < a.tiles_per_unit; ++t, ++tile_counter) {
+            const uint32_t u = t * TILE + tid;                  // sample index inside the unit
+            const uint32_t ray_in_unit = u / S;
+            const uint32_t k = u - ray_in_unit * S;
+            const uint32_t k0_tile = (t * TILE) % S;
+            const uint64_t ray = unit * a.rays_per_unit + ray_in_unit;
+            const bool valid = ray < a.R;
+
+            // ---- ray + sample position (nerf_renderer.py:127, oracle/sampler.py)
+            float ox = 0.f, oy = 0.f, oz = 0.f, dx = 1.f, dy = 0.f, dz = 0.f, jit = 0.f;
+            if (valid) {
+                if constexpr (PANO) {
+                    const int row = a.row0 + (int)(ray / (uint64_t)a.W), col = (int)(ray % (uint64_t)a.W);
+                    const float yy = linspace_val_r(row, a.H), xx = linspace_val_r(col, a.W);
+                    const float beta = -(yy - 0.5f) * 3.14159274101257324f;
+                    const float alpha = -(xx - 0.5f) * 6.28318548202514648f;
+                    float sa, ca, sb, cb;
+                    sincosf(alpha, &sa, &ca); sincosf(beta, &sb, &cb);
+                    const float cx = ca * cb, cy = sa * cb, cz = sb;
+                    dx = a.pose_r[0] * cx + a.pose_r[1] * cy + a.pose_r[2] * cz;
+                    dy = a.pose_r[3] * cx + a.pose_r[4] * cy + a.pose_r[5] * cz;
+                    dz = a.pose_r[6] * cx + a.pose_r[7] * cy + a.pose_r[8] * cz;
+                    ox = a.pose_t[0]; oy = a.pose_t[1]; oz = a.pose_t[2];
+                } else {
+                    ox = a.rays_o[3 * ray]; oy = a.rays_o[3 * ray + 1]; oz = a.rays_o[3 * ray + 2];
+                    dx = a.rays_d[3 * ray]; dy = a.rays_d[3 * ray + 1]; dz = a.rays_d[3 * ray + 2];
+                }
+                if (a.training && a.jitter) jit = a.jitter[ray];
+            }
+            const float ts = __fadd_rn(a.near, __fmul_rn(__fadd_rn((float)k, jit), step));
+            const float te = __fadd_rn(a.near, __fmul_rn(__fadd_rn((float)(k + 1), jit), step));
+            const float tsum = __fadd_rn(ts, te);
+            const float px = __fadd_rn(ox, __fmul_rn(dx, tsum) * 0.5f);
+            const float py = __fadd_rn(oy, __fmul_rn(dy, tsum) * 0.5f);
+            const float pz = __fadd_rn(oz, __fmul_rn(dz, tsum) * 0.5f);
+            // ngp_nerf.py:137-140
+            const float x = __fdiv_rn(__fsub_rn(px, a.aabb_min[0]), a.aabb_ext[0]);
+            const float y = __fdiv_rn(__fsub_rn(py, a.aabb_min[1]), a.aabb_ext[1]);
+            const float z = __fdiv_rn(__fsub_rn(pz, a.aabb_min[2]), a.aabb_ext[2]);
+            const bool selector = valid && x > 0.f && x < 1.f && y > 0.f && y < 1.f && z > 0.f && z < 1.f;
+
+            // ---- encode both fields: 16 levels x 8 corners, one 8-byte gather per corner
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint32_t pg[4], pa[4];
+#pragma unroll
+                for (int ll = 0; ll < 4; ++ll) {
+                    const int l = 4 * q + ll;
+                    Corner8 c; level_corners(a.lt, l, x, y, z, c);
+                    uint2 v[8];
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk) v[kk] = __ldg(a.table + c.idx[kk]);
+                    float g0 = 0.f, g1 = 0.f, a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk) {
+                        const float2 tg = unpack_half2(v[kk].x), ta = unpack_half2(v[kk].y);
+                        g0 = fmaf(c.w[kk], tg.x, g0); g1 = fmaf(c.w[kk], tg.y, g1);
+                        a0 = fmaf(c.w[kk], ta.x, a0); a1 = fmaf(c.w[kk], ta.y, a1);
+                    }
+                    pg[ll] = pack_half2(g0, g1); pa[ll] = pack_half2(a0, a1);
+                }
+                *reinterpret_cast<uint4*>(sAg + (q * TILE + tid) * 16) = make_uint4(pg[0], pg[1], pg[2], pg[3]);
+                *reinterpret_cast<uint4*>(sAa + (q * TILE + tid) * 16) = make_uint4(pa[0], pa[1], pa[2], pa[3]);
+            }
+
+            // ---- layer 1 of both nets
+            if constexpr (!SIMT) {
+                fence_proxy_async();
+                tc_fence_before();
+                __syncthreads();
+                if (tid == 0) {
+                    tc_fence_after();
+                    issue_layer(tmem_base, smem_u32(sAg), smem_u32(sW1g), 32);
+                    issue_layer(tmem_base + 64, smem_u32(sAa), smem_u32(sW1a), 32);
+                    umma_commit(bar);
+                }
+                mbar_wait(bar, parity); parity ^= 1u;
+                tc_fence_after();
+            } else {
+                __syncthreads();
+            }
+
+            // density: ReLU hidden -> 64-long dot -> fp16 logit -> exp     (ngp_nerf.py:141-150)
+            float og[1] = {0.f};
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+                float v[32];
+                acc_chunk<SIMT>(c, 32, tmem_row, sAg, sW1g, tid, v);
+                relu_round(v);
+                out_dots<1>(v, sWoutG, c, 1, og);
+            }
+            const float sigma = selector ? expf(finish_output(og[0], 0)) : 0.f;
+
+            // colour hidden 1 -> H tile (aliases the feature tiles: both layer-1 MMAs are complete)
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+                float v[32];
+                acc_chunk<SIMT>(c, 32, tmem_row + 64, sAa, sW1a, tid, v);
+                relu_round(v);
+                store_chunk_canonical(sA, tid, 4 * c, v);
+            }
+            if constexpr (!SIMT) {
+                fence_proxy_async();
+                tc_fence_before();
+                __syncthreads();
+                if (tid == 0) {
+                    tc_fence_after();
+                    issue_layer(tmem_base + 64, smem_u32(sA), smem_u32(sW2a), 64);
+                    umma_commit(bar);
+                }
+                mbar_wait(bar, parity); parity ^= 1u;
+                tc_fence_after();
+            } else {
+                __syncthreads();
+            }
+            float oa[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+                float v[32];
+                acc_chunk<SIMT>(c, 64, tmem_row + 64, sA, sW2a, tid, v);
+                relu_round(v);
+                out_dots<3>(v, sWoutA, c, 3, oa);
+            }
+            const float cr = selector ? finish_output(oa[0], 1) : 0.f;      // ngp_nerf.py:156-161
+            const float cg = selector ? finish_output(oa[1], 1) : 0.f;
+            const float cb = selector ? finish_output(oa[2], 1) : 0.f;
+
+            // ---- composite (nerf_renderer.py:170-183; oracle/composite.py)
+            const float dt = __fsub_rn(te, ts);
+            const float sd = valid ? sigma * dt : 0.f;
+            float* carry_prev = sCarry + (tile_counter & 1u) * 8;
+            float* carry_next = sCarry + ((tile_counter + 1u) & 1u) * 8;
+            const bool has_carry = (t > 0);
+            float sc[1] = {sd}, sx[1];
+            ray_scan<1>(sc, sx, k, k0_tile, S, tid, sTails, has_carry ? carry_prev : nullptr, carry_next);
+            const float T = expf(-sx[0]);
+            const float alpha = 1.f - expf(-sd);
+            const float w = T * alpha;
+            const float tmid = tsum * 0.5f;
+            float q[5] = {w, w * tmid, w * cr, w * cg, w * cb}, qx[5];
+            ray_scan<5>(q, qx, k, k0_tile, S, tid, sTails + 32, has_carry ? carry_prev + 1 : nullptr, carry_next + 1);
+
+            if (valid && k == S - 1) {
+                const float op = q[0], one_m = 1.f - op;
+                float dist = q[1], r = q[2], g = q[3], b = q[4];
+                if (a.training) {                                 // nerf_renderer.py:192-194
+                    float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
+                    if (a.bg_noise) { n0 = a.bg_noise[4 * ray]; n1 = a.bg_noise[4 * ray + 1]; n2 = a.bg_noise[4 * ray + 2]; n3 = a.bg_noise[4 * ray + 3]; }
+                    dist = fmaxf(dist + (n3 * 2.f - 1.f) * one_m, 0.f);
+                    r += n0 * one_m; g += n1 * one_m; b += n2 * one_m;
+                } else {                                          // nerf_renderer.py:195-197
+                    dist += 5.f * one_m;
+                    r += 0.5f * one_m; g += 0.5f * one_m; b += 0.5f * one_m;
+                }
+                a.rgb[3 * ray] = r; a.rgb[3 * ray + 1] = g; a.rgb[3 * ray + 2] = b;
+                a.distance[ray] = dist;
+                if (a.opacity) a.opacity[ray] = op;
+            }
+            // the feature tiles / TMEM are rewritten by the next tile; every read of this tile
+            // (MMA via mbarrier, tcgen05.ld via wait::ld, smem rows in SIMT mode) is complete and
+            // the barrier before the next MMA issue orders them.
+            if constexpr (SIMT) __syncthreads();
+        }
+    }
+
+    if (!SIMT) {
+        tc_fence_before();
+        __syncthreads();
+        if (warp == 0) tmem_dealloc<128>(tmem_base);
+    }
+}
+
+static uint32_t gcd_u32(uint32_t a, uint32_t b) { while (b) { uint32_t t = a % b; a = b; b = t; } return a; }
+
+static int launch_render(const perf_render_args* args, RenderArgs& a, bool pano, cudaStream_t stream)
+{
+    PERF_CHECK_ARG(args->d_packed_table && args->d_geo_mlp_half && args->d_app_mlp_half, "NULL table / weights");
+    PERF_CHECK_ARG(args->d_rgb && args->d_distance, "NULL output");
+    PERF_CHECK_ARG(args->n_samples >= 1 && args->n_samples <= 4096, "n_samples=%u not in [1,4096]", args->n_samples);
+    PERF_CHECK_ARG(args->far > args->near, "far <= near");
+    PERF_CHECK_ARG((uintptr_t)args->d_packed_table % 8 == 0 && (uintptr_t)args->d_geo_mlp_half % 16 == 0 && (uintptr_t)args->d_app_mlp_half % 16 == 0, "misaligned table / weights");
+    int rc = build_level_table(&args->grid, &a.lt, nullptr); if (rc) return rc;
+    PERF_CHECK_SUP(args->grid.n_levels == 16, "fused renderer needs n_levels == 16 (got %u)", args->grid.n_levels);
+    a.table = (const uint2*)args->d_packed_table;
+    a.geo_w = (const __half*)args->d_geo_mlp_half; a.app_w = (const __half*)args->d_app_mlp_half;
+    for (int i = 0; i < 3; ++i) { a.aabb_min[i] = args->aabb[i]; a.aabb_ext[i] = args->aabb[3 + i] - args->aabb[i]; }
+    a.S = args->n_samples; a.near = args->near; a.far = args->far;
+    a.training = (args->flags & PERF_FLAG_TRAINING) ? 1u : 0u;
+    a.jitter = args->d_jitter; a.bg_noise = args->d_bg_noise;
+    a.rgb = args->d_rgb; a.distance = args->d_distance; a.opacity = args->d_opacity;
+    const uint32_t g = gcd_u32(a.S, TILE);
+    a.rays_per_unit = TILE / g; a.tiles_per_unit = a.S / g;       // unit = lcm(S,128) samples
+    if (a.R == 0) return PERF_OK;
+    const uint64_t n_units = (a.R + a.rays_per_unit - 1) / a.rays_per_unit;
+    const unsigned grid = (unsigned)(n_units < (uint64_t)num_sms() * 4 ? n_units : (uint64_t)num_sms() * 4);
+    const bool simt = (args->flags & PERF_FLAG_SIMT_MLP) != 0;
+#define PERF_RENDER_LAUNCH(P, SM) do { \
+        auto k = render_kernel<P, SM>; \
+        PERF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_TOTAL)); \
+        k<<<grid, TILE, RS_TOTAL, stream>>>(a); } while (0)
+    if (pano) { if (simt) PERF_RENDER_LAUNCH(true, true); else PERF_RENDER_LAUNCH(true, false); }
+    else      { if (simt) PERF_RENDER_LAUNCH(false, true); else PERF_RENDER_LAUNCH(false, false); }
+#undef PERF_RENDER_LAUNCH
+    PERF_LAUNCH_CHECK();
+    return PERF_OK;
+}
+
+}  // namespace perf
+
+using namespace perf;
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int perf_render_rays(const perf_render_args* args, const float* d_rays_o, const float* d_rays_d, uint64_t R, void* stream)
+{
+    PERF_CHECK_ARG(args && d_rays_o && d_rays_d, "NULL pointer");
+    RenderArgs a; memset(&a, 0, sizeof(a));
+    a.rays_o = d_rays_o; a.rays_d = d_rays_d; a.R = R;
+    return launch_render(args, a, false, (cudaStream_t)stream);
+}
+
+int perf_render_pano(const perf_render_args* args, const float* h_pose, int H, int W, int row0, int rows, void* stream)
+{
+    PERF_CHECK_ARG(args && h_pose, "NULL pointer");
+    PERF_CHECK_ARG(H > 0 && W > 0 && row0 >= 0 && rows >= 0 && row0 + rows <= H, "bad panorama window H=%d W=%d row0=%d rows=%d", H, W, row0, rows);
+    RenderArgs a; memset(&a, 0, sizeof(a));
+    for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) a.pose_r[3 * r + c] = h_pose[4 * r + c]; a.pose_t[r] = h_pose[4 * r + 3]; }
+    a.H = H; a.W = W; a.row0 = row0; a.R = (uint64_t)rows * W;
+    return launch_render(args, a, true, (cudaStream_t)stream);
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

@@ -1,0 +1,323 @@
+"""torch-facing wrappers over the C-ABI of libperfb200.so + the autograd Functions built on them.
+
+PyTorch is plumbing here: it owns device memory and the current stream; every op below hands raw
+pointers to the library, which enqueues hand-written sm_100a kernels on that stream.  There is no
+CPU path: a non-CUDA tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from .config import APP_MLP, GEO_MLP, PERF_GRID, GridConfig, MLPConfig
+
+_L = _lib.load
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[C.c_void_p]:
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _chk(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"perf_b200: `{name}` must be a CUDA tensor (there is no CPU path)")
+    if t.dtype != dtype:
+        raise TypeError(f"perf_b200: `{name}` must be {dtype}, got {t.dtype}")
+    return t.contiguous()
+
+
+def launch_count() -> int:
+    """Number of libperfb200 kernel launches issued through this module (bench.py reports it)."""
+    return _LAUNCHES[0]
+
+
+_LAUNCHES = [0]
+
+
+def _call(fn, *args, launches: int = 1):
+    _lib.check(fn(*args))
+    _LAUNCHES[0] += launches
+
+
+# ------------------------------------------------------------------ parameters / tables
+def params_to_half(params: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    params = _chk(params, torch.float32, "params")
+    if out is None:
+        out = torch.empty_like(params, dtype=torch.float16)
+    with torch.cuda.device(params.device):
+        _call(_L().perf_params_to_half, _p(params), _p(out), params.numel(), _stream())
+    return out
+
+
+def pack_tables(geo_half: torch.Tensor, app_half: torch.Tensor, grid: GridConfig = PERF_GRID,
+                geo_mlp: MLPConfig = GEO_MLP, app_mlp: MLPConfig = APP_MLP,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Interleaved {geo.f0, geo.f1, app.f0, app.f1} fp16 table [n_entries, 4]."""
+    geo_half, app_half = _chk(geo_half, torch.float16, "geo_half"), _chk(app_half, torch.float16, "app_half")
+    if out is None:
+        out = torch.empty(grid.n_entries, 4, dtype=torch.float16, device=geo_half.device)
+    with torch.cuda.device(geo_half.device):
+        _call(_L().perf_pack_tables, grid.c(), geo_mlp.c(), app_mlp.c(), _p(geo_half), _p(app_half), _p(out), _stream())
+    return out
+
+
+# ------------------------------------------------------------------ ray generation
+def _pose_array(pose) -> "C.Array":
+    flat = [float(v) for v in torch.as_tensor(pose, dtype=torch.float32).cpu().reshape(-1).tolist()]
+    assert len(flat) == 16, "pose must be 4x4"
+    return (C.c_float * 16)(*flat)
+
+
+def raygen_pano(pose, H: int, W: int, row0: int = 0, rows: Optional[int] = None, device="cuda"):
+    """(rays_o, rays_d) [rows, W, 3]; `utils/camera_utils.py:229-234` gen_pano_rays."""
+    rows = H - row0 if rows is None else rows
+    dev = torch.device(device)
+    o = torch.empty(rows, W, 3, dtype=torch.float32, device=dev)
+    d = torch.empty(rows, W, 3, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _call(_L().perf_raygen_pano, _pose_array(pose), H, W, row0, rows, _p(o), _p(d), _stream())
+    return o, d
+
+
+# ------------------------------------------------------------------ hash grid
+def hashgrid_fwd(table_half: torch.Tensor, x01: torch.Tensor, grid: GridConfig = PERF_GRID) -> torch.Tensor:
+    table_half, x01 = _chk(table_half, torch.float16, "table"), _chk(x01, torch.float32, "x01")
+    N = x01.shape[0]
+    feat = torch.empty(N, grid.n_features, dtype=torch.float16, device=x01.device)
+    with torch.cuda.device(x01.device):
+        _call(_L().perf_hashgrid_fwd, grid.c(), _p(table_half), _p(x01), N, _p(feat), _stream())
+    return feat
+
+
+def hashgrid_bwd(x01: torch.Tensor, dfeat: torch.Tensor, grid: GridConfig = PERF_GRID,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """d(table) [n_entries, 2] fp32 (+= into ``out`` when given)."""
+    x01, dfeat = _chk(x01, torch.float32, "x01"), _chk(dfeat, torch.float32, "dfeat")
+    if out is None:
+        out = torch.zeros(grid.n_entries, 2, dtype=torch.float32, device=x01.device)
+    with torch.cuda.device(x01.device):
+        _call(_L().perf_hashgrid_bwd, grid.c(), _p(x01), _p(dfeat), x01.shape[0], _p(out), _stream())
+    return out
+
+
+# ------------------------------------------------------------------ network (encode + MLP)
+def network_fwd(params_half: torch.Tensor, x01: torch.Tensor, grid: GridConfig, mlp: MLPConfig,
+                save: bool = False, simt: bool = False):
+    """tcnn NetworkWithInputEncoding.forward.  Returns out [N, n_out] fp16, or
+    (out, feat, h1, h2) when ``save`` (h2 is None for 1-hidden-layer nets)."""
+    params_half, x01 = _chk(params_half, torch.float16, "params_half"), _chk(x01, torch.float32, "x01")
+    N, dev = x01.shape[0], x01.device
+    out = torch.empty(N, mlp.n_out, dtype=torch.float16, device=dev)
+    feat = h1 = h2 = None
+    if save:
+        feat = torch.empty(N, 32, dtype=torch.float16, device=dev)
+        h1 = torch.empty(N, 64, dtype=torch.float16, device=dev)
+        if mlp.n_hidden_layers == 2:
+            h2 = torch.empty(N, 64, dtype=torch.float16, device=dev)
+    with torch.cuda.device(dev):
+        _call(_L().perf_network_fwd, grid.c(), mlp.c(), _p(params_half), _p(x01), N, _p(out),
+              _p(feat), _p(h1), _p(h2), _lib.PERF_FLAG_SIMT_MLP if simt else 0, _stream())
+    return (out, feat, h1, h2) if save else out
+
+
+def mlp_fwd(weights_half: torch.Tensor, feat: torch.Tensor, mlp: MLPConfig, save: bool = False, simt: bool = False):
+    weights_half, feat = _chk(weights_half, torch.float16, "weights_half"), _chk(feat, torch.float16, "feat")
+    N, dev = feat.shape[0], feat.device
+    out = torch.empty(N, mlp.n_out, dtype=torch.float16, device=dev)
+    h1 = torch.empty(N, 64, dtype=torch.float16, device=dev) if save else None
+    h2 = torch.empty(N, 64, dtype=torch.float16, device=dev) if save and mlp.n_hidden_layers == 2 else None
+    with torch.cuda.device(dev):
+        _call(_L().perf_mlp_fwd, mlp.c(), _p(weights_half), _p(feat), N, _p(out), _p(h1), _p(h2),
+              _lib.PERF_FLAG_SIMT_MLP if simt else 0, _stream())
+    return (out, h1, h2) if save else out
+
+
+def mlp_backward(mlp: MLPConfig, weights_half: torch.Tensor, feat, h1, h2, out, dout: torch.Tensor):
+    """Backward of the bias-free MLP from the saved fp16 activations.  Returns
+    (d_weights_flat fp32 [mlp.n_params], dfeat fp32 [N,32]).
+
+    The three weight-gradient products and the two activation-gradient products are plain GEMMs
+    (cuBLAS through torch.matmul, fp32); the ReLU / sigmoid masks are elementwise."""
+    W = weights_half.float()
+    w1 = W[:64 * 32].view(64, 32)
+    p = 64 * 32
+    w2 = None
+    if mlp.n_hidden_layers == 2:
+        w2 = W[p:p + 64 * 64].view(64, 64); p += 64 * 64
+    wout = W[p:p + mlp.padded_out * 64].view(mlp.padded_out, 64)[:mlp.n_out]
+    dz = dout.float()
+    if mlp.output_activation == "Sigmoid":
+        y = out.float()
+        dz = dz * y * (1.0 - y)
+    h_last = (h2 if w2 is not None else h1).float()
+    d_wout = torch.zeros(mlp.padded_out, 64, dtype=torch.float32, device=dz.device)
+    d_wout[:mlp.n_out] = dz.t() @ h_last
+    dh = (dz @ wout) * (h_last > 0)
+    grads = []
+    if w2 is not None:
+        h1f = h1.float()
+        d_w2 = dh.t() @ h1f
+        dh = (dh @ w2) * (h1f > 0)
+        grads.append(d_w2.reshape(-1))
+    d_w1 = dh.t() @ feat.float()
+    dfeat = dh @ w1
+    return torch.cat([d_w1.reshape(-1)] + grads + [d_wout.reshape(-1)]), dfeat.contiguous()
+
+
+class _NetworkFunction(torch.autograd.Function):
+    """out = MLP(encode(x01; params[grid]); params[mlp]), differentiable w.r.t. ``params``."""
+
+    @staticmethod
+    def forward(ctx, params, x01, grid, mlp, params_half):
+        need_grad = params.requires_grad and torch.is_grad_enabled()
+        if params_half is None:
+            params_half = params_to_half(params.detach())
+        x01 = x01.detach().float().contiguous()
+        if need_grad:
+            out, feat, h1, h2 = network_fwd(params_half, x01, grid, mlp, save=True)
+            ctx.save_for_backward(x01, params_half, feat, h1, h2 if h2 is not None else h1, out)
+        else:
+            out = network_fwd(params_half, x01, grid, mlp)
+        ctx.grid, ctx.mlp = grid, mlp
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x01, params_half, feat, h1, h2, out = ctx.saved_tensors
+        grid, mlp = ctx.grid, ctx.mlp
+        d_w, dfeat = mlp_backward(mlp, params_half[:mlp.n_params], feat, h1,
+                                  h2 if mlp.n_hidden_layers == 2 else None, out, dout)
+        d_table = hashgrid_bwd(x01, dfeat, grid)
+        return torch.cat([d_w, d_table.reshape(-1)]), None, None, None, None
+
+
+def network_apply(params: torch.Tensor, x01: torch.Tensor, grid: GridConfig, mlp: MLPConfig,
+                  params_half: Optional[torch.Tensor] = None) -> torch.Tensor:
+    return _NetworkFunction.apply(params, x01, grid, mlp, params_half)
+
+
+class _EncodingFunction(torch.autograd.Function):
+    """tcnn.Encoding: feat = encode(x01; params), differentiable w.r.t. ``params`` only."""
+
+    @staticmethod
+    def forward(ctx, params, x01, grid):
+        x01 = x01.detach().float().contiguous()
+        feat = hashgrid_fwd(params_to_half(params.detach()).view(-1, 2), x01, grid)
+        ctx.save_for_backward(x01)
+        ctx.grid = grid
+        return feat
+
+    @staticmethod
+    def backward(ctx, dfeat):
+        (x01,) = ctx.saved_tensors
+        return hashgrid_bwd(x01, dfeat.float().contiguous(), ctx.grid).reshape(-1), None, None
+
+
+def encoding_apply(params: torch.Tensor, x01: torch.Tensor, grid: GridConfig) -> torch.Tensor:
+    return _EncodingFunction.apply(params, x01, grid)
+
+
+# ------------------------------------------------------------------ packed composite (nerfacc semantics)
+def weights_from_density(t_starts, t_ends, sigmas, ray_indices, n_rays: int):
+    t_starts, t_ends = _chk(t_starts, torch.float32, "t_starts"), _chk(t_ends, torch.float32, "t_ends")
+    sigmas, ray_indices = _chk(sigmas, torch.float32, "sigmas"), _chk(ray_indices, torch.int64, "ray_indices")
+    N = sigmas.numel()
+    w, T, a = torch.empty_like(sigmas), torch.empty_like(sigmas), torch.empty_like(sigmas)
+    with torch.cuda.device(sigmas.device):
+        _call(_L().perf_weights_from_density, _p(t_starts), _p(t_ends), _p(sigmas), _p(ray_indices), N, n_rays,
+              _p(w), _p(T), _p(a), _stream())
+    return w, T, a
+
+
+def weights_from_density_bwd(t_starts, t_ends, sigmas, ray_indices, n_rays, weights, trans, grad_w, grad_T=None):
+    gs = torch.empty_like(sigmas)
+    grad_w = _chk(grad_w, torch.float32, "grad_weights")
+    grad_T = None if grad_T is None else _chk(grad_T, torch.float32, "grad_trans")
+    with torch.cuda.device(sigmas.device):
+        _call(_L().perf_weights_from_density_bwd, _p(t_starts), _p(t_ends), _p(sigmas), _p(ray_indices),
+              sigmas.numel(), n_rays, _p(weights), _p(trans), _p(grad_w), _p(grad_T), _p(gs), _stream())
+    return gs
+
+
+def accumulate_along_rays(weights, values, ray_indices, n_rays: int) -> torch.Tensor:
+    weights, ray_indices = _chk(weights, torch.float32, "weights"), _chk(ray_indices, torch.int64, "ray_indices")
+    D = 1 if values is None else values.shape[-1]
+    values = None if values is None else _chk(values, torch.float32, "values")
+    out = torch.empty(n_rays, D, dtype=torch.float32, device=weights.device)
+    with torch.cuda.device(weights.device):
+        _call(_L().perf_accumulate_along_rays, _p(weights), _p(values), D, _p(ray_indices), weights.numel(), n_rays,
+              _p(out), _stream())
+    return out
+
+
+# ------------------------------------------------------------------ fused renderer
+def _render_args(packed_table, geo_mlp_half, app_mlp_half, aabb, n_samples, near, far, training, simt,
+                 jitter, bg_noise, rgb, distance, opacity, grid: GridConfig) -> "_lib.RenderArgs":
+    a = _lib.RenderArgs()
+    a.grid = grid.c()
+    a.d_packed_table, a.d_geo_mlp_half, a.d_app_mlp_half = packed_table.data_ptr(), geo_mlp_half.data_ptr(), app_mlp_half.data_ptr()
+    a.aabb = (C.c_float * 6)(*[float(v) for v in aabb])
+    a.n_samples, a.near, a.far = int(n_samples), float(near), float(far)
+    a.flags = (_lib.PERF_FLAG_TRAINING if training else 0) | (_lib.PERF_FLAG_SIMT_MLP if simt else 0)
+    a.d_jitter = None if jitter is None else jitter.data_ptr()
+    a.d_bg_noise = None if bg_noise is None else bg_noise.data_ptr()
+    a.d_rgb, a.d_distance = rgb.data_ptr(), distance.data_ptr()
+    a.d_opacity = None if opacity is None else opacity.data_ptr()
+    return a
+
+
+def render_rays(packed_table, geo_mlp_half, app_mlp_half, rays_o, rays_d, n_samples: int, near=1e-2, far=1.0,
+                aabb=(-1., -1., -1., 1., 1., 1.), training=False, jitter=None, bg_noise=None,
+                grid: GridConfig = PERF_GRID, simt=False):
+    """Fused render of explicit rays [R,3] -> (rgb [R,3], distance [R,1], opacity [R,1])."""
+    rays_o, rays_d = _chk(rays_o, torch.float32, "rays_o"), _chk(rays_d, torch.float32, "rays_d")
+    R, dev = rays_o.shape[0], rays_o.device
+    rgb = torch.empty(R, 3, dtype=torch.float32, device=dev)
+    dist = torch.empty(R, 1, dtype=torch.float32, device=dev)
+    op = torch.empty(R, 1, dtype=torch.float32, device=dev)
+    jitter = None if jitter is None else _chk(jitter, torch.float32, "jitter")
+    bg_noise = None if bg_noise is None else _chk(bg_noise, torch.float32, "bg_noise")
+    a = _render_args(packed_table, geo_mlp_half, app_mlp_half, aabb, n_samples, near, far, training, simt,
+                     jitter, bg_noise, rgb, dist, op, grid)
+    with torch.cuda.device(dev):
+        _call(_L().perf_render_rays, C.byref(a), _p(rays_o), _p(rays_d), R, _stream())
+    return rgb, dist, op
+
+
+def render_pano(packed_table, geo_mlp_half, app_mlp_half, pose, H: int, W: int, n_samples: int, near=1e-2, far=1.0,
+                row0: int = 0, rows: Optional[int] = None, aabb=(-1., -1., -1., 1., 1., 1.),
+                grid: GridConfig = PERF_GRID, simt=False, out=None):
+    """Fused render of rows [row0,row0+rows) of an HxW equirect panorama (ray-gen inside the kernel).
+    Returns (rgb [rows,W,3], distance [rows,W,1], opacity [rows,W,1])."""
+    rows = H - row0 if rows is None else rows
+    dev = packed_table.device
+    if out is None:
+        rgb = torch.empty(rows, W, 3, dtype=torch.float32, device=dev)
+        dist = torch.empty(rows, W, 1, dtype=torch.float32, device=dev)
+        op = torch.empty(rows, W, 1, dtype=torch.float32, device=dev)
+    else:
+        rgb, dist, op = out
+    a = _render_args(packed_table, geo_mlp_half, app_mlp_half, aabb, n_samples, near, far, False, simt,
+                     None, None, rgb, dist, op, grid)
+    with torch.cuda.device(dev):
+        _call(_L().perf_render_pano, C.byref(a), _pose_array(pose), H, W, row0, rows, _stream())
+    return rgb, dist, op
+
+
+# ------------------------------------------------------------------ optimiser
+def adam_step(params, grads, exp_avg, exp_avg_sq, step: int, lr: float, params_half=None,
+              beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
+    """In-place fused Adam (torch.optim.Adam semantics) + optional fp16 shadow refresh."""
+    for t, n in ((params, "params"), (grads, "grads"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise RuntimeError(f"perf_b200.adam_step: `{n}` must be a contiguous fp32 CUDA tensor")
+    with torch.cuda.device(params.device):
+        _call(_L().perf_adam_step, _p(params), _p(grads), _p(exp_avg), _p(exp_avg_sq), _p(params_half),
+              params.numel(), lr, beta1, beta2, eps, step, grad_scale, _stream())

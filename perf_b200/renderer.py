@@ -1,0 +1,78 @@
+"""FusedPanoRenderer -- the fast path behind ``NeRFScene.render`` / ``render_dense``.
+
+Mirrors the reference's renderer interface for the fixed-S sampler:
+``NeRFScene.render(rays, query_keys)`` (`/root/reference/modules/scene/nerf.py:74-99`) and the
+inner loop of ``CoreRunner.render_dense`` (`/root/reference/core_exp_runner.py:229-238`), but as
+ONE kernel launch per call (no 32768-ray chunk loop, no per-sample tensors in HBM).
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+
+from . import ops
+from .config import APP_MLP, GEO_MLP, PERF_GRID, GridConfig
+
+
+class FusedPanoRenderer:
+    """Holds the fp16 shadow of both field networks (the flat tcnn ``params`` vectors stored in
+    PeRF checkpoints under ``nerf.geo_mlp.params`` / ``nerf.app_mlp.params``) in kernel layout."""
+
+    def __init__(self, grid: GridConfig = PERF_GRID, aabb: Sequence[float] = (-1., -1., -1., 1., 1., 1.),
+                 near: float = 1e-2, far: float = 1.0):
+        self.grid, self.aabb, self.near, self.far = grid, tuple(float(v) for v in aabb), near, far
+        self.geo_half = self.app_half = self.packed = None
+
+    @classmethod
+    def from_params(cls, geo_params: torch.Tensor, app_params: torch.Tensor, **kw) -> "FusedPanoRenderer":
+        r = cls(**kw)
+        r.set_params(geo_params, app_params)
+        return r
+
+    @classmethod
+    def from_state_dict(cls, nerf_state: dict, device="cuda", **kw) -> "FusedPanoRenderer":
+        """``nerf_state`` = ``checkpoint['scene']['nerf']`` of a PeRF ``ckpt.pth``
+        (`modules/scene/nerf.py:374-380`): keys ``aabb``, ``geo_mlp.params``, ``app_mlp.params``."""
+        kw.setdefault("aabb", nerf_state["aabb"].tolist())
+        return cls.from_params(nerf_state["geo_mlp.params"].to(device), nerf_state["app_mlp.params"].to(device), **kw)
+
+    def set_params(self, geo_params: torch.Tensor, app_params: torch.Tensor) -> None:
+        """fp32 master params -> fp16 shadows + interleaved gather table (3 small kernels).
+        Call again after every optimiser step that changed them."""
+        n_g = GEO_MLP.n_params + 2 * self.grid.n_entries
+        n_a = APP_MLP.n_params + 2 * self.grid.n_entries
+        if geo_params.numel() != n_g or app_params.numel() != n_a:
+            raise ValueError(f"params have {geo_params.numel()}/{app_params.numel()} values, expected {n_g}/{n_a}")
+        self.geo_half = ops.params_to_half(geo_params.detach().float(), out=self.geo_half)
+        self.app_half = ops.params_to_half(app_params.detach().float(), out=self.app_half)
+        self.packed = ops.pack_tables(self.geo_half, self.app_half, self.grid, out=self.packed)
+
+    def _ready(self):
+        if self.packed is None:
+            raise RuntimeError("FusedPanoRenderer: call set_params() first")
+
+    def render_rays(self, rays_o: torch.Tensor, rays_d: torch.Tensor, n_samples: int, near: Optional[float] = None,
+                    far: Optional[float] = None, training: bool = False, jitter: Optional[torch.Tensor] = None,
+                    bg_noise: Optional[torch.Tensor] = None, simt: bool = False) -> dict:
+        self._ready()
+        rgb, dist, op = ops.render_rays(self.packed, self.geo_half, self.app_half, rays_o.reshape(-1, 3), rays_d.reshape(-1, 3),
+                                        n_samples, self.near if near is None else near, self.far if far is None else far,
+                                        self.aabb, training, jitter, bg_noise, self.grid, simt)
+        return {"rgb": rgb, "distance": dist, "opacities": op, "is_valid": True}
+
+    def render_pano(self, pose, H: int, W: int, n_samples: int, row0: int = 0, rows: Optional[int] = None,
+                    near: Optional[float] = None, far: Optional[float] = None, simt: bool = False, out=None) -> dict:
+        self._ready()
+        rgb, dist, op = ops.render_pano(self.packed, self.geo_half, self.app_half, pose, H, W, n_samples,
+                                        self.near if near is None else near, self.far if far is None else far,
+                                        row0, rows, self.aabb, self.grid, simt, out)
+        return {"rgb": rgb, "distance": dist, "opacities": op, "is_valid": True}
+
+    @torch.no_grad()
+    def render(self, rays, query_keys=("rgb",), n_samples: int = 128) -> dict:
+        """Drop-in for ``NeRFScene.render(rays, query_keys)``: ``rays`` has ``.o`` / ``.d`` of shape
+        [..., 3]; returns ``{key: tensor[..., C]}`` (eval-mode background rule)."""
+        pre_shape = list(rays.o.shape[:-1])
+        out = self.render_rays(rays.o.reshape(-1, 3).float(), rays.d.reshape(-1, 3).float(), n_samples)
+        return {k: out[k].reshape(pre_shape + [-1]) for k in query_keys}

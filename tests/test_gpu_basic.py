@@ -1,0 +1,153 @@
+"""GPU parity tests (through the C-ABI) of the non-tensor-core kernels: ray-gen, hash-grid
+encode forward/backward, packed composite kernels, Adam.  Oracle = oracle/ on CPU."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle.hashgrid import GridConfig as OGrid, encode, encode_backward_table, n_table_entries
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from perf_b200 import ops as _ops
+    return _ops
+
+
+def edge_points(g, n):
+    x = torch.rand(n, 3, generator=g)
+    x[:6] = torch.tensor([[0., 0., 0.], [1., 1., 1.], [0.5, 0.5, 0.5], [1., 0., 0.5], [1e-7, 0.999999, 0.25],
+                          [0.9999999, 0.9999999, 0.9999999]])
+    x[6:12] = torch.rand(6, 3, generator=g) * 1.1 - 0.05        # slightly outside the box
+    # points exactly on cell boundaries of level 0 (scale 15): x = (v - 0.5) / 15
+    x[12:20, 0] = (torch.arange(8, dtype=torch.float32) + 1 - 0.5) / 15.0
+    return x
+
+
+def test_raygen_matches_reference_golden(ops, golden_dir):
+    g = np.load(os.path.join(golden_dir, "raygen.npz"))
+    for name in ("eye_8x16", "rot_6x10", "rot_128x256", "rot_1024x2048"):
+        h, w = (int(v) for v in g[name + "_hw"])
+        o, d = ops.raygen_pano(g[name + "_pose"], h, w)
+        rows = g[name + "_rows"]
+        np.testing.assert_array_equal(o.cpu().numpy()[rows], g[name + "_o"])
+        np.testing.assert_allclose(d.cpu().numpy()[rows], g[name + "_d"], atol=2e-6, rtol=0, err_msg=name)
+    # row window == slice of the full image, bit for bit
+    pose = g["rot_128x256_pose"]
+    o_full, d_full = ops.raygen_pano(pose, 128, 256)
+    o_win, d_win = ops.raygen_pano(pose, 128, 256, row0=40, rows=17)
+    assert torch.equal(d_win, d_full[40:57]) and torch.equal(o_win, o_full[40:57])
+
+
+@pytest.mark.parametrize("cfg", [OGrid(), OGrid(n_levels=5, log2_hashmap_size=17, per_level_scale=1.6817928305074292),
+                                 OGrid(n_levels=8, log2_hashmap_size=12, interpolation="Smoothstep")])
+def test_hashgrid_fwd_matches_oracle(ops, cfg):
+    from perf_b200.config import GridConfig
+    g = torch.Generator().manual_seed(11)
+    n = n_table_entries(cfg)
+    table = ((torch.rand(n, 2, generator=g) * 2 - 1) * 0.5).half()
+    x = edge_points(g, 4096)
+    want = encode(x, table.float(), cfg, out_half=True)
+    pg = GridConfig(cfg.n_levels, 2, cfg.log2_hashmap_size, cfg.base_resolution, cfg.per_level_scale, cfg.interpolation)
+    got = ops.hashgrid_fwd(table.cuda(), x.cuda(), pg).float().cpu()
+    diff = (got - want).abs()
+    # fp32 fmaf chain in the same order on both sides: identical up to rare double-rounding ties
+    assert (diff == 0).float().mean() > 0.995, float((diff == 0).float().mean())
+    assert diff.max() <= 1e-3 * max(1.0, float(want.abs().max()))
+
+
+def test_hashgrid_bwd_matches_oracle(ops):
+    from perf_b200.config import GridConfig
+    cfg = OGrid()
+    g = torch.Generator().manual_seed(12)
+    x = edge_points(g, 3000)
+    dfeat = torch.randn(3000, 32, generator=g)
+    dfeat[:50] = 0                                          # zero rows are skipped by the kernel
+    want = encode_backward_table(x, dfeat, cfg)
+    got = ops.hashgrid_bwd(x.cuda(), dfeat.cuda(), GridConfig()).cpu()
+    assert got.shape == want.shape
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=1e-4, atol=1e-5)
+    # accumulate into an existing buffer
+    acc = ops.hashgrid_bwd(x.cuda(), dfeat.cuda(), GridConfig(), out=torch.from_numpy(want.numpy()).cuda().clone())
+    np.testing.assert_allclose(acc.cpu().numpy(), 2 * want.numpy(), rtol=1e-4, atol=2e-5)
+
+
+def ragged_rays(g, n_rays, max_len):
+    lens = torch.randint(0, max_len, (n_rays,), generator=g)
+    lens[3] = 0; lens[n_rays - 1] = 0; lens[5] = 1; lens[7] = 33; lens[8] = 32; lens[9] = 65
+    ri = torch.repeat_interleave(torch.arange(n_rays), lens)
+    N = int(lens.sum())
+    ts = torch.rand(N, generator=g)
+    te = ts + torch.rand(N, generator=g) * 0.05
+    sig = torch.rand(N, generator=g) * 30
+    sig[::17] = 0
+    return ri, ts, te, sig
+
+
+def test_packed_composite_matches_oracle(ops):
+    g = torch.Generator().manual_seed(13)
+    n_rays = 200
+    ri, ts, te, sig = ragged_rays(g, n_rays, 150)
+    w0, T0, a0 = oracle.render_weight_from_density(ts, te, sig, ri)
+    w, T, a = ops.weights_from_density(ts.cuda(), te.cuda(), sig.cuda(), ri.cuda(), n_rays)
+    np.testing.assert_allclose(w.cpu().numpy(), w0.numpy(), rtol=2e-5, atol=1e-7)
+    np.testing.assert_allclose(T.cpu().numpy(), T0.numpy(), rtol=2e-5, atol=1e-7)
+    np.testing.assert_allclose(a.cpu().numpy(), a0.numpy(), rtol=2e-5, atol=1e-7)
+    vals = torch.rand(ri.numel(), 3, generator=g)
+    acc0 = oracle.accumulate_along_rays(w0, vals, ri, n_rays)
+    acc = ops.accumulate_along_rays(w, vals.cuda(), ri.cuda(), n_rays)
+    np.testing.assert_allclose(acc.cpu().numpy(), acc0.numpy(), rtol=2e-5, atol=1e-6)
+    op0 = oracle.accumulate_along_rays(w0, None, ri, n_rays)
+    op = ops.accumulate_along_rays(w, None, ri.cuda(), n_rays)
+    np.testing.assert_allclose(op.cpu().numpy(), op0.numpy(), rtol=2e-5, atol=1e-6)
+    assert float(op.max()) <= 1 + 1e-5 and float(op[3]) == 0.0
+
+
+def test_packed_composite_backward_matches_autograd(ops):
+    g = torch.Generator().manual_seed(14)
+    n_rays = 64
+    ri, ts, te, sig = ragged_rays(g, n_rays, 90)
+    sig = sig.clone().requires_grad_(True)
+    w0, T0, _ = oracle.render_weight_from_density(ts, te, sig, ri)
+    gw, gT = torch.randn(w0.shape, generator=g), torch.randn(w0.shape, generator=g)
+    ((w0 * gw).sum() + (T0 * gT).sum()).backward()
+    w, T, _ = ops.weights_from_density(ts.cuda(), te.cuda(), sig.detach().cuda(), ri.cuda(), n_rays)
+    gs = ops.weights_from_density_bwd(ts.cuda(), te.cuda(), sig.detach().cuda(), ri.cuda(), n_rays, w, T, gw.cuda(), gT.cuda())
+    np.testing.assert_allclose(gs.cpu().numpy(), sig.grad.numpy(), rtol=2e-4, atol=2e-6)
+
+
+def test_adam_matches_torch(ops):
+    g = torch.Generator().manual_seed(15)
+    n = 10007
+    p0 = torch.randn(n, generator=g)
+    ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=0.0)
+    p = p0.clone().cuda()
+    m, v, ph = torch.zeros_like(p), torch.zeros_like(p), torch.empty(n, dtype=torch.float16, device="cuda")
+    for step in range(1, 6):
+        grad = torch.randn(n, generator=g) * 128
+        lr = 1e-2 * step / 5
+        for grp in opt.param_groups:
+            grp["lr"] = lr
+        ref.grad = grad.clone()
+        opt.step()
+        ops.adam_step(p, grad.cuda(), m, v, step, lr, params_half=ph)
+    np.testing.assert_allclose(p.cpu().numpy(), ref.detach().numpy(), rtol=1e-5, atol=1e-6)
+    assert torch.equal(ph.cpu(), p.cpu().half())
+
+
+def test_params_to_half_and_pack(ops):
+    from perf_b200.config import APP_MLP, GEO_MLP, PERF_GRID
+    g = torch.Generator().manual_seed(16)
+    n_e = PERF_GRID.n_entries
+    geo = torch.randn(GEO_MLP.n_params + 2 * n_e, generator=g)
+    app = torch.randn(APP_MLP.n_params + 2 * n_e, generator=g)
+    gh, ah = ops.params_to_half(geo.cuda()), ops.params_to_half(app.cuda())
+    assert torch.equal(gh.cpu(), geo.half()) and torch.equal(ah.cpu(), app.half())
+    packed = ops.pack_tables(gh, ah).cpu()
+    assert torch.equal(packed[:, :2], geo.half()[GEO_MLP.n_params:].view(-1, 2))
+    assert torch.equal(packed[:, 2:], app.half()[APP_MLP.n_params:].view(-1, 2))

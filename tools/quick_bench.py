@@ -1,0 +1,26 @@
+"""Throw-away timing probe (not the bench contract): fused render at several sizes."""
+import sys, time, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from perf_b200.renderer import FusedPanoRenderer
+from perf_b200.config import GEO_MLP, APP_MLP, PERF_GRID
+
+torch.manual_seed(0)
+n_e = PERF_GRID.n_entries
+def rand_params(mlp):
+    w = (torch.rand(mlp.n_params, device="cuda") * 2 - 1) * 0.3
+    g = (torch.rand(2 * n_e, device="cuda") * 2 - 1) * 0.5
+    return torch.cat([w, g])
+r = FusedPanoRenderer.from_params(rand_params(GEO_MLP), rand_params(APP_MLP))
+pose = torch.eye(4)
+for (H, W, S, rows) in [(128, 256, 32, 128), (1024, 2048, 128, 128), (1024, 2048, 128, 1024)]:
+    out = r.render_pano(pose, H, W, S, rows=rows); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 3
+    e0.record()
+    for _ in range(n):
+        r.render_pano(pose, H, W, S, rows=rows, out=(out["rgb"], out["distance"], out["opacities"]))
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    ns = rows * W * S
+    print(f"render {H}x{W} rows={rows} S={S}: {ms:.3f} ms  {ns/ms/1e3:.1f} Msamples/s  algGB/s={ns*1024/ms/1e6:.0f}", flush=True)
