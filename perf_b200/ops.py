@@ -176,7 +176,7 @@ class _NetworkFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, params, x01, grid, mlp, params_half):
-        need_grad = params.requires_grad and torch.is_grad_enabled()
+        need_grad = ctx.needs_input_grad[0]
         if params_half is None:
             params_half = params_to_half(params.detach())
         x01 = x01.detach().float().contiguous()
@@ -282,6 +282,8 @@ def render_rays(packed_table, geo_mlp_half, app_mlp_half, rays_o, rays_d, n_samp
     rgb = torch.empty(R, 3, dtype=torch.float32, device=dev)
     dist = torch.empty(R, 1, dtype=torch.float32, device=dev)
     op = torch.empty(R, 1, dtype=torch.float32, device=dev)
+    if R == 0:
+        return rgb, dist, op
     jitter = None if jitter is None else _chk(jitter, torch.float32, "jitter")
     bg_noise = None if bg_noise is None else _chk(bg_noise, torch.float32, "bg_noise")
     a = _render_args(packed_table, geo_mlp_half, app_mlp_half, aabb, n_samples, near, far, training, simt,
