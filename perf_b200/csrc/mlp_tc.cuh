@@ -84,41 +84,41 @@ __device__ __forceinline__ void acc_chunk(int c, int K, uint32_t tmem_row, const
     }
 }
 
-// ReLU + round to fp16 (tcnn keeps hidden activations in __half)
-__device__ __forceinline__ void relu_round(float (&v)[32])
+// ReLU + round to fp16 (tcnn keeps hidden activations in __half), two values per instruction:
+// cvt.rn.f16x2.f32 packs a pair, HMNMX2 clamps at zero (max(round(x),0) == round(max(x,0))).
+__device__ __forceinline__ void relu_pack(const float (&v)[32], uint32_t (&p)[16])
 {
+    const __half2 zero = __float2half2_rn(0.f);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = round_half(fmaxf(v[j], 0.f));
+    for (int j = 0; j < 16; ++j) {
+        __half2 h = __hmax2(__floats2half2_rn(v[2 * j], v[2 * j + 1]), zero);
+        p[j] = *reinterpret_cast<uint32_t*>(&h);
+    }
 }
 
-// write 32 fp16-valued floats as k-groups [kg0, kg0+4) of this thread's row of an activation tile
-__device__ __forceinline__ void store_chunk_canonical(uint8_t* A, int row, int kg0, const float (&v)[32])
+// write 32 packed fp16 values as k-groups [kg0, kg0+4) of this thread's row of an activation tile
+__device__ __forceinline__ void store_chunk_canonical(uint8_t* A, int row, int kg0, const uint32_t (&p)[16])
 {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        uint4 u;
-        u.x = pack_half2(v[8 * q + 0], v[8 * q + 1]); u.y = pack_half2(v[8 * q + 2], v[8 * q + 3]);
-        u.z = pack_half2(v[8 * q + 4], v[8 * q + 5]); u.w = pack_half2(v[8 * q + 6], v[8 * q + 7]);
-        *reinterpret_cast<uint4*>(A + ((kg0 + q) * TILE + row) * 16) = u;
-    }
+    for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<uint4*>(A + ((kg0 + q) * TILE + row) * 16) = make_uint4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
 }
 // same 32 values to a row-major [N,64] fp16 global buffer (activation save for the backward pass)
-__device__ __forceinline__ void store_chunk_global(uint4* row_ptr /* 8 uint4 per row */, int c, const float (&v)[32])
+__device__ __forceinline__ void store_chunk_global(uint4* row_ptr /* 8 uint4 per row */, int c, const uint32_t (&p)[16])
 {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        uint4 u;
-        u.x = pack_half2(v[8 * q + 0], v[8 * q + 1]); u.y = pack_half2(v[8 * q + 2], v[8 * q + 3]);
-        u.z = pack_half2(v[8 * q + 4], v[8 * q + 5]); u.w = pack_half2(v[8 * q + 6], v[8 * q + 7]);
-        row_ptr[4 * c + q] = u;
-    }
+    for (int q = 0; q < 4; ++q)
+        row_ptr[4 * c + q] = make_uint4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
 }
 
-// out[o] += sum_j v[j] * wout[o][32c + j]   (output layer on CUDA cores: n_out is 1 or 3, a
+// out[o] += sum_j h[j] * wout[o][32c + j]   (output layer on CUDA cores: n_out is 1 or 3, a
 // padded N=16 MMA + another smem round trip would cost more than 64*n_out FMAs per row)
 template <int NOUT_MAX>
-__device__ __forceinline__ void out_dots(const float (&v)[32], const float* wout, int c, int n_out, float (&acc)[NOUT_MAX])
+__device__ __forceinline__ void out_dots(const uint32_t (&p)[16], const float* wout, int c, int n_out, float (&acc)[NOUT_MAX])
 {
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { const float2 f = unpack_half2(p[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
 #pragma unroll
     for (int o = 0; o < NOUT_MAX; ++o) {
         if (o < n_out) {

@@ -124,12 +124,12 @@ __global__ void __launch_bounds__(TILE, 4) network_fwd_kernel(const __grid_const
 
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
-            float v[32];
+            float v[32]; uint32_t hp[16];
             acc_chunk<SIMT>(c, 32, tmem_row, sA, sW1, tid, v);
-            relu_round(v);
-            if (a.h1_save && valid) store_chunk_global(a.h1_save + i * 8, c, v);
-            if constexpr (TWO_HIDDEN) store_chunk_canonical(sH, tid, 4 * c, v);
-            else out_dots<16>(v, sWout, c, (int)a.n_out, out_acc);
+            relu_pack(v, hp);
+            if (a.h1_save && valid) store_chunk_global(a.h1_save + i * 8, c, hp);
+            if constexpr (TWO_HIDDEN) store_chunk_canonical(sH, tid, 4 * c, hp);
+            else out_dots<16>(hp, sWout, c, (int)a.n_out, out_acc);
         }
 
         if constexpr (TWO_HIDDEN) {
@@ -150,11 +150,11 @@ __global__ void __launch_bounds__(TILE, 4) network_fwd_kernel(const __grid_const
             }
 #pragma unroll 1
             for (int c = 0; c < 2; ++c) {
-                float v[32];
+                float v[32]; uint32_t hp[16];
                 acc_chunk<SIMT>(c, 64, tmem_row, sH, sW2, tid, v);
-                relu_round(v);
-                if (a.h2_save && valid) store_chunk_global(a.h2_save + i * 8, c, v);
-                out_dots<16>(v, sWout, c, (int)a.n_out, out_acc);
+                relu_pack(v, hp);
+                if (a.h2_save && valid) store_chunk_global(a.h2_save + i * 8, c, hp);
+                out_dots<16>(hp, sWout, c, (int)a.n_out, out_acc);
             }
         }
 

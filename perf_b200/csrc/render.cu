@@ -117,6 +117,109 @@ __device__ __forceinline__ void ray_scan(float (&val)[NV], float (&excl)[NV], ui
     }
 }
 
+struct RenderSmem {
+    uint8_t *sA, *sAg, *sAa, *sW1g, *sW1a, *sW2a;
+    float *sWoutG, *sWoutA;
+    uint64_t* bar;
+};
+
+// Encode + both MLPs for the CTA's current 128 samples (thread t = sample t at normalised
+// position (x,y,z)).  Contains 2 block-wide barriers + 2 mbarrier waits; all 128 threads call it.
+template <bool SIMT>
+__device__ __forceinline__ void eval_fields(const RenderArgs& a, const RenderSmem& sm, float x, float y, float z, bool selector,
+                                            uint32_t tmem_base, uint32_t tmem_row, uint32_t& parity, int tid,
+                                            float& sigma, float& cr, float& cg, float& cb)
+{
+    uint8_t* const sA = sm.sA; uint8_t* const sAg = sm.sAg; uint8_t* const sAa = sm.sAa;
+    uint8_t* const sW1g = sm.sW1g; uint8_t* const sW1a = sm.sW1a; uint8_t* const sW2a = sm.sW2a;
+    float* const sWoutG = sm.sWoutG; float* const sWoutA = sm.sWoutA; uint64_t* const bar = sm.bar;
+    // ---- encode both fields: 16 levels x 8 corners, one 8-byte gather per corner
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint32_t pg[4], pa[4];
+#pragma unroll
+        for (int ll = 0; ll < 4; ++ll) {
+            const int l = 4 * q + ll;
+            Corner8 c; level_corners(a.lt, l, x, y, z, c);
+            uint2 v[8];
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) v[kk] = __ldg(a.table + c.idx[kk]);
+            float g0 = 0.f, g1 = 0.f, a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+                const float2 tg = unpack_half2(v[kk].x), ta = unpack_half2(v[kk].y);
+                g0 = fmaf(c.w[kk], tg.x, g0); g1 = fmaf(c.w[kk], tg.y, g1);
+                a0 = fmaf(c.w[kk], ta.x, a0); a1 = fmaf(c.w[kk], ta.y, a1);
+            }
+            pg[ll] = pack_half2(g0, g1); pa[ll] = pack_half2(a0, a1);
+        }
+        *reinterpret_cast<uint4*>(sAg + (q * TILE + tid) * 16) = make_uint4(pg[0], pg[1], pg[2], pg[3]);
+        *reinterpret_cast<uint4*>(sAa + (q * TILE + tid) * 16) = make_uint4(pa[0], pa[1], pa[2], pa[3]);
+    }
+
+    // ---- layer 1 of both nets
+    if constexpr (!SIMT) {
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            issue_layer(tmem_base, smem_u32(sAg), smem_u32(sW1g), 32);
+            issue_layer(tmem_base + 64, smem_u32(sAa), smem_u32(sW1a), 32);
+            umma_commit(bar);
+        }
+        mbar_wait(bar, parity); parity ^= 1u;
+        tc_fence_after();
+    } else {
+        __syncthreads();
+    }
+
+    // density: ReLU hidden -> 64-long dot -> fp16 logit -> exp     (ngp_nerf.py:141-150)
+    float og[1] = {0.f};
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+        float v[32]; uint32_t hp[16];
+        acc_chunk<SIMT>(c, 32, tmem_row, sAg, sW1g, tid, v);
+        relu_pack(v, hp);
+        out_dots<1>(hp, sWoutG, c, 1, og);
+    }
+    sigma = selector ? expf(finish_output(og[0], 0)) : 0.f;
+
+    // colour hidden 1 -> H tile (aliases the feature tiles: both layer-1 MMAs are complete)
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+        float v[32]; uint32_t hp[16];
+        acc_chunk<SIMT>(c, 32, tmem_row + 64, sAa, sW1a, tid, v);
+        relu_pack(v, hp);
+        store_chunk_canonical(sA, tid, 4 * c, hp);
+    }
+    if constexpr (!SIMT) {
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            issue_layer(tmem_base + 64, smem_u32(sA), smem_u32(sW2a), 64);
+            umma_commit(bar);
+        }
+        mbar_wait(bar, parity); parity ^= 1u;
+        tc_fence_after();
+    } else {
+        __syncthreads();
+    }
+    float oa[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+        float v[32]; uint32_t hp[16];
+        acc_chunk<SIMT>(c, 64, tmem_row + 64, sA, sW2a, tid, v);
+        relu_pack(v, hp);
+        out_dots<3>(hp, sWoutA, c, 3, oa);
+    }
+    cr = selector ? finish_output(oa[0], 1) : 0.f;      // ngp_nerf.py:156-161
+    cg = selector ? finish_output(oa[1], 1) : 0.f;
+    cb = selector ? finish_output(oa[2], 1) : 0.f;
+}
+
 template <bool PANO, bool SIMT>
 __global__ void __launch_bounds__(TILE, 4) render_kernel(const __grid_constant__ RenderArgs a)
 {
@@ -135,6 +238,7 @@ __global__ void __launch_bounds__(TILE, 4) render_kernel(const __grid_constant__
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + RS_BAR + 8);
 
     const int tid = threadIdx.x, warp = tid >> 5;
+    const RenderSmem sm = {sA, sAg, sAa, sW1g, sW1a, sW2a, sWoutG, sWoutA, bar};
 
     load_weight_canonical(a.geo_w, 32, sW1g, tid, TILE);
     load_wout(a.geo_w + HID * 32, 1, sWoutG, tid, TILE);
@@ -204,91 +308,8 @@ __global__ void __launch_bounds__(TILE, 4) render_kernel(const __grid_constant__
             const float z = __fdiv_rn(__fsub_rn(pz, a.aabb_min[2]), a.aabb_ext[2]);
             const bool selector = valid && x > 0.f && x < 1.f && y > 0.f && y < 1.f && z > 0.f && z < 1.f;
 
-            // ---- encode both fields: 16 levels x 8 corners, one 8-byte gather per corner
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                uint32_t pg[4], pa[4];
-#pragma unroll
-                for (int ll = 0; ll < 4; ++ll) {
-                    const int l = 4 * q + ll;
-                    Corner8 c; level_corners(a.lt, l, x, y, z, c);
-                    uint2 v[8];
-#pragma unroll
-                    for (int kk = 0; kk < 8; ++kk) v[kk] = __ldg(a.table + c.idx[kk]);
-                    float g0 = 0.f, g1 = 0.f, a0 = 0.f, a1 = 0.f;
-#pragma unroll
-                    for (int kk = 0; kk < 8; ++kk) {
-                        const float2 tg = unpack_half2(v[kk].x), ta = unpack_half2(v[kk].y);
-                        g0 = fmaf(c.w[kk], tg.x, g0); g1 = fmaf(c.w[kk], tg.y, g1);
-                        a0 = fmaf(c.w[kk], ta.x, a0); a1 = fmaf(c.w[kk], ta.y, a1);
-                    }
-                    pg[ll] = pack_half2(g0, g1); pa[ll] = pack_half2(a0, a1);
-                }
-                *reinterpret_cast<uint4*>(sAg + (q * TILE + tid) * 16) = make_uint4(pg[0], pg[1], pg[2], pg[3]);
-                *reinterpret_cast<uint4*>(sAa + (q * TILE + tid) * 16) = make_uint4(pa[0], pa[1], pa[2], pa[3]);
-            }
-
-            // ---- layer 1 of both nets
-            if constexpr (!SIMT) {
-                fence_proxy_async();
-                tc_fence_before();
-                __syncthreads();
-                if (tid == 0) {
-                    tc_fence_after();
-                    issue_layer(tmem_base, smem_u32(sAg), smem_u32(sW1g), 32);
-                    issue_layer(tmem_base + 64, smem_u32(sAa), smem_u32(sW1a), 32);
-                    umma_commit(bar);
-                }
-                mbar_wait(bar, parity); parity ^= 1u;
-                tc_fence_after();
-            } else {
-                __syncthreads();
-            }
-
-            // density: ReLU hidden -> 64-long dot -> fp16 logit -> exp     (ngp_nerf.py:141-150)
-            float og[1] = {0.f};
-#pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
-                float v[32];
-                acc_chunk<SIMT>(c, 32, tmem_row, sAg, sW1g, tid, v);
-                relu_round(v);
-                out_dots<1>(v, sWoutG, c, 1, og);
-            }
-            const float sigma = selector ? expf(finish_output(og[0], 0)) : 0.f;
-
-            // colour hidden 1 -> H tile (aliases the feature tiles: both layer-1 MMAs are complete)
-#pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
-                float v[32];
-                acc_chunk<SIMT>(c, 32, tmem_row + 64, sAa, sW1a, tid, v);
-                relu_round(v);
-                store_chunk_canonical(sA, tid, 4 * c, v);
-            }
-            if constexpr (!SIMT) {
-                fence_proxy_async();
-                tc_fence_before();
-                __syncthreads();
-                if (tid == 0) {
-                    tc_fence_after();
-                    issue_layer(tmem_base + 64, smem_u32(sA), smem_u32(sW2a), 64);
-                    umma_commit(bar);
-                }
-                mbar_wait(bar, parity); parity ^= 1u;
-                tc_fence_after();
-            } else {
-                __syncthreads();
-            }
-            float oa[3] = {0.f, 0.f, 0.f};
-#pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
-                float v[32];
-                acc_chunk<SIMT>(c, 64, tmem_row + 64, sA, sW2a, tid, v);
-                relu_round(v);
-                out_dots<3>(v, sWoutA, c, 3, oa);
-            }
-            const float cr = selector ? finish_output(oa[0], 1) : 0.f;      // ngp_nerf.py:156-161
-            const float cg = selector ? finish_output(oa[1], 1) : 0.f;
-            const float cb = selector ? finish_output(oa[2], 1) : 0.f;
+            float sigma, cr, cg, cb;
+            eval_fields<SIMT>(a, sm, x, y, z, selector, tmem_base, tmem_row, parity, tid, sigma, cr, cg, cb);
 
             // ---- composite (nerf_renderer.py:170-183; oracle/composite.py)
             const float dt = __fsub_rn(te, ts);
@@ -335,6 +356,140 @@ __global__ void __launch_bounds__(TILE, 4) render_kernel(const __grid_constant__
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// render_march_kernel: thread = RAY, the 128 rows of an MMA tile are 128 neighbouring rays at the
+// same sample index k.  For a panorama a warp is an 8x4 pixel patch and a CTA a 16x8 patch, so the
+// 32 lanes of every gather instruction sit next to each other in space (few distinct cache lines
+// per request at the coarse and middle levels) and a thread revisits the same cells from k to k+1
+// (temporal L1 reuse).  The composite is a per-thread running sum: no shuffles, no carries.
+// Transmittance uses the sequential exclusive sum, the order of the oracle's cumsum.
+template <bool PANO, bool SIMT>
+__global__ void __launch_bounds__(TILE, 4) render_march_kernel(const __grid_constant__ RenderArgs a)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sA   = smem + RS_A;
+    uint8_t* sW1g = smem + RS_W1G;
+    uint8_t* sW1a = smem + RS_W1A;
+    uint8_t* sW2a = smem + RS_W2A;
+    float*   sWoutG = reinterpret_cast<float*>(smem + RS_WOUT);
+    float*   sWoutA = sWoutG + HID;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + RS_BAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + RS_BAR + 8);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const RenderSmem sm = {sA, sA, sA + A32_BYTES, sW1g, sW1a, sW2a, sWoutG, sWoutA, bar};
+
+    load_weight_canonical(a.geo_w, 32, sW1g, tid, TILE);
+    load_wout(a.geo_w + HID * 32, 1, sWoutG, tid, TILE);
+    load_weight_canonical(a.app_w, 32, sW1a, tid, TILE);
+    load_weight_canonical(a.app_w + HID * 32, 64, sW2a, tid, TILE);
+    load_wout(a.app_w + HID * 32 + HID * HID, 3, sWoutA, tid, TILE);
+    uint32_t tmem_base = 0;
+    if (!SIMT) {
+        if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+        __syncwarp();
+        if (warp == 0) tmem_alloc<128>(tmem_slot);
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        tmem_base = *tmem_slot;
+    } else {
+        __syncthreads();
+    }
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    uint32_t parity = 0;
+
+    const uint32_t S = a.S;
+    const float step = __fdiv_rn(__fsub_rn(a.far, a.near), (float)S);
+    const int rows = PANO ? (int)(a.R / (uint64_t)a.W) : 0;
+    const uint32_t tiles_x = PANO ? (uint32_t)((a.W + 15) / 16) : 0u;
+    const uint64_t n_tiles = PANO ? (uint64_t)tiles_x * (uint64_t)((rows + 7) / 8) : (a.R + TILE - 1) / TILE;
+
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        // ---- this thread's ray
+        uint64_t ray; bool valid;
+        float ox = 0.f, oy = 0.f, oz = 0.f, dx = 1.f, dy = 0.f, dz = 0.f, jit = 0.f;
+        if constexpr (PANO) {
+            const int ty = (int)(tile / tiles_x), tx = (int)(tile % tiles_x);
+            const int prow = ty * 8 + (warp >> 1) * 4 + (lane >> 3);          // row inside the window
+            const int pcol = tx * 16 + (warp & 1) * 8 + (lane & 7);
+            valid = prow < rows && pcol < a.W;
+            ray = (uint64_t)prow * (uint64_t)a.W + (uint64_t)pcol;
+            if (valid) {
+                const float yy = linspace_val_r(a.row0 + prow, a.H), xx = linspace_val_r(pcol, a.W);
+                const float beta = -(yy - 0.5f) * 3.14159274101257324f;
+                const float alpha = -(xx - 0.5f) * 6.28318548202514648f;
+                float sa, ca, sb, cb;
+                sincosf(alpha, &sa, &ca); sincosf(beta, &sb, &cb);
+                const float cx = ca * cb, cy = sa * cb, cz = sb;
+                dx = a.pose_r[0] * cx + a.pose_r[1] * cy + a.pose_r[2] * cz;
+                dy = a.pose_r[3] * cx + a.pose_r[4] * cy + a.pose_r[5] * cz;
+                dz = a.pose_r[6] * cx + a.pose_r[7] * cy + a.pose_r[8] * cz;
+                ox = a.pose_t[0]; oy = a.pose_t[1]; oz = a.pose_t[2];
+            }
+        } else {
+            ray = tile * TILE + tid;
+            valid = ray < a.R;
+            if (valid) {
+                ox = a.rays_o[3 * ray]; oy = a.rays_o[3 * ray + 1]; oz = a.rays_o[3 * ray + 2];
+                dx = a.rays_d[3 * ray]; dy = a.rays_d[3 * ray + 1]; dz = a.rays_d[3 * ray + 2];
+            }
+        }
+        if (valid && a.training && a.jitter) jit = a.jitter[ray];
+
+        float sum_sd = 0.f;                                   // exclusive running sum of sigma*dt
+        float acc_w = 0.f, acc_d = 0.f, acc_r = 0.f, acc_g = 0.f, acc_b = 0.f;
+#pragma unroll 1
+        for (uint32_t k = 0; k < S; ++k) {
+            const float ts = __fadd_rn(a.near, __fmul_rn(__fadd_rn((float)k, jit), step));
+            const float te = __fadd_rn(a.near, __fmul_rn(__fadd_rn((float)(k + 1), jit), step));
+            const float tsum = __fadd_rn(ts, te);
+            const float px = __fadd_rn(ox, __fmul_rn(dx, tsum) * 0.5f);
+            const float py = __fadd_rn(oy, __fmul_rn(dy, tsum) * 0.5f);
+            const float pz = __fadd_rn(oz, __fmul_rn(dz, tsum) * 0.5f);
+            const float x = __fdiv_rn(__fsub_rn(px, a.aabb_min[0]), a.aabb_ext[0]);
+            const float y = __fdiv_rn(__fsub_rn(py, a.aabb_min[1]), a.aabb_ext[1]);
+            const float z = __fdiv_rn(__fsub_rn(pz, a.aabb_min[2]), a.aabb_ext[2]);
+            const bool selector = valid && x > 0.f && x < 1.f && y > 0.f && y < 1.f && z > 0.f && z < 1.f;
+
+            float sigma, cr, cg, cb;
+            eval_fields<SIMT>(a, sm, x, y, z, selector, tmem_base, tmem_row, parity, tid, sigma, cr, cg, cb);
+
+            const float sd = sigma * __fsub_rn(te, ts);
+            const float w = expf(-sum_sd) * (1.f - expf(-sd));
+            sum_sd += sd;
+            acc_w += w; acc_d = fmaf(w, tsum * 0.5f, acc_d);
+            acc_r = fmaf(w, cr, acc_r); acc_g = fmaf(w, cg, acc_g); acc_b = fmaf(w, cb, acc_b);
+            if constexpr (SIMT) __syncthreads();
+        }
+
+        if (valid) {
+            const float one_m = 1.f - acc_w;
+            float dist = acc_d, r = acc_r, g = acc_g, b = acc_b;
+            if (a.training) {                                     // nerf_renderer.py:192-194
+                float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
+                if (a.bg_noise) { n0 = a.bg_noise[4 * ray]; n1 = a.bg_noise[4 * ray + 1]; n2 = a.bg_noise[4 * ray + 2]; n3 = a.bg_noise[4 * ray + 3]; }
+                dist = fmaxf(dist + (n3 * 2.f - 1.f) * one_m, 0.f);
+                r += n0 * one_m; g += n1 * one_m; b += n2 * one_m;
+            } else {                                              // nerf_renderer.py:195-197
+                dist += 5.f * one_m;
+                r += 0.5f * one_m; g += 0.5f * one_m; b += 0.5f * one_m;
+            }
+            a.rgb[3 * ray] = r; a.rgb[3 * ray + 1] = g; a.rgb[3 * ray + 2] = b;
+            a.distance[ray] = dist;
+            if (a.opacity) a.opacity[ray] = acc_w;
+        }
+    }
+
+    if (!SIMT) {
+        tc_fence_before();
+        __syncthreads();
+        if (warp == 0) tmem_dealloc<128>(tmem_base);
+    }
+}
+
 static uint32_t gcd_u32(uint32_t a, uint32_t b) { while (b) { uint32_t t = a % b; a = b; b = t; } return a; }
 
 static int launch_render(const perf_render_args* args, RenderArgs& a, bool pano, cudaStream_t stream)
@@ -356,15 +511,24 @@ static int launch_render(const perf_render_args* args, RenderArgs& a, bool pano,
     const uint32_t g = gcd_u32(a.S, TILE);
     a.rays_per_unit = TILE / g; a.tiles_per_unit = a.S / g;       // unit = lcm(S,128) samples
     if (a.R == 0) return PERF_OK;
-    const uint64_t n_units = (a.R + a.rays_per_unit - 1) / a.rays_per_unit;
-    const unsigned grid = (unsigned)(n_units < (uint64_t)num_sms() * 4 ? n_units : (uint64_t)num_sms() * 4);
     const bool simt = (args->flags & PERF_FLAG_SIMT_MLP) != 0;
-#define PERF_RENDER_LAUNCH(P, SM) do { \
-        auto k = render_kernel<P, SM>; \
+    const bool scan = (args->flags & PERF_FLAG_SCAN_KERNEL) != 0;
+    uint64_t n_work;
+    if (scan) n_work = (a.R + a.rays_per_unit - 1) / a.rays_per_unit;
+    else if (pano) n_work = (uint64_t)((a.W + 15) / 16) * (uint64_t)(((int)(a.R / (uint64_t)a.W) + 7) / 8);
+    else n_work = (a.R + TILE - 1) / TILE;
+    const unsigned grid = (unsigned)(n_work < (uint64_t)num_sms() * 4 ? n_work : (uint64_t)num_sms() * 4);
+#define PERF_RENDER_LAUNCH(K, P, SM) do { \
+        auto k = K<P, SM>; \
         PERF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_TOTAL)); \
         k<<<grid, TILE, RS_TOTAL, stream>>>(a); } while (0)
-    if (pano) { if (simt) PERF_RENDER_LAUNCH(true, true); else PERF_RENDER_LAUNCH(true, false); }
-    else      { if (simt) PERF_RENDER_LAUNCH(false, true); else PERF_RENDER_LAUNCH(false, false); }
+    if (scan) {
+        if (pano) { if (simt) PERF_RENDER_LAUNCH(render_kernel, true, true); else PERF_RENDER_LAUNCH(render_kernel, true, false); }
+        else      { if (simt) PERF_RENDER_LAUNCH(render_kernel, false, true); else PERF_RENDER_LAUNCH(render_kernel, false, false); }
+    } else {
+        if (pano) { if (simt) PERF_RENDER_LAUNCH(render_march_kernel, true, true); else PERF_RENDER_LAUNCH(render_march_kernel, true, false); }
+        else      { if (simt) PERF_RENDER_LAUNCH(render_march_kernel, false, true); else PERF_RENDER_LAUNCH(render_march_kernel, false, false); }
+    }
 #undef PERF_RENDER_LAUNCH
     PERF_LAUNCH_CHECK();
     return PERF_OK;

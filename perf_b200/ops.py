@@ -259,13 +259,16 @@ def accumulate_along_rays(weights, values, ray_indices, n_rays: int) -> torch.Te
 
 # ------------------------------------------------------------------ fused renderer
 def _render_args(packed_table, geo_mlp_half, app_mlp_half, aabb, n_samples, near, far, training, simt,
-                 jitter, bg_noise, rgb, distance, opacity, grid: GridConfig) -> "_lib.RenderArgs":
+                 jitter, bg_noise, rgb, distance, opacity, grid: GridConfig, kernel: str = "march") -> "_lib.RenderArgs":
     a = _lib.RenderArgs()
     a.grid = grid.c()
     a.d_packed_table, a.d_geo_mlp_half, a.d_app_mlp_half = packed_table.data_ptr(), geo_mlp_half.data_ptr(), app_mlp_half.data_ptr()
     a.aabb = (C.c_float * 6)(*[float(v) for v in aabb])
     a.n_samples, a.near, a.far = int(n_samples), float(near), float(far)
-    a.flags = (_lib.PERF_FLAG_TRAINING if training else 0) | (_lib.PERF_FLAG_SIMT_MLP if simt else 0)
+    if kernel not in ("march", "scan"):
+        raise ValueError(f"unknown render kernel {kernel!r}")
+    a.flags = ((_lib.PERF_FLAG_TRAINING if training else 0) | (_lib.PERF_FLAG_SIMT_MLP if simt else 0)
+               | (_lib.PERF_FLAG_SCAN_KERNEL if kernel == "scan" else 0))
     a.d_jitter = None if jitter is None else jitter.data_ptr()
     a.d_bg_noise = None if bg_noise is None else bg_noise.data_ptr()
     a.d_rgb, a.d_distance = rgb.data_ptr(), distance.data_ptr()
@@ -275,7 +278,7 @@ def _render_args(packed_table, geo_mlp_half, app_mlp_half, aabb, n_samples, near
 
 def render_rays(packed_table, geo_mlp_half, app_mlp_half, rays_o, rays_d, n_samples: int, near=1e-2, far=1.0,
                 aabb=(-1., -1., -1., 1., 1., 1.), training=False, jitter=None, bg_noise=None,
-                grid: GridConfig = PERF_GRID, simt=False):
+                grid: GridConfig = PERF_GRID, simt=False, kernel="march"):
     """Fused render of explicit rays [R,3] -> (rgb [R,3], distance [R,1], opacity [R,1])."""
     rays_o, rays_d = _chk(rays_o, torch.float32, "rays_o"), _chk(rays_d, torch.float32, "rays_d")
     R, dev = rays_o.shape[0], rays_o.device
@@ -287,7 +290,7 @@ def render_rays(packed_table, geo_mlp_half, app_mlp_half, rays_o, rays_d, n_samp
     jitter = None if jitter is None else _chk(jitter, torch.float32, "jitter")
     bg_noise = None if bg_noise is None else _chk(bg_noise, torch.float32, "bg_noise")
     a = _render_args(packed_table, geo_mlp_half, app_mlp_half, aabb, n_samples, near, far, training, simt,
-                     jitter, bg_noise, rgb, dist, op, grid)
+                     jitter, bg_noise, rgb, dist, op, grid, kernel)
     with torch.cuda.device(dev):
         _call(_L().perf_render_rays, C.byref(a), _p(rays_o), _p(rays_d), R, _stream())
     return rgb, dist, op
@@ -295,7 +298,7 @@ def render_rays(packed_table, geo_mlp_half, app_mlp_half, rays_o, rays_d, n_samp
 
 def render_pano(packed_table, geo_mlp_half, app_mlp_half, pose, H: int, W: int, n_samples: int, near=1e-2, far=1.0,
                 row0: int = 0, rows: Optional[int] = None, aabb=(-1., -1., -1., 1., 1., 1.),
-                grid: GridConfig = PERF_GRID, simt=False, out=None):
+                grid: GridConfig = PERF_GRID, simt=False, out=None, kernel="march"):
     """Fused render of rows [row0,row0+rows) of an HxW equirect panorama (ray-gen inside the kernel).
     Returns (rgb [rows,W,3], distance [rows,W,1], opacity [rows,W,1])."""
     rows = H - row0 if rows is None else rows
@@ -307,7 +310,7 @@ def render_pano(packed_table, geo_mlp_half, app_mlp_half, pose, H: int, W: int, 
     else:
         rgb, dist, op = out
     a = _render_args(packed_table, geo_mlp_half, app_mlp_half, aabb, n_samples, near, far, False, simt,
-                     None, None, rgb, dist, op, grid)
+                     None, None, rgb, dist, op, grid, kernel)
     with torch.cuda.device(dev):
         _call(_L().perf_render_pano, C.byref(a), _pose_array(pose), H, W, row0, rows, _stream())
     return rgb, dist, op

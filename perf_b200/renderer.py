@@ -20,8 +20,9 @@ class FusedPanoRenderer:
     PeRF checkpoints under ``nerf.geo_mlp.params`` / ``nerf.app_mlp.params``) in kernel layout."""
 
     def __init__(self, grid: GridConfig = PERF_GRID, aabb: Sequence[float] = (-1., -1., -1., 1., 1., 1.),
-                 near: float = 1e-2, far: float = 1.0):
+                 near: float = 1e-2, far: float = 1.0, kernel: str = "march"):
         self.grid, self.aabb, self.near, self.far = grid, tuple(float(v) for v in aabb), near, far
+        self.kernel = kernel          # "march": thread = ray (default); "scan": lanes = samples of one ray
         self.geo_half = self.app_half = self.packed = None
 
     @classmethod
@@ -58,7 +59,7 @@ class FusedPanoRenderer:
         self._ready()
         rgb, dist, op = ops.render_rays(self.packed, self.geo_half, self.app_half, rays_o.reshape(-1, 3), rays_d.reshape(-1, 3),
                                         n_samples, self.near if near is None else near, self.far if far is None else far,
-                                        self.aabb, training, jitter, bg_noise, self.grid, simt)
+                                        self.aabb, training, jitter, bg_noise, self.grid, simt, self.kernel)
         return {"rgb": rgb, "distance": dist, "opacities": op, "is_valid": True}
 
     def render_pano(self, pose, H: int, W: int, n_samples: int, row0: int = 0, rows: Optional[int] = None,
@@ -66,7 +67,7 @@ class FusedPanoRenderer:
         self._ready()
         rgb, dist, op = ops.render_pano(self.packed, self.geo_half, self.app_half, pose, H, W, n_samples,
                                         self.near if near is None else near, self.far if far is None else far,
-                                        row0, rows, self.aabb, self.grid, simt, out)
+                                        row0, rows, self.aabb, self.grid, simt, out, self.kernel)
         return {"rgb": rgb, "distance": dist, "opacities": op, "is_valid": True}
 
     @torch.no_grad()

@@ -12,6 +12,11 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
+    try:                                   # the oracle is many small torch ops: 64 threads thrash
+        import torch
+        torch.set_num_threads(min(8, os.cpu_count() or 1))
+    except Exception:
+        pass
 
 
 def pytest_collection_modifyitems(config, items):

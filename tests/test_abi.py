@@ -1,0 +1,96 @@
+"""CPU tests of the C-ABI boundary: the library builds/loads, exports exactly the symbols
+include/perfb200.h declares, and its host-side logic (level table, parameter layout, argument
+validation) agrees with the oracle.  No kernels are launched (no GPU here)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle.hashgrid import GridConfig as OGrid, level_table
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from perf_b200 import _lib
+    return _lib.load()
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "perfb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(perf_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from perf_b200 import _lib
+    names = header_symbols()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in perfb200.h but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
+    assert sorted(_lib.SIGNATURES) == names
+    assert lib.perf_abi_version() == 1
+
+
+@pytest.mark.parametrize("cfg", [OGrid(), OGrid(n_levels=5, log2_hashmap_size=17, per_level_scale=float(np.exp((np.log(128) - np.log(16)) / 4))),
+                                 OGrid(n_levels=16, log2_hashmap_size=19, per_level_scale=1.3819)])
+def test_level_table_matches_oracle(cfg):
+    from perf_b200.config import GridConfig
+    lv, n = GridConfig(cfg.n_levels, 2, cfg.log2_hashmap_size, cfg.base_resolution, cfg.per_level_scale).levels()
+    want = level_table(cfg)
+    assert n == oracle.hashgrid.n_table_entries(cfg)
+    for a, b in zip(lv, want):
+        assert np.float32(a.scale) == b.scale          # bit-identical fp32 scale
+        assert (a.resolution, a.size, a.offset, bool(a.hashed)) == (b.resolution, b.size, b.offset, b.hashed)
+
+
+def test_param_counts_match_checkpoint_layout():
+    # nerf.geo_mlp.params / nerf.app_mlp.params lengths of a PeRF checkpoint
+    from perf_b200.config import APP_MLP, GEO_MLP, PERF_GRID, network_param_count
+    assert network_param_count(PERF_GRID, GEO_MLP) == 6644288 == 3072 + 6641216
+    assert network_param_count(PERF_GRID, APP_MLP) == 6648384 == 7168 + 6641216
+    assert GEO_MLP.n_params == 3072 and APP_MLP.n_params == 7168
+
+
+def test_bad_arguments_fail_loudly(lib):
+    from perf_b200 import _lib
+    from perf_b200.config import GridConfig, MLPConfig
+    n = _lib.u64(0)
+    bad = GridConfig(n_levels=17).c()
+    assert lib.perf_grid_describe(bad, None, n) == -2 and b"n_levels" in lib.perf_last_error()
+    bad = GridConfig(n_features_per_level=4).c()
+    assert lib.perf_grid_describe(bad, None, n) == -2
+    assert lib.perf_network_param_count(GridConfig().c(), MLPConfig(n_neurons=128).c(), n) == -2
+    assert lib.perf_network_param_count(GridConfig().c(), MLPConfig(n_hidden_layers=3).c(), n) == -2
+    with pytest.raises(_lib.PerfError):
+        _lib.check(lib.perf_params_to_half(None, None, 10, None))
+    with pytest.raises(ValueError):
+        GridConfig.from_dict({"otype": "Frequency"})
+    with pytest.raises(ValueError):
+        MLPConfig.from_dict({"otype": "FullyFusedMLP", "activation": "Tanh"}, 32, 1)
+
+
+def test_no_cpu_path():
+    """The product refuses CPU tensors instead of silently computing something else."""
+    import torch
+    from perf_b200 import ops
+    from perf_b200.renderer import FusedPanoRenderer
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        ops.params_to_half(torch.zeros(16))
+    with pytest.raises(RuntimeError):
+        FusedPanoRenderer.from_params(torch.zeros(6644288), torch.zeros(6648384))
+
+
+def test_product_does_not_import_oracle():
+    import subprocess, sys
+    code = "import sys; import perf_b200, perf_b200.ops, perf_b200.renderer; assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules), 'oracle imported'"
+    subprocess.run([sys.executable, "-c", code], check=True, cwd=ROOT)
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "perf_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                assert "import oracle" not in open(os.path.join(dirpath, f)).read(), f

@@ -93,8 +93,10 @@ def test_network_fwd_matches_oracle(ops, golden_field, net, simt):
 
 @pytest.mark.parametrize("net", ["geo", "app"])
 def test_network_autograd_matches_oracle_autograd(ops, golden_field, net):
-    """dL/dparams through encode+MLP.  Oracle: plain fp32 torch autograd of the same network
-    evaluated at the fp16-rounded parameters (the kernels' forward operating point)."""
+    """dL/dparams through encode+MLP.  Oracle: torch autograd through the mixed-precision
+    restatement (fp16 rounding points are straight-through casts, ReLU masks come from the
+    rounded activations) evaluated at the fp16-rounded parameters -- the same operating point
+    and the same saved activations the kernels use."""
     from perf_b200.config import PERF_GRID
     ocfg, pcfg = cfgs()[net]
     params = (golden_field.geo_params if net == "geo" else golden_field.app_params).half().float()
@@ -104,20 +106,18 @@ def test_network_autograd_matches_oracle_autograd(ops, golden_field, net):
     dout = torch.randn(N, ocfg.n_out, generator=g)
     n_mlp = flat_param_count(ocfg)
     p_ref = params.clone().requires_grad_(True)
-    feat = encode(x, p_ref[n_mlp:], O_GRID)
-    y = mlp_forward(feat, split_params(p_ref[:n_mlp], ocfg), ocfg, mixed=False)
+    feat = encode(x, p_ref[n_mlp:], O_GRID, out_half=True)
+    y = mlp_forward(feat, split_params(p_ref[:n_mlp], ocfg), ocfg, mixed=True)
     (y * dout).sum().backward()
     p = params.cuda().requires_grad_(True)
     out = ops.network_apply(p, x.cuda(), PERF_GRID, pcfg)
     (out.float() * dout.cuda()).sum().backward()
     got, want = p.grad.cpu(), p_ref.grad
     assert got.shape == want.shape
-    # MLP-matrix gradients: dense sums over N samples
-    gm, wm = got[:n_mlp], want[:n_mlp]
-    assert (gm - wm).abs().max() <= 2e-2 * wm.abs().max()
-    # grid gradients: sparse; compare where the oracle has signal
-    gg, wg = got[n_mlp:], want[n_mlp:]
+    gm, wm = got[:n_mlp], want[:n_mlp]                    # MLP matrices: dense sums over N samples
+    assert (gm - wm).abs().max() <= 1e-2 * wm.abs().max(), float((gm - wm).abs().max() / wm.abs().max())
+    gg, wg = got[n_mlp:], want[n_mlp:]                    # grid: sparse scatter
     assert ((wg != 0) == (gg != 0)).float().mean() > 0.999
-    assert (gg - wg).abs().max() <= 2e-2 * wg.abs().max()
+    assert (gg - wg).abs().max() <= 1e-2 * wg.abs().max(), float((gg - wg).abs().max() / wg.abs().max())
     cos = torch.nn.functional.cosine_similarity(gg, wg, dim=0)
-    assert cos > 0.9995, float(cos)
+    assert cos > 0.9999, float(cos)

@@ -23,10 +23,11 @@ def psnr(a, b):
     return 99.0 if mse == 0 else -10.0 * np.log10(mse)
 
 
-@pytest.fixture(scope="module")
-def renderer(golden_field):
+@pytest.fixture(scope="module", params=["march", "scan"])
+def renderer(golden_field, request):
+    """Both fused kernels: "march" (thread = ray, the default) and "scan" (lanes = samples)."""
     from perf_b200.renderer import FusedPanoRenderer
-    return FusedPanoRenderer.from_params(golden_field.geo_params.cuda(), golden_field.app_params.cuda())
+    return FusedPanoRenderer.from_params(golden_field.geo_params.cuda(), golden_field.app_params.cuda(), kernel=request.param)
 
 
 @pytest.mark.parametrize("simt", [True, False], ids=["simt", "tcgen05"])

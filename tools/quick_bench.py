@@ -13,7 +13,9 @@ def rand_params(mlp):
     return torch.cat([w, g])
 r = FusedPanoRenderer.from_params(rand_params(GEO_MLP), rand_params(APP_MLP))
 pose = torch.eye(4)
-for (H, W, S, rows) in [(128, 256, 32, 128), (1024, 2048, 128, 128), (1024, 2048, 128, 1024)]:
+import itertools
+for kern, (H, W, S, rows) in itertools.product(["march", "scan"], [(128, 256, 32, 128), (1024, 2048, 128, 128), (1024, 2048, 128, 1024), (2048, 4096, 256, 256)]):
+    r.kernel = kern
     out = r.render_pano(pose, H, W, S, rows=rows); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n = 3
@@ -23,4 +25,4 @@ for (H, W, S, rows) in [(128, 256, 32, 128), (1024, 2048, 128, 128), (1024, 2048
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
     ns = rows * W * S
-    print(f"render {H}x{W} rows={rows} S={S}: {ms:.3f} ms  {ns/ms/1e3:.1f} Msamples/s  algGB/s={ns*1024/ms/1e6:.0f}", flush=True)
+    print(f"[{kern}] render {H}x{W} rows={rows} S={S}: {ms:.3f} ms  {ns/ms/1e3:.1f} Msamples/s  algGB/s={ns*1024/ms/1e6:.0f}", flush=True)
