@@ -66,6 +66,7 @@ typedef struct perf_mlp_cfg {
 /* flags of the render / field entry points */
 #define PERF_FLAG_TRAINING   1u   /* stratified jitter + training background rule        */
 #define PERF_FLAG_SIMT_MLP   2u   /* debug only: MLP on CUDA cores instead of tcgen05     */
+#define PERF_FLAG_GENERIC_ADDR 8u  /* render: disable the specialised (4 dense + hashed pow2) addressing path */
 #define PERF_FLAG_SCAN_KERNEL 4u   /* render: samples-along-lanes kernel (warp-shuffle scan composite) instead of ray marching */
 
 int         perf_abi_version(void);

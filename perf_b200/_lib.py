@@ -15,6 +15,7 @@ u32, u64, f32, i32, vp = C.c_uint32, C.c_uint64, C.c_float, C.c_int, C.c_void_p
 PERF_FLAG_TRAINING = 1
 PERF_FLAG_SIMT_MLP = 2
 PERF_FLAG_SCAN_KERNEL = 4
+PERF_FLAG_GENERIC_ADDR = 8
 
 
 class GridCfg(C.Structure):

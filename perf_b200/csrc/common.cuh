@@ -81,6 +81,55 @@ __device__ __forceinline__ void level_corners(const LevelTable& lt, int l, float
     }
 }
 
+// Specialised addressing for the hot kernels: the level kind is a compile-time constant
+// (HASHED levels must have a power-of-two size, dense levels use idx < 2*size), coordinates must
+// lie in [0,1] (callers clamp masked-out samples) and interpolation is Linear.  Produces exactly
+// the indices / weights of level_corners() under those preconditions -- no divisions, no branches.
+template <bool HASHED>
+__device__ __forceinline__ void level_corners_fast(const LevelTable& lt, int l, float x, float y, float z, Corner8& c)
+{
+    const float scale = lt.scale[l];
+    const uint32_t res = lt.res[l], size = lt.size[l], off = lt.offset[l];
+    const float px = fmaf(scale, x, 0.5f), py = fmaf(scale, y, 0.5f), pz = fmaf(scale, z, 0.5f);
+    const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+    const uint32_t gx = (uint32_t)(int)fx, gy = (uint32_t)(int)fy, gz = (uint32_t)(int)fz;
+    const float wx = px - fx, wy = py - fy, wz = pz - fz;
+    const float ox = 1.0f - wx, oy = 1.0f - wy, oz = 1.0f - wz;
+    const float wxy[4] = {__fmul_rn(ox, oy), __fmul_rn(wx, oy), __fmul_rn(ox, wy), __fmul_rn(wx, wy)};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) c.w[k] = __fmul_rn(wxy[k & 3], (k & 4) ? wz : oz);
+    if constexpr (HASHED) {
+        const uint32_t mask = size - 1u;
+        const uint32_t hy0 = gy * 2654435761u, hy1 = hy0 + 2654435761u;
+        const uint32_t hz0 = gz * 805459861u,  hz1 = hz0 + 805459861u;
+        const uint32_t hyz[4] = {hy0 ^ hz0, hy1 ^ hz0, hy0 ^ hz1, hy1 ^ hz1};
+        const uint32_t gx1 = gx + 1u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) c.idx[k] = off + ((((k & 1) ? gx1 : gx) ^ hyz[k >> 1]) & mask);
+    } else {
+        const uint32_t r2 = res * res;
+        const uint32_t b00 = gx + gy * res + gz * r2;
+        const uint32_t base[4] = {b00, b00 + res, b00 + r2, b00 + res + r2};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            uint32_t i = base[k >> 1] + (uint32_t)(k & 1);
+            i = (i >= size) ? i - size : i;                 // == i % size for i < 2*size
+            c.idx[k] = off + i;
+        }
+    }
+}
+// host-side precondition of the fast path: `n_dense` leading dense levels, every other level
+// hashed with a power-of-two size, Linear interpolation
+inline bool fast_addressing_ok(const LevelTable& lt, uint32_t n_dense)
+{
+    if (lt.smoothstep) return false;
+    for (uint32_t l = 0; l < lt.n_levels; ++l) {
+        const bool hashed = (lt.hashed_mask >> l) & 1u, pow2 = (lt.pow2_mask >> l) & 1u;
+        if (l < n_dense ? hashed : !(hashed && pow2)) return false;
+    }
+    return true;
+}
+
 __device__ __forceinline__ uint32_t pack_half2(float a, float b)
 {
     __half2 h = __floats2half2_rn(a, b);

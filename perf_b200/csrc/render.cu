@@ -125,7 +125,9 @@ struct RenderSmem {
 
 // Encode + both MLPs for the CTA's current 128 samples (thread t = sample t at normalised
 // position (x,y,z)).  Contains 2 block-wide barriers + 2 mbarrier waits; all 128 threads call it.
-template <bool SIMT>
+// NDENSE >= 0: specialised addressing (level_corners_fast; first NDENSE levels dense, rest hashed
+// power-of-two) -- branch-free and ~1/3 smaller code; NDENSE < 0: generic addressing.
+template <bool SIMT, int NDENSE>
 __device__ __forceinline__ void eval_fields(const RenderArgs& a, const RenderSmem& sm, float x, float y, float z, bool selector,
                                             uint32_t tmem_base, uint32_t tmem_row, uint32_t& parity, int tid,
                                             float& sigma, float& cr, float& cg, float& cb)
@@ -133,6 +135,7 @@ __device__ __forceinline__ void eval_fields(const RenderArgs& a, const RenderSme
     uint8_t* const sA = sm.sA; uint8_t* const sAg = sm.sAg; uint8_t* const sAa = sm.sAa;
     uint8_t* const sW1g = sm.sW1g; uint8_t* const sW1a = sm.sW1a; uint8_t* const sW2a = sm.sW2a;
     float* const sWoutG = sm.sWoutG; float* const sWoutA = sm.sWoutA; uint64_t* const bar = sm.bar;
+    if (NDENSE >= 0 && !selector) { x = 0.5f; y = 0.5f; z = 0.5f; }   // masked sample: any in-box address will do
     // ---- encode both fields: 16 levels x 8 corners, one 8-byte gather per corner
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -140,7 +143,10 @@ __device__ __forceinline__ void eval_fields(const RenderArgs& a, const RenderSme
 #pragma unroll
         for (int ll = 0; ll < 4; ++ll) {
             const int l = 4 * q + ll;
-            Corner8 c; level_corners(a.lt, l, x, y, z, c);
+            Corner8 c;
+            if constexpr (NDENSE < 0) level_corners(a.lt, l, x, y, z, c);
+            else if (l < NDENSE) level_corners_fast<false>(a.lt, l, x, y, z, c);
+            else level_corners_fast<true>(a.lt, l, x, y, z, c);
             uint2 v[8];
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) v[kk] = __ldg(a.table + c.idx[kk]);
@@ -309,7 +315,7 @@ __global__ void __launch_bounds__(TILE, 4) render_kernel(const __grid_constant__
             const bool selector = valid && x > 0.f && x < 1.f && y > 0.f && y < 1.f && z > 0.f && z < 1.f;
 
             float sigma, cr, cg, cb;
-            eval_fields<SIMT>(a, sm, x, y, z, selector, tmem_base, tmem_row, parity, tid, sigma, cr, cg, cb);
+            eval_fields<SIMT, -1>(a, sm, x, y, z, selector, tmem_base, tmem_row, parity, tid, sigma, cr, cg, cb);
 
             // ---- composite (nerf_renderer.py:170-183; oracle/composite.py)
             const float dt = __fsub_rn(te, ts);
@@ -364,7 +370,7 @@ __global__ void __launch_bounds__(TILE, 4) render_kernel(const __grid_constant__
 // per request at the coarse and middle levels) and a thread revisits the same cells from k to k+1
 // (temporal L1 reuse).  The composite is a per-thread running sum: no shuffles, no carries.
 // Transmittance uses the sequential exclusive sum, the order of the oracle's cumsum.
-template <bool PANO, bool SIMT>
+template <bool PANO, bool SIMT, int NDENSE>
 __global__ void __launch_bounds__(TILE, 4) render_march_kernel(const __grid_constant__ RenderArgs a)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -455,7 +461,7 @@ __global__ void __launch_bounds__(TILE, 4) render_march_kernel(const __grid_cons
             const bool selector = valid && x > 0.f && x < 1.f && y > 0.f && y < 1.f && z > 0.f && z < 1.f;
 
             float sigma, cr, cg, cb;
-            eval_fields<SIMT>(a, sm, x, y, z, selector, tmem_base, tmem_row, parity, tid, sigma, cr, cg, cb);
+            eval_fields<SIMT, NDENSE>(a, sm, x, y, z, selector, tmem_base, tmem_row, parity, tid, sigma, cr, cg, cb);
 
             const float sd = sigma * __fsub_rn(te, ts);
             const float w = expf(-sum_sd) * (1.f - expf(-sd));
@@ -518,16 +524,20 @@ static int launch_render(const perf_render_args* args, RenderArgs& a, bool pano,
     else if (pano) n_work = (uint64_t)((a.W + 15) / 16) * (uint64_t)(((int)(a.R / (uint64_t)a.W) + 7) / 8);
     else n_work = (a.R + TILE - 1) / TILE;
     const unsigned grid = (unsigned)(n_work < (uint64_t)num_sms() * 4 ? n_work : (uint64_t)num_sms() * 4);
-#define PERF_RENDER_LAUNCH(K, P, SM) do { \
-        auto k = K<P, SM>; \
+#define PERF_RENDER_LAUNCH(...) do { \
+        auto k = __VA_ARGS__; \
         PERF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_TOTAL)); \
         k<<<grid, TILE, RS_TOTAL, stream>>>(a); } while (0)
+    const bool fast = fast_addressing_ok(a.lt, 4) && (args->flags & PERF_FLAG_GENERIC_ADDR) == 0;   // PeRF's grid: 4 dense + 12 hashed levels
     if (scan) {
-        if (pano) { if (simt) PERF_RENDER_LAUNCH(render_kernel, true, true); else PERF_RENDER_LAUNCH(render_kernel, true, false); }
-        else      { if (simt) PERF_RENDER_LAUNCH(render_kernel, false, true); else PERF_RENDER_LAUNCH(render_kernel, false, false); }
+        if (pano) { if (simt) PERF_RENDER_LAUNCH(render_kernel<true, true>); else PERF_RENDER_LAUNCH(render_kernel<true, false>); }
+        else      { if (simt) PERF_RENDER_LAUNCH(render_kernel<false, true>); else PERF_RENDER_LAUNCH(render_kernel<false, false>); }
+    } else if (simt) {
+        if (pano) PERF_RENDER_LAUNCH(render_march_kernel<true, true, -1>); else PERF_RENDER_LAUNCH(render_march_kernel<false, true, -1>);
+    } else if (fast) {
+        if (pano) PERF_RENDER_LAUNCH(render_march_kernel<true, false, 4>); else PERF_RENDER_LAUNCH(render_march_kernel<false, false, 4>);
     } else {
-        if (pano) { if (simt) PERF_RENDER_LAUNCH(render_march_kernel, true, true); else PERF_RENDER_LAUNCH(render_march_kernel, true, false); }
-        else      { if (simt) PERF_RENDER_LAUNCH(render_march_kernel, false, true); else PERF_RENDER_LAUNCH(render_march_kernel, false, false); }
+        if (pano) PERF_RENDER_LAUNCH(render_march_kernel<true, false, -1>); else PERF_RENDER_LAUNCH(render_march_kernel<false, false, -1>);
     }
 #undef PERF_RENDER_LAUNCH
     PERF_LAUNCH_CHECK();

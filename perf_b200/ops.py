@@ -265,10 +265,11 @@ def _render_args(packed_table, geo_mlp_half, app_mlp_half, aabb, n_samples, near
     a.d_packed_table, a.d_geo_mlp_half, a.d_app_mlp_half = packed_table.data_ptr(), geo_mlp_half.data_ptr(), app_mlp_half.data_ptr()
     a.aabb = (C.c_float * 6)(*[float(v) for v in aabb])
     a.n_samples, a.near, a.far = int(n_samples), float(near), float(far)
-    if kernel not in ("march", "scan"):
+    if kernel not in ("march", "march_generic", "scan"):
         raise ValueError(f"unknown render kernel {kernel!r}")
     a.flags = ((_lib.PERF_FLAG_TRAINING if training else 0) | (_lib.PERF_FLAG_SIMT_MLP if simt else 0)
-               | (_lib.PERF_FLAG_SCAN_KERNEL if kernel == "scan" else 0))
+               | (_lib.PERF_FLAG_SCAN_KERNEL if kernel == "scan" else 0)
+               | (_lib.PERF_FLAG_GENERIC_ADDR if kernel == "march_generic" else 0))
     a.d_jitter = None if jitter is None else jitter.data_ptr()
     a.d_bg_noise = None if bg_noise is None else bg_noise.data_ptr()
     a.d_rgb, a.d_distance = rgb.data_ptr(), distance.data_ptr()

@@ -23,9 +23,10 @@ def psnr(a, b):
     return 99.0 if mse == 0 else -10.0 * np.log10(mse)
 
 
-@pytest.fixture(scope="module", params=["march", "scan"])
+@pytest.fixture(scope="module", params=["march", "march_generic", "scan"])
 def renderer(golden_field, request):
-    """Both fused kernels: "march" (thread = ray, the default) and "scan" (lanes = samples)."""
+    """All fused kernels: "march" (thread = ray, specialised addressing; the default), the same with
+    generic addressing, and "scan" (lanes = samples of one ray, warp-shuffle composite)."""
     from perf_b200.renderer import FusedPanoRenderer
     return FusedPanoRenderer.from_params(golden_field.geo_params.cuda(), golden_field.app_params.cuda(), kernel=request.param)
 
@@ -124,3 +125,13 @@ def test_empty_and_zero_density(renderer, golden_field):
     assert torch.equal(out["rgb"], torch.full_like(out["rgb"], 0.5))
     assert torch.equal(out["distance"], torch.full_like(out["distance"], 5.0))
     assert torch.equal(out["opacities"], torch.zeros_like(out["opacities"]))
+
+
+def test_fast_addressing_is_bit_identical_to_generic(golden_field):
+    from perf_b200.renderer import FusedPanoRenderer
+    a = FusedPanoRenderer.from_params(golden_field.geo_params.cuda(), golden_field.app_params.cuda(), kernel="march")
+    b = FusedPanoRenderer.from_params(golden_field.geo_params.cuda(), golden_field.app_params.cuda(), kernel="march_generic")
+    pose = torch.eye(4); pose[:3, 3] = torch.tensor([0.3, -0.2, 0.1])     # many samples leave the box
+    ra, rb = a.render_pano(pose, 64, 128, 96, far=1.6), b.render_pano(pose, 64, 128, 96, far=1.6)
+    for k in ("rgb", "distance", "opacities"):
+        assert torch.equal(ra[k], rb[k]), k

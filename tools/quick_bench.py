@@ -14,7 +14,7 @@ def rand_params(mlp):
 r = FusedPanoRenderer.from_params(rand_params(GEO_MLP), rand_params(APP_MLP))
 pose = torch.eye(4)
 import itertools
-for kern, (H, W, S, rows) in itertools.product(["march", "scan"], [(128, 256, 32, 128), (1024, 2048, 128, 128), (1024, 2048, 128, 1024), (2048, 4096, 256, 256)]):
+for kern, (H, W, S, rows) in itertools.product(["march", "march_generic"], [(128, 256, 32, 128), (1024, 2048, 128, 128), (1024, 2048, 128, 1024), (2048, 4096, 256, 256)]):
     r.kernel = kern
     out = r.render_pano(pose, H, W, S, rows=rows); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
