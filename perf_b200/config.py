@@ -96,3 +96,69 @@ def network_param_count(grid: GridConfig, mlp: MLPConfig) -> int:
     n = _lib.u64(0)
     _lib.check(_lib.load().perf_network_param_count(grid.c(), mlp.c(), n))
     return int(n.value)
+
+
+# ------------------------------------------------------------------ experiment configuration
+class Conf(dict):
+    """Attribute-style dict (stands in for the OmegaConf node the reference receives from Hydra)."""
+    __getattr__ = dict.__getitem__
+
+    @staticmethod
+    def wrap(v):
+        if isinstance(v, dict):
+            return Conf({k: Conf.wrap(x) for k, x in v.items()})
+        if isinstance(v, list):
+            return [Conf.wrap(x) for x in v]
+        return v
+
+
+def _coerce(text: str):
+    import yaml
+    v = yaml.safe_load(text)
+    if isinstance(v, str):
+        try:
+            return float(v)                      # YAML 1.1 reads "1e-2" as a string; Hydra reads a float
+        except ValueError:
+            return v
+    return v
+
+
+def _fix_floats(node):
+    if isinstance(node, dict):
+        return {k: _fix_floats(v) for k, v in node.items()}
+    if isinstance(node, list):
+        return [_fix_floats(v) for v in node]
+    if isinstance(node, str):
+        try:
+            return float(node)
+        except ValueError:
+            return node
+    return node
+
+
+def load_config(config_dir: str, config_name: str = "nerf", overrides=()) -> Conf:
+    """Read PeRF's Hydra YAML (`/root/reference/configs/nerf.yaml` + its ``defaults`` list, e.g.
+    ``device: local`` -> ``configs/device/local.yaml``) without hydra, then apply dotted
+    ``key=value`` overrides exactly like the reference's command line
+    (`/root/reference/core_exp_runner.py:259`)."""
+    import os
+    import yaml
+    with open(os.path.join(config_dir, config_name + ".yaml")) as f:
+        root = yaml.safe_load(f)
+    merged = {}
+    for item in root.pop("defaults", []):
+        if item == "_self_":
+            continue
+        for group, choice in item.items():
+            with open(os.path.join(config_dir, group, str(choice) + ".yaml")) as f:
+                merged[group] = yaml.safe_load(f)
+    merged.update(root)
+    merged = _fix_floats(merged)
+    for ov in overrides:
+        key, _, val = ov.partition("=")
+        node = merged
+        parts = key.split(".")
+        for p in parts[:-1]:
+            node = node.setdefault(p, {})
+        node[parts[-1]] = _coerce(val)
+    return Conf.wrap(merged)

@@ -123,6 +123,35 @@ struct RenderSmem {
     uint64_t* bar;
 };
 
+// Levels [4q, 4q+4) of both fields -> one 16-byte k-group of each feature tile.
+// KIND 0: generic addressing, 1: dense (fast), 2: hashed power-of-two (fast).
+template <int KIND>
+__device__ __forceinline__ void encode_group(const RenderArgs& a, const RenderSmem& sm, int q, float x, float y, float z, int tid)
+{
+    uint32_t pg[4], pa[4];
+#pragma unroll
+    for (int ll = 0; ll < 4; ++ll) {
+        const int l = 4 * q + ll;
+        Corner8 c;
+        if constexpr (KIND == 0) level_corners(a.lt, l, x, y, z, c);
+        else if constexpr (KIND == 1) level_corners_fast<false>(a.lt, l, x, y, z, c);
+        else level_corners_fast<true>(a.lt, l, x, y, z, c);
+        uint2 v[8];
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) v[kk] = __ldg(a.table + c.idx[kk]);
+        float g0 = 0.f, g1 = 0.f, a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+            const float2 tg = unpack_half2(v[kk].x), ta = unpack_half2(v[kk].y);
+            g0 = fmaf(c.w[kk], tg.x, g0); g1 = fmaf(c.w[kk], tg.y, g1);
+            a0 = fmaf(c.w[kk], ta.x, a0); a1 = fmaf(c.w[kk], ta.y, a1);
+        }
+        pg[ll] = pack_half2(g0, g1); pa[ll] = pack_half2(a0, a1);
+    }
+    *reinterpret_cast<uint4*>(sm.sAg + (q * TILE + tid) * 16) = make_uint4(pg[0], pg[1], pg[2], pg[3]);
+    *reinterpret_cast<uint4*>(sm.sAa + (q * TILE + tid) * 16) = make_uint4(pa[0], pa[1], pa[2], pa[3]);
+}
+
 // Encode + both MLPs for the CTA's current 128 samples (thread t = sample t at normalised
 // position (x,y,z)).  Contains 2 block-wide barriers + 2 mbarrier waits; all 128 threads call it.
 // NDENSE >= 0: specialised addressing (level_corners_fast; first NDENSE levels dense, rest hashed
@@ -137,30 +166,15 @@ __device__ __forceinline__ void eval_fields(const RenderArgs& a, const RenderSme
     float* const sWoutG = sm.sWoutG; float* const sWoutA = sm.sWoutA; uint64_t* const bar = sm.bar;
     if (NDENSE >= 0 && !selector) { x = 0.5f; y = 0.5f; z = 0.5f; }   // masked sample: any in-box address will do
     // ---- encode both fields: 16 levels x 8 corners, one 8-byte gather per corner
+    if constexpr (NDENSE == 4) {
+        // dense group unrolled; the three hashed groups share ONE copy of the code (the fully
+        // unrolled body was ~70 KB of SASS and stalled on instruction fetch)
+        encode_group<1>(a, sm, 0, x, y, z, tid);
+#pragma unroll 1
+        for (int q = 1; q < 4; ++q) encode_group<2>(a, sm, q, x, y, z, tid);
+    } else {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        uint32_t pg[4], pa[4];
-#pragma unroll
-        for (int ll = 0; ll < 4; ++ll) {
-            const int l = 4 * q + ll;
-            Corner8 c;
-            if constexpr (NDENSE < 0) level_corners(a.lt, l, x, y, z, c);
-            else if (l < NDENSE) level_corners_fast<false>(a.lt, l, x, y, z, c);
-            else level_corners_fast<true>(a.lt, l, x, y, z, c);
-            uint2 v[8];
-#pragma unroll
-            for (int kk = 0; kk < 8; ++kk) v[kk] = __ldg(a.table + c.idx[kk]);
-            float g0 = 0.f, g1 = 0.f, a0 = 0.f, a1 = 0.f;
-#pragma unroll
-            for (int kk = 0; kk < 8; ++kk) {
-                const float2 tg = unpack_half2(v[kk].x), ta = unpack_half2(v[kk].y);
-                g0 = fmaf(c.w[kk], tg.x, g0); g1 = fmaf(c.w[kk], tg.y, g1);
-                a0 = fmaf(c.w[kk], ta.x, a0); a1 = fmaf(c.w[kk], ta.y, a1);
-            }
-            pg[ll] = pack_half2(g0, g1); pa[ll] = pack_half2(a0, a1);
-        }
-        *reinterpret_cast<uint4*>(sAg + (q * TILE + tid) * 16) = make_uint4(pg[0], pg[1], pg[2], pg[3]);
-        *reinterpret_cast<uint4*>(sAa + (q * TILE + tid) * 16) = make_uint4(pa[0], pa[1], pa[2], pa[3]);
+        for (int q = 0; q < 4; ++q) encode_group<0>(a, sm, q, x, y, z, tid);
     }
 
     // ---- layer 1 of both nets

@@ -1,0 +1,330 @@
+"""Host-side mirror of PeRF's scene layer for the fixed-S sampler, on libperfb200.
+
+Mirrors (same method names, argument meaning, dict keys, error behaviour):
+  ``NeRFScene``            `/root/reference/modules/scene/nerf.py:28-396`
+  ``NeRFOCCRenderer``      `/root/reference/modules/scene/nerf_renderer.py:105-209`
+  ``SupInfoPool.rand_ray_color_data``  `/root/reference/modules/dataset/sup_info.py:236-259`
+What differs by design: ``render`` (eval, no grad) is ONE fused-kernel launch instead of a
+32768-ray chunk loop; the optimiser is the fused Adam kernel; with WORLD_SIZE > 1 the ray batch is
+sharded over ranks and the flat gradient is all-reduced once per step.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import ops, parallel
+from .config import Conf
+from .field import NGPNeRF
+from .renderer import FusedPanoRenderer
+from .shims import nerfacc
+from .shims.torch_efficient_distloss import flatten_eff_distloss
+
+
+@dataclass
+class Rays:                                   # utils/camera_utils.py:9-20
+    o: torch.Tensor
+    d: torch.Tensor
+
+    def __len__(self):
+        return len(self.o)
+
+    def __getitem__(self, idx):
+        return Rays(self.o[idx], self.d[idx])
+
+    def collapse(self):
+        return self.o, self.d
+
+
+def gen_pano_rays(pose, height=512, width=1024, device="cuda") -> Rays:
+    """`utils/camera_utils.py:229-234` on the GPU (perf_raygen_pano)."""
+    o, d = ops.raygen_pano(pose, height, width, device=device)
+    return Rays(o, d)
+
+
+class FixedSampleEstimator(torch.nn.Module):
+    """Stands where ``OccGridEstimator`` stands in the renderer: the benchmark's fixed-S sampler
+    (SURVEY.md 8 a7'): ``t_s[k] = near + (k + u_r) * step``, one jitter ``u_r`` per ray when
+    stratified.  Returns packed (ray_indices, t_starts, t_ends) like nerfacc."""
+
+    def __init__(self, n_samples: int = 128, near: float = 1e-2, far: float = 1.0):
+        super().__init__()
+        self.n_samples, self.near, self.far = n_samples, near, far
+        self._ri = None
+
+    @torch.no_grad()
+    def sampling(self, rays_o, rays_d, sigma_fn=None, stratified=False, jitter=None, **_):
+        R, S, dev = rays_o.shape[0], self.n_samples, rays_o.device
+        near, far = torch.tensor(self.near, device=dev), torch.tensor(self.far, device=dev)
+        step = (far - near) / float(S)
+        k = torch.arange(S + 1, device=dev, dtype=torch.float32)[None, :]
+        if jitter is None:
+            jitter = torch.rand(R, device=dev) if stratified else torch.zeros(R, device=dev)
+        edges = near + (k + jitter.reshape(R, 1)) * step
+        if self._ri is None or self._ri.numel() != R * S or self._ri.device != dev:
+            self._ri = torch.arange(R, device=dev).repeat_interleave(S)
+        return self._ri, edges[:, :-1].reshape(-1), edges[:, 1:].reshape(-1)
+
+
+class NeRFOCCRenderer(torch.nn.Module):
+    """Differentiable (training) render path = the reference's renderer line by line on the plugin
+    functions; `nerf_renderer.py:112-209`."""
+
+    def __init__(self, max_radius=2, bg_color="rand_noise"):
+        super().__init__()
+        assert bg_color in ["rand_noise", "black", "white"]
+        self.max_radius, self.bg_color = max_radius, bg_color
+
+    def render(self, nerf: NGPNeRF, estimator, rays_o, rays_d, near=None, far=None, geo_inference=False, app_inference=False):
+        n_rays, dev = rays_o.shape[0], rays_o.device
+
+        def positions(t_starts, t_ends, ray_indices):
+            return rays_o[ray_indices] + rays_d[ray_indices] * (t_starts + t_ends)[:, None] / 2.0
+
+        def sigma_fn(t_starts, t_ends, ray_indices):
+            return nerf.query_density(positions(t_starts, t_ends, ray_indices)).squeeze(-1)
+
+        ray_indices, t_starts, t_ends = estimator.sampling(rays_o, rays_d, sigma_fn=sigma_fn, near_plane=0., far_plane=1.5,
+                                                           render_step_size=5e-4, stratified=nerf.training,
+                                                           cone_angle=0., alpha_thre=0.)
+        if ray_indices.numel() <= 0:
+            return {"is_valid": False, "rgb": torch.zeros(n_rays, 3, device=dev), "distance": torch.zeros(n_rays, 1, device=dev),
+                    "opacities": torch.zeros(n_rays, 1, device=dev)}
+        pos = positions(t_starts, t_ends, ray_indices)
+        with torch.set_grad_enabled(torch.is_grad_enabled() and not geo_inference):
+            sigmas = nerf.query_density(pos).squeeze(-1)
+        weights, trans, alphas = nerfacc.render_weight_from_density(t_starts, t_ends, sigmas, ray_indices=ray_indices, n_rays=n_rays)
+        opacities = nerfacc.accumulate_along_rays(weights, values=None, ray_indices=ray_indices, n_rays=n_rays)
+        sampled_distances = ((t_starts + t_ends) / 2.0)[..., None]
+        distances = nerfacc.accumulate_along_rays(weights, sampled_distances, ray_indices=ray_indices, n_rays=n_rays)
+        with torch.set_grad_enabled(torch.is_grad_enabled() and not app_inference):
+            rgbs = nerf.query_rgb(pos)
+        colors = nerfacc.accumulate_along_rays(weights.detach(), values=rgbs, ray_indices=ray_indices, n_rays=n_rays)
+        if self.bg_color == "rand_noise":
+            bg_color = torch.rand(n_rays, 3, device=dev)
+        elif self.bg_color == "white":
+            bg_color = torch.ones(n_rays, 3, device=dev)
+        else:
+            bg_color = torch.zeros(n_rays, 3, device=dev)
+        if nerf.training:
+            distances = torch.relu(distances + (torch.rand_like(distances) * 2. - 1.) * (1. - opacities))
+            colors = colors + bg_color * (1. - opacities).detach()
+        else:
+            distances = distances + 5. * (1. - opacities).detach()
+            colors = colors + .5 * (1. - opacities).detach()
+        return {"is_valid": True, "rgb": colors, "distance": distances, "weights": weights, "opacities": opacities,
+                "trans": trans, "t_starts": t_starts, "t_ends": t_ends, "ray_indices": ray_indices}
+
+
+class RaySupervision:
+    """Flat pool of supervised rays = what ``SupInfoPool`` exposes to the trainer
+    (`sup_info.py:236-259`: ``all_sup_rays / all_sup_colors / all_sup_distances``)."""
+
+    def __init__(self, rays: Rays, colors: torch.Tensor, distances: torch.Tensor, normals: Optional[torch.Tensor] = None, seed: int = 0):
+        self.all_sup_rays, self.all_sup_colors = rays, colors
+        self.all_sup_distances = distances.reshape(-1, 1)
+        self.all_sup_normals = torch.zeros_like(colors) if normals is None else normals
+        self.generator = torch.Generator(device=colors.device).manual_seed(seed + parallel.rank())
+
+    @staticmethod
+    def from_panorama(pose, rgb: torch.Tensor, distance: torch.Tensor, seed: int = 0) -> "RaySupervision":
+        h, w = distance.shape[:2]
+        rays = gen_pano_rays(pose, h, w, device=rgb.device)
+        return RaySupervision(Rays(rays.o.reshape(-1, 3), rays.d.reshape(-1, 3)), rgb.reshape(-1, 3).float(), distance.reshape(-1, 1).float(), seed=seed)
+
+    def rand_ray_color_data(self, batch_size, rand_mode="by_all_pixels"):
+        idx = torch.randint(0, len(self.all_sup_colors), (batch_size,), device=self.all_sup_colors.device, generator=self.generator)
+        return self.all_sup_rays[idx], self.all_sup_colors[idx], self.all_sup_distances[idx], self.all_sup_normals[idx]
+
+
+class FusedAdam:
+    """``torch.optim.Adam(params, lr)`` semantics (defaults betas=(.9,.999), eps=1e-8) on one flat
+    fp32 parameter through perf_adam_step; exposes ``param_groups`` so ``update_lr`` reads as in
+    `nerf.py:300-311`.  Gradients are averaged over ranks first when distributed."""
+
+    def __init__(self, param: torch.nn.Parameter, lr: float = 0.0, betas=(0.9, 0.999), eps: float = 1e-8, module=None):
+        self.param, self.betas, self.eps = param, betas, eps
+        self.module = module        # tinycudann shim module owning `param`: its fp16 shadow is refreshed by the Adam kernel
+        self.param_groups = [{"lr": lr}]
+        self.exp_avg, self.exp_avg_sq = torch.zeros_like(param.data), torch.zeros_like(param.data)
+        self.step_count = 0
+
+    def zero_grad(self):
+        self.param.grad = None
+
+    def step(self):
+        if self.param.grad is None:
+            return
+        g = parallel.allreduce_mean_(self.param.grad.contiguous())
+        self.step_count += 1
+        half = None
+        if self.module is not None:
+            half = self.module._half()                       # allocate / reuse the module's fp16 shadow buffer
+        ops.adam_step(self.param.data, g, self.exp_avg, self.exp_avg_sq, self.step_count, self.param_groups[0]["lr"],
+                      params_half=half, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps)
+        # the kernel wrote through .data: bump autograd's version counter so version-keyed caches notice
+        torch._C._increment_version(self.param)
+        if self.module is not None:                          # the shadow is already current for the new version
+            self.module._half_key = (self.param._version, self.param.data_ptr())
+
+
+DEFAULT_TRAIN_CONF = Conf.wrap({
+    "raw_phase_iter_geo": 3000, "raw_phase_iter_app": 1500,
+    "geo_optimizer": {"init_lr": 0.0, "peak_lr": 1e-2, "peak_at": 0.2, "lr_alpha": 1e-2},
+    "app_optimizer": {"init_lr": 0.0, "peak_lr": 1e-2, "peak_at": 0.2, "lr_alpha": 1e-2},
+    "color_loss_weight": 1., "depth_loss_weight": 1., "distortion_loss_weight": 0.1, "density_loss_weight": 0.,
+    "pixel_loss_batch_size": 8192})                                   # configs/nerf.yaml:28-66
+
+
+class NeRFScene:
+    """`nerf.py:28-396` for ``sampler: fixed``.  ``train_conf`` takes the reference's YAML node."""
+
+    LOSS_SCALE = 2 ** 7                                               # GradScaler(2**7), never unscaled (nerf.py:139,249-253)
+
+    def __init__(self, base_exp_dir=".", train_conf=None, estimator_type="fixed", renderer_conf=None,
+                 n_samples: int = 128, near: float = 1e-2, far: float = 1.0, device="cuda", writer=None):
+        if estimator_type not in ("fixed",):
+            raise NotImplementedError(f"perf_b200 NeRFScene: estimator_type={estimator_type!r}; the native scene implements the "
+                                      "fixed-S sampler (run the reference's own NeRFScene on perf_b200.shims for 'occ')")
+        self.device = torch.device(device)
+        self.aabb = torch.tensor([-1.0, -1.0, -1.0, 1.0, 1.0, 1.0], device=self.device)        # nerf.py:35
+        self.base_exp_dir, self.writer = base_exp_dir, writer
+        self.train_conf = DEFAULT_TRAIN_CONF if train_conf is None else Conf.wrap(train_conf)
+        self.nerf = NGPNeRF(aabb=self.aabb).to(self.device)
+        self.estimator = FixedSampleEstimator(n_samples, near, far)
+        self.renderer = NeRFOCCRenderer(**(renderer_conf or {"max_radius": 2, "bg_color": "rand_noise"}))
+        self.fused = FusedPanoRenderer(aabb=self.aabb.tolist(), near=near, far=far)
+        self._fused_key = None
+        self.global_iter_step_geo = self.global_iter_step_app = 0
+
+    # ---- inference ---------------------------------------------------------------------------
+    def _sync_fused(self):
+        g, a = self.nerf.geo_mlp.params, self.nerf.app_mlp.params
+        key = (g._version, a._version, g.data_ptr(), a.data_ptr())
+        if key != self._fused_key:
+            self.fused.set_params(g.detach(), a.detach())
+            self._fused_key = key
+
+    @torch.no_grad()
+    def render(self, rays: Rays, query_keys=("rgb",), sampling_requires_grad=False):
+        """`nerf.py:74-99`: eval-mode render of arbitrarily shaped rays -> {key: [..., C]}."""
+        self._sync_fused()
+        rays_o, rays_d = rays.collapse()
+        pre_shape = list(rays_o.shape[:-1])
+        out = self.fused.render_rays(rays_o.reshape(-1, 3), rays_d.reshape(-1, 3), self.estimator.n_samples)
+        return {k: out[k].reshape(pre_shape + [-1]) for k in query_keys}
+
+    @torch.no_grad()
+    def render_pano(self, pose, height, width, row0=0, rows=None):
+        """render_dense inner loop (`core_exp_runner.py:229-238`) with ray generation fused in."""
+        self._sync_fused()
+        return self.fused.render_pano(pose, height, width, self.estimator.n_samples, row0=row0, rows=rows)
+
+    def render_once(self, rays: Rays, query_keys=("rgb",), sampling_requires_grad=False, geo_inference=False, app_inference=False):
+        """`nerf.py:101-123` (differentiable path used by the train steps)."""
+        rays_o, rays_d = rays.collapse()
+        assert len(rays_o.shape) == 2
+        res = self.renderer.render(self.nerf, self.estimator, rays_o, rays_d, geo_inference=geo_inference, app_inference=app_inference)
+        if (res is None) or (not res["is_valid"]):
+            return res
+        return {k: res[k] for k in list(query_keys) + ["is_valid"]}
+
+    # ---- training ----------------------------------------------------------------------------
+    def fit(self, sup_pool):
+        self.train_one_episode(sup_pool, self.train_conf.raw_phase_iter_geo, self.train_conf.raw_phase_iter_app, "by_all_pixels")
+
+    def train_one_episode(self, sup_pool, geo_res_iters, app_res_iters, pixel_sup_rand_mode="by_all_pixels"):
+        """`nerf.py:137-184`: fresh density net, geo phase then app phase."""
+        self.set_train()
+        self.nerf.reset_geo()
+        geo_optimizer = FusedAdam(self.nerf.geo_mlp.params, lr=self.train_conf.geo_optimizer.init_lr, module=self.nerf.geo_mlp)
+        for iter_i in range(geo_res_iters):
+            self.update_lr(geo_optimizer, self.train_conf.geo_optimizer, iter_i / geo_res_iters)
+            # NB the reference divides by app_res_iters here (nerf.py:178); kept
+            self.train_one_step_geo(geo_optimizer, sup_pool, pixel_sup_rand_mode, progress=iter_i / max(app_res_iters, 1))
+        app_optimizer = FusedAdam(self.nerf.app_mlp.params, lr=self.train_conf.app_optimizer.init_lr, module=self.nerf.app_mlp)
+        for iter_i in range(app_res_iters):
+            self.update_lr(app_optimizer, self.train_conf.app_optimizer, iter_i / app_res_iters)
+            self.train_one_step_app(app_optimizer, sup_pool, pixel_sup_rand_mode, progress=iter_i / app_res_iters)
+
+    def _local_batch(self):
+        return max(1, int(self.train_conf.pixel_loss_batch_size) // parallel.world_size())
+
+    def _log(self, tag, value, step):
+        if self.writer is not None:
+            self.writer.add_scalar(tag, value, step)
+
+    def train_one_step_geo(self, optimizer, sup_pool, pixel_sup_rand_mode="by_all_pixels", progress=0.0):
+        """`nerf.py:186-257`: depth smooth-L1 + ramped distortion loss; colour under no_grad."""
+        conf, eps, loss = self.train_conf, 1e-7, 0.
+        optimizer.zero_grad()
+        rays, gt_colors, gt_depths, _ = sup_pool.rand_ray_color_data(self._local_batch(), rand_mode=pixel_sup_rand_mode)
+        res = self.render_once(rays, ["rgb", "distance", "weights", "t_starts", "t_ends", "trans", "ray_indices"], app_inference=True)
+        if (res is None) or (not res["is_valid"]):
+            self.global_iter_step_geo += 1
+            return None
+        if conf.depth_loss_weight > eps:
+            depth_loss = F.smooth_l1_loss(res["distance"], gt_depths, beta=1e-2, reduction="mean")
+            loss = loss + depth_loss * conf.depth_loss_weight
+            self._log("nerf_loss/depth_loss", depth_loss, self.global_iter_step_geo)
+        if conf.distortion_loss_weight > eps:
+            mid_dis = (res["t_ends"] + res["t_starts"]) * .5
+            sec_lens = res["t_ends"] - res["t_starts"]
+            dist_loss = flatten_eff_distloss(res["weights"], mid_dis, sec_lens, res["ray_indices"])
+            loss = loss + dist_loss * conf.distortion_loss_weight * float(np.min([progress * 2., 1]))
+            self._log("nerf_loss/dist_loss", dist_loss, self.global_iter_step_geo)
+        if conf.density_loss_weight > eps:
+            rand_pts = (torch.rand(8192, 3, device=self.device) * 2. - 1.) * 0.99
+            loss = loss + self.nerf.query_density(rand_pts).mean() * conf.density_loss_weight
+        (loss * self.LOSS_SCALE).backward()
+        optimizer.step()
+        self.global_iter_step_geo += 1
+        return loss.detach()
+
+    def train_one_step_app(self, optimizer, sup_pool, pixel_sup_rand_mode="by_all_pixels", progress=0.0):
+        """`nerf.py:259-297`: colour smooth-L1; density under no_grad."""
+        conf, eps, loss = self.train_conf, 1e-7, 0.
+        optimizer.zero_grad()
+        rays, gt_colors, _, _ = sup_pool.rand_ray_color_data(self._local_batch(), rand_mode=pixel_sup_rand_mode)
+        res = self.render_once(rays, ["rgb", "distance", "weights", "t_starts", "t_ends", "trans", "ray_indices"], geo_inference=True)
+        if (res is None) or (not res["is_valid"]):
+            self.global_iter_step_app += 1
+            return None
+        if conf.color_loss_weight > eps:
+            color_loss = F.smooth_l1_loss(res["rgb"], gt_colors, beta=5e-2, reduction="mean")
+            loss = loss + color_loss * conf.color_loss_weight
+            self._log("nerf_loss/color_loss", color_loss, self.global_iter_step_app)
+        (loss * self.LOSS_SCALE).backward()
+        optimizer.step()
+        self.global_iter_step_app += 1
+        return loss.detach()
+
+    def update_lr(self, optimizer, optim_conf, progress):
+        """`nerf.py:300-311`: linear warm-up to peak_lr at peak_at, cosine to lr_alpha * peak_lr."""
+        if progress < optim_conf.peak_at:
+            local = progress / optim_conf.peak_at
+            lr = optim_conf.peak_lr * local + optim_conf.init_lr * (1. - local)
+        else:
+            local = (progress - optim_conf.peak_at) / (1. - optim_conf.peak_at)
+            lr = optim_conf.peak_lr * ((np.cos(local * np.pi) + 1.) * .5 * (1. - optim_conf.lr_alpha) + optim_conf.lr_alpha)
+        for p in optimizer.param_groups:
+            p["lr"] = float(lr)
+
+    # ---- state -------------------------------------------------------------------------------
+    def state_dict(self):
+        """`nerf.py:374-380` keys."""
+        return {"render": self.renderer.state_dict(), "nerf": self.nerf.state_dict(), "estimator": self.estimator.state_dict()}
+
+    def load_state_dict(self, state_dict):
+        self.nerf.load_state_dict(state_dict["nerf"])
+        self._fused_key = None
+
+    def set_train(self):
+        self.nerf.train(); self.estimator.train(); self.renderer.train()
+
+    def set_eval(self):
+        self.nerf.eval(); self.estimator.eval(); self.renderer.eval()

@@ -1,0 +1,131 @@
+"""``nerfacc.estimators.occ_grid.OccGridEstimator`` (0.5.3 API, ``levels=1``) for PeRF's call sites
+(`/root/reference/modules/scene/nerf.py:68,144,159-168`, `/root/reference/modules/scene/nerf_renderer.py:145-155`).
+
+ROUND-1 STATUS: the occupancy-grid ray marcher is SURVEY.md section 8(f) row 1 ("next").  This
+module keeps the reference's estimator interface alive (buffers ``resolution/aabbs/occs/binaries``
+for checkpoints, ``update_every_n_steps``, ``sampling``) with vectorised torch ops for the marching
+itself; the per-sample work it feeds (sigma_fn -> field kernels, transmittance culling) runs on
+libperfb200.  Sampling rule (nerfacc's DDA for ``cone_angle=0``, restated; upstream source is not
+vendored so the exact phase of the lattice is unpinned): fixed lattice
+``t_k = near + (k + u_r) * step`` (one uniform offset ``u_r`` per ray when ``stratified``), a
+sample ``[t_k, t_k + step)`` is kept when its midpoint lies inside the aabb in an occupied cell,
+then samples whose transmittance fell below ``early_stop_eps`` are dropped.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+
+from perf_b200 import ops
+
+__perf_b200_shim__ = True
+
+
+class OccGridEstimator(torch.nn.Module):
+    DIM = 3
+
+    def __init__(self, roi_aabb, resolution=128, levels: int = 1, **kwargs):
+        super().__init__()
+        if levels != 1:
+            raise NotImplementedError("perf_b200 nerfacc: OccGridEstimator levels != 1 is not implemented (PeRF uses 1)")
+        if isinstance(resolution, int):
+            resolution = [resolution] * 3
+        res = torch.tensor(resolution, dtype=torch.int32)
+        roi = torch.as_tensor(roi_aabb, dtype=torch.float32).flatten()
+        assert roi.numel() == 6
+        self.levels = levels
+        self.cells_per_lvl = int(res.prod().item())
+        self.register_buffer("resolution", res)
+        self.register_buffer("aabbs", roi[None, :].clone())
+        self.register_buffer("occs", torch.zeros(self.cells_per_lvl * levels))
+        self.register_buffer("binaries", torch.zeros([levels] + res.tolist(), dtype=torch.bool))
+
+    # -- helpers -------------------------------------------------------------------------------
+    def _cell_index(self, x: torch.Tensor) -> torch.Tensor:
+        """Flat cell index (x slowest, z fastest: meshgrid 'ij' order) of points inside the aabb."""
+        res = self.resolution.to(x.device)
+        amin, amax = self.aabbs[0, :3], self.aabbs[0, 3:]
+        u = ((x - amin) / (amax - amin) * res).floor().long()
+        u = torch.minimum(u.clamp_(min=0), (res - 1).long())
+        return (u[..., 0] * int(res[1]) + u[..., 1]) * int(res[2]) + u[..., 2]
+
+    @torch.no_grad()
+    def sampling(self, rays_o, rays_d, sigma_fn: Optional[Callable] = None, alpha_fn: Optional[Callable] = None,
+                 near_plane: float = 0.0, far_plane: float = 1e10, t_min=None, t_max=None,
+                 render_step_size: float = 1e-3, early_stop_eps: float = 1e-4, alpha_thre: float = 0.0,
+                 stratified: bool = False, cone_angle: float = 0.0):
+        if cone_angle != 0.0:
+            raise NotImplementedError("perf_b200 nerfacc: cone_angle != 0 is not implemented (PeRF passes 0)")
+        if alpha_fn is not None:
+            raise NotImplementedError("perf_b200 nerfacc: alpha_fn is not implemented (PeRF passes sigma_fn)")
+        dev, R = rays_o.device, rays_o.shape[0]
+        amin, amax = self.aabbs[0, :3], self.aabbs[0, 3:]
+        # ray / aabb slab intersection
+        inv = 1.0 / torch.where(rays_d.abs() < 1e-12, torch.full_like(rays_d, 1e-12), rays_d)
+        t0, t1 = (amin - rays_o) * inv, (amax - rays_o) * inv
+        tn = torch.minimum(t0, t1).amax(-1).clamp(min=near_plane)
+        tf = torch.maximum(t0, t1).amin(-1).clamp(max=far_plane)
+        if t_min is not None:
+            tn = torch.maximum(tn, t_min)
+        if t_max is not None:
+            tf = torch.minimum(tf, t_max)
+        step = float(render_step_size)
+        u = torch.rand(R, device=dev) if stratified else torch.zeros(R, device=dev)
+        k_hi = int(torch.ceil(((tf - near_plane) / step).clamp(min=0).max()).item()) if R else 0
+        ri_all, ts_all = [], []
+        binaries = self.binaries.reshape(-1)
+        chunk = max(1, (1 << 24) // max(k_hi, 1))
+        ks = torch.arange(k_hi, device=dev, dtype=torch.float32)
+        for s in range(0, R, chunk):
+            o, d = rays_o[s:s + chunk], rays_d[s:s + chunk]
+            ts = near_plane + (ks[None, :] + u[s:s + chunk, None]) * step           # [r, K]
+            mid = ts + 0.5 * step
+            ok = (mid >= tn[s:s + chunk, None]) & (mid <= tf[s:s + chunk, None])
+            pts = o[:, None, :] + d[:, None, :] * mid[..., None]
+            ok &= binaries[self._cell_index(pts)]
+            r_idx, k_idx = ok.nonzero(as_tuple=True)
+            ri_all.append(r_idx + s)
+            ts_all.append(ts[r_idx, k_idx])
+        ray_indices = torch.cat(ri_all) if ri_all else torch.zeros(0, dtype=torch.long, device=dev)
+        t_starts = torch.cat(ts_all) if ts_all else torch.zeros(0, device=dev)
+        t_ends = t_starts + step
+        # visibility culling (nerfacc render_visibility_from_density): keep T >= early_stop_eps
+        if sigma_fn is not None and early_stop_eps > 0 and ray_indices.numel() > 0:
+            sigmas = sigma_fn(t_starts, t_ends, ray_indices).float().reshape(-1)
+            _, trans, alphas = ops.weights_from_density(t_starts, t_ends, sigmas.contiguous(), ray_indices, R)
+            thre = min(alpha_thre, float(self.occs.mean().item()))
+            keep = (trans >= early_stop_eps) & (alphas >= thre)
+            ray_indices, t_starts, t_ends = ray_indices[keep], t_starts[keep], t_ends[keep]
+        return ray_indices, t_starts, t_ends
+
+    @torch.no_grad()
+    def update_every_n_steps(self, step: int, occ_eval_fn: Callable, occ_thre: float = 1e-2, ema_decay: float = 0.95,
+                             warmup_steps: int = 256, n: int = 16) -> None:
+        if not self.training:
+            raise RuntimeError("update_every_n_steps() should only be called in training mode")
+        if step % n == 0:
+            self._update(step, occ_eval_fn, occ_thre, ema_decay, warmup_steps)
+
+    @torch.no_grad()
+    def _update(self, step, occ_eval_fn, occ_thre, ema_decay, warmup_steps):
+        dev = self.occs.device
+        res = self.resolution.to(dev)
+        if step < warmup_steps:
+            idx = torch.arange(self.cells_per_lvl, device=dev)
+        else:
+            n = self.cells_per_lvl // 4
+            uni = torch.randint(self.cells_per_lvl, (n,), device=dev)
+            occ_idx = torch.nonzero(self.binaries.reshape(-1))[:, 0]
+            if occ_idx.numel() > n:
+                occ_idx = occ_idx[torch.randint(occ_idx.numel(), (n,), device=dev)]
+            idx = torch.cat([uni, occ_idx])
+        ry, rz = int(res[1]), int(res[2])
+        coords = torch.stack([idx // (ry * rz), (idx // rz) % ry, idx % rz], -1).float()
+        x = (coords + torch.rand_like(coords)) / res.float()
+        amin, amax = self.aabbs[0, :3], self.aabbs[0, 3:]
+        x = amin + x * (amax - amin)
+        occ = occ_eval_fn(x).reshape(-1).float()
+        self.occs[idx] = torch.maximum(self.occs[idx] * ema_decay, occ)
+        thre = torch.clamp(self.occs[self.occs >= 0].mean(), max=occ_thre)
+        self.binaries = (self.occs > thre).view(self.binaries.shape)

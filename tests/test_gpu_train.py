@@ -1,0 +1,140 @@
+"""GPU tests of the training path (differentiable render -> losses -> backward -> fused Adam)
+through the host mirror of NeRFScene, against the oracle's autograd and torch.optim.Adam."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import oracle
+from oracle.field import APP_MLP as O_APP, GEO_MLP as O_GEO, PERF_GRID as O_GRID
+from oracle.hashgrid import encode
+from oracle.mlp import flat_param_count, mlp_forward, split_params
+
+pytestmark = pytest.mark.gpu
+
+
+def make_scene(golden_field, S=32, **kw):
+    from perf_b200.scene import NeRFScene
+    sc = NeRFScene(n_samples=S, **kw)
+    with torch.no_grad():
+        sc.nerf.geo_mlp.params.copy_(golden_field.geo_params.half().float())
+        sc.nerf.app_mlp.params.copy_(golden_field.app_params.half().float())
+    return sc
+
+
+def oracle_train_forward(field, p_geo, p_app, o, d, S, jitter, noise):
+    """oracle.render_rays with differentiable parameters (mixed precision, straight-through)."""
+    ts, te = oracle.fixed_samples(o.shape[0], S, 1e-2, 1.0, jitter)
+    pos = o[:, None, :] + d[:, None, :] * (ts + te)[..., None] / 2.0
+    x01 = ((pos + 1) / 2).reshape(-1, 3)
+    sel = ((x01 > 0) & (x01 < 1)).all(-1)
+    ng, na = flat_param_count(O_GEO), flat_param_count(O_APP)
+    raw = mlp_forward(encode(x01, p_geo[ng:], O_GRID, out_half=True), split_params(p_geo[:ng], O_GEO), O_GEO, mixed=True)
+    sig = (torch.exp(raw[:, 0]) * sel).reshape(-1, S)
+    rgb = (mlp_forward(encode(x01, p_app[na:], O_GRID, out_half=True), split_params(p_app[:na], O_APP), O_APP, mixed=True)
+           * sel[:, None]).reshape(-1, S, 3)
+    w, T, _ = oracle.render_weight_from_density(ts, te, sig)
+    op = w.sum(-1, keepdim=True)
+    dist = (w * (ts + te) / 2).sum(-1, keepdim=True)
+    col = (w.detach()[..., None] * rgb).sum(1)
+    dist = torch.relu(dist + (noise[:, 3:4] * 2 - 1) * (1 - op))
+    col = col + noise[:, :3] * (1 - op).detach()
+    return {"rgb": col, "distance": dist, "weights": w, "t_starts": ts, "t_ends": te}
+
+
+@pytest.mark.parametrize("phase", ["geo", "app"])
+def test_train_step_gradient_matches_oracle(golden_field, phase):
+    from perf_b200.scene import Rays
+    S, R = 32, 96
+    sc = make_scene(golden_field, S)
+    sc.set_train()
+    g = torch.Generator().manual_seed(41)
+    o = (torch.rand(R, 3, generator=g) - .5) * .3
+    d = F.normalize(torch.randn(R, 3, generator=g), dim=-1)
+    gt_d, gt_c = torch.rand(R, 1, generator=g) * .8, torch.rand(R, 3, generator=g)
+    jitter = torch.rand(R, generator=g)
+    # the scene draws its random numbers from torch's CUDA generator: bg colour, then distance noise
+    sc.estimator.sampling_jitter = jitter
+    orig = sc.estimator.sampling
+    sc.estimator.sampling = lambda *a, **k: orig(*a, **{**k, "jitter": jitter.cuda()})
+    torch.manual_seed(5)
+    res = sc.render_once(Rays(o.cuda(), d.cuda()), ["rgb", "distance", "weights", "t_starts", "t_ends", "ray_indices"],
+                         app_inference=(phase == "geo"), geo_inference=(phase == "app"))
+    torch.manual_seed(5)
+    noise = torch.cat([torch.rand(R, 3, device="cuda"), torch.rand(R, 1, device="cuda")], 1).cpu()
+    p_geo = golden_field.geo_params.half().float().requires_grad_(phase == "geo")
+    p_app = golden_field.app_params.half().float().requires_grad_(phase == "app")
+    ref = oracle_train_forward(golden_field, p_geo, p_app, o, d, S, jitter, noise)
+    np.testing.assert_allclose(res["distance"].detach().cpu().numpy(), ref["distance"].detach().numpy(), atol=4e-3)
+    np.testing.assert_allclose(res["rgb"].detach().cpu().numpy(), ref["rgb"].detach().numpy(), atol=4e-3)
+    if phase == "geo":
+        mid = (res["t_starts"] + res["t_ends"]) * .5
+        from perf_b200.shims.torch_efficient_distloss import flatten_eff_distloss
+        loss = F.smooth_l1_loss(res["distance"], gt_d.cuda(), beta=1e-2) \
+            + 0.1 * flatten_eff_distloss(res["weights"], mid, res["t_ends"] - res["t_starts"], res["ray_indices"])
+        ri = torch.arange(R).repeat_interleave(S)
+        loss_ref = F.smooth_l1_loss(ref["distance"], gt_d, beta=1e-2) \
+            + 0.1 * oracle.flatten_eff_distloss(ref["weights"].reshape(-1), ((ref["t_starts"] + ref["t_ends"]) * .5).reshape(-1),
+                                                (ref["t_ends"] - ref["t_starts"]).reshape(-1), ri)
+        param, pref = sc.nerf.geo_mlp.params, p_geo
+    else:
+        loss = F.smooth_l1_loss(res["rgb"], gt_c.cuda(), beta=5e-2)
+        loss_ref = F.smooth_l1_loss(ref["rgb"], gt_c, beta=5e-2)
+        param, pref = sc.nerf.app_mlp.params, p_app
+    assert abs(float(loss) - float(loss_ref)) <= 2e-3 * max(1.0, abs(float(loss_ref)))
+    (loss * 128).backward()
+    (loss_ref * 128).backward()
+    got, want = param.grad.cpu(), pref.grad
+    cos = F.cosine_similarity(got, want, dim=0)
+    assert cos > 0.999, float(cos)
+    assert (got - want).abs().max() <= 3e-2 * want.abs().max(), float((got - want).abs().max() / want.abs().max())
+
+
+def test_fit_reduces_losses_and_checkpoint_roundtrip(golden_field, tmp_path):
+    from perf_b200 import synthetic
+    from perf_b200.config import Conf
+    from perf_b200.scene import NeRFScene, RaySupervision
+    h, w = 64, 128
+    rgb = synthetic.smooth_rgb(h, w, seed=0, device="cuda")
+    dist = synthetic.box_room_distance(h, w, device="cuda")
+    conf = dict(NeRFScene(n_samples=8).train_conf)           # defaults of configs/nerf.yaml
+    conf.update(pixel_loss_batch_size=2048, raw_phase_iter_geo=150, raw_phase_iter_app=100)
+    sc = NeRFScene(train_conf=conf, n_samples=48)
+    pool = RaySupervision.from_panorama(torch.eye(4), rgb, dist, seed=0)
+
+    def errors():
+        out = sc.render_pano(torch.eye(4), h, w)
+        return float((out["distance"] - dist).abs().mean()), float((out["rgb"] - rgb).abs().mean())
+    torch.manual_seed(0)
+    d0, c0 = errors()
+    sc.fit(pool)
+    d1, c1 = errors()
+    assert d1 < 0.25 * d0 and d1 < 0.05, (d0, d1)
+    assert c1 < 0.5 * c0, (c0, c1)
+    # checkpoint dict has the reference's keys and reloads into a fresh scene bit-for-bit
+    sd = sc.state_dict()
+    assert set(sd) == {"render", "nerf", "estimator"} and set(sd["nerf"]) == {"aabb", "geo_mlp.params", "app_mlp.params"}
+    torch.save({"scene": sd, "phase": 0}, tmp_path / "ckpt.pth")
+    sc2 = NeRFScene(train_conf=conf, n_samples=48)
+    sc2.load_state_dict(torch.load(tmp_path / "ckpt.pth")["scene"])
+    a, b = sc.render_pano(torch.eye(4), h, w), sc2.render_pano(torch.eye(4), h, w)
+    assert torch.equal(a["rgb"], b["rgb"]) and torch.equal(a["distance"], b["distance"])
+
+
+def test_fused_adam_tracks_torch_adam_through_scene_params(golden_field):
+    from perf_b200.scene import FusedAdam
+    from perf_b200.shims import tinycudann as tcnn
+    from perf_b200.field import ENCODING_CONFIG, GEO_NETWORK_CONFIG
+    torch.manual_seed(0)
+    net = tcnn.NetworkWithInputEncoding(3, 1, ENCODING_CONFIG, GEO_NETWORK_CONFIG).cuda()
+    ref = net.params.detach().clone().requires_grad_(True)
+    opt_ref, opt = torch.optim.Adam([ref], lr=1e-3), FusedAdam(net.params, lr=1e-3, module=net)
+    x = torch.rand(4096, 3, device="cuda")
+    for _ in range(3):
+        opt.zero_grad()
+        (net(x).float().sum() * 128).backward()
+        ref.grad = net.params.grad.clone()
+        opt_ref.step()
+        opt.step()
+        assert torch.equal(net._half(), net.params.detach().half())         # shadow refreshed by the Adam kernel
+    np.testing.assert_allclose(net.params.detach().cpu().numpy(), ref.detach().cpu().numpy(), rtol=1e-5, atol=1e-7)
