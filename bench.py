@@ -114,8 +114,7 @@ def cpu_oracle_sample(n_rays, threads=None):
     first `n_rays` rays of the benchmark panorama.  Returns (Msamples/s, seconds, cores)."""
     import torch
     import oracle
-    if threads:
-        torch.set_num_threads(threads)
+    torch.set_num_threads(threads or min(16, os.cpu_count() or 1))
     g = torch.Generator().manual_seed(SEED)
     n_e = oracle.hashgrid.n_table_entries(oracle.field.PERF_GRID)
 
@@ -140,7 +139,7 @@ def run_reference(args, rank, world):
     bounded sample per step."""
     if rank != 0:
         return
-    n_rays = 1024                                     # 131 072 samples per step
+    n_rays = 4096                                     # 524 288 samples per step
     for _ in range(args.warmup):
         cpu_oracle_sample(n_rays)
     ts = []

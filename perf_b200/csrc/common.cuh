@@ -159,14 +159,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
-    for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+    long long t0 = 0;
+    for (uint32_t spin = 0;; ++spin) {
         asm volatile("{\n\t.reg .pred p;\n\t"
                      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
                      "selp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done) : "r"(addr), "r"(parity) : "memory");
         if (done) return;
+        if (spin == 64) t0 = clock64();
+        if (spin > 64 && clock64() - t0 > 4000000000ll) __trap();    // ~2 s at 2 GHz: a lost MMA completion
     }
-    __trap();
 }
 
 template <int COLS>

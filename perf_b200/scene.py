@@ -167,7 +167,7 @@ class FusedAdam:
         ops.adam_step(self.param.data, g, self.exp_avg, self.exp_avg_sq, self.step_count, self.param_groups[0]["lr"],
                       params_half=half, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps)
         # the kernel wrote through .data: bump autograd's version counter so version-keyed caches notice
-        torch._C._increment_version(self.param)
+        torch._C._increment_version([self.param])   # takes an ITERABLE of tensors
         if self.module is not None:                          # the shadow is already current for the new version
             self.module._half_key = (self.param._version, self.param.data_ptr())
 

@@ -9,6 +9,6 @@ r = FusedPanoRenderer.from_params(geo, app)
 pose = bench.bench_pose()
 rows = int(os.environ.get("ROWS", 256))
 for _ in range(2):
-    out = r.render_pano(pose, bench.H, bench.W, bench.S, row0=384, rows=rows)
+    out = r.render_pano(pose, bench.H, bench.W, bench.S, row0=(bench.H - rows) // 2, rows=rows)
 torch.cuda.synchronize()
 print("ok", float(out["rgb"].mean()))
