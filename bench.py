@@ -11,7 +11,7 @@ row-tiled across the ranks (`render_dense`): total work is
 slowest rank's device time.
 
 JSON keys beyond the base contract:
-  roofline      dominant kernel (render_kernel): ALGORITHMIC bytes = 1024 B/sample (16 levels x 8
+  roofline      dominant kernel (render_march_kernel): ALGORITHMIC bytes = 1024 B/sample (16 levels x 8
                 corners x 2 features x 2 B x 2 fields) / CUDA-event time, against the
                 measured HBM copy bandwidth in MEASURED_PEAKS.json.
   cpu_baseline  the oracle (oracle/render.py, fp32 accumulate) timed on this box's host cores on
@@ -233,6 +233,12 @@ def run_ours(args, rank, world, local_rank):
     e2e_value = samples / (e2e_ms / args.steps / 1e3) / 1e6
     peak, peak_src = measured_peak_hbm()
     achieved = ALG_BYTES_PER_SAMPLE * samples / world / (ms_per_step / 1e3) / 1e9     # per-GPU kernel
+    traffic = None
+    try:                                              # dram__bytes of this very launch from the committed ncu capture
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        traffic = (t["dram_bytes_read"] + t["dram_bytes_write"]) if world == 1 else None
+    except Exception:
+        pass
     cpu_v, cpu_s, cores = cpu_oracle_sample(4096) if world == 1 else (None, None, None)
     line = {"metric": "Msamples/sec (rays x samples)", "value": value, "unit": "Msamples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -242,8 +248,8 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": 64,
                     "d2h_bytes_per_step": rows * W * 16 * world, "note": "input is a 4x4 pose; output rgb+distance images to pinned host memory"},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "perf::render_kernel<PANO=true,SIMT=false>", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "roofline": {"bound": "hbm", "kernel": "perf::render_march_kernel<PANO=true,SIMT=false,NDENSE=4>", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_sample": ALG_BYTES_PER_SAMPLE,
                          "note": "tables (26.6 MB fp16) are L2-resident: DRAM traffic is far below algorithmic bytes, see profiles/"}}
     if cpu_v is not None:
