@@ -162,6 +162,46 @@ int perf_render_rays(const perf_render_args* args, const float* d_rays_o, const 
 int perf_render_pano(const perf_render_args* args, const float* h_pose, int H, int W,
                      int row0, int rows, void* stream);
 
+/* ---- fused training step (fixed-S sampler): forward with saves, composite backward, grid scatter ----
+ * All per-sample buffers are SAMPLE-MAJOR: row = k * R + ray (k = sample index along the ray), so
+ * that a warp of neighbouring rays reads/writes contiguous rows.  Replaces, for one optimisation
+ * step, the call chain modules/scene/nerf.py:186-297 -> nerf_renderer.py:112-209 -> tcnn/nerfacc
+ * forward + the autograd backward through them. */
+#define PERF_PHASE_GEO 1   /* density net trained: nerf.py:186-257 (colour under no_grad)           */
+#define PERF_PHASE_APP 2   /* colour net trained:  nerf.py:259-297 (density under no_grad)           */
+typedef struct perf_train_buffers {
+    float* d_sigma;      /* [S*R] density                                                   */
+    float* d_weights;    /* [S*R] w = T * alpha                                             */
+    float* d_trans;      /* [S*R] T                                                         */
+    void*  d_rgb;        /* [S*R,4] fp16 sample colours (PHASE_APP only, 4th lane unused)   */
+    void*  d_feat;       /* [S*R,32] fp16 features of the trained network                   */
+    void*  d_h1;         /* [S*R,64] fp16 hidden 1                                          */
+    void*  d_h2;         /* [S*R,64] fp16 hidden 2 (PHASE_APP only)                         */
+    float* d_dist_acc;   /* [R] sum w*t_mid before the background rule                      */
+    float* d_distloss;   /* [R] distortion-loss numerator per ray (flatten_eff_distloss * n_rays) */
+} perf_train_buffers;
+
+/* Forward of a training step: like perf_render_rays (PERF_FLAG_TRAINING semantics: jitter, training
+ * background rule) and additionally fills `buf`. */
+int perf_train_forward(const perf_render_args* args, const float* d_rays_o, const float* d_rays_d,
+                       uint64_t R, int phase, const perf_train_buffers* buf, void* stream);
+
+/* Backward through the composite given per-ray gradients of the renderer outputs.
+ * PHASE_GEO: d_out [S*R]   = dL/d(raw density logit)   (trunc_exp backward included)
+ * PHASE_APP: d_out [S*R,3] = dL/d(colour pre-sigmoid)  (weights are detached, nerf_renderer.py:183)
+ * d_g_* may be NULL (zero gradient).  d_distance_out: the forward's distance output (ReLU mask). */
+int perf_train_backward_composite(int phase, uint32_t n_samples, float near, float far, uint64_t R,
+                                  const float* d_jitter, const float* d_bg_noise, const perf_train_buffers* buf,
+                                  const float* d_g_rgb, const float* d_g_distance, const float* d_g_opacity,
+                                  const float* d_g_distloss, const float* d_distance_out, const float* d_opacity_out,
+                                  float* d_out, void* stream);
+
+/* Grid gradient for sample-major rows whose positions are recomputed from the rays:
+ * d_dfeat [S*R, 32] fp32.  Same-cell neighbours inside a warp are merged before the atomics. */
+int perf_hashgrid_bwd_rays(const perf_grid_cfg* cfg, const float* aabb6, const float* d_rays_o, const float* d_rays_d,
+                           const float* d_jitter, uint64_t R, uint32_t n_samples, float near, float far,
+                           const float* d_dfeat, float* d_dtable, void* stream);
+
 /* Fused Adam on a flat fp32 parameter vector + refresh of its fp16 shadow
  * (torch.optim.Adam at nerf.py:171,180,253,293; betas/eps defaults).  grad_scale multiplies
  * the gradient first (the reference never unscales its 128x GradScaler; pass 1 to keep that). */

@@ -38,6 +38,13 @@ class RenderArgs(C.Structure):
                 ("d_jitter", vp), ("d_bg_noise", vp), ("d_rgb", vp), ("d_distance", vp), ("d_opacity", vp)]
 
 
+class TrainBuffers(C.Structure):
+    _fields_ = [("d_sigma", vp), ("d_weights", vp), ("d_trans", vp), ("d_rgb", vp), ("d_feat", vp), ("d_h1", vp),
+                ("d_h2", vp), ("d_dist_acc", vp), ("d_distloss", vp)]
+
+
+PERF_PHASE_GEO, PERF_PHASE_APP = 1, 2
+
 P = C.POINTER
 # name -> (restype, argtypes); must list every symbol include/perfb200.h declares
 SIGNATURES = {
@@ -58,6 +65,9 @@ SIGNATURES = {
     "perf_accumulate_along_rays": (i32, [vp, vp, i32, vp, u64, u64, vp, vp]),
     "perf_render_rays": (i32, [P(RenderArgs), vp, vp, u64, vp]),
     "perf_render_pano": (i32, [P(RenderArgs), P(f32), i32, i32, i32, i32, vp]),
+    "perf_train_forward": (i32, [P(RenderArgs), vp, vp, u64, i32, P(TrainBuffers), vp]),
+    "perf_train_backward_composite": (i32, [i32, u32, f32, f32, u64, vp, vp, P(TrainBuffers), vp, vp, vp, vp, vp, vp, vp, vp]),
+    "perf_hashgrid_bwd_rays": (i32, [P(GridCfg), P(f32), vp, vp, vp, u64, u32, f32, f32, vp, vp, vp]),
     "perf_adam_step": (i32, [vp, vp, vp, vp, vp, u64, f32, f32, f32, f32, u32, f32, vp]),
 }
 

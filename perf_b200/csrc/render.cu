@@ -35,6 +35,16 @@ struct RenderArgs {
     const float*  rays_d;
     float         pose_r[9], pose_t[3];
     int           H, W, row0;   // (PANO == true): ray r is pixel (row0 + r / W, r % W)
+    // training-forward saves (SAVE != 0), all sample-major: row = k * R + ray
+    float*        s_sigma;      // [S*R]
+    float*        s_w;          // [S*R]
+    float*        s_trans;      // [S*R]
+    __half*       s_rgb;        // [S*R, 4] (colour phase only; 4th lane unused)
+    uint4*        s_feat;       // [S*R, 32] fp16 of the network being trained
+    uint4*        s_h1;         // [S*R, 64] fp16
+    uint4*        s_h2;         // [S*R, 64] fp16 (colour phase only)
+    float*        s_dacc;       // [R] distance accumulate BEFORE the background rule
+    float*        s_dl;         // [R] distortion-loss numerator of the ray
 };
 
 constexpr int RS_A     = 0;                         // 16 KB: A_geo | A_app, later H (K=64)
@@ -125,8 +135,8 @@ struct RenderSmem {
 
 // Levels [4q, 4q+4) of both fields -> one 16-byte k-group of each feature tile.
 // KIND 0: generic addressing, 1: dense (fast), 2: hashed power-of-two (fast).
-template <int KIND>
-__device__ __forceinline__ void encode_group(const RenderArgs& a, const RenderSmem& sm, int q, float x, float y, float z, int tid)
+template <int KIND, int SAVE>
+__device__ __forceinline__ void encode_group(const RenderArgs& a, const RenderSmem& sm, int q, float x, float y, float z, int tid, uint64_t srow)
 {
     uint32_t pg[4], pa[4];
 #pragma unroll
@@ -150,16 +160,20 @@ __device__ __forceinline__ void encode_group(const RenderArgs& a, const RenderSm
     }
     *reinterpret_cast<uint4*>(sm.sAg + (q * TILE + tid) * 16) = make_uint4(pg[0], pg[1], pg[2], pg[3]);
     *reinterpret_cast<uint4*>(sm.sAa + (q * TILE + tid) * 16) = make_uint4(pa[0], pa[1], pa[2], pa[3]);
+    if constexpr (SAVE == 1) { if (srow != ~0ull) a.s_feat[srow * 4 + q] = make_uint4(pg[0], pg[1], pg[2], pg[3]); }
+    if constexpr (SAVE == 2) { if (srow != ~0ull) a.s_feat[srow * 4 + q] = make_uint4(pa[0], pa[1], pa[2], pa[3]); }
 }
 
 // Encode + both MLPs for the CTA's current 128 samples (thread t = sample t at normalised
 // position (x,y,z)).  Contains 2 block-wide barriers + 2 mbarrier waits; all 128 threads call it.
 // NDENSE >= 0: specialised addressing (level_corners_fast; first NDENSE levels dense, rest hashed
 // power-of-two) -- branch-free and ~1/3 smaller code; NDENSE < 0: generic addressing.
-template <bool SIMT, int NDENSE>
+// SAVE 1 / 2: also write the fp16 features and hidden activations of the density / colour network
+// to row `srow` of the training buffers (srow == ~0: masked-out thread).
+template <bool SIMT, int NDENSE, int SAVE = 0>
 __device__ __forceinline__ void eval_fields(const RenderArgs& a, const RenderSmem& sm, float x, float y, float z, bool selector,
                                             uint32_t tmem_base, uint32_t tmem_row, uint32_t& parity, int tid,
-                                            float& sigma, float& cr, float& cg, float& cb)
+                                            float& sigma, float& cr, float& cg, float& cb, uint64_t srow = ~0ull)
 {
     uint8_t* const sA = sm.sA; uint8_t* const sAg = sm.sAg; uint8_t* const sAa = sm.sAa;
     uint8_t* const sW1g = sm.sW1g; uint8_t* const sW1a = sm.sW1a; uint8_t* const sW2a = sm.sW2a;
@@ -169,12 +183,12 @@ __device__ __forceinline__ void eval_fields(const RenderArgs& a, const RenderSme
     if constexpr (NDENSE == 4) {
         // dense group unrolled; the three hashed groups share ONE copy of the code (the fully
         // unrolled body was ~70 KB of SASS and stalled on instruction fetch)
-        encode_group<1>(a, sm, 0, x, y, z, tid);
+        encode_group<1, SAVE>(a, sm, 0, x, y, z, tid, srow);
 #pragma unroll 1
-        for (int q = 1; q < 4; ++q) encode_group<2>(a, sm, q, x, y, z, tid);
+        for (int q = 1; q < 4; ++q) encode_group<2, SAVE>(a, sm, q, x, y, z, tid, srow);
     } else {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) encode_group<0>(a, sm, q, x, y, z, tid);
+        for (int q = 0; q < 4; ++q) encode_group<0, SAVE>(a, sm, q, x, y, z, tid, srow);
     }
 
     // ---- layer 1 of both nets
@@ -201,6 +215,7 @@ __device__ __forceinline__ void eval_fields(const RenderArgs& a, const RenderSme
         float v[32]; uint32_t hp[16];
         acc_chunk<SIMT>(c, 32, tmem_row, sAg, sW1g, tid, v);
         relu_pack(v, hp);
+        if constexpr (SAVE == 1) { if (srow != ~0ull) store_chunk_global(a.s_h1 + srow * 8, c, hp); }
         out_dots<1>(hp, sWoutG, c, 1, og);
     }
     sigma = selector ? expf(finish_output(og[0], 0)) : 0.f;
@@ -211,6 +226,7 @@ __device__ __forceinline__ void eval_fields(const RenderArgs& a, const RenderSme
         float v[32]; uint32_t hp[16];
         acc_chunk<SIMT>(c, 32, tmem_row + 64, sAa, sW1a, tid, v);
         relu_pack(v, hp);
+        if constexpr (SAVE == 2) { if (srow != ~0ull) store_chunk_global(a.s_h1 + srow * 8, c, hp); }
         store_chunk_canonical(sA, tid, 4 * c, hp);
     }
     if constexpr (!SIMT) {
@@ -233,6 +249,7 @@ __device__ __forceinline__ void eval_fields(const RenderArgs& a, const RenderSme
         float v[32]; uint32_t hp[16];
         acc_chunk<SIMT>(c, 64, tmem_row + 64, sA, sW2a, tid, v);
         relu_pack(v, hp);
+        if constexpr (SAVE == 2) { if (srow != ~0ull) store_chunk_global(a.s_h2 + srow * 8, c, hp); }
         out_dots<3>(hp, sWoutA, c, 3, oa);
     }
     cr = selector ? finish_output(oa[0], 1) : 0.f;      // ngp_nerf.py:156-161
@@ -384,7 +401,7 @@ __global__ void __launch_bounds__(TILE, 4) render_kernel(const __grid_constant__
 // per request at the coarse and middle levels) and a thread revisits the same cells from k to k+1
 // (temporal L1 reuse).  The composite is a per-thread running sum: no shuffles, no carries.
 // Transmittance uses the sequential exclusive sum, the order of the oracle's cumsum.
-template <bool PANO, bool SIMT, int NDENSE>
+template <bool PANO, bool SIMT, int NDENSE, int SAVE = 0>
 __global__ void __launch_bounds__(TILE, 4) render_march_kernel(const __grid_constant__ RenderArgs a)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -461,6 +478,7 @@ __global__ void __launch_bounds__(TILE, 4) render_march_kernel(const __grid_cons
 
         float sum_sd = 0.f;                                   // exclusive running sum of sigma*dt
         float acc_w = 0.f, acc_d = 0.f, acc_r = 0.f, acc_g = 0.f, acc_b = 0.f;
+        float dl_uni = 0.f, dl_bi = 0.f;                      // distortion loss pieces (SAVE only)
 #pragma unroll 1
         for (uint32_t k = 0; k < S; ++k) {
             const float ts = __fadd_rn(a.near, __fmul_rn(__fadd_rn((float)k, jit), step));
@@ -475,11 +493,27 @@ __global__ void __launch_bounds__(TILE, 4) render_march_kernel(const __grid_cons
             const bool selector = valid && x > 0.f && x < 1.f && y > 0.f && y < 1.f && z > 0.f && z < 1.f;
 
             float sigma, cr, cg, cb;
-            eval_fields<SIMT, NDENSE>(a, sm, x, y, z, selector, tmem_base, tmem_row, parity, tid, sigma, cr, cg, cb);
+            const uint64_t srow = (SAVE != 0 && valid) ? (uint64_t)k * a.R + ray : ~0ull;
+            eval_fields<SIMT, NDENSE, SAVE>(a, sm, x, y, z, selector, tmem_base, tmem_row, parity, tid, sigma, cr, cg, cb, srow);
 
-            const float sd = sigma * __fsub_rn(te, ts);
-            const float w = expf(-sum_sd) * (1.f - expf(-sd));
+            const float dt = __fsub_rn(te, ts);
+            const float sd = sigma * dt;
+            const float T = expf(-sum_sd);
+            const float w = T * (1.f - expf(-sd));
             sum_sd += sd;
+            if constexpr (SAVE != 0) {
+                if (valid) {
+                    a.s_sigma[srow] = sigma; a.s_w[srow] = w; a.s_trans[srow] = T;
+                    if constexpr (SAVE == 2) {
+                        const __half2 c01 = __floats2half2_rn(cr, cg), c2 = __floats2half2_rn(cb, 0.f);
+                        *reinterpret_cast<uint2*>(a.s_rgb + srow * 4) = make_uint2(*reinterpret_cast<const uint32_t*>(&c01), *reinterpret_cast<const uint32_t*>(&c2));
+                    }
+                }
+                // torch_efficient_distloss, per ray: sum iv w^2 / 3 + 2 sum w (m W_excl - WM_excl)
+                const float m = tsum * 0.5f;
+                dl_uni = fmaf(dt * w, w, dl_uni);
+                dl_bi = fmaf(w, m * acc_w - acc_d, dl_bi);
+            }
             acc_w += w; acc_d = fmaf(w, tsum * 0.5f, acc_d);
             acc_r = fmaf(w, cr, acc_r); acc_g = fmaf(w, cg, acc_g); acc_b = fmaf(w, cb, acc_b);
             if constexpr (SIMT) __syncthreads();
@@ -488,6 +522,7 @@ __global__ void __launch_bounds__(TILE, 4) render_march_kernel(const __grid_cons
         if (valid) {
             const float one_m = 1.f - acc_w;
             float dist = acc_d, r = acc_r, g = acc_g, b = acc_b;
+            if constexpr (SAVE != 0) { a.s_dacc[ray] = acc_d; a.s_dl[ray] = dl_uni * (1.f / 3.f) + 2.f * dl_bi; }
             if (a.training) {                                     // nerf_renderer.py:192-194
                 float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
                 if (a.bg_noise) { n0 = a.bg_noise[4 * ray]; n1 = a.bg_noise[4 * ray + 1]; n2 = a.bg_noise[4 * ray + 2]; n3 = a.bg_noise[4 * ray + 3]; }
@@ -512,7 +547,7 @@ __global__ void __launch_bounds__(TILE, 4) render_march_kernel(const __grid_cons
 
 static uint32_t gcd_u32(uint32_t a, uint32_t b) { while (b) { uint32_t t = a % b; a = b; b = t; } return a; }
 
-static int launch_render(const perf_render_args* args, RenderArgs& a, bool pano, cudaStream_t stream)
+static int launch_render(const perf_render_args* args, RenderArgs& a, bool pano, cudaStream_t stream, int save = 0)
 {
     PERF_CHECK_ARG(args->d_packed_table && args->d_geo_mlp_half && args->d_app_mlp_half, "NULL table / weights");
     PERF_CHECK_ARG(args->d_rgb && args->d_distance, "NULL output");
@@ -543,7 +578,11 @@ static int launch_render(const perf_render_args* args, RenderArgs& a, bool pano,
         PERF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_TOTAL)); \
         k<<<grid, TILE, RS_TOTAL, stream>>>(a); } while (0)
     const bool fast = fast_addressing_ok(a.lt, 4) && (args->flags & PERF_FLAG_GENERIC_ADDR) == 0;   // PeRF's grid: 4 dense + 12 hashed levels
-    if (scan) {
+    if (save != 0) {
+        PERF_CHECK_SUP(!pano && !simt && !scan, "training forward runs on the ray-marching tensor-core kernel only");
+        if (fast) { if (save == 1) PERF_RENDER_LAUNCH(render_march_kernel<false, false, 4, 1>); else PERF_RENDER_LAUNCH(render_march_kernel<false, false, 4, 2>); }
+        else      { if (save == 1) PERF_RENDER_LAUNCH(render_march_kernel<false, false, -1, 1>); else PERF_RENDER_LAUNCH(render_march_kernel<false, false, -1, 2>); }
+    } else if (scan) {
         if (pano) { if (simt) PERF_RENDER_LAUNCH(render_kernel<true, true>); else PERF_RENDER_LAUNCH(render_kernel<true, false>); }
         else      { if (simt) PERF_RENDER_LAUNCH(render_kernel<false, true>); else PERF_RENDER_LAUNCH(render_kernel<false, false>); }
     } else if (simt) {
@@ -571,6 +610,23 @@ int perf_render_rays(const perf_render_args* args, const float* d_rays_o, const 
     RenderArgs a; memset(&a, 0, sizeof(a));
     a.rays_o = d_rays_o; a.rays_d = d_rays_d; a.R = R;
     return launch_render(args, a, false, (cudaStream_t)stream);
+}
+
+int perf_train_forward(const perf_render_args* args, const float* d_rays_o, const float* d_rays_d, uint64_t R, int phase,
+                       const perf_train_buffers* buf, void* stream)
+{
+    PERF_CHECK_ARG(args && d_rays_o && d_rays_d && buf, "NULL pointer");
+    PERF_CHECK_ARG(phase == PERF_PHASE_GEO || phase == PERF_PHASE_APP, "phase must be PERF_PHASE_GEO or PERF_PHASE_APP");
+    PERF_CHECK_ARG(buf->d_sigma && buf->d_weights && buf->d_trans && buf->d_feat && buf->d_h1 && buf->d_dist_acc && buf->d_distloss, "NULL training buffer");
+    PERF_CHECK_ARG(phase == PERF_PHASE_GEO || (buf->d_rgb && buf->d_h2), "colour phase needs d_rgb and d_h2");
+    PERF_CHECK_ARG(((uintptr_t)buf->d_feat | (uintptr_t)buf->d_h1 | (uintptr_t)buf->d_h2) % 16 == 0 && (uintptr_t)buf->d_rgb % 8 == 0, "misaligned training buffer");
+    RenderArgs a; memset(&a, 0, sizeof(a));
+    a.rays_o = d_rays_o; a.rays_d = d_rays_d; a.R = R;
+    a.s_sigma = buf->d_sigma; a.s_w = buf->d_weights; a.s_trans = buf->d_trans; a.s_rgb = (__half*)buf->d_rgb;
+    a.s_feat = (uint4*)buf->d_feat; a.s_h1 = (uint4*)buf->d_h1; a.s_h2 = (uint4*)buf->d_h2;
+    a.s_dacc = buf->d_dist_acc; a.s_dl = buf->d_distloss;
+    perf_render_args t = *args; t.flags |= PERF_FLAG_TRAINING;
+    return launch_render(&t, a, false, (cudaStream_t)stream, phase);
 }
 
 int perf_render_pano(const perf_render_args* args, const float* h_pose, int H, int W, int row0, int rows, void* stream)

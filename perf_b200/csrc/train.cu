@@ -1,0 +1,214 @@
+// train.cu -- backward half of the fused training step: composite backward (thread = ray, marching
+// back along the saved samples) and the grid-gradient scatter for ray-ordered samples.
+#include "common.cuh"
+
+namespace perf {
+
+struct CompBwdArgs {
+    uint32_t S; float near, far; uint64_t R;
+    const float* jitter; const float* bg_noise;
+    const float *sigma, *w, *T; const __half* rgb;
+    const float *dist_acc;
+    const float *g_rgb, *g_dist, *g_op, *g_dl, *dist_out, *op_out;
+    float* out;
+};
+
+// dL/dw_i for the density phase:
+//   distance_out = relu(D + c (1 - O)),  D = sum w m,  O = sum w,  c = 2 u - 1      (nerf_renderer.py:192)
+//   distortion numerator DL = sum iv w^2 / 3 + 2 sum_i w_i (m_i Wx_i - WMx_i)        
+//   dDL/dw_i = 2/3 iv_i w_i + 2 (m_i Wx_i - WMx_i) + 2 (WMsuf_i - m_i Wsuf_i)
+// and dL/d(sigma_i dt_i) = (T_i - w_i) g_i - sum_{j>i} w_j g_j.
+template <int PHASE>
+__global__ void __launch_bounds__(128) composite_bwd_kernel(const CompBwdArgs a)
+{
+    const uint64_t ray = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ray >= a.R) return;
+    const uint32_t S = a.S;
+    const float step = __fdiv_rn(__fsub_rn(a.far, a.near), (float)S);
+    const float jit = a.jitter ? a.jitter[ray] : 0.f;
+    if constexpr (PHASE == PERF_PHASE_APP) {
+        float gr = 0.f, gg = 0.f, gb = 0.f;
+        if (a.g_rgb) { gr = a.g_rgb[3 * ray]; gg = a.g_rgb[3 * ray + 1]; gb = a.g_rgb[3 * ray + 2]; }
+        for (uint32_t k = 0; k < S; ++k) {
+            const uint64_t row = (uint64_t)k * a.R + ray;
+            const float w = a.w[row];
+            const uint2 c = *reinterpret_cast<const uint2*>(a.rgb + row * 4);
+            const float2 c01 = unpack_half2(c.x), c2 = unpack_half2(c.y);
+            // colours = sum w.detach() * rgb; rgb = sigmoid(z): dz = g * w * y (1 - y)
+            a.out[row * 3 + 0] = gr * w * c01.x * (1.f - c01.x);
+            a.out[row * 3 + 1] = gg * w * c01.y * (1.f - c01.y);
+            a.out[row * 3 + 2] = gb * w * c2.x * (1.f - c2.x);
+        }
+    } else {
+        const float O = a.op_out[ray], D = a.dist_acc[ray];
+        float c = 0.f;
+        if (a.bg_noise) c = a.bg_noise[4 * ray + 3] * 2.f - 1.f;
+        const float mask = a.dist_out[ray] > 0.f ? 1.f : 0.f;
+        const float gd = (a.g_dist ? a.g_dist[ray] : 0.f) * mask;
+        const float gO = (a.g_op ? a.g_op[ray] : 0.f) - gd * c;
+        const float gdl = a.g_dl ? a.g_dl[ray] : 0.f;
+        float Wsuf = 0.f, WMsuf = 0.f, suf_wg = 0.f;
+        for (uint32_t kk = S; kk-- > 0;) {
+            const uint64_t row = (uint64_t)kk * a.R + ray;
+            const float w = a.w[row], T = a.T[row], sig = a.sigma[row];
+            const float ts = __fadd_rn(a.near, __fmul_rn(__fadd_rn((float)kk, jit), step));
+            const float te = __fadd_rn(a.near, __fmul_rn(__fadd_rn((float)(kk + 1), jit), step));
+            const float m = __fadd_rn(ts, te) * 0.5f, dt = __fsub_rn(te, ts);
+            const float Wx = O - Wsuf - w, WMx = D - WMsuf - w * m;
+            const float ddl = (2.f / 3.f) * dt * w + 2.f * (m * Wx - WMx) + 2.f * (WMsuf - m * Wsuf);
+            const float g = gd * m + gO + gdl * ddl;
+            const float dsd = (T - w) * g - suf_wg;
+            // trunc_exp backward (ngp_nerf.py:36-38): g * exp(clamp(raw, max=15)); sigma = exp(raw)
+            a.out[row] = dsd * dt * fminf(sig, 3269017.3724721107f);
+            suf_wg = fmaf(w, g, suf_wg); Wsuf += w; WMsuf = fmaf(w, m, WMsuf);
+        }
+    }
+}
+
+// ---- grid-gradient scatter, rows sample-major, positions recomputed from the rays.
+// One thread per (row, level); lanes are neighbouring rays at the same sample index.  Lanes whose
+// sample sits in the same cell as the previous lane's form a run; the run is summed with warp
+// shuffles and its last lane issues the 8 float2 atomics (near the camera ALL rays share the coarse
+// cells: without this the same 8 addresses receive tens of thousands of atomics).
+struct GridBwdRaysArgs {
+    LevelTable lt;
+    float aabb_min[3], aabb_ext[3];
+    const float *rays_o, *rays_d, *jitter;
+    uint64_t R; uint32_t S; float near, far;
+    const float* dfeat; float2* dtable;
+};
+
+template <bool AGG>
+__global__ void __launch_bounds__(256) hashgrid_bwd_rays_kernel(const __grid_constant__ GridBwdRaysArgs a)
+{
+    const int l = blockIdx.y, lane = threadIdx.x & 31;
+    const uint64_t N = a.R * a.S;
+    const uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = row < N;
+    float2 g = make_float2(0.f, 0.f);
+    float x = 0.5f, y = 0.5f, z = 0.5f;
+    if (live) {
+        g = *reinterpret_cast<const float2*>(a.dfeat + row * (2 * a.lt.n_levels) + 2 * l);
+        const uint64_t ray = row % a.R; const uint32_t k = (uint32_t)(row / a.R);
+        const float step = __fdiv_rn(__fsub_rn(a.far, a.near), (float)a.S);
+        const float jit = a.jitter ? a.jitter[ray] : 0.f;
+        const float ts = __fadd_rn(a.near, __fmul_rn(__fadd_rn((float)k, jit), step));
+        const float te = __fadd_rn(a.near, __fmul_rn(__fadd_rn((float)(k + 1), jit), step));
+        const float tsum = __fadd_rn(ts, te);
+        x = __fdiv_rn(__fsub_rn(__fadd_rn(a.rays_o[3 * ray], __fmul_rn(a.rays_d[3 * ray], tsum) * 0.5f), a.aabb_min[0]), a.aabb_ext[0]);
+        y = __fdiv_rn(__fsub_rn(__fadd_rn(a.rays_o[3 * ray + 1], __fmul_rn(a.rays_d[3 * ray + 1], tsum) * 0.5f), a.aabb_min[1]), a.aabb_ext[1]);
+        z = __fdiv_rn(__fsub_rn(__fadd_rn(a.rays_o[3 * ray + 2], __fmul_rn(a.rays_d[3 * ray + 2], tsum) * 0.5f), a.aabb_min[2]), a.aabb_ext[2]);
+    }
+    const bool active = live && (g.x != 0.f || g.y != 0.f);
+    // level addressing with a dynamic level index (constant bank, uniform per block)
+    const float scale = a.lt.scale[l];
+    const uint32_t res = a.lt.res[l], size = a.lt.size[l], off = a.lt.offset[l];
+    const bool hashed = (a.lt.hashed_mask >> l) & 1u, pow2 = (a.lt.pow2_mask >> l) & 1u;
+    const float px = fmaf(scale, x, 0.5f), py = fmaf(scale, y, 0.5f), pz = fmaf(scale, z, 0.5f);
+    const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+    const uint32_t gx = (uint32_t)(int)fx, gy = (uint32_t)(int)fy, gz = (uint32_t)(int)fz;
+    float wx = px - fx, wy = py - fy, wz = pz - fz;
+    if (a.lt.smoothstep) { wx = wx * wx * (3.f - 2.f * wx); wy = wy * wy * (3.f - 2.f * wy); wz = wz * wz * (3.f - 2.f * wz); }
+    const float ox = 1.f - wx, oy = 1.f - wy, oz = 1.f - wz;
+    float2 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float w = active ? __fmul_rn(__fmul_rn((k & 1) ? wx : ox, (k & 2) ? wy : oy), (k & 4) ? wz : oz) : 0.f;
+        v[k] = make_float2(w * g.x, w * g.y);
+    }
+    bool tail = true;
+    if constexpr (AGG) {
+        // run = maximal group of consecutive lanes in the same cell (inactive lanes never join)
+        const uint32_t pgx = __shfl_up_sync(0xffffffffu, gx, 1), pgy = __shfl_up_sync(0xffffffffu, gy, 1), pgz = __shfl_up_sync(0xffffffffu, gz, 1);
+        const bool pact = __shfl_up_sync(0xffffffffu, (int)active, 1) != 0;
+        const bool head = lane == 0 || !active || !pact || pgx != gx || pgy != gy || pgz != gz;
+        const uint32_t heads = __ballot_sync(0xffffffffu, head);
+        const int seg_start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+#pragma unroll
+        for (int offs = 1; offs < 32; offs <<= 1) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float tx = __shfl_up_sync(0xffffffffu, v[k].x, offs), ty = __shfl_up_sync(0xffffffffu, v[k].y, offs);
+                if (lane - offs >= seg_start) { v[k].x += tx; v[k].y += ty; }
+            }
+        }
+        tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+    }
+    if (active && tail) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t idx = off + level_index(gx + (k & 1), gy + ((k >> 1) & 1), gz + ((k >> 2) & 1), hashed, pow2, res, size);
+            atomicAdd(a.dtable + idx, v[k]);
+        }
+    }
+}
+
+}  // namespace perf
+
+using namespace perf;
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int perf_train_backward_composite(int phase, uint32_t n_samples, float near, float far, uint64_t R,
+                                  const float* d_jitter, const float* d_bg_noise, const perf_train_buffers* buf,
+                                  const float* d_g_rgb, const float* d_g_distance, const float* d_g_opacity,
+                                  const float* d_g_distloss, const float* d_distance_out, const float* d_opacity_out,
+                                  float* d_out, void* stream)
+{
+    PERF_CHECK_ARG(buf && d_out, "NULL pointer");
+    PERF_CHECK_ARG(phase == PERF_PHASE_GEO || phase == PERF_PHASE_APP, "bad phase");
+    PERF_CHECK_ARG(n_samples >= 1 && far > near, "bad sampling range");
+    CompBwdArgs a; memset(&a, 0, sizeof(a));
+    a.S = n_samples; a.near = near; a.far = far; a.R = R; a.jitter = d_jitter; a.bg_noise = d_bg_noise;
+    a.sigma = buf->d_sigma; a.w = buf->d_weights; a.T = buf->d_trans; a.rgb = (const __half*)buf->d_rgb; a.dist_acc = buf->d_dist_acc;
+    a.g_rgb = d_g_rgb; a.g_dist = d_g_distance; a.g_op = d_g_opacity; a.g_dl = d_g_distloss;
+    a.dist_out = d_distance_out; a.op_out = d_opacity_out; a.out = d_out;
+    if (R == 0) return PERF_OK;
+    const unsigned grid = (unsigned)((R + 127) / 128);
+    if (phase == PERF_PHASE_GEO) {
+        PERF_CHECK_ARG(a.sigma && a.w && a.T && a.dist_acc && a.dist_out && a.op_out, "density phase needs sigma/w/T/dist_acc and the forward outputs");
+        composite_bwd_kernel<PERF_PHASE_GEO><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+    } else {
+        PERF_CHECK_ARG(a.w && a.rgb, "colour phase needs w and rgb");
+        composite_bwd_kernel<PERF_PHASE_APP><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+    }
+    PERF_LAUNCH_CHECK();
+    return PERF_OK;
+}
+
+int perf_hashgrid_bwd_rays(const perf_grid_cfg* cfg, const float* aabb6, const float* d_rays_o, const float* d_rays_d,
+                           const float* d_jitter, uint64_t R, uint32_t n_samples, float near, float far,
+                           const float* d_dfeat, float* d_dtable, void* stream)
+{
+    PERF_CHECK_ARG(aabb6 && d_rays_o && d_rays_d && d_dfeat && d_dtable, "NULL pointer");
+    PERF_CHECK_ARG((uintptr_t)d_dtable % 8 == 0 && (uintptr_t)d_dfeat % 8 == 0, "misaligned dtable/dfeat");
+    GridBwdRaysArgs a; memset(&a, 0, sizeof(a));
+    int rc = build_level_table(cfg, &a.lt, nullptr); if (rc) return rc;
+    for (int i = 0; i < 3; ++i) { a.aabb_min[i] = aabb6[i]; a.aabb_ext[i] = aabb6[3 + i] - aabb6[i]; }
+    a.rays_o = d_rays_o; a.rays_d = d_rays_d; a.jitter = d_jitter; a.R = R; a.S = n_samples; a.near = near; a.far = far;
+    a.dfeat = d_dfeat; a.dtable = (float2*)d_dtable;
+    const uint64_t N = R * n_samples;
+    if (N == 0) return PERF_OK;
+    // coarse levels (few cells across a warp's footprint): merge runs; fine levels: direct atomics
+    const uint32_t n_agg = a.lt.n_levels < 8 ? a.lt.n_levels : 8;
+    dim3 g_agg((unsigned)((N + 255) / 256), n_agg);
+    hashgrid_bwd_rays_kernel<true><<<g_agg, 256, 0, (cudaStream_t)stream>>>(a);
+    PERF_LAUNCH_CHECK();
+    if (a.lt.n_levels > n_agg) {
+        // shift the level window: pass the remaining levels by offsetting blockIdx.y through a copy
+        GridBwdRaysArgs b = a;
+        for (uint32_t l = n_agg; l < a.lt.n_levels; ++l) {
+            b.lt.scale[l - n_agg] = a.lt.scale[l]; b.lt.res[l - n_agg] = a.lt.res[l]; b.lt.size[l - n_agg] = a.lt.size[l]; b.lt.offset[l - n_agg] = a.lt.offset[l];
+        }
+        b.lt.hashed_mask = a.lt.hashed_mask >> n_agg; b.lt.pow2_mask = a.lt.pow2_mask >> n_agg;
+        b.dfeat = a.dfeat + 2 * n_agg;                       // column window; row stride stays 2 * n_levels
+        dim3 g_rest((unsigned)((N + 255) / 256), a.lt.n_levels - n_agg);
+        hashgrid_bwd_rays_kernel<false><<<g_rest, 256, 0, (cudaStream_t)stream>>>(b);
+        PERF_LAUNCH_CHECK();
+    }
+    return PERF_OK;
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

@@ -317,6 +317,113 @@ def render_pano(packed_table, geo_mlp_half, app_mlp_half, pose, H: int, W: int, 
     return rgb, dist, op
 
 
+# ------------------------------------------------------------------ fused training step
+class FusedTrainContext:
+    """Everything one fused training step needs besides the rays: the fp16 shadows / gather table,
+    sampler constants, and the per-sample buffers (cached per (R, S, phase); sample-major rows)."""
+
+    def __init__(self, grid: GridConfig = PERF_GRID, aabb=(-1., -1., -1., 1., 1., 1.), n_samples=128, near=1e-2, far=1.0):
+        self.grid, self.aabb, self.n_samples, self.near, self.far = grid, tuple(float(v) for v in aabb), n_samples, near, far
+        self.packed = self.geo_half = self.app_half = None
+        self._bufs = {}
+
+    def buffers(self, R: int, phase: int, dev):
+        key = (R, self.n_samples, phase, str(dev))
+        if key not in self._bufs:
+            N = R * self.n_samples
+            f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+            f16 = lambda *s: torch.empty(*s, dtype=torch.float16, device=dev)
+            b = {"sigma": f32(N), "w": f32(N), "T": f32(N), "feat": f16(N, 32), "h1": f16(N, 64),
+                 "dacc": f32(R), "dl": f32(R), "rgb": None, "h2": None}
+            if phase == _lib.PERF_PHASE_APP:
+                b["rgb"], b["h2"] = f16(N, 4), f16(N, 64)
+            self._bufs = {key: b}                                  # keep only the latest shape
+        return self._bufs[key]
+
+    @staticmethod
+    def c_buffers(b) -> "_lib.TrainBuffers":
+        ptr = lambda t: None if t is None else t.data_ptr()
+        return _lib.TrainBuffers(ptr(b["sigma"]), ptr(b["w"]), ptr(b["T"]), ptr(b["rgb"]), ptr(b["feat"]), ptr(b["h1"]),
+                                 ptr(b["h2"]), ptr(b["dacc"]), ptr(b["dl"]))
+
+
+def mlp_backward_half(mlp: MLPConfig, weights_half: torch.Tensor, feat, h1, h2, dz: torch.Tensor):
+    """MLP backward from saved fp16 activations with fp16 tensor-core GEMMs (cuBLAS, fp32 out).
+    ``dz`` [N, n_out] fp32: gradient w.r.t. the output layer's pre-activation.
+    Returns (d_weights_flat fp32 [mlp.n_params], dfeat fp32 [N,32])."""
+    W = weights_half
+    w1 = W[:64 * 32].view(64, 32)
+    p = 64 * 32
+    w2 = None
+    if mlp.n_hidden_layers == 2:
+        w2 = W[p:p + 64 * 64].view(64, 64); p += 64 * 64
+    wout = W[p:p + mlp.padded_out * 64].view(mlp.padded_out, 64)[:mlp.n_out]
+    h_last = h2 if w2 is not None else h1
+    dzh = dz.half()
+    d_wout = torch.zeros(mlp.padded_out, 64, dtype=torch.float32, device=dz.device)
+    d_wout[:mlp.n_out] = torch.mm(dzh.t(), h_last, out_dtype=torch.float32)
+    dh = (dzh @ wout) * (h_last > 0)
+    grads = []
+    if w2 is not None:
+        grads.append(torch.mm(dh.t(), h1, out_dtype=torch.float32).reshape(-1))
+        dh = (dh @ w2) * (h1 > 0)
+    d_w1 = torch.mm(dh.t(), feat, out_dtype=torch.float32)
+    dfeat = torch.mm(dh, w1, out_dtype=torch.float32)
+    return torch.cat([d_w1.reshape(-1)] + grads + [d_wout.reshape(-1)]), dfeat
+
+
+class _FusedTrainStep(torch.autograd.Function):
+    """(rgb, distance, opacity, distloss_numerator_per_ray) of a training-mode render, differentiable
+    w.r.t. the flat params of the network selected by ``phase``.  Forward = ONE kernel
+    (perf_train_forward), backward = composite-backward kernel, 5-8 cuBLAS GEMMs, grid scatter."""
+
+    @staticmethod
+    def forward(ctx, params, rays_o, rays_d, jitter, bg_noise, tc: FusedTrainContext, phase: int):
+        R, dev = rays_o.shape[0], rays_o.device
+        b = tc.buffers(R, phase, dev)
+        rgb = torch.empty(R, 3, dtype=torch.float32, device=dev)
+        dist = torch.empty(R, 1, dtype=torch.float32, device=dev)
+        op = torch.empty(R, 1, dtype=torch.float32, device=dev)
+        a = _render_args(tc.packed, tc.geo_half, tc.app_half, tc.aabb, tc.n_samples, tc.near, tc.far, True, False,
+                         jitter, bg_noise, rgb, dist, op, tc.grid)
+        cb = FusedTrainContext.c_buffers(b)
+        with torch.cuda.device(dev):
+            _call(_L().perf_train_forward, C.byref(a), _p(rays_o), _p(rays_d), R, phase, C.byref(cb), _stream())
+        ctx.tc, ctx.phase, ctx.b = tc, phase, b
+        ctx.save_for_backward(rays_o, rays_d, jitter, bg_noise, dist, op)
+        return rgb, dist, op, b["dl"].clone()
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_dist, g_op, g_dl):
+        rays_o, rays_d, jitter, bg_noise, dist, op = ctx.saved_tensors
+        tc, phase, b = ctx.tc, ctx.phase, ctx.b
+        R, S, dev = rays_o.shape[0], tc.n_samples, rays_o.device
+        N = R * S
+        geo = phase == _lib.PERF_PHASE_GEO
+        mlp = GEO_MLP if geo else APP_MLP
+        dz = torch.empty(N, mlp.n_out, dtype=torch.float32, device=dev)
+        c = lambda t: None if t is None else t.contiguous().float()
+        g_rgb, g_dist, g_op, g_dl = c(g_rgb), c(g_dist), c(g_op), c(g_dl)
+        cb = FusedTrainContext.c_buffers(b)
+        with torch.cuda.device(dev):
+            _call(_L().perf_train_backward_composite, phase, S, tc.near, tc.far, R, _p(jitter), _p(bg_noise), C.byref(cb),
+                  _p(g_rgb), _p(g_dist), _p(g_op), _p(g_dl), _p(dist), _p(op), _p(dz), _stream())
+        half = tc.geo_half if geo else tc.app_half
+        d_w, dfeat = mlp_backward_half(mlp, half[:mlp.n_params], b["feat"], b["h1"], b["h2"], dz)
+        d_table = torch.zeros(tc.grid.n_entries, 2, dtype=torch.float32, device=dev)
+        aabb = (C.c_float * 6)(*tc.aabb)
+        with torch.cuda.device(dev):
+            _call(_L().perf_hashgrid_bwd_rays, tc.grid.c(), aabb, _p(rays_o), _p(rays_d), _p(jitter), R, S, tc.near, tc.far,
+                  _p(dfeat), _p(d_table), _stream(), launches=2)
+        return torch.cat([d_w, d_table.reshape(-1)]), None, None, None, None, None, None
+
+
+def fused_train_step(params, rays_o, rays_d, jitter, bg_noise, tc: FusedTrainContext, phase: int):
+    rays_o, rays_d = _chk(rays_o, torch.float32, "rays_o"), _chk(rays_d, torch.float32, "rays_d")
+    jitter, bg_noise = _chk(jitter, torch.float32, "jitter"), _chk(bg_noise, torch.float32, "bg_noise")
+    return _FusedTrainStep.apply(params, rays_o, rays_d, jitter, bg_noise, tc, phase)
+
+
 # ------------------------------------------------------------------ optimiser
 def adam_step(params, grads, exp_avg, exp_avg_sq, step: int, lr: float, params_half=None,
               beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):

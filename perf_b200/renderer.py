@@ -49,6 +49,12 @@ class FusedPanoRenderer:
         self.app_half = ops.params_to_half(app_params.detach().float(), out=self.app_half)
         self.packed = ops.pack_tables(self.geo_half, self.app_half, self.grid, out=self.packed)
 
+    def set_halves(self, geo_half: torch.Tensor, app_half: torch.Tensor) -> None:
+        """Adopt already-cast fp16 shadows (e.g. the ones the fused Adam kernel maintains) and
+        rebuild the interleaved gather table (one kernel)."""
+        self.geo_half, self.app_half = geo_half, app_half
+        self.packed = ops.pack_tables(geo_half, app_half, self.grid, out=self.packed)
+
     def _ready(self):
         if self.packed is None:
             raise RuntimeError("FusedPanoRenderer: call set_params() first")

@@ -186,7 +186,7 @@ class NeRFScene:
     LOSS_SCALE = 2 ** 7                                               # GradScaler(2**7), never unscaled (nerf.py:139,249-253)
 
     def __init__(self, base_exp_dir=".", train_conf=None, estimator_type="fixed", renderer_conf=None,
-                 n_samples: int = 128, near: float = 1e-2, far: float = 1.0, device="cuda", writer=None):
+                 n_samples: int = 128, near: float = 1e-2, far: float = 1.0, device="cuda", writer=None, fused_train: bool = True):
         if estimator_type not in ("fixed",):
             raise NotImplementedError(f"perf_b200 NeRFScene: estimator_type={estimator_type!r}; the native scene implements the "
                                       "fixed-S sampler (run the reference's own NeRFScene on perf_b200.shims for 'occ')")
@@ -199,6 +199,10 @@ class NeRFScene:
         self.renderer = NeRFOCCRenderer(**(renderer_conf or {"max_radius": 2, "bg_color": "rand_noise"}))
         self.fused = FusedPanoRenderer(aabb=self.aabb.tolist(), near=near, far=far)
         self._fused_key = None
+        # fused training step (one forward kernel + composite-backward kernel); False = the modular
+        # path through the plugin functions, op for op like the reference
+        self.fused_train = fused_train
+        self.train_ctx = ops.FusedTrainContext(aabb=self.aabb.tolist(), n_samples=n_samples, near=near, far=far)
         self.global_iter_step_geo = self.global_iter_step_app = 0
 
     # ---- inference ---------------------------------------------------------------------------
@@ -206,7 +210,8 @@ class NeRFScene:
         g, a = self.nerf.geo_mlp.params, self.nerf.app_mlp.params
         key = (g._version, a._version, g.data_ptr(), a.data_ptr())
         if key != self._fused_key:
-            self.fused.set_params(g.detach(), a.detach())
+            # the plugin modules keep version-tracked fp16 shadows (refreshed in place by the Adam kernel)
+            self.fused.set_halves(self.nerf.geo_mlp._half(), self.nerf.app_mlp._half())
             self._fused_key = key
 
     @torch.no_grad()
@@ -224,10 +229,34 @@ class NeRFScene:
         self._sync_fused()
         return self.fused.render_pano(pose, height, width, self.estimator.n_samples, row0=row0, rows=rows)
 
+    def _render_once_fused(self, rays: Rays, geo_inference: bool, app_inference: bool):
+        """Training-mode render as ONE forward kernel; gradients reach the network that is not in
+        inference mode.  Same outputs as the modular path except the per-sample tensors: instead of
+        `weights/t_starts/t_ends/ray_indices` it returns `dist_loss` (= flatten_eff_distloss)."""
+        from . import _lib
+        rays_o, rays_d = rays.collapse()
+        R, dev = rays_o.shape[0], rays_o.device
+        self._sync_fused()
+        tc = self.train_ctx
+        tc.packed, tc.geo_half, tc.app_half = self.fused.packed, self.fused.geo_half, self.fused.app_half
+        jitter = torch.rand(R, device=dev) if self.nerf.training else torch.zeros(R, device=dev)
+        if self.nerf.training and self.renderer.bg_color == "rand_noise":
+            bg = torch.rand(R, 3, device=dev)
+        else:
+            bg = torch.full((R, 3), 1.0 if self.renderer.bg_color == "white" else 0.0, device=dev)
+        noise = torch.cat([bg, torch.rand(R, 1, device=dev)], 1)
+        phase = _lib.PERF_PHASE_APP if geo_inference else _lib.PERF_PHASE_GEO
+        param = self.nerf.app_mlp.params if geo_inference else self.nerf.geo_mlp.params
+        rgb, dist, op, dl = ops.fused_train_step(param, rays_o, rays_d, jitter, noise, tc, phase)
+        return {"is_valid": True, "rgb": rgb, "distance": dist, "opacities": op, "dist_loss": dl.sum() / R}
+
     def render_once(self, rays: Rays, query_keys=("rgb",), sampling_requires_grad=False, geo_inference=False, app_inference=False):
         """`nerf.py:101-123` (differentiable path used by the train steps)."""
         rays_o, rays_d = rays.collapse()
         assert len(rays_o.shape) == 2
+        if self.fused_train and self.nerf.training and (geo_inference != app_inference) and "weights" not in query_keys:
+            res = self._render_once_fused(rays, geo_inference, app_inference)
+            return {k: res[k] for k in list(query_keys) + ["is_valid"]}
         res = self.renderer.render(self.nerf, self.estimator, rays_o, rays_d, geo_inference=geo_inference, app_inference=app_inference)
         if (res is None) or (not res["is_valid"]):
             return res
@@ -263,7 +292,8 @@ class NeRFScene:
         conf, eps, loss = self.train_conf, 1e-7, 0.
         optimizer.zero_grad()
         rays, gt_colors, gt_depths, _ = sup_pool.rand_ray_color_data(self._local_batch(), rand_mode=pixel_sup_rand_mode)
-        res = self.render_once(rays, ["rgb", "distance", "weights", "t_starts", "t_ends", "trans", "ray_indices"], app_inference=True)
+        keys = ["rgb", "distance", "dist_loss"] if self.fused_train else ["rgb", "distance", "weights", "t_starts", "t_ends", "trans", "ray_indices"]
+        res = self.render_once(rays, keys, app_inference=True)
         if (res is None) or (not res["is_valid"]):
             self.global_iter_step_geo += 1
             return None
@@ -272,9 +302,12 @@ class NeRFScene:
             loss = loss + depth_loss * conf.depth_loss_weight
             self._log("nerf_loss/depth_loss", depth_loss, self.global_iter_step_geo)
         if conf.distortion_loss_weight > eps:
-            mid_dis = (res["t_ends"] + res["t_starts"]) * .5
-            sec_lens = res["t_ends"] - res["t_starts"]
-            dist_loss = flatten_eff_distloss(res["weights"], mid_dis, sec_lens, res["ray_indices"])
+            if self.fused_train:
+                dist_loss = res["dist_loss"]
+            else:
+                mid_dis = (res["t_ends"] + res["t_starts"]) * .5
+                sec_lens = res["t_ends"] - res["t_starts"]
+                dist_loss = flatten_eff_distloss(res["weights"], mid_dis, sec_lens, res["ray_indices"])
             loss = loss + dist_loss * conf.distortion_loss_weight * float(np.min([progress * 2., 1]))
             self._log("nerf_loss/dist_loss", dist_loss, self.global_iter_step_geo)
         if conf.density_loss_weight > eps:
@@ -290,7 +323,8 @@ class NeRFScene:
         conf, eps, loss = self.train_conf, 1e-7, 0.
         optimizer.zero_grad()
         rays, gt_colors, _, _ = sup_pool.rand_ray_color_data(self._local_batch(), rand_mode=pixel_sup_rand_mode)
-        res = self.render_once(rays, ["rgb", "distance", "weights", "t_starts", "t_ends", "trans", "ray_indices"], geo_inference=True)
+        keys = ["rgb", "distance"] if self.fused_train else ["rgb", "distance", "weights", "t_starts", "t_ends", "trans", "ray_indices"]
+        res = self.render_once(rays, keys, geo_inference=True)
         if (res is None) or (not res["is_valid"]):
             self.global_iter_step_app += 1
             return None

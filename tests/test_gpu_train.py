@@ -90,6 +90,36 @@ def test_train_step_gradient_matches_oracle(golden_field, phase):
     assert (got - want).abs().max() <= 3e-2 * want.abs().max(), float((got - want).abs().max() / want.abs().max())
 
 
+@pytest.mark.parametrize("phase", ["geo", "app"])
+def test_fused_train_step_equals_modular_step(golden_field, phase):
+    """The fused training step (one forward kernel + composite-backward kernel + fp16 GEMMs +
+    merged grid scatter) against the modular op-for-op path: same random numbers, same loss, same
+    parameter gradient."""
+    from perf_b200 import synthetic
+    from perf_b200.scene import RaySupervision, FusedAdam
+    h, w = 32, 64
+    rgb, dist = synthetic.smooth_rgb(h, w, device="cuda"), synthetic.box_room_distance(h, w, device="cuda")
+    out = {}
+    for fused in (True, False):
+        sc = make_scene(golden_field, 40, fused_train=fused)
+        sc.train_conf["pixel_loss_batch_size"] = 1000
+        sc.set_train()
+        pool = RaySupervision.from_panorama(torch.eye(4), rgb, dist, seed=3)
+        net = sc.nerf.geo_mlp if phase == "geo" else sc.nerf.app_mlp
+        opt = FusedAdam(net.params, lr=0.0, module=net)          # lr 0: keep the gradient, do not move
+        torch.manual_seed(11)
+        step = sc.train_one_step_geo if phase == "geo" else sc.train_one_step_app
+        loss = step(opt, pool, progress=0.4)
+        out[fused] = (float(loss), net.params.grad.detach().clone())
+    (lf, gf), (lm, gm) = out[True], out[False]
+    assert abs(lf - lm) <= 1e-4 * max(1.0, abs(lm)), (lf, lm)
+    cos = F.cosine_similarity(gf, gm, dim=0)
+    assert cos > 0.9995, float(cos)
+    assert (gf - gm).abs().max() <= 2e-2 * gm.abs().max(), float((gf - gm).abs().max() / gm.abs().max())
+    n_mlp = 3072 if phase == "geo" else 7168
+    assert (gf[:n_mlp] - gm[:n_mlp]).abs().max() <= 2e-2 * gm[:n_mlp].abs().max()
+
+
 def test_fit_reduces_losses_and_checkpoint_roundtrip(golden_field, tmp_path):
     from perf_b200 import synthetic
     from perf_b200.config import Conf

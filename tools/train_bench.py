@@ -9,7 +9,7 @@ rank, world, local = parallel.init()
 torch.cuda.set_device(local)
 h, w, S, B = 512, 1024, 128, 8192
 rgb = synthetic.smooth_rgb(h, w, device="cuda"); dist = synthetic.box_room_distance(h, w, device="cuda")
-sc = NeRFScene(n_samples=S)
+sc = NeRFScene(n_samples=S, fused_train=os.environ.get('FUSED', '1') == '1')
 sc.set_train()
 pool = RaySupervision.from_panorama(torch.eye(4), rgb, dist)
 for phase in os.environ.get("PHASES", "geo,app").split(","):
@@ -27,4 +27,4 @@ for phase in os.environ.get("PHASES", "geo,app").split(","):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
     if rank == 0:
-        print(f"[{phase}] train step B={B} S={S} world={world}: {ms:.3f} ms/step  {B*S/ms/1e3:.1f} Msamples/s", flush=True)
+        print(f"[{phase}] fused={sc.fused_train} train step B={B} S={S} world={world}: {ms:.3f} ms/step  {B*S/ms/1e3:.1f} Msamples/s", flush=True)
