@@ -143,6 +143,67 @@ __global__ void __launch_bounds__(256) hashgrid_bwd_rays_kernel(const __grid_con
     }
 }
 
+// Coarse levels: one thread per (ray, level) walks the ray's S samples in order and keeps the 8
+// corner sums of the CURRENT cell in registers; the 8 float2 atomics are issued only when the ray
+// leaves the cell (consecutive samples of a ray stay ~17 / 12 / 8 / 5 ... samples in a level-0/1/2/3
+// cell).  This divides the atomic count of the coarse levels -- the ones whose few addresses are hit
+// by every ray near the camera -- by the run length.
+__global__ void __launch_bounds__(128) hashgrid_bwd_march_kernel(const __grid_constant__ GridBwdRaysArgs a)
+{
+    const int l = blockIdx.y;
+    const uint64_t ray = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ray >= a.R) return;
+    const float step = __fdiv_rn(__fsub_rn(a.far, a.near), (float)a.S);
+    const float jit = a.jitter ? a.jitter[ray] : 0.f;
+    const float ox = a.rays_o[3 * ray], oy = a.rays_o[3 * ray + 1], oz = a.rays_o[3 * ray + 2];
+    const float dx = a.rays_d[3 * ray], dy = a.rays_d[3 * ray + 1], dz = a.rays_d[3 * ray + 2];
+    const float scale = a.lt.scale[l];
+    const uint32_t res = a.lt.res[l], size = a.lt.size[l], off = a.lt.offset[l];
+    const bool hashed = (a.lt.hashed_mask >> l) & 1u, pow2 = (a.lt.pow2_mask >> l) & 1u;
+    const uint32_t stride = 2 * a.lt.n_levels;
+    uint32_t cx = 0xffffffffu, cy = 0xffffffffu, cz = 0xffffffffu;
+    bool have = false;
+    float2 acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = make_float2(0.f, 0.f);
+    auto flush = [&]() {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (acc[k].x != 0.f || acc[k].y != 0.f) {
+                const uint32_t idx = off + level_index(cx + (k & 1), cy + ((k >> 1) & 1), cz + ((k >> 2) & 1), hashed, pow2, res, size);
+                atomicAdd(a.dtable + idx, acc[k]);
+            }
+            acc[k] = make_float2(0.f, 0.f);
+        }
+    };
+    for (uint32_t ks = 0; ks < a.S; ++ks) {
+        const float2 g = *reinterpret_cast<const float2*>(a.dfeat + ((uint64_t)ks * a.R + ray) * stride + 2 * l);
+        if (g.x == 0.f && g.y == 0.f) continue;
+        const float ts = __fadd_rn(a.near, __fmul_rn(__fadd_rn((float)ks, jit), step));
+        const float te = __fadd_rn(a.near, __fmul_rn(__fadd_rn((float)(ks + 1), jit), step));
+        const float tsum = __fadd_rn(ts, te);
+        const float x = __fdiv_rn(__fsub_rn(__fadd_rn(ox, __fmul_rn(dx, tsum) * 0.5f), a.aabb_min[0]), a.aabb_ext[0]);
+        const float y = __fdiv_rn(__fsub_rn(__fadd_rn(oy, __fmul_rn(dy, tsum) * 0.5f), a.aabb_min[1]), a.aabb_ext[1]);
+        const float z = __fdiv_rn(__fsub_rn(__fadd_rn(oz, __fmul_rn(dz, tsum) * 0.5f), a.aabb_min[2]), a.aabb_ext[2]);
+        const float px = fmaf(scale, x, 0.5f), py = fmaf(scale, y, 0.5f), pz = fmaf(scale, z, 0.5f);
+        const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+        const uint32_t gx = (uint32_t)(int)fx, gy = (uint32_t)(int)fy, gz = (uint32_t)(int)fz;
+        if (!have || gx != cx || gy != cy || gz != cz) {
+            if (have) flush();
+            cx = gx; cy = gy; cz = gz; have = true;
+        }
+        float wx = px - fx, wy = py - fy, wz = pz - fz;
+        if (a.lt.smoothstep) { wx = wx * wx * (3.f - 2.f * wx); wy = wy * wy * (3.f - 2.f * wy); wz = wz * wz * (3.f - 2.f * wz); }
+        const float oxw = 1.f - wx, oyw = 1.f - wy, ozw = 1.f - wz;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float w = __fmul_rn(__fmul_rn((k & 1) ? wx : oxw, (k & 2) ? wy : oyw), (k & 4) ? wz : ozw);
+            acc[k].x = fmaf(w, g.x, acc[k].x); acc[k].y = fmaf(w, g.y, acc[k].y);
+        }
+    }
+    if (have) flush();
+}
+
 }  // namespace perf
 
 using namespace perf;
@@ -190,10 +251,10 @@ int perf_hashgrid_bwd_rays(const perf_grid_cfg* cfg, const float* aabb6, const f
     a.dfeat = d_dfeat; a.dtable = (float2*)d_dtable;
     const uint64_t N = R * n_samples;
     if (N == 0) return PERF_OK;
-    // coarse levels (few cells across a warp's footprint): merge runs; fine levels: direct atomics
+    // coarse levels: per-ray marching with register accumulation per cell; fine levels: direct atomics
     const uint32_t n_agg = a.lt.n_levels < 8 ? a.lt.n_levels : 8;
-    dim3 g_agg((unsigned)((N + 255) / 256), n_agg);
-    hashgrid_bwd_rays_kernel<true><<<g_agg, 256, 0, (cudaStream_t)stream>>>(a);
+    dim3 g_agg((unsigned)((R + 127) / 128), n_agg);
+    hashgrid_bwd_march_kernel<<<g_agg, 128, 0, (cudaStream_t)stream>>>(a);
     PERF_LAUNCH_CHECK();
     if (a.lt.n_levels > n_agg) {
         // shift the level window: pass the remaining levels by offsetting blockIdx.y through a copy

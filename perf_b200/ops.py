@@ -107,6 +107,21 @@ def hashgrid_bwd(x01: torch.Tensor, dfeat: torch.Tensor, grid: GridConfig = PERF
     return out
 
 
+def hashgrid_bwd_rays(rays_o, rays_d, jitter, n_samples: int, near: float, far: float, dfeat: torch.Tensor,
+                      aabb=(-1., -1., -1., 1., 1., 1.), grid: GridConfig = PERF_GRID, out: Optional[torch.Tensor] = None):
+    """d(table) from sample-major rows (row = k * R + ray) whose positions are recomputed from the
+    rays (fixed-S sampler); coarse levels are accumulated per cell along each ray before the atomics."""
+    rays_o, rays_d, dfeat = _chk(rays_o, torch.float32, "rays_o"), _chk(rays_d, torch.float32, "rays_d"), _chk(dfeat, torch.float32, "dfeat")
+    jitter = None if jitter is None else _chk(jitter, torch.float32, "jitter")
+    if out is None:
+        out = torch.zeros(grid.n_entries, 2, dtype=torch.float32, device=rays_o.device)
+    a6 = (C.c_float * 6)(*[float(v) for v in aabb])
+    with torch.cuda.device(rays_o.device):
+        _call(_L().perf_hashgrid_bwd_rays, grid.c(), a6, _p(rays_o), _p(rays_d), _p(jitter), rays_o.shape[0], n_samples,
+              near, far, _p(dfeat), _p(out), _stream(), launches=2)
+    return out
+
+
 # ------------------------------------------------------------------ network (encode + MLP)
 def network_fwd(params_half: torch.Tensor, x01: torch.Tensor, grid: GridConfig, mlp: MLPConfig,
                 save: bool = False, simt: bool = False):

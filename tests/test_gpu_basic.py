@@ -151,3 +151,21 @@ def test_params_to_half_and_pack(ops):
     packed = ops.pack_tables(gh, ah).cpu()
     assert torch.equal(packed[:, :2], geo.half()[GEO_MLP.n_params:].view(-1, 2))
     assert torch.equal(packed[:, 2:], app.half()[APP_MLP.n_params:].view(-1, 2))
+
+
+def test_hashgrid_bwd_rays_matches_oracle(ops):
+    """Ray-ordered grid scatter (per-ray cell accumulation for coarse levels, direct atomics for the
+    fine ones) == the oracle's scatter on the same positions."""
+    g = torch.Generator().manual_seed(17)
+    R, S, near, far = 333, 40, 1e-2, 1.0
+    o = (torch.rand(R, 3, generator=g) - .5) * .2
+    d = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1)
+    jit = torch.rand(R, generator=g)
+    dfeat = torch.randn(S * R, 32, generator=g)
+    dfeat[::7] = 0
+    ts, te = oracle.fixed_samples(R, S, near, far, jit)                       # [R,S]
+    pos = o[:, None, :] + d[:, None, :] * (ts + te)[..., None] / 2.0
+    x01 = ((pos + 1.0) / 2.0).permute(1, 0, 2).reshape(-1, 3)                 # sample-major rows
+    want = encode_backward_table(x01, dfeat, OGrid())
+    got = ops.hashgrid_bwd_rays(o.cuda(), d.cuda(), jit.cuda(), S, near, far, dfeat.cuda()).cpu()
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=2e-4, atol=2e-5)

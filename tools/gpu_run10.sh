@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 400 python -m pytest tests/test_gpu_train.py tests/test_gpu_render.py -q -m gpu --no-header -p no:cacheprovider --durations=5 --timeout=150 -x > gpurun_out/pytest_train.log 2>&1; echo "pytest exit=$?" | tee gpurun_out/summary.txt
+timeout 400 python -m pytest tests/test_gpu_train.py tests/test_gpu_basic.py -q -m gpu --no-header -p no:cacheprovider --durations=5 --timeout=150 -x > gpurun_out/pytest_train.log 2>&1; echo "pytest exit=$?" | tee gpurun_out/summary.txt
 tail -12 gpurun_out/pytest_train.log
 FUSED=1 timeout 200 python tools/train_bench.py > gpurun_out/train_bench.log 2>&1; echo "train_bench exit=$?" | tee -a gpurun_out/summary.txt
 tail -4 gpurun_out/train_bench.log
