@@ -159,6 +159,45 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def bench_train(dev, rank, world, steps=20, warmup=5):
+    """Secondary measurement (not `value`): the optimisation step of configs[1]/[2] -- 8192 rays x 128
+    samples GLOBAL batch (configs/nerf.yaml pixel_loss_batch_size), forward + backward + fused Adam, one
+    gradient all-reduce when world > 1 -- on a synthetic box-room RGB-D panorama."""
+    import torch
+    import torch.distributed as dist
+    from perf_b200 import synthetic
+    from perf_b200.scene import FusedAdam, NeRFScene, RaySupervision
+    h, w = 512, 1024
+    rgb, distance = synthetic.smooth_rgb(h, w, device=dev), synthetic.box_room_distance(h, w, device=dev)
+    sc = NeRFScene(n_samples=S, device=dev)
+    sc.set_train()
+    pool = RaySupervision.from_panorama(torch.eye(4), rgb, distance)
+    out = {"rays_per_step_global": 8192, "samples_per_ray": S, "world": world,
+           "note": "forward+backward+Adam per step, strong scaling of the reference's 8192-ray batch; random-init field, synthetic RGB-D"}
+    for phase in ("geo", "app"):
+        net = sc.nerf.geo_mlp if phase == "geo" else sc.nerf.app_mlp
+        opt = FusedAdam(net.params, lr=1e-3, module=net)
+        step = sc.train_one_step_geo if phase == "geo" else sc.train_one_step_app
+        for _ in range(warmup):
+            step(opt, pool, progress=0.5)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step(opt, pool, progress=0.5)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        out[f"{phase}_ms_per_step"] = ms
+        out[f"{phase}_msamples_per_s"] = 8192 * S / ms / 1e3
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -221,6 +260,8 @@ def run_ours(args, rank, world, local_rank):
     e2e_ms = t_e2e[0].elapsed_time(t_e2e[1])
     clocks = sampler.stop()
 
+    train = bench_train(dev, rank, world) if not args.no_train else None
+
     t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -252,6 +293,8 @@ def run_ours(args, rank, world, local_rank):
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_sample": ALG_BYTES_PER_SAMPLE,
                          "note": "tables (26.6 MB fp16) are L2-resident: DRAM traffic is far below algorithmic bytes, see profiles/"}}
+    if train is not None:
+        line["train"] = train
     if cpu_v is not None:
         line["cpu_baseline"] = {"value": cpu_v, "unit": "Msamples/s", "cores": cores, "kind": "port",
                                 "sample": f"4096 rays x {S} samples (row {H // 2} of the panorama), oracle/render.py mixed-precision restatement, {cpu_s:.1f} s"}
@@ -264,6 +307,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-train", action="store_true", help="skip the secondary training-step measurement")
     args = ap.parse_args()
     rank, world, local_rank = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":

@@ -129,15 +129,28 @@ class RaySupervision:
         self.all_sup_distances = distances.reshape(-1, 1)
         self.all_sup_normals = torch.zeros_like(colors) if normals is None else normals
         self.generator = torch.Generator(device=colors.device).manual_seed(seed + parallel.rank())
+        self.locality_key = None      # optional int64 key per ray; batches are ordered by it (see from_panorama)
 
     @staticmethod
     def from_panorama(pose, rgb: torch.Tensor, distance: torch.Tensor, seed: int = 0) -> "RaySupervision":
         h, w = distance.shape[:2]
         rays = gen_pano_rays(pose, h, w, device=rgb.device)
-        return RaySupervision(Rays(rays.o.reshape(-1, 3), rays.d.reshape(-1, 3)), rgb.reshape(-1, 3).float(), distance.reshape(-1, 1).float(), seed=seed)
+        pool = RaySupervision(Rays(rays.o.reshape(-1, 3), rays.d.reshape(-1, 3)), rgb.reshape(-1, 3).float(), distance.reshape(-1, 1).float(), seed=seed)
+        # Morton (Z-order) code of the pixel: a batch sorted by it puts rays that are neighbours on the
+        # sphere into the same warp, so their hash-grid gathers share cache lines at the coarse levels.
+        # The batch is the same multiset of rays torch.randint drew (sup_info.py:253-257); only its order changes.
+        yy, xx = torch.meshgrid(torch.arange(h, device=rgb.device), torch.arange(w, device=rgb.device), indexing="ij")
+        key = torch.zeros(h, w, dtype=torch.int64, device=rgb.device)
+        for b in range(16):
+            key |= ((xx >> b) & 1) << (2 * b)
+            key |= ((yy >> b) & 1) << (2 * b + 1)
+        pool.locality_key = key.reshape(-1)
+        return pool
 
     def rand_ray_color_data(self, batch_size, rand_mode="by_all_pixels"):
         idx = torch.randint(0, len(self.all_sup_colors), (batch_size,), device=self.all_sup_colors.device, generator=self.generator)
+        if self.locality_key is not None:
+            idx = idx[torch.argsort(self.locality_key[idx])]
         return self.all_sup_rays[idx], self.all_sup_colors[idx], self.all_sup_distances[idx], self.all_sup_normals[idx]
 
 

@@ -141,6 +141,19 @@ def test_fit_reduces_losses_and_checkpoint_roundtrip(golden_field, tmp_path):
     d1, c1 = errors()
     assert d1 < 0.25 * d0 and d1 < 0.05, (d0, d1)
     assert c1 < 0.5 * c0, (c0, c1)
+    # PSNR delta vs the reference restatement on the TRAINED field (north star: within 0.1 dB):
+    # the same parameters rendered by the CPU oracle (mixed precision, and plain fp32) and by the kernel
+    fld = oracle.Field(sc.nerf.geo_mlp.params.detach().cpu(), sc.nerf.app_mlp.params.detach().cpu())
+    ours = sc.render_pano(torch.eye(4), h, w)["rgb"].cpu()
+    ref_mixed = oracle.render_pano(fld, torch.eye(4), h, w, 48, mixed=True)["rgb"]
+    ref_fp32 = oracle.render_pano(fld, torch.eye(4), h, w, 48, mixed=False)["rgb"]
+    psnr = lambda a, b: -10.0 * np.log10(float(((a - b) ** 2).mean()))
+    gt = rgb.cpu()
+    p_ours, p_mixed, p_fp32 = psnr(ours, gt), psnr(ref_mixed, gt), psnr(ref_fp32, gt)
+    print(f"PSNR vs ground truth: kernel {p_ours:.3f} dB, oracle(mixed) {p_mixed:.3f} dB, oracle(fp32) {p_fp32:.3f} dB; "
+          f"PSNR(kernel, oracle mixed) {psnr(ours, ref_mixed):.1f} dB")
+    assert abs(p_ours - p_mixed) <= 0.1 and abs(p_ours - p_fp32) <= 0.1
+    assert psnr(ours, ref_mixed) >= 45.0
     # checkpoint dict has the reference's keys and reloads into a fresh scene bit-for-bit
     sd = sc.state_dict()
     assert set(sd) == {"render", "nerf", "estimator"} and set(sd["nerf"]) == {"aabb", "geo_mlp.params", "app_mlp.params"}
