@@ -202,6 +202,23 @@ int perf_hashgrid_bwd_rays(const perf_grid_cfg* cfg, const float* aabb6, const f
                            const float* d_jitter, uint64_t R, uint32_t n_samples, float near, float far,
                            const float* d_dfeat, float* d_dtable, void* stream);
 
+/* Occupancy-grid interval sampler (nerfacc OccGridEstimator.sampling, levels=1, cone_angle=0;
+ * nerf_renderer.py:145-155).  d_binaries: bool/uint8 [rx*ry*rz] (x slowest).
+ * Pass 1 writes the per-ray sample counts; the caller exclusive-scans them into d_offsets and
+ * allocates the packed outputs; pass 2 writes (ray_indices int64, t_starts, t_ends), sorted by ray. */
+int perf_occ_count(const uint8_t* d_binaries, const int* h_res3, const float* h_aabb6, const float* d_rays_o, const float* d_rays_d,
+                   const float* d_jitter, uint64_t R, float near, float far, float step, int32_t* d_counts, void* stream);
+int perf_occ_write(const uint8_t* d_binaries, const int* h_res3, const float* h_aabb6, const float* d_rays_o, const float* d_rays_d,
+                   const float* d_jitter, uint64_t R, float near, float far, float step, const int64_t* d_offsets,
+                   int64_t* d_ray_indices, float* d_t_starts, float* d_t_ends, void* stream);
+
+/* MLP backward helpers on the saved fp16 activations (tcnn kernel_mlp_fused_backward pieces; the
+ * matrix products themselves are plain GEMMs left to cuBLAS):
+ *   perf_mlp_bwd_out: d_dh [N,64] fp16 = (d_dz [N,n_out] fp32 @ Wout[:n_out] fp16) * (d_h > 0)
+ *   perf_relu_mask:   d_dh *= (d_h > 0), in place, n_values fp16 values each */
+int perf_mlp_bwd_out(const float* d_dz, int n_out, const void* d_wout_half, const void* d_h, void* d_dh, uint64_t N, void* stream);
+int perf_relu_mask(void* d_dh, const void* d_h, uint64_t n_values, void* stream);
+
 /* Fused Adam on a flat fp32 parameter vector + refresh of its fp16 shadow
  * (torch.optim.Adam at nerf.py:171,180,253,293; betas/eps defaults).  grad_scale multiplies
  * the gradient first (the reference never unscales its 128x GradScaler; pass 1 to keep that). */

@@ -1,0 +1,109 @@
+// occ.cu -- occupancy-grid interval sampler (nerfacc OccGridEstimator.sampling semantics for
+// levels=1, cone_angle=0; call site modules/scene/nerf_renderer.py:145-155).
+// Rule (restated in oracle/occ_sampler.py): lattice t_k = near + (k + u_r) * step; the interval
+// [t_k, t_k + step) is emitted when its midpoint lies inside the ray/aabb overlap and in an occupied
+// cell.  Two passes (count, write) around an exclusive scan of the per-ray counts done by the caller.
+#include "common.cuh"
+
+namespace perf {
+
+struct OccArgs {
+    const uint8_t* binaries; int rx, ry, rz;
+    float amin[3], aext[3], amax[3];
+    const float *rays_o, *rays_d, *jitter;
+    uint64_t R; float near, far, step;
+    int32_t* counts; const int64_t* offsets;
+    int64_t* ray_indices; float *t_starts, *t_ends;
+};
+
+template <bool WRITE>
+__global__ void __launch_bounds__(128) occ_march_kernel(const OccArgs a)
+{
+    const uint64_t ray = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ray >= a.R) return;
+    const float o[3] = {a.rays_o[3 * ray], a.rays_o[3 * ray + 1], a.rays_o[3 * ray + 2]};
+    const float d[3] = {a.rays_d[3 * ray], a.rays_d[3 * ray + 1], a.rays_d[3 * ray + 2]};
+    float tn = -INFINITY, tf = INFINITY;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float inv = __fdiv_rn(1.0f, fabsf(d[i]) < 1e-12f ? 1e-12f : d[i]);
+        const float t0 = __fmul_rn(__fsub_rn(a.amin[i], o[i]), inv), t1 = __fmul_rn(__fsub_rn(a.amax[i], o[i]), inv);
+        tn = fmaxf(tn, fminf(t0, t1)); tf = fminf(tf, fmaxf(t0, t1));
+    }
+    tn = fmaxf(tn, a.near); tf = fminf(tf, a.far);
+    const float u = a.jitter ? a.jitter[ray] : 0.f;
+    const float half_step = __fmul_rn(0.5f, a.step);
+    int64_t pos = WRITE ? a.offsets[ray] : 0;
+    int32_t n = 0;
+    if (tf >= tn) {
+        // first lattice index whose midpoint can reach tn (minus a safety margin; exact test below)
+        float kf = floorf((tn - a.near) / a.step - u - 0.5f) - 2.0f;
+        uint32_t k = kf > 0.f ? (uint32_t)kf : 0u;
+        for (;; ++k) {
+            const float ts = __fadd_rn(a.near, __fmul_rn(__fadd_rn((float)k, u), a.step));
+            const float mid = __fadd_rn(ts, half_step);
+            if (mid > tf) break;
+            if (mid < tn) continue;
+            int c[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const float p = __fadd_rn(o[i], __fmul_rn(d[i], mid));
+                const int res = i == 0 ? a.rx : (i == 1 ? a.ry : a.rz);
+                int ci = (int)floorf(__fmul_rn(__fdiv_rn(__fsub_rn(p, a.amin[i]), a.aext[i]), (float)res));
+                c[i] = ci < 0 ? 0 : (ci > res - 1 ? res - 1 : ci);
+            }
+            if (a.binaries[((int64_t)c[0] * a.ry + c[1]) * a.rz + c[2]]) {
+                if (WRITE) { a.ray_indices[pos] = (int64_t)ray; a.t_starts[pos] = ts; a.t_ends[pos] = __fadd_rn(ts, a.step); ++pos; }
+                ++n;
+            }
+        }
+    }
+    if (!WRITE) a.counts[ray] = n;
+}
+
+}  // namespace perf
+
+using namespace perf;
+
+static int fill(OccArgs& a, const uint8_t* bin, const int* res3, const float* aabb6, const float* o, const float* d, const float* jit,
+                uint64_t R, float near, float far, float step)
+{
+    PERF_CHECK_ARG(bin && res3 && aabb6 && o && d, "NULL pointer");
+    PERF_CHECK_ARG(res3[0] > 0 && res3[1] > 0 && res3[2] > 0 && step > 0.f && far > near, "bad occupancy sampling arguments");
+    memset(&a, 0, sizeof(a));
+    a.binaries = bin; a.rx = res3[0]; a.ry = res3[1]; a.rz = res3[2];
+    for (int i = 0; i < 3; ++i) { a.amin[i] = aabb6[i]; a.amax[i] = aabb6[3 + i]; a.aext[i] = aabb6[3 + i] - aabb6[i]; }
+    a.rays_o = o; a.rays_d = d; a.jitter = jit; a.R = R; a.near = near; a.far = far; a.step = step;
+    return PERF_OK;
+}
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int perf_occ_count(const uint8_t* d_binaries, const int* h_res3, const float* h_aabb6, const float* d_rays_o, const float* d_rays_d,
+                   const float* d_jitter, uint64_t R, float near, float far, float step, int32_t* d_counts, void* stream)
+{
+    OccArgs a; int rc = fill(a, d_binaries, h_res3, h_aabb6, d_rays_o, d_rays_d, d_jitter, R, near, far, step); if (rc) return rc;
+    PERF_CHECK_ARG(d_counts, "NULL counts");
+    a.counts = d_counts;
+    if (R == 0) return PERF_OK;
+    occ_march_kernel<false><<<(unsigned)((R + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a);
+    PERF_LAUNCH_CHECK();
+    return PERF_OK;
+}
+
+int perf_occ_write(const uint8_t* d_binaries, const int* h_res3, const float* h_aabb6, const float* d_rays_o, const float* d_rays_d,
+                   const float* d_jitter, uint64_t R, float near, float far, float step, const int64_t* d_offsets,
+                   int64_t* d_ray_indices, float* d_t_starts, float* d_t_ends, void* stream)
+{
+    OccArgs a; int rc = fill(a, d_binaries, h_res3, h_aabb6, d_rays_o, d_rays_d, d_jitter, R, near, far, step); if (rc) return rc;
+    PERF_CHECK_ARG(d_offsets && d_ray_indices && d_t_starts && d_t_ends, "NULL output");
+    a.offsets = d_offsets; a.ray_indices = d_ray_indices; a.t_starts = d_t_starts; a.t_ends = d_t_ends;
+    if (R == 0) return PERF_OK;
+    occ_march_kernel<true><<<(unsigned)((R + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a);
+    PERF_LAUNCH_CHECK();
+    return PERF_OK;
+}
+
+#pragma GCC visibility pop
+}

@@ -65,6 +65,50 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(const CompBwdArgs a)
     }
 }
 
+// dh[n][j] = (sum_o dz[n][o] * wout[o][j]) * (h[n][j] > 0)   -- output layer backward + ReLU mask,
+// one pass over the saved fp16 activations (8 columns per thread).
+__global__ void __launch_bounds__(256)
+mlp_bwd_out_kernel(const float* __restrict__ dz, int n_out, const __half* __restrict__ wout /*[n_out,64]*/,
+                   const uint4* __restrict__ h /*[N,64] fp16*/, uint4* __restrict__ dh, uint64_t N)
+{
+    __shared__ float sw[16 * 64];
+    for (int i = threadIdx.x; i < n_out * 64; i += blockDim.x) sw[i] = __half2float(wout[i]);
+    __syncthreads();
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;       // one uint4 (8 halves)
+    if (t >= N * 8) return;
+    const uint64_t n = t >> 3; const int c0 = (int)(t & 7) * 8;
+    float z[16];
+    for (int o = 0; o < n_out; ++o) z[o] = dz[n * n_out + o];
+    const uint4 hv = h[t];
+    const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+    uint32_t ow[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float2 hh = unpack_half2(hw[q]);
+        float a = 0.f, b = 0.f;
+        for (int o = 0; o < n_out; ++o) { a = fmaf(z[o], sw[o * 64 + c0 + 2 * q], a); b = fmaf(z[o], sw[o * 64 + c0 + 2 * q + 1], b); }
+        ow[q] = pack_half2(hh.x > 0.f ? a : 0.f, hh.y > 0.f ? b : 0.f);
+    }
+    dh[t] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+}
+
+// dh[n][j] *= (h[n][j] > 0) in place (ReLU mask after a hidden-layer GEMM)
+__global__ void __launch_bounds__(256)
+relu_mask_kernel(uint4* __restrict__ dh, const uint4* __restrict__ h, uint64_t n16)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n16) return;
+    const uint4 hv = h[t]; uint4 d = dh[t];
+    const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}; uint32_t dw[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float2 hh = unpack_half2(hw[q]);
+        if (!(hh.x > 0.f)) dw[q] &= 0xffff0000u;
+        if (!(hh.y > 0.f)) dw[q] &= 0x0000ffffu;
+    }
+    dh[t] = make_uint4(dw[0], dw[1], dw[2], dw[3]);
+}
+
 // ---- grid-gradient scatter, rows sample-major, positions recomputed from the rays.
 // One thread per (row, level); lanes are neighbouring rays at the same sample index.  Lanes whose
 // sample sits in the same cell as the previous lane's form a run; the run is summed with warp
@@ -268,6 +312,27 @@ int perf_hashgrid_bwd_rays(const perf_grid_cfg* cfg, const float* aabb6, const f
         hashgrid_bwd_rays_kernel<false><<<g_rest, 256, 0, (cudaStream_t)stream>>>(b);
         PERF_LAUNCH_CHECK();
     }
+    return PERF_OK;
+}
+
+int perf_mlp_bwd_out(const float* d_dz, int n_out, const void* d_wout_half, const void* d_h, void* d_dh, uint64_t N, void* stream)
+{
+    PERF_CHECK_ARG(d_dz && d_wout_half && d_h && d_dh, "NULL pointer");
+    PERF_CHECK_ARG(n_out >= 1 && n_out <= 16, "n_out=%d not in [1,16]", n_out);
+    PERF_CHECK_ARG(((uintptr_t)d_h | (uintptr_t)d_dh) % 16 == 0, "misaligned activations");
+    if (N == 0) return PERF_OK;
+    mlp_bwd_out_kernel<<<(unsigned)((N * 8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_dz, n_out, (const __half*)d_wout_half, (const uint4*)d_h, (uint4*)d_dh, N);
+    PERF_LAUNCH_CHECK();
+    return PERF_OK;
+}
+
+int perf_relu_mask(void* d_dh, const void* d_h, uint64_t n_values, void* stream)
+{
+    PERF_CHECK_ARG(d_dh && d_h, "NULL pointer");
+    PERF_CHECK_ARG(n_values % 8 == 0 && ((uintptr_t)d_h | (uintptr_t)d_dh) % 16 == 0, "n_values must be a multiple of 8 and buffers 16-byte aligned");
+    if (n_values == 0) return PERF_OK;
+    relu_mask_kernel<<<(unsigned)((n_values / 8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>((uint4*)d_dh, (const uint4*)d_h, n_values / 8);
+    PERF_LAUNCH_CHECK();
     return PERF_OK;
 }
 

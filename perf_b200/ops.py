@@ -272,6 +272,33 @@ def accumulate_along_rays(weights, values, ray_indices, n_rays: int) -> torch.Te
     return out
 
 
+# ------------------------------------------------------------------ occupancy-grid sampler
+def occ_sample(binaries: torch.Tensor, aabb, rays_o, rays_d, near: float, far: float, step: float, jitter=None):
+    """Packed (ray_indices, t_starts, t_ends) of the lattice samples whose midpoint is inside the aabb
+    in an occupied cell (two kernels around one cumsum; one host sync for the total, as nerfacc)."""
+    rays_o, rays_d = _chk(rays_o, torch.float32, "rays_o"), _chk(rays_d, torch.float32, "rays_d")
+    jitter = None if jitter is None else _chk(jitter, torch.float32, "jitter")
+    if not binaries.is_cuda or binaries.dim() != 3:
+        raise RuntimeError("perf_b200.occ_sample: `binaries` must be a CUDA bool tensor [rx, ry, rz]")
+    bins = binaries.contiguous().view(torch.uint8) if binaries.dtype == torch.bool else _chk(binaries, torch.uint8, "binaries")
+    R, dev = rays_o.shape[0], rays_o.device
+    res3 = (C.c_int * 3)(*[int(v) for v in binaries.shape])
+    a6 = (C.c_float * 6)(*[float(v) for v in aabb])
+    counts = torch.empty(R, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _call(_L().perf_occ_count, _p(bins), res3, a6, _p(rays_o), _p(rays_d), _p(jitter), R, near, far, step, _p(counts), _stream())
+    incl = torch.cumsum(counts, 0, dtype=torch.int64)
+    total = int(incl[-1].item()) if R else 0
+    offsets = (incl - counts).contiguous()
+    ri = torch.empty(total, dtype=torch.int64, device=dev)
+    ts, te = torch.empty(total, dtype=torch.float32, device=dev), torch.empty(total, dtype=torch.float32, device=dev)
+    if total:
+        with torch.cuda.device(dev):
+            _call(_L().perf_occ_write, _p(bins), res3, a6, _p(rays_o), _p(rays_d), _p(jitter), R, near, far, step, _p(offsets),
+                  _p(ri), _p(ts), _p(te), _stream())
+    return ri, ts, te
+
+
 # ------------------------------------------------------------------ fused renderer
 def _render_args(packed_table, geo_mlp_half, app_mlp_half, aabb, n_samples, near, far, training, simt,
                  jitter, bg_noise, rgb, distance, opacity, grid: GridConfig, kernel: str = "march") -> "_lib.RenderArgs":
@@ -362,29 +389,39 @@ class FusedTrainContext:
                                  ptr(b["h2"]), ptr(b["dacc"]), ptr(b["dl"]))
 
 
-def mlp_backward_half(mlp: MLPConfig, weights_half: torch.Tensor, feat, h1, h2, dz: torch.Tensor):
-    """MLP backward from saved fp16 activations with fp16 tensor-core GEMMs (cuBLAS, fp32 out).
+def mlp_backward_half(mlp: MLPConfig, weights_half: torch.Tensor, feat, h1, h2, dz: torch.Tensor,
+                      grad_out: Optional[torch.Tensor] = None):
+    """MLP backward from saved fp16 activations: fp16 tensor-core GEMMs (cuBLAS, fp32 out) for the
+    matrix products, libperfb200 kernels for the fused output-layer backward + ReLU masks.
     ``dz`` [N, n_out] fp32: gradient w.r.t. the output layer's pre-activation.
-    Returns (d_weights_flat fp32 [mlp.n_params], dfeat fp32 [N,32])."""
+    Returns (d_weights_flat fp32 [mlp.n_params] -- written into ``grad_out`` when given --, dfeat fp32 [N,32])."""
+    N, dev = dz.shape[0], dz.device
     W = weights_half
     w1 = W[:64 * 32].view(64, 32)
     p = 64 * 32
     w2 = None
     if mlp.n_hidden_layers == 2:
         w2 = W[p:p + 64 * 64].view(64, 64); p += 64 * 64
-    wout = W[p:p + mlp.padded_out * 64].view(mlp.padded_out, 64)[:mlp.n_out]
+    wout = W[p:p + mlp.padded_out * 64].view(mlp.padded_out, 64)[:mlp.n_out].contiguous()
     h_last = h2 if w2 is not None else h1
-    dzh = dz.half()
-    d_wout = torch.zeros(mlp.padded_out, 64, dtype=torch.float32, device=dz.device)
-    d_wout[:mlp.n_out] = torch.mm(dzh.t(), h_last, out_dtype=torch.float32)
-    dh = (dzh @ wout) * (h_last > 0)
-    grads = []
+    if grad_out is None:
+        grad_out = torch.zeros(mlp.n_params, dtype=torch.float32, device=dev)
+    g_w1 = grad_out[:2048].view(64, 32)
+    g_w2 = grad_out[2048:2048 + 4096].view(64, 64) if w2 is not None else None
+    g_wout = grad_out[p:p + mlp.padded_out * 64].view(mlp.padded_out, 64)
+    dz = dz.contiguous()
+    g_wout[:mlp.n_out] = torch.mm(dz.half().t(), h_last, out_dtype=torch.float32)
+    dh = torch.empty(N, 64, dtype=torch.float16, device=dev)
+    with torch.cuda.device(dev):
+        _call(_L().perf_mlp_bwd_out, _p(dz), mlp.n_out, _p(wout), _p(h_last), _p(dh), N, _stream())
     if w2 is not None:
-        grads.append(torch.mm(dh.t(), h1, out_dtype=torch.float32).reshape(-1))
-        dh = (dh @ w2) * (h1 > 0)
-    d_w1 = torch.mm(dh.t(), feat, out_dtype=torch.float32)
+        g_w2.copy_(torch.mm(dh.t(), h1, out_dtype=torch.float32))
+        dh = dh @ w2
+        with torch.cuda.device(dev):
+            _call(_L().perf_relu_mask, _p(dh), _p(h1), N * 64, _stream())
+    g_w1.copy_(torch.mm(dh.t(), feat, out_dtype=torch.float32))
     dfeat = torch.mm(dh, w1, out_dtype=torch.float32)
-    return torch.cat([d_w1.reshape(-1)] + grads + [d_wout.reshape(-1)]), dfeat
+    return grad_out, dfeat
 
 
 class _FusedTrainStep(torch.autograd.Function):
@@ -424,13 +461,15 @@ class _FusedTrainStep(torch.autograd.Function):
             _call(_L().perf_train_backward_composite, phase, S, tc.near, tc.far, R, _p(jitter), _p(bg_noise), C.byref(cb),
                   _p(g_rgb), _p(g_dist), _p(g_op), _p(g_dl), _p(dist), _p(op), _p(dz), _stream())
         half = tc.geo_half if geo else tc.app_half
-        d_w, dfeat = mlp_backward_half(mlp, half[:mlp.n_params], b["feat"], b["h1"], b["h2"], dz)
-        d_table = torch.zeros(tc.grid.n_entries, 2, dtype=torch.float32, device=dev)
+        # ONE flat gradient in the parameter layout [MLP | grid]: the GEMMs and the scatter write into it
+        grad = torch.zeros(mlp.n_params + 2 * tc.grid.n_entries, dtype=torch.float32, device=dev)
+        _, dfeat = mlp_backward_half(mlp, half[:mlp.n_params], b["feat"], b["h1"], b["h2"], dz, grad_out=grad[:mlp.n_params])
+        d_table = grad[mlp.n_params:]
         aabb = (C.c_float * 6)(*tc.aabb)
         with torch.cuda.device(dev):
             _call(_L().perf_hashgrid_bwd_rays, tc.grid.c(), aabb, _p(rays_o), _p(rays_d), _p(jitter), R, S, tc.near, tc.far,
                   _p(dfeat), _p(d_table), _stream(), launches=2)
-        return torch.cat([d_w, d_table.reshape(-1)]), None, None, None, None, None, None
+        return grad, None, None, None, None, None, None
 
 
 def fused_train_step(params, rays_o, rays_d, jitter, bg_noise, tc: FusedTrainContext, phase: int):

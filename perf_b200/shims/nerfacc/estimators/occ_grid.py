@@ -1,11 +1,11 @@
 """``nerfacc.estimators.occ_grid.OccGridEstimator`` (0.5.3 API, ``levels=1``) for PeRF's call sites
 (`/root/reference/modules/scene/nerf.py:68,144,159-168`, `/root/reference/modules/scene/nerf_renderer.py:145-155`).
 
-ROUND-1 STATUS: the occupancy-grid ray marcher is SURVEY.md section 8(f) row 1 ("next").  This
-module keeps the reference's estimator interface alive (buffers ``resolution/aabbs/occs/binaries``
-for checkpoints, ``update_every_n_steps``, ``sampling``) with vectorised torch ops for the marching
-itself; the per-sample work it feeds (sigma_fn -> field kernels, transmittance culling) runs on
-libperfb200.  Sampling rule (nerfacc's DDA for ``cone_angle=0``, restated; upstream source is not
+SURVEY.md section 8(f) row 1.  Keeps the reference's estimator interface (buffers
+``resolution/aabbs/occs/binaries`` for checkpoints, ``update_every_n_steps``, ``sampling``); the
+marching is two libperfb200 kernels (perf_occ_count / perf_occ_write) around one cumsum, the
+per-sample work it feeds (sigma_fn -> field kernels, transmittance culling) runs on libperfb200
+too; the grid update is torch elementwise code.  Sampling rule (nerfacc's DDA for ``cone_angle=0``, restated; upstream source is not
 vendored so the exact phase of the lattice is unpinned): fixed lattice
 ``t_k = near + (k + u_r) * step`` (one uniform offset ``u_r`` per ray when ``stratified``), a
 sample ``[t_k, t_k + step)`` is kept when its midpoint lies inside the aabb in an occupied cell,
@@ -60,36 +60,11 @@ class OccGridEstimator(torch.nn.Module):
         if alpha_fn is not None:
             raise NotImplementedError("perf_b200 nerfacc: alpha_fn is not implemented (PeRF passes sigma_fn)")
         dev, R = rays_o.device, rays_o.shape[0]
-        amin, amax = self.aabbs[0, :3], self.aabbs[0, 3:]
-        # ray / aabb slab intersection
-        inv = 1.0 / torch.where(rays_d.abs() < 1e-12, torch.full_like(rays_d, 1e-12), rays_d)
-        t0, t1 = (amin - rays_o) * inv, (amax - rays_o) * inv
-        tn = torch.minimum(t0, t1).amax(-1).clamp(min=near_plane)
-        tf = torch.maximum(t0, t1).amin(-1).clamp(max=far_plane)
-        if t_min is not None:
-            tn = torch.maximum(tn, t_min)
-        if t_max is not None:
-            tf = torch.minimum(tf, t_max)
-        step = float(render_step_size)
-        u = torch.rand(R, device=dev) if stratified else torch.zeros(R, device=dev)
-        k_hi = int(torch.ceil(((tf - near_plane) / step).clamp(min=0).max()).item()) if R else 0
-        ri_all, ts_all = [], []
-        binaries = self.binaries.reshape(-1)
-        chunk = max(1, (1 << 24) // max(k_hi, 1))
-        ks = torch.arange(k_hi, device=dev, dtype=torch.float32)
-        for s in range(0, R, chunk):
-            o, d = rays_o[s:s + chunk], rays_d[s:s + chunk]
-            ts = near_plane + (ks[None, :] + u[s:s + chunk, None]) * step           # [r, K]
-            mid = ts + 0.5 * step
-            ok = (mid >= tn[s:s + chunk, None]) & (mid <= tf[s:s + chunk, None])
-            pts = o[:, None, :] + d[:, None, :] * mid[..., None]
-            ok &= binaries[self._cell_index(pts)]
-            r_idx, k_idx = ok.nonzero(as_tuple=True)
-            ri_all.append(r_idx + s)
-            ts_all.append(ts[r_idx, k_idx])
-        ray_indices = torch.cat(ri_all) if ri_all else torch.zeros(0, dtype=torch.long, device=dev)
-        t_starts = torch.cat(ts_all) if ts_all else torch.zeros(0, device=dev)
-        t_ends = t_starts + step
+        if t_min is not None or t_max is not None:
+            raise NotImplementedError("perf_b200 nerfacc: per-ray t_min / t_max are not implemented (PeRF does not pass them)")
+        jitter = torch.rand(R, device=dev) if stratified else None
+        ray_indices, t_starts, t_ends = ops.occ_sample(self.binaries[0], self.aabbs[0].tolist(), rays_o.float(), rays_d.float(),
+                                                       float(near_plane), float(min(far_plane, 3.0e38)), float(render_step_size), jitter)
         # visibility culling (nerfacc render_visibility_from_density): keep T >= early_stop_eps
         if sigma_fn is not None and early_stop_eps > 0 and ray_indices.numel() > 0:
             sigmas = sigma_fn(t_starts, t_ends, ray_indices).float().reshape(-1)
