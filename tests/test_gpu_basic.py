@@ -218,7 +218,8 @@ def test_occ_estimator_shim_end_to_end(ops, golden_field):
     ri, ts, te = est.sampling(o, d, sigma_fn=sigma_fn, near_plane=0., far_plane=1.5, render_step_size=5e-3, stratified=False,
                               cone_angle=0., alpha_thre=0.)
     assert ri.numel() > 0 and bool((ri[1:] >= ri[:-1]).all())
-    sig = sigma_fn(ts, te, ri)
+    with torch.no_grad():
+        sig = sigma_fn(ts, te, ri)
     w0, T0, _ = oracle.render_weight_from_density(ts.cpu(), te.cpu(), sig.cpu(), ri.cpu())
     assert float(T0.min()) >= 1e-4 * 0.999                     # culled below early_stop_eps
     from perf_b200.shims import nerfacc

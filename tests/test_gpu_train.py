@@ -181,3 +181,16 @@ def test_fused_adam_tracks_torch_adam_through_scene_params(golden_field):
         opt.step()
         assert torch.equal(net._half(), net.params.detach().half())         # shadow refreshed by the Adam kernel
     np.testing.assert_allclose(net.params.detach().cpu().numpy(), ref.detach().cpu().numpy(), rtol=1e-5, atol=1e-7)
+
+
+def test_render_dense_entry_point(golden_field, tmp_path):
+    """`python -m perf_b200.render_dense` on a PeRF-format checkpoint writes the frames."""
+    from perf_b200 import render_dense
+    sd = {"aabb": torch.tensor([-1., -1., -1., 1., 1., 1.]), "geo_mlp.params": golden_field.geo_params, "app_mlp.params": golden_field.app_params}
+    torch.save({"scene": {"render": {}, "nerf": sd, "estimator": {}}, "phase": 0}, tmp_path / "ckpt.pth")
+    np.save(tmp_path / "poses.npy", render_dense.default_poses(2))
+    render_dense.main(["--ckpt", str(tmp_path / "ckpt.pth"), "--poses", str(tmp_path / "poses.npy"), "--out", str(tmp_path / "out"),
+                       "--height", "32", "--width", "64", "--n-samples", "16"])
+    import cv2
+    img = cv2.imread(str(tmp_path / "out" / "image_1.png"))
+    assert img is not None and img.shape == (32, 64, 3) and img.std() > 0
