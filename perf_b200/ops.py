@@ -368,6 +368,7 @@ class FusedTrainContext:
         self.grid, self.aabb, self.n_samples, self.near, self.far = grid, tuple(float(v) for v in aabb), n_samples, near, far
         self.packed = self.geo_half = self.app_half = None
         self._bufs = {}
+        self.generation = 0          # bumped by every forward; backward refuses stale per-sample buffers
 
     def buffers(self, R: int, phase: int, dev):
         key = (R, self.n_samples, phase, str(dev))
@@ -441,7 +442,8 @@ class _FusedTrainStep(torch.autograd.Function):
         cb = FusedTrainContext.c_buffers(b)
         with torch.cuda.device(dev):
             _call(_L().perf_train_forward, C.byref(a), _p(rays_o), _p(rays_d), R, phase, C.byref(cb), _stream())
-        ctx.tc, ctx.phase, ctx.b = tc, phase, b
+        tc.generation += 1
+        ctx.tc, ctx.phase, ctx.b, ctx.generation = tc, phase, b, tc.generation
         ctx.save_for_backward(rays_o, rays_d, jitter, bg_noise, dist, op)
         return rgb, dist, op, b["dl"].clone()
 
@@ -449,6 +451,9 @@ class _FusedTrainStep(torch.autograd.Function):
     def backward(ctx, g_rgb, g_dist, g_op, g_dl):
         rays_o, rays_d, jitter, bg_noise, dist, op = ctx.saved_tensors
         tc, phase, b = ctx.tc, ctx.phase, ctx.b
+        if ctx.generation != tc.generation:
+            raise RuntimeError("perf_b200 fused training step: backward() after a newer forward() on the same context -- the "
+                               "per-sample buffers are reused between steps; call backward before the next forward")
         R, S, dev = rays_o.shape[0], tc.n_samples, rays_o.device
         N = R * S
         geo = phase == _lib.PERF_PHASE_GEO

@@ -29,7 +29,7 @@ def header_symbols():
 def test_library_exports_every_declared_symbol(lib):
     from perf_b200 import _lib
     names = header_symbols()
-    assert len(names) >= 18
+    assert len(names) >= 25
     for n in names:
         assert hasattr(lib, n), f"{n} declared in perfb200.h but not exported"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
