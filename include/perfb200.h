@@ -157,6 +157,11 @@ typedef struct perf_render_args {
 /* Render explicit rays: d_rays_o / d_rays_d [R,3] fp32. */
 int perf_render_rays(const perf_render_args* args, const float* d_rays_o, const float* d_rays_d,
                      uint64_t R, void* stream);
+/* Render rays whose samples are given as packed intervals sorted by ray (the output of an occupancy
+ * estimator, nerf_renderer.py:145-155): ray r owns samples [d_offsets[r], d_offsets[r+1]) of
+ * d_t_starts / d_t_ends.  args->n_samples / near / far are ignored; eval-mode background rule. */
+int perf_render_packed(const perf_render_args* args, const float* d_rays_o, const float* d_rays_d, uint64_t R,
+                       const int64_t* d_offsets, const float* d_t_starts, const float* d_t_ends, void* stream);
 /* Render rows [row0,row0+rows) of an H x W equirect panorama with ray generation fused in
  * (core_exp_runner.py:229-238 render_dense inner loop).  Outputs are [rows*W, .]. */
 int perf_render_pano(const perf_render_args* args, const float* h_pose, int H, int W,

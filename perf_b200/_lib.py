@@ -64,6 +64,7 @@ SIGNATURES = {
     "perf_weights_from_density_bwd": (i32, [vp, vp, vp, vp, u64, u64, vp, vp, vp, vp, vp, vp]),
     "perf_accumulate_along_rays": (i32, [vp, vp, i32, vp, u64, u64, vp, vp]),
     "perf_render_rays": (i32, [P(RenderArgs), vp, vp, u64, vp]),
+    "perf_render_packed": (i32, [P(RenderArgs), vp, vp, u64, vp, vp, vp, vp]),
     "perf_render_pano": (i32, [P(RenderArgs), P(f32), i32, i32, i32, i32, vp]),
     "perf_train_forward": (i32, [P(RenderArgs), vp, vp, u64, i32, P(TrainBuffers), vp]),
     "perf_train_backward_composite": (i32, [i32, u32, f32, f32, u64, vp, vp, P(TrainBuffers), vp, vp, vp, vp, vp, vp, vp, vp]),

@@ -35,6 +35,10 @@ struct RenderArgs {
     const float*  rays_d;
     float         pose_r[9], pose_t[3];
     int           H, W, row0;   // (PANO == true): ray r is pixel (row0 + r / W, r % W)
+    // packed variable-length samples (perf_render_packed): ray r owns samples [pk_offsets[r], pk_offsets[r+1])
+    const int64_t* pk_offsets;  // [R+1] or null (fixed-S lattice)
+    const float*   pk_ts;       // [N]
+    const float*   pk_te;       // [N]
     // training-forward saves (SAVE != 0), all sample-major: row = k * R + ray
     float*        s_sigma;      // [S*R]
     float*        s_w;          // [S*R]
@@ -479,10 +483,30 @@ __global__ void __launch_bounds__(TILE, 4) render_march_kernel(const __grid_cons
         float sum_sd = 0.f;                                   // exclusive running sum of sigma*dt
         float acc_w = 0.f, acc_d = 0.f, acc_r = 0.f, acc_g = 0.f, acc_b = 0.f;
         float dl_uni = 0.f, dl_bi = 0.f;                      // distortion loss pieces (SAVE only)
+        // packed mode: every thread walks ITS ray's samples; the tile iterates to the longest ray
+        // (neighbouring rays cross the same occupied shells, so lengths inside a tile are similar)
+        uint32_t n_iter = S, my_count = S;
+        int64_t pk_base = 0;
+        if (!PANO && a.pk_offsets != nullptr) {
+            my_count = 0;
+            if (valid) { pk_base = a.pk_offsets[ray]; my_count = (uint32_t)(a.pk_offsets[ray + 1] - pk_base); }
+            const uint32_t wmax = __reduce_max_sync(0xffffffffu, my_count);
+            uint32_t* s_max = reinterpret_cast<uint32_t*>(smem + RS_TAILS);
+            __syncthreads();                                  // previous tile's readers are done
+            if (lane == 0) s_max[warp] = wmax;
+            __syncthreads();
+            n_iter = max(max(s_max[0], s_max[1]), max(s_max[2], s_max[3]));
+        }
 #pragma unroll 1
-        for (uint32_t k = 0; k < S; ++k) {
-            const float ts = __fadd_rn(a.near, __fmul_rn(__fadd_rn((float)k, jit), step));
-            const float te = __fadd_rn(a.near, __fmul_rn(__fadd_rn((float)(k + 1), jit), step));
+        for (uint32_t k = 0; k < n_iter; ++k) {
+            const bool live = valid && k < my_count;
+            float ts, te;
+            if (!PANO && a.pk_offsets != nullptr) {
+                ts = live ? a.pk_ts[pk_base + k] : 0.f; te = live ? a.pk_te[pk_base + k] : 0.f;
+            } else {
+                ts = __fadd_rn(a.near, __fmul_rn(__fadd_rn((float)k, jit), step));
+                te = __fadd_rn(a.near, __fmul_rn(__fadd_rn((float)(k + 1), jit), step));
+            }
             const float tsum = __fadd_rn(ts, te);
             const float px = __fadd_rn(ox, __fmul_rn(dx, tsum) * 0.5f);
             const float py = __fadd_rn(oy, __fmul_rn(dy, tsum) * 0.5f);
@@ -490,7 +514,7 @@ __global__ void __launch_bounds__(TILE, 4) render_march_kernel(const __grid_cons
             const float x = __fdiv_rn(__fsub_rn(px, a.aabb_min[0]), a.aabb_ext[0]);
             const float y = __fdiv_rn(__fsub_rn(py, a.aabb_min[1]), a.aabb_ext[1]);
             const float z = __fdiv_rn(__fsub_rn(pz, a.aabb_min[2]), a.aabb_ext[2]);
-            const bool selector = valid && x > 0.f && x < 1.f && y > 0.f && y < 1.f && z > 0.f && z < 1.f;
+            const bool selector = live && x > 0.f && x < 1.f && y > 0.f && y < 1.f && z > 0.f && z < 1.f;
 
             float sigma, cr, cg, cb;
             const uint64_t srow = (SAVE != 0 && valid) ? (uint64_t)k * a.R + ray : ~0ull;
@@ -610,6 +634,18 @@ int perf_render_rays(const perf_render_args* args, const float* d_rays_o, const 
     RenderArgs a; memset(&a, 0, sizeof(a));
     a.rays_o = d_rays_o; a.rays_d = d_rays_d; a.R = R;
     return launch_render(args, a, false, (cudaStream_t)stream);
+}
+
+int perf_render_packed(const perf_render_args* args, const float* d_rays_o, const float* d_rays_d, uint64_t R,
+                       const int64_t* d_offsets, const float* d_t_starts, const float* d_t_ends, void* stream)
+{
+    PERF_CHECK_ARG(args && d_rays_o && d_rays_d && d_offsets, "NULL pointer");
+    PERF_CHECK_SUP((args->flags & (PERF_FLAG_SCAN_KERNEL | PERF_FLAG_TRAINING)) == 0, "packed rendering: eval mode on the ray-marching kernel only");
+    RenderArgs a; memset(&a, 0, sizeof(a));
+    a.rays_o = d_rays_o; a.rays_d = d_rays_d; a.R = R;
+    a.pk_offsets = d_offsets; a.pk_ts = d_t_starts; a.pk_te = d_t_ends;
+    perf_render_args t = *args; t.n_samples = 1; if (!(t.far > t.near)) { t.near = 0.f; t.far = 1.f; }
+    return launch_render(&t, a, false, (cudaStream_t)stream);
 }
 
 int perf_train_forward(const perf_render_args* args, const float* d_rays_o, const float* d_rays_d, uint64_t R, int phase,

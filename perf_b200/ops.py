@@ -339,6 +339,27 @@ def render_rays(packed_table, geo_mlp_half, app_mlp_half, rays_o, rays_d, n_samp
     return rgb, dist, op
 
 
+def render_packed(packed_table, geo_mlp_half, app_mlp_half, rays_o, rays_d, ray_indices, t_starts, t_ends,
+                  aabb=(-1., -1., -1., 1., 1., 1.), grid: GridConfig = PERF_GRID, simt=False):
+    """Fused eval render of packed variable-length samples (sorted by ray, as an occupancy estimator
+    returns them) -> (rgb [R,3], distance [R,1], opacity [R,1])."""
+    rays_o, rays_d = _chk(rays_o, torch.float32, "rays_o"), _chk(rays_d, torch.float32, "rays_d")
+    ray_indices = _chk(ray_indices, torch.int64, "ray_indices")
+    t_starts, t_ends = _chk(t_starts, torch.float32, "t_starts"), _chk(t_ends, torch.float32, "t_ends")
+    R, dev = rays_o.shape[0], rays_o.device
+    rgb = torch.empty(R, 3, dtype=torch.float32, device=dev)
+    dist = torch.empty(R, 1, dtype=torch.float32, device=dev)
+    op = torch.empty(R, 1, dtype=torch.float32, device=dev)
+    if R == 0:
+        return rgb, dist, op
+    offsets = torch.zeros(R + 1, dtype=torch.int64, device=dev)
+    offsets[1:] = torch.cumsum(torch.bincount(ray_indices, minlength=R), 0)
+    a = _render_args(packed_table, geo_mlp_half, app_mlp_half, aabb, 1, 0.0, 1.0, False, simt, None, None, rgb, dist, op, grid)
+    with torch.cuda.device(dev):
+        _call(_L().perf_render_packed, C.byref(a), _p(rays_o), _p(rays_d), R, _p(offsets), _p(t_starts), _p(t_ends), _stream())
+    return rgb, dist, op
+
+
 def render_pano(packed_table, geo_mlp_half, app_mlp_half, pose, H: int, W: int, n_samples: int, near=1e-2, far=1.0,
                 row0: int = 0, rows: Optional[int] = None, aabb=(-1., -1., -1., 1., 1., 1.),
                 grid: GridConfig = PERF_GRID, simt=False, out=None, kernel="march"):

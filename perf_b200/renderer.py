@@ -68,6 +68,15 @@ class FusedPanoRenderer:
                                         self.aabb, training, jitter, bg_noise, self.grid, simt, self.kernel)
         return {"rgb": rgb, "distance": dist, "opacities": op, "is_valid": True}
 
+    def render_packed(self, rays_o: torch.Tensor, rays_d: torch.Tensor, ray_indices: torch.Tensor, t_starts: torch.Tensor,
+                      t_ends: torch.Tensor, simt: bool = False) -> dict:
+        """Eval render of packed per-ray intervals (``OccGridEstimator.sampling`` output) in one launch:
+        the body of ``NeRFOCCRenderer.render`` after the sampling call (`nerf_renderer.py:164-197`)."""
+        self._ready()
+        rgb, dist, op = ops.render_packed(self.packed, self.geo_half, self.app_half, rays_o.reshape(-1, 3), rays_d.reshape(-1, 3),
+                                          ray_indices, t_starts, t_ends, self.aabb, self.grid, simt)
+        return {"rgb": rgb, "distance": dist, "opacities": op, "is_valid": True}
+
     def render_pano(self, pose, H: int, W: int, n_samples: int, row0: int = 0, rows: Optional[int] = None,
                     near: Optional[float] = None, far: Optional[float] = None, simt: bool = False, out=None) -> dict:
         self._ready()

@@ -147,6 +147,23 @@ class RaySupervision:
         pool.locality_key = key.reshape(-1)
         return pool
 
+    def gen_occ_grid(self, res: int):
+        """`sup_info.py:304-330`: voxels within +-1 cell of every un-projected RGB-D point ->
+        (uint8 grid [res^3] with x slowest, centres of the occupied voxels)."""
+        rays_o, rays_d = self.all_sup_rays.collapse()
+        pts = rays_o + rays_d * self.all_sup_distances.squeeze()[..., None]
+        occ_grid = torch.zeros(res * res * res, dtype=torch.uint8, device=pts.device)
+        shift = 1. / res
+        lin = torch.linspace(-shift, shift, 3, device=pts.device)
+        shifts = torch.stack(torch.meshgrid(lin, lin, lin, indexing="ij"), -1).reshape(-1, 3)
+        for shift_xyz in shifts:
+            shifted = ((shift_xyz[None, :] + pts).clip(-0.999, 0.999) * .5 + .5) * res
+            shifted = shifted.to(torch.int64)
+            occ_grid[shifted[..., 0] * res * res + shifted[..., 1] * res + shifted[..., 2]] = 1
+        valid_idx = torch.where(occ_grid > 0)[0]
+        valid_pts = torch.stack([valid_idx // (res * res), (valid_idx // res) % res, valid_idx % res], -1)
+        return occ_grid, (valid_pts / float(res) - .5) * 2.
+
     def rand_ray_color_data(self, batch_size, rand_mode="by_all_pixels"):
         idx = torch.randint(0, len(self.all_sup_colors), (batch_size,), device=self.all_sup_colors.device, generator=self.generator)
         if self.locality_key is not None:
@@ -199,16 +216,23 @@ class NeRFScene:
     LOSS_SCALE = 2 ** 7                                               # GradScaler(2**7), never unscaled (nerf.py:139,249-253)
 
     def __init__(self, base_exp_dir=".", train_conf=None, estimator_type="fixed", renderer_conf=None,
-                 n_samples: int = 128, near: float = 1e-2, far: float = 1.0, device="cuda", writer=None, fused_train: bool = True):
-        if estimator_type not in ("fixed",):
-            raise NotImplementedError(f"perf_b200 NeRFScene: estimator_type={estimator_type!r}; the native scene implements the "
-                                      "fixed-S sampler (run the reference's own NeRFScene on perf_b200.shims for 'occ')")
+                 n_samples: int = 128, near: float = 1e-2, far: float = 1.0, device="cuda", writer=None, fused_train: bool = True,
+                 occ_resolution: int = 256):
+        if estimator_type not in ("fixed", "occ"):
+            raise NotImplementedError(f"perf_b200 NeRFScene: estimator_type={estimator_type!r} (the reference's 'prop' renderer is "
+                                      "broken upstream, nerf_renderer.py:73, and not implemented)")
+        self.estimator_type, self.occ_resolution = estimator_type, occ_resolution
         self.device = torch.device(device)
         self.aabb = torch.tensor([-1.0, -1.0, -1.0, 1.0, 1.0, 1.0], device=self.device)        # nerf.py:35
         self.base_exp_dir, self.writer = base_exp_dir, writer
         self.train_conf = DEFAULT_TRAIN_CONF if train_conf is None else Conf.wrap(train_conf)
         self.nerf = NGPNeRF(aabb=self.aabb).to(self.device)
-        self.estimator = FixedSampleEstimator(n_samples, near, far)
+        if estimator_type == "occ":                                    # nerf.py:68
+            from .shims.nerfacc.estimators.occ_grid import OccGridEstimator
+            self.estimator = OccGridEstimator(roi_aabb=self.aabb, resolution=occ_resolution, levels=1).to(self.device)
+            fused_train = False                                        # the fused step is the fixed-S one
+        else:
+            self.estimator = FixedSampleEstimator(n_samples, near, far)
         self.renderer = NeRFOCCRenderer(**(renderer_conf or {"max_radius": 2, "bg_color": "rand_noise"}))
         self.fused = FusedPanoRenderer(aabb=self.aabb.tolist(), near=near, far=far)
         self._fused_key = None
@@ -233,13 +257,34 @@ class NeRFScene:
         self._sync_fused()
         rays_o, rays_d = rays.collapse()
         pre_shape = list(rays_o.shape[:-1])
-        out = self.fused.render_rays(rays_o.reshape(-1, 3), rays_d.reshape(-1, 3), self.estimator.n_samples)
+        rays_o, rays_d = rays_o.reshape(-1, 3).float(), rays_d.reshape(-1, 3).float()
+        if self.estimator_type == "occ":
+            # nerf_renderer.py:145-197: occupancy sampling (+ visibility culling through the density
+            # kernels), then ONE fused launch for sigma / rgb / composite of the packed samples
+            was_training = self.nerf.training
+            self.set_eval()
+
+            def sigma_fn(t_starts, t_ends, ray_indices):
+                pos = rays_o[ray_indices] + rays_d[ray_indices] * (t_starts + t_ends)[:, None] / 2.0
+                return self.nerf.query_density(pos).squeeze(-1)
+            ri, ts, te = self.estimator.sampling(rays_o, rays_d, sigma_fn=sigma_fn, near_plane=0., far_plane=1.5,
+                                                 render_step_size=5e-4, stratified=False, cone_angle=0., alpha_thre=0.)
+            out = self.fused.render_packed(rays_o, rays_d, ri, ts, te)
+            if was_training:
+                self.set_train()
+        else:
+            out = self.fused.render_rays(rays_o, rays_d, self.estimator.n_samples)
         return {k: out[k].reshape(pre_shape + [-1]) for k in query_keys}
 
     @torch.no_grad()
     def render_pano(self, pose, height, width, row0=0, rows=None):
         """render_dense inner loop (`core_exp_runner.py:229-238`) with ray generation fused in."""
         self._sync_fused()
+        if self.estimator_type == "occ":
+            rows = height - row0 if rows is None else rows
+            o, d = ops.raygen_pano(pose, height, width, row0, rows, device=self.device)
+            out = self.render(Rays(o, d), ["rgb", "distance", "opacities"])
+            return {**out, "is_valid": True}
         return self.fused.render_pano(pose, height, width, self.estimator.n_samples, row0=row0, rows=rows)
 
     def _render_once_fused(self, rays: Rays, geo_inference: bool, app_inference: bool):
@@ -280,8 +325,20 @@ class NeRFScene:
         self.train_one_episode(sup_pool, self.train_conf.raw_phase_iter_geo, self.train_conf.raw_phase_iter_app, "by_all_pixels")
 
     def train_one_episode(self, sup_pool, geo_res_iters, app_res_iters, pixel_sup_rand_mode="by_all_pixels"):
-        """`nerf.py:137-184`: fresh density net, geo phase then app phase."""
+        """`nerf.py:137-184`: (occupancy grid from the supervision,) fresh density net, geo phase then app phase."""
         self.set_train()
+        if self.estimator_type == "occ":                                       # nerf.py:143-168
+            from .shims.nerfacc.estimators.occ_grid import OccGridEstimator
+            occ_res = self.occ_resolution
+            self.estimator = OccGridEstimator(roi_aabb=self.aabb, resolution=occ_res, levels=1).to(self.device)
+            self.estimator.train()
+            pre_grid, _ = sup_pool.gen_occ_grid(res=occ_res)
+
+            def occ_eval_fn(x):
+                x = ((x.clip(-0.999, 0.999) * .5 + .5) * occ_res).to(torch.int64)
+                return pre_grid[x[..., 0] * occ_res * occ_res + x[..., 1] * occ_res + x[..., 2]].float()
+            for i in range(256):
+                self.estimator.update_every_n_steps(step=i, occ_eval_fn=occ_eval_fn, occ_thre=1e-2, ema_decay=0.1, warmup_steps=256, n=1)
         self.nerf.reset_geo()
         geo_optimizer = FusedAdam(self.nerf.geo_mlp.params, lr=self.train_conf.geo_optimizer.init_lr, module=self.nerf.geo_mlp)
         for iter_i in range(geo_res_iters):

@@ -135,3 +135,31 @@ def test_fast_addressing_is_bit_identical_to_generic(golden_field):
     ra, rb = a.render_pano(pose, 64, 128, 96, far=1.6), b.render_pano(pose, 64, 128, 96, far=1.6)
     for k in ("rgb", "distance", "opacities"):
         assert torch.equal(ra[k], rb[k]), k
+
+
+def test_render_packed_matches_oracle(golden_field):
+    """Variable-length packed samples (occupancy-estimator output) through the fused kernel ==
+    the reference's post-sampling renderer body restated with the oracle (nerf_renderer.py:164-197)."""
+    from oracle.occ_sampler import occ_sample
+    from perf_b200.renderer import FusedPanoRenderer
+    r = FusedPanoRenderer.from_params(golden_field.geo_params.cuda(), golden_field.app_params.cuda())
+    g = torch.Generator().manual_seed(51)
+    R = 300
+    binaries = torch.rand(24, 24, 24, generator=g) < 0.3
+    o = (torch.rand(R, 3, generator=g) - .5) * .4
+    d = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1)
+    o[:5] = 4.0                                                # rays that miss the box: zero samples
+    ri, ts, te = occ_sample(binaries, torch.tensor([-1., -1., -1., 1., 1., 1.]), o, d, 0.0, 1.5, 1.0e-2)
+    assert ri.numel() > 3000 and int(torch.bincount(ri, minlength=R).max()) > int(torch.bincount(ri, minlength=R).float().mean()) + 5
+    pos = o[ri] + d[ri] * (ts + te)[:, None] / 2.0
+    sig = oracle.query_density(golden_field, pos, mixed=True).squeeze(-1)
+    rgbs = oracle.query_rgb(golden_field, pos, mixed=True)
+    w, _, _ = oracle.render_weight_from_density(ts, te, sig, ri)
+    op = oracle.accumulate_along_rays(w, None, ri, R)
+    dist = oracle.accumulate_along_rays(w, ((ts + te) / 2.0)[:, None], ri, R) + 5.0 * (1 - op)
+    col = oracle.accumulate_along_rays(w, rgbs, ri, R) + 0.5 * (1 - op)
+    out = r.render_packed(o.cuda(), d.cuda(), ri.cuda(), ts.cuda(), te.cuda())
+    np.testing.assert_allclose(out["opacities"].cpu().numpy(), op.numpy(), atol=RGB_ATOL, rtol=0)
+    np.testing.assert_allclose(out["rgb"].cpu().numpy(), col.numpy(), atol=RGB_ATOL, rtol=0)
+    np.testing.assert_allclose(out["distance"].cpu().numpy(), dist.numpy(), atol=DIST_ATOL, rtol=0)
+    assert torch.equal(out["rgb"][:5].cpu(), torch.full((5, 3), 0.5))
