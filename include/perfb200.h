@@ -96,6 +96,11 @@ int perf_pack_tables(const perf_grid_cfg* grid, const perf_mlp_cfg* geo_mlp, con
 int perf_raygen_pano(const float* h_pose, int H, int W, int row0, int rows,
                      float* d_rays_o, float* d_rays_d, void* stream);
 
+/* Perspective (OpenCV-style) rays of an H x W camera with vertical field of view `fovy` (radians).
+ * Replaces utils/camera_utils.py:237-241 gen_pers_rays (+ :60-80 cam_rays_cam_space), the
+ * cam_type != 'pano' branch of render_dense (core_exp_runner.py:234-235). */
+int perf_raygen_pers(const float* h_pose, float fovy, int H, int W, float* d_rays_o, float* d_rays_d, void* stream);
+
 /* Hash-grid encode forward: d_x01 [N,3] fp32 in [0,1] -> d_feat [N, L*2] fp16.
  * d_table: fp16 [n_entries,2].  Replaces tcnn kernel_grid (Encoding.forward). */
 int perf_hashgrid_fwd(const perf_grid_cfg* cfg, const void* d_table, const float* d_x01,
@@ -152,6 +157,8 @@ typedef struct perf_render_args {
     float*        d_rgb;          /* [R,3]                                                      */
     float*        d_distance;     /* [R]                                                        */
     float*        d_opacity;      /* [R] or NULL                                                */
+    uint32_t      image_width;    /* perf_render_rays only: >0 = the R rays are a row-major image of this
+                                     width (locality hint: threads are tiled as 16x8 pixel patches); 0 = no structure */
 } perf_render_args;
 
 /* Render explicit rays: d_rays_o / d_rays_d [R,3] fp32. */

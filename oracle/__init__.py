@@ -28,7 +28,7 @@ background rules) and the chunking in `modules/scene/nerf.py`.
 from .hashgrid import GridConfig, level_table, encode, encode_backward_table  # noqa: F401
 from .mlp import MLPConfig, mlp_forward, split_params, flat_param_count          # noqa: F401
 from .field import Field, query_density, query_rgb                               # noqa: F401
-from .raygen import pano_dirs, gen_pano_rays                                     # noqa: F401
+from .raygen import pano_dirs, gen_pano_rays, gen_pers_rays                                     # noqa: F401
 from .sampler import fixed_samples                                               # noqa: F401
 from .composite import (render_weight_from_density, accumulate_along_rays,      # noqa: F401
                         composite_fixed, flatten_eff_distloss)

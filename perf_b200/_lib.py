@@ -35,7 +35,7 @@ class MlpCfg(C.Structure):
 class RenderArgs(C.Structure):
     _fields_ = [("grid", GridCfg), ("d_packed_table", vp), ("d_geo_mlp_half", vp), ("d_app_mlp_half", vp),
                 ("aabb", f32 * 6), ("n_samples", u32), ("near", f32), ("far", f32), ("flags", u32),
-                ("d_jitter", vp), ("d_bg_noise", vp), ("d_rgb", vp), ("d_distance", vp), ("d_opacity", vp)]
+                ("d_jitter", vp), ("d_bg_noise", vp), ("d_rgb", vp), ("d_distance", vp), ("d_opacity", vp), ("image_width", u32)]
 
 
 class TrainBuffers(C.Structure):
@@ -56,6 +56,7 @@ SIGNATURES = {
     "perf_params_to_half": (i32, [vp, vp, u64, vp]),
     "perf_pack_tables": (i32, [P(GridCfg), P(MlpCfg), P(MlpCfg), vp, vp, vp, vp]),
     "perf_raygen_pano": (i32, [P(f32), i32, i32, i32, i32, vp, vp, vp]),
+    "perf_raygen_pers": (i32, [P(f32), f32, i32, i32, vp, vp, vp]),
     "perf_hashgrid_fwd": (i32, [P(GridCfg), vp, vp, u64, vp, vp]),
     "perf_hashgrid_bwd": (i32, [P(GridCfg), vp, vp, u64, vp, vp]),
     "perf_network_fwd": (i32, [P(GridCfg), P(MlpCfg), vp, vp, u64, vp, vp, vp, vp, u32, vp]),

@@ -142,6 +142,27 @@ __global__ void raygen_pano_kernel(Pose pose, int H, int W, int row0, int rows, 
     o[3 * i + 0] = pose.t[0]; o[3 * i + 1] = pose.t[1]; o[3 * i + 2] = pose.t[2];
 }
 
+// perspective camera rays, OpenCV convention: camera_utils.py:60-80 (cam_rays_cam_space) + :237-241
+__device__ __forceinline__ float linspace_sym(float start, float end, int i, int n)
+{
+    if (n == 1) return start;
+    const float step = (end - start) / (float)(n - 1);
+    return (i < n / 2) ? __fadd_rn(start, __fmul_rn(step, (float)i)) : __fsub_rn(end, __fmul_rn(step, (float)(n - i - 1)));
+}
+__global__ void raygen_pers_kernel(Pose pose, float span_x, float span_y, int H, int W, float* __restrict__ o, float* __restrict__ d)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (uint64_t)H * W) return;
+    const int row = (int)(i / W), col = (int)(i % W);
+    const float y = linspace_sym(-span_y, span_y, row, H), x = linspace_sym(-span_x, span_x, col, W);
+    const float n = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), 1.0f));
+    const float cx = x / n, cy = y / n, cz = 1.0f / n;
+    d[3 * i + 0] = pose.r[0] * cx + pose.r[1] * cy + pose.r[2] * cz;
+    d[3 * i + 1] = pose.r[3] * cx + pose.r[4] * cy + pose.r[5] * cz;
+    d[3 * i + 2] = pose.r[6] * cx + pose.r[7] * cy + pose.r[8] * cz;
+    o[3 * i + 0] = pose.t[0]; o[3 * i + 1] = pose.t[1]; o[3 * i + 2] = pose.t[2];
+}
+
 // ---- stand-alone hash-grid encode (tcnn kernel_grid): one thread per sample, all levels.
 __global__ void __launch_bounds__(256)
 hashgrid_fwd_kernel(LevelTable lt, const uint32_t* __restrict__ table, const float* __restrict__ x01,
@@ -404,6 +425,18 @@ int perf_raygen_pano(const float* h_pose, int H, int W, int row0, int rows, floa
     Pose p;
     for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) p.r[3 * r + c] = h_pose[4 * r + c]; p.t[r] = h_pose[4 * r + 3]; }
     raygen_pano_kernel<<<blocks_for((uint64_t)rows * W, 256), 256, 0, S(stream)>>>(p, H, W, row0, rows, d_rays_o, d_rays_d);
+    PERF_LAUNCH_CHECK();
+    return PERF_OK;
+}
+
+int perf_raygen_pers(const float* h_pose, float fovy, int H, int W, float* d_rays_o, float* d_rays_d, void* stream)
+{
+    PERF_CHECK_ARG(h_pose && d_rays_o && d_rays_d, "NULL pointer");
+    PERF_CHECK_ARG(H > 0 && W > 0 && fovy > 0.f && fovy < 3.14159f, "bad perspective camera H=%d W=%d fovy=%f", H, W, fovy);
+    Pose p;
+    for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) p.r[3 * r + c] = h_pose[4 * r + c]; p.t[r] = h_pose[4 * r + 3]; }
+    const double span_y = tan((double)fovy * 0.5), span_x = span_y * ((double)W / (double)H);
+    raygen_pers_kernel<<<blocks_for((uint64_t)H * W, 256), 256, 0, S(stream)>>>(p, (float)span_x, (float)span_y, H, W, d_rays_o, d_rays_d);
     PERF_LAUNCH_CHECK();
     return PERF_OK;
 }

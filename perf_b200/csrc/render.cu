@@ -444,9 +444,12 @@ __global__ void __launch_bounds__(TILE, 4) render_march_kernel(const __grid_cons
 
     const uint32_t S = a.S;
     const float step = __fdiv_rn(__fsub_rn(a.far, a.near), (float)S);
-    const int rows = PANO ? (int)(a.R / (uint64_t)a.W) : 0;
-    const uint32_t tiles_x = PANO ? (uint32_t)((a.W + 15) / 16) : 0u;
-    const uint64_t n_tiles = PANO ? (uint64_t)tiles_x * (uint64_t)((rows + 7) / 8) : (a.R + TILE - 1) / TILE;
+    // PANO, or explicit rays that form a row-major image of width a.W (perf_render_args.image_width):
+    // tiles are 16x8 pixel patches; otherwise 128 consecutive rays
+    const bool patch = PANO || a.W > 0;
+    const int rows = patch ? (int)(a.R / (uint64_t)a.W) : 0;
+    const uint32_t tiles_x = patch ? (uint32_t)((a.W + 15) / 16) : 0u;
+    const uint64_t n_tiles = patch ? (uint64_t)tiles_x * (uint64_t)((rows + 7) / 8) : (a.R + TILE - 1) / TILE;
 
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         // ---- this thread's ray
@@ -471,8 +474,15 @@ __global__ void __launch_bounds__(TILE, 4) render_march_kernel(const __grid_cons
                 ox = a.pose_t[0]; oy = a.pose_t[1]; oz = a.pose_t[2];
             }
         } else {
-            ray = tile * TILE + tid;
-            valid = ray < a.R;
+            if (patch) {
+                const int ty = (int)(tile / tiles_x), tx = (int)(tile % tiles_x);
+                const int prow = ty * 8 + (warp >> 1) * 4 + (lane >> 3), pcol = tx * 16 + (warp & 1) * 8 + (lane & 7);
+                valid = prow < rows && pcol < a.W;
+                ray = (uint64_t)prow * (uint64_t)a.W + (uint64_t)pcol;
+            } else {
+                ray = tile * TILE + tid;
+                valid = ray < a.R;
+            }
             if (valid) {
                 ox = a.rays_o[3 * ray]; oy = a.rays_o[3 * ray + 1]; oz = a.rays_o[3 * ray + 2];
                 dx = a.rays_d[3 * ray]; dy = a.rays_d[3 * ray + 1]; dz = a.rays_d[3 * ray + 2];
@@ -595,6 +605,7 @@ static int launch_render(const perf_render_args* args, RenderArgs& a, bool pano,
     uint64_t n_work;
     if (scan) n_work = (a.R + a.rays_per_unit - 1) / a.rays_per_unit;
     else if (pano) n_work = (uint64_t)((a.W + 15) / 16) * (uint64_t)(((int)(a.R / (uint64_t)a.W) + 7) / 8);
+    else if (a.W > 0) n_work = (uint64_t)((a.W + 15) / 16) * (uint64_t)(((int)(a.R / (uint64_t)a.W) + 7) / 8);
     else n_work = (a.R + TILE - 1) / TILE;
     const unsigned grid = (unsigned)(n_work < (uint64_t)num_sms() * 4 ? n_work : (uint64_t)num_sms() * 4);
 #define PERF_RENDER_LAUNCH(...) do { \
@@ -633,6 +644,10 @@ int perf_render_rays(const perf_render_args* args, const float* d_rays_o, const 
     PERF_CHECK_ARG(args && d_rays_o && d_rays_d, "NULL pointer");
     RenderArgs a; memset(&a, 0, sizeof(a));
     a.rays_o = d_rays_o; a.rays_d = d_rays_d; a.R = R;
+    if (args->image_width > 0 && (args->flags & PERF_FLAG_SCAN_KERNEL) == 0) {
+        PERF_CHECK_ARG(R % args->image_width == 0, "image_width=%u does not divide the %llu rays", args->image_width, (unsigned long long)R);
+        a.W = (int)args->image_width;
+    }
     return launch_render(args, a, false, (cudaStream_t)stream);
 }
 

@@ -86,6 +86,17 @@ def raygen_pano(pose, H: int, W: int, row0: int = 0, rows: Optional[int] = None,
     return o, d
 
 
+def raygen_pers(pose, fov: float, res: int, width: Optional[int] = None, device="cuda"):
+    """(rays_o, rays_d) [res, width, 3]; `utils/camera_utils.py:237-241` gen_pers_rays (width defaults to res)."""
+    width = res if width is None else width
+    dev = torch.device(device)
+    o = torch.empty(res, width, 3, dtype=torch.float32, device=dev)
+    d = torch.empty(res, width, 3, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _call(_L().perf_raygen_pers, _pose_array(pose), float(fov), res, width, _p(o), _p(d), _stream())
+    return o, d
+
+
 # ------------------------------------------------------------------ hash grid
 def hashgrid_fwd(table_half: torch.Tensor, x01: torch.Tensor, grid: GridConfig = PERF_GRID) -> torch.Tensor:
     table_half, x01 = _chk(table_half, torch.float16, "table"), _chk(x01, torch.float32, "x01")
@@ -321,8 +332,9 @@ def _render_args(packed_table, geo_mlp_half, app_mlp_half, aabb, n_samples, near
 
 def render_rays(packed_table, geo_mlp_half, app_mlp_half, rays_o, rays_d, n_samples: int, near=1e-2, far=1.0,
                 aabb=(-1., -1., -1., 1., 1., 1.), training=False, jitter=None, bg_noise=None,
-                grid: GridConfig = PERF_GRID, simt=False, kernel="march"):
-    """Fused render of explicit rays [R,3] -> (rgb [R,3], distance [R,1], opacity [R,1])."""
+                grid: GridConfig = PERF_GRID, simt=False, kernel="march", image_width: int = 0):
+    """Fused render of explicit rays [R,3] -> (rgb [R,3], distance [R,1], opacity [R,1]).
+    ``image_width`` > 0 declares the rays a row-major image of that width (pixel-patch tiling)."""
     rays_o, rays_d = _chk(rays_o, torch.float32, "rays_o"), _chk(rays_d, torch.float32, "rays_d")
     R, dev = rays_o.shape[0], rays_o.device
     rgb = torch.empty(R, 3, dtype=torch.float32, device=dev)
@@ -334,6 +346,7 @@ def render_rays(packed_table, geo_mlp_half, app_mlp_half, rays_o, rays_d, n_samp
     bg_noise = None if bg_noise is None else _chk(bg_noise, torch.float32, "bg_noise")
     a = _render_args(packed_table, geo_mlp_half, app_mlp_half, aabb, n_samples, near, far, training, simt,
                      jitter, bg_noise, rgb, dist, op, grid, kernel)
+    a.image_width = int(image_width) if image_width and R % int(image_width) == 0 else 0
     with torch.cuda.device(dev):
         _call(_L().perf_render_rays, C.byref(a), _p(rays_o), _p(rays_d), R, _stream())
     return rgb, dist, op

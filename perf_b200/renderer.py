@@ -63,9 +63,11 @@ class FusedPanoRenderer:
                     far: Optional[float] = None, training: bool = False, jitter: Optional[torch.Tensor] = None,
                     bg_noise: Optional[torch.Tensor] = None, simt: bool = False) -> dict:
         self._ready()
+        # [H, W, 3] ray images are tiled as pixel patches (same locality as render_pano)
+        image_width = rays_o.shape[-2] if rays_o.dim() == 3 else 0
         rgb, dist, op = ops.render_rays(self.packed, self.geo_half, self.app_half, rays_o.reshape(-1, 3), rays_d.reshape(-1, 3),
                                         n_samples, self.near if near is None else near, self.far if far is None else far,
-                                        self.aabb, training, jitter, bg_noise, self.grid, simt, self.kernel)
+                                        self.aabb, training, jitter, bg_noise, self.grid, simt, self.kernel, image_width)
         return {"rgb": rgb, "distance": dist, "opacities": op, "is_valid": True}
 
     def render_packed(self, rays_o: torch.Tensor, rays_d: torch.Tensor, ray_indices: torch.Tensor, t_starts: torch.Tensor,
@@ -90,5 +92,8 @@ class FusedPanoRenderer:
         """Drop-in for ``NeRFScene.render(rays, query_keys)``: ``rays`` has ``.o`` / ``.d`` of shape
         [..., 3]; returns ``{key: tensor[..., C]}`` (eval-mode background rule)."""
         pre_shape = list(rays.o.shape[:-1])
-        out = self.render_rays(rays.o.reshape(-1, 3).float(), rays.d.reshape(-1, 3).float(), n_samples)
+        o, d = rays.o.float(), rays.d.float()
+        if o.dim() != 3:
+            o, d = o.reshape(-1, 3), d.reshape(-1, 3)
+        out = self.render_rays(o, d, n_samples)
         return {k: out[k].reshape(pre_shape + [-1]) for k in query_keys}

@@ -46,6 +46,29 @@ def gen_pano_rays(pose, height=512, width=1024, device="cuda") -> Rays:
     return Rays(o, d)
 
 
+def gen_pers_rays(pose, fov, res, device="cuda") -> Rays:
+    """`utils/camera_utils.py:237-241` on the GPU (perf_raygen_pers)."""
+    o, d = ops.raygen_pers(pose, fov, res, device=device)
+    return Rays(o, d)
+
+
+@dataclass
+class BoundedRays:                            # utils/camera_utils.py:22-35
+    o: torch.Tensor
+    d: torch.Tensor
+    near: torch.Tensor
+    far: torch.Tensor
+
+    def __len__(self):
+        return len(self.o)
+
+    def __getitem__(self, idx):
+        return BoundedRays(self.o[idx], self.d[idx], self.near[idx], self.far[idx])
+
+    def collapse(self):
+        return self.o, self.d, self.near, self.far
+
+
 class FixedSampleEstimator(torch.nn.Module):
     """Stands where ``OccGridEstimator`` stands in the renderer: the benchmark's fixed-S sampler
     (SURVEY.md 8 a7'): ``t_s[k] = near + (k + u_r) * step``, one jitter ``u_r`` per ray when
@@ -257,6 +280,8 @@ class NeRFScene:
         self._sync_fused()
         rays_o, rays_d = rays.collapse()
         pre_shape = list(rays_o.shape[:-1])
+        image = rays_o.dim() == 3                      # [H, W, 3] image of rays: keep the shape as a locality hint
+        rays_o_img, rays_d_img = rays_o.float(), rays_d.float()
         rays_o, rays_d = rays_o.reshape(-1, 3).float(), rays_d.reshape(-1, 3).float()
         if self.estimator_type == "occ":
             # nerf_renderer.py:145-197: occupancy sampling (+ visibility culling through the density
@@ -273,7 +298,7 @@ class NeRFScene:
             if was_training:
                 self.set_train()
         else:
-            out = self.fused.render_rays(rays_o, rays_d, self.estimator.n_samples)
+            out = self.fused.render_rays(rays_o_img if image else rays_o, rays_d_img if image else rays_d, self.estimator.n_samples)
         return {k: out[k].reshape(pre_shape + [-1]) for k in query_keys}
 
     @torch.no_grad()
@@ -417,6 +442,12 @@ class NeRFScene:
             lr = optim_conf.peak_lr * ((np.cos(local * np.pi) + 1.) * .5 * (1. - optim_conf.lr_alpha) + optim_conf.lr_alpha)
         for p in optimizer.param_groups:
             p["lr"] = float(lr)
+
+    def to_bounded_rays(self, rays: Rays) -> BoundedRays:
+        """`nerf.py:313-319` (near 1e-2 / far 1 tensors; like the reference's OCC renderer, the
+        native renderer takes its range from the estimator, not from these)."""
+        n = len(rays.o)
+        return BoundedRays(rays.o, rays.d, 1e-2 * torch.ones(n, 1, device=rays.o.device), torch.ones(n, 1, device=rays.o.device))
 
     # ---- state -------------------------------------------------------------------------------
     def state_dict(self):

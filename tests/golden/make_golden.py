@@ -119,6 +119,11 @@ def make_raygen():
         out[name + "_pose"] = pose.numpy(); out[name + "_hw"] = np.array([h, w])
         out[name + "_rows"] = np.array(rows)
         out[name + "_o"] = rays.o[rows].numpy(); out[name + "_d"] = rays.d[rows].numpy()
+    from utils.camera_utils import gen_pers_rays
+    for name, (pose, fov, res) in {"pers75_64": (rand_pose(g), float(np.deg2rad(75.)), 64), "pers90_33": (rand_pose(g), float(np.deg2rad(90.)), 33)}.items():
+        rays = gen_pers_rays(pose, fov=fov, res=res)
+        out[name + "_pose"], out[name + "_fov"], out[name + "_res"] = pose.numpy(), np.array(fov), np.array(res)
+        out[name + "_o"], out[name + "_d"] = rays.o.numpy(), rays.d.numpy()
     np.savez_compressed(os.path.join(HERE, "raygen.npz"), **out)
 
 

@@ -36,6 +36,10 @@ def test_raygen_matches_reference_golden(ops, golden_dir):
         rows = g[name + "_rows"]
         np.testing.assert_array_equal(o.cpu().numpy()[rows], g[name + "_o"])
         np.testing.assert_allclose(d.cpu().numpy()[rows], g[name + "_d"], atol=2e-6, rtol=0, err_msg=name)
+    for name in ("pers75_64", "pers90_33"):                      # perspective cameras (render_dense cam_type != pano)
+        o, d = ops.raygen_pers(g[name + "_pose"], float(g[name + "_fov"]), int(g[name + "_res"]))
+        np.testing.assert_array_equal(o.cpu().numpy(), g[name + "_o"])
+        np.testing.assert_allclose(d.cpu().numpy(), g[name + "_d"], atol=2e-6, rtol=0, err_msg=name)
     # row window == slice of the full image, bit for bit
     pose = g["rot_128x256_pose"]
     o_full, d_full = ops.raygen_pano(pose, 128, 256)

@@ -83,6 +83,8 @@ def test_pano_equals_explicit_rays_and_row_tiling(renderer):
     full = renderer.render_pano(pose, H, W, S)
     o, d = ops.raygen_pano(pose, H, W)
     rays = renderer.render_rays(o.reshape(-1, 3), d.reshape(-1, 3), S)
+    rays_img = renderer.render_rays(o, d, S)                       # [H,W,3] rays: pixel-patch tiling, same numbers
+    assert torch.equal(rays_img["rgb"], rays["rgb"]) and torch.equal(rays_img["distance"], rays["distance"])
     assert torch.equal(full["rgb"].reshape(-1, 3), rays["rgb"])
     assert torch.equal(full["distance"].reshape(-1, 1), rays["distance"])
     top = renderer.render_pano(pose, H, W, S, row0=0, rows=13)

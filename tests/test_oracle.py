@@ -43,6 +43,9 @@ def test_raygen_matches_reference(golden_dir):
         rows = g[name + "_rows"]
         assert np.array_equal(o[rows].numpy(), g[name + "_o"])
         assert np.array_equal(d[rows].numpy(), g[name + "_d"])
+    for name in ("pers75_64", "pers90_33"):
+        o, d = oracle.gen_pers_rays(torch.from_numpy(g[name + "_pose"]), float(g[name + "_fov"]), int(g[name + "_res"]))
+        assert np.array_equal(o.numpy(), g[name + "_o"]) and np.array_equal(d.numpy(), g[name + "_d"])
     d = oracle.pano_dirs(16, 32)
     assert torch.allclose(d.norm(dim=-1), torch.ones(16, 32), atol=1e-6)
     assert d[0, 0, 2] > 0.99 and d[8, 16, 0] > 0.99        # row 0 looks +z, centre looks +x

@@ -26,3 +26,18 @@ for kern, (H, W, S, rows) in itertools.product(["march", "march_generic"], [(128
     ms = e0.elapsed_time(e1) / n
     ns = rows * W * S
     print(f"[{kern}] render {H}x{W} rows={rows} S={S}: {ms:.3f} ms  {ns/ms/1e3:.1f} Msamples/s  algGB/s={ns*1024/ms/1e6:.0f}", flush=True)
+
+# explicit rays: image-shaped (pixel-patch tiling) vs flattened (128 consecutive rays per tile)
+from perf_b200 import ops
+r.kernel = "march"
+H, W, S, rows = 1024, 2048, 128, 256
+o, d = ops.raygen_pano(pose, H, W, row0=384, rows=rows)
+for name, (oo, dd) in {"image [H,W,3]": (o, d), "flat [R,3]": (o.reshape(-1, 3), d.reshape(-1, 3))}.items():
+    r.render_rays(oo, dd, S); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        r.render_rays(oo, dd, S)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    print(f"render_rays {name}: {ms:.3f} ms  {rows*W*S/ms/1e3:.1f} Msamples/s", flush=True)
