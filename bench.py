@@ -316,6 +316,7 @@ def main():
     import torch.distributed as dist
     if world > 1:
         import torch
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep stdout = the one JSON line
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
