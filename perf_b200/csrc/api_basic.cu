@@ -327,13 +327,16 @@ accumulate_along_rays_kernel(const float* __restrict__ w, const float* __restric
 }
 
 // ---- fused Adam (torch.optim.Adam semantics, amsgrad=False, weight_decay=0) + fp16 shadow.
+// `hyper` (device, optional): {lr, 1 - beta1^t, sqrt(1 - beta2^t)} read at run time, so a CUDA graph
+// holding this launch can be replayed with a new learning rate / step count.
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
             __half* __restrict__ ph, uint64_t n, float lr, float b1, float b2, float eps,
-            float bc1, float bc2_sqrt, float gscale)
+            float bc1, float bc2_sqrt, float gscale, const float* __restrict__ hyper)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (hyper) { lr = hyper[0]; bc1 = hyper[1]; bc2_sqrt = hyper[2]; }
     const float gi = g[i] * gscale;
     const float mi = b1 * m[i] + (1.f - b1) * gi;          // exp_avg.lerp_(grad, 1-beta1)
     const float vi = b2 * v[i] + (1.f - b2) * gi * gi;     // exp_avg_sq.mul_(b2).addcmul_(g, g, 1-b2)
@@ -511,7 +514,18 @@ int perf_adam_step(float* d_params, const float* d_grads, float* d_exp_avg, floa
     const float bc1 = 1.0f - powf(beta1, (float)step);
     const float bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
     adam_kernel<<<blocks_for(n, 256), 256, 0, S(stream)>>>(d_params, d_grads, d_exp_avg, d_exp_avg_sq, (__half*)d_params_half,
-                                                           n, lr, beta1, beta2, eps, bc1, bc2_sqrt, grad_scale);
+                                                           n, lr, beta1, beta2, eps, bc1, bc2_sqrt, grad_scale, nullptr);
+    PERF_LAUNCH_CHECK();
+    return PERF_OK;
+}
+
+int perf_adam_step_dev(float* d_params, const float* d_grads, float* d_exp_avg, float* d_exp_avg_sq, void* d_params_half,
+                       uint64_t n, const float* d_hyper, float beta1, float beta2, float eps, float grad_scale, void* stream)
+{
+    PERF_CHECK_ARG(d_params && d_grads && d_exp_avg && d_exp_avg_sq && d_hyper, "NULL pointer");
+    if (n == 0) return PERF_OK;
+    adam_kernel<<<blocks_for(n, 256), 256, 0, S(stream)>>>(d_params, d_grads, d_exp_avg, d_exp_avg_sq, (__half*)d_params_half,
+                                                           n, 0.f, beta1, beta2, eps, 1.f, 1.f, grad_scale, d_hyper);
     PERF_LAUNCH_CHECK();
     return PERF_OK;
 }

@@ -610,7 +610,8 @@ static int launch_render(const perf_render_args* args, RenderArgs& a, bool pano,
     const unsigned grid = (unsigned)(n_work < (uint64_t)num_sms() * 4 ? n_work : (uint64_t)num_sms() * 4);
 #define PERF_RENDER_LAUNCH(...) do { \
         auto k = __VA_ARGS__; \
-        PERF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_TOTAL)); \
+        static thread_local int attr_dev = -1; int dev_ = 0; PERF_CUDA(cudaGetDevice(&dev_)); \
+        if (attr_dev != dev_) { PERF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_TOTAL)); attr_dev = dev_; } \
         k<<<grid, TILE, RS_TOTAL, stream>>>(a); } while (0)
     const bool fast = fast_addressing_ok(a.lt, 4) && (args->flags & PERF_FLAG_GENERIC_ADDR) == 0;   // PeRF's grid: 4 dense + 12 hashed levels
     if (save != 0) {

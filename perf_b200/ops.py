@@ -527,3 +527,11 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, step: int, lr: float, params_h
     with torch.cuda.device(params.device):
         _call(_L().perf_adam_step, _p(params), _p(grads), _p(exp_avg), _p(exp_avg_sq), _p(params_half),
               params.numel(), lr, beta1, beta2, eps, step, grad_scale, _stream())
+
+
+def adam_step_dev(params, grads, exp_avg, exp_avg_sq, hyper: torch.Tensor, params_half=None,
+                  beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
+    """``adam_step`` with {lr, 1-beta1^t, sqrt(1-beta2^t)} in the device tensor ``hyper`` [3] (graph-replayable)."""
+    with torch.cuda.device(params.device):
+        _call(_L().perf_adam_step_dev, _p(params), _p(grads), _p(exp_avg), _p(exp_avg_sq), _p(params_half),
+              params.numel(), _p(hyper), beta1, beta2, eps, grad_scale, _stream())

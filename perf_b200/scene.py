@@ -153,6 +153,7 @@ class RaySupervision:
         self.all_sup_normals = torch.zeros_like(colors) if normals is None else normals
         self.generator = torch.Generator(device=colors.device).manual_seed(seed + parallel.rank())
         self.locality_key = None      # optional int64 key per ray; batches are ordered by it (see from_panorama)
+        self.use_default_generator = False
 
     @staticmethod
     def from_panorama(pose, rgb: torch.Tensor, distance: torch.Tensor, seed: int = 0) -> "RaySupervision":
@@ -188,7 +189,8 @@ class RaySupervision:
         return occ_grid, (valid_pts / float(res) - .5) * 2.
 
     def rand_ray_color_data(self, batch_size, rand_mode="by_all_pixels"):
-        idx = torch.randint(0, len(self.all_sup_colors), (batch_size,), device=self.all_sup_colors.device, generator=self.generator)
+        gen = None if self.use_default_generator else self.generator     # default generator: CUDA-graph safe
+        idx = torch.randint(0, len(self.all_sup_colors), (batch_size,), device=self.all_sup_colors.device, generator=gen)
         if self.locality_key is not None:
             idx = idx[torch.argsort(self.locality_key[idx])]
         return self.all_sup_rays[idx], self.all_sup_colors[idx], self.all_sup_distances[idx], self.all_sup_normals[idx]
@@ -205,6 +207,22 @@ class FusedAdam:
         self.param_groups = [{"lr": lr}]
         self.exp_avg, self.exp_avg_sq = torch.zeros_like(param.data), torch.zeros_like(param.data)
         self.step_count = 0
+        # graph mode: lr / bias corrections live in a device tensor refreshed from pinned memory before each replay
+        self.hyper = None
+        self._hyper_host = None
+
+    def enable_graph_mode(self):
+        self.hyper = torch.zeros(3, dtype=torch.float32, device=self.param.device)
+        self._hyper_host = torch.zeros(3, dtype=torch.float32).pin_memory()
+
+    def push_hyper(self):
+        """(graph mode) advance the step count and upload {lr, 1-b1^t, sqrt(1-b2^t)}; call before replay."""
+        self.step_count += 1
+        t = self.step_count
+        self._hyper_host[0] = self.param_groups[0]["lr"]
+        self._hyper_host[1] = 1.0 - self.betas[0] ** t
+        self._hyper_host[2] = (1.0 - self.betas[1] ** t) ** 0.5
+        self.hyper.copy_(self._hyper_host, non_blocking=True)
 
     def zero_grad(self):
         self.param.grad = None
@@ -213,12 +231,16 @@ class FusedAdam:
         if self.param.grad is None:
             return
         g = parallel.allreduce_mean_(self.param.grad.contiguous())
-        self.step_count += 1
         half = None
         if self.module is not None:
             half = self.module._half()                       # allocate / reuse the module's fp16 shadow buffer
-        ops.adam_step(self.param.data, g, self.exp_avg, self.exp_avg_sq, self.step_count, self.param_groups[0]["lr"],
-                      params_half=half, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps)
+        if self.hyper is not None:                           # graph mode: schedule comes from device memory
+            ops.adam_step_dev(self.param.data, g, self.exp_avg, self.exp_avg_sq, self.hyper, params_half=half,
+                              beta1=self.betas[0], beta2=self.betas[1], eps=self.eps)
+        else:
+            self.step_count += 1
+            ops.adam_step(self.param.data, g, self.exp_avg, self.exp_avg_sq, self.step_count, self.param_groups[0]["lr"],
+                          params_half=half, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps)
         # the kernel wrote through .data: bump autograd's version counter so version-keyed caches notice
         torch._C._increment_version([self.param])   # takes an ITERABLE of tensors
         if self.module is not None:                          # the shadow is already current for the new version
@@ -240,7 +262,7 @@ class NeRFScene:
 
     def __init__(self, base_exp_dir=".", train_conf=None, estimator_type="fixed", renderer_conf=None,
                  n_samples: int = 128, near: float = 1e-2, far: float = 1.0, device="cuda", writer=None, fused_train: bool = True,
-                 occ_resolution: int = 256):
+                 occ_resolution: int = 256, graph_train: bool = False):
         if estimator_type not in ("fixed", "occ"):
             raise NotImplementedError(f"perf_b200 NeRFScene: estimator_type={estimator_type!r} (the reference's 'prop' renderer is "
                                       "broken upstream, nerf_renderer.py:73, and not implemented)")
@@ -262,6 +284,7 @@ class NeRFScene:
         # fused training step (one forward kernel + composite-backward kernel); False = the modular
         # path through the plugin functions, op for op like the reference
         self.fused_train = fused_train
+        self.graph_train = graph_train and fused_train    # capture each phase's step into a CUDA graph (GraphedTrainStep)
         self.train_ctx = ops.FusedTrainContext(aabb=self.aabb.tolist(), n_samples=n_samples, near=near, far=far)
         self.global_iter_step_geo = self.global_iter_step_app = 0
 
@@ -366,14 +389,23 @@ class NeRFScene:
                 self.estimator.update_every_n_steps(step=i, occ_eval_fn=occ_eval_fn, occ_thre=1e-2, ema_decay=0.1, warmup_steps=256, n=1)
         self.nerf.reset_geo()
         geo_optimizer = FusedAdam(self.nerf.geo_mlp.params, lr=self.train_conf.geo_optimizer.init_lr, module=self.nerf.geo_mlp)
+        geo_step = GraphedTrainStep(self, "geo", sup_pool, geo_optimizer) if self.graph_train and geo_res_iters > 0 else None
         for iter_i in range(geo_res_iters):
             self.update_lr(geo_optimizer, self.train_conf.geo_optimizer, iter_i / geo_res_iters)
             # NB the reference divides by app_res_iters here (nerf.py:178); kept
-            self.train_one_step_geo(geo_optimizer, sup_pool, pixel_sup_rand_mode, progress=iter_i / max(app_res_iters, 1))
+            progress = iter_i / max(app_res_iters, 1)
+            if geo_step is not None:
+                geo_step(progress)
+            else:
+                self.train_one_step_geo(geo_optimizer, sup_pool, pixel_sup_rand_mode, progress=progress)
         app_optimizer = FusedAdam(self.nerf.app_mlp.params, lr=self.train_conf.app_optimizer.init_lr, module=self.nerf.app_mlp)
+        app_step = GraphedTrainStep(self, "app", sup_pool, app_optimizer) if self.graph_train and app_res_iters > 0 else None
         for iter_i in range(app_res_iters):
             self.update_lr(app_optimizer, self.train_conf.app_optimizer, iter_i / app_res_iters)
-            self.train_one_step_app(app_optimizer, sup_pool, pixel_sup_rand_mode, progress=iter_i / app_res_iters)
+            if app_step is not None:
+                app_step(iter_i / app_res_iters)
+            else:
+                self.train_one_step_app(app_optimizer, sup_pool, pixel_sup_rand_mode, progress=iter_i / app_res_iters)
 
     def _local_batch(self):
         return max(1, int(self.train_conf.pixel_loss_batch_size) // parallel.world_size())
@@ -403,7 +435,8 @@ class NeRFScene:
                 mid_dis = (res["t_ends"] + res["t_starts"]) * .5
                 sec_lens = res["t_ends"] - res["t_starts"]
                 dist_loss = flatten_eff_distloss(res["weights"], mid_dis, sec_lens, res["ray_indices"])
-            loss = loss + dist_loss * conf.distortion_loss_weight * float(np.min([progress * 2., 1]))
+            ratio = progress if torch.is_tensor(progress) else float(np.min([progress * 2., 1]))   # tensor: pre-computed ramp (graph mode)
+            loss = loss + dist_loss * conf.distortion_loss_weight * ratio
             self._log("nerf_loss/dist_loss", dist_loss, self.global_iter_step_geo)
         if conf.density_loss_weight > eps:
             rand_pts = (torch.rand(8192, 3, device=self.device) * 2. - 1.) * 0.99
@@ -463,3 +496,65 @@ class NeRFScene:
 
     def set_eval(self):
         self.nerf.eval(); self.estimator.eval(); self.renderer.eval()
+
+
+class GraphedTrainStep:
+    """One optimisation step (batch draw -> fused forward -> losses -> backward -> all-reduce -> Adam)
+    captured ONCE into a CUDA graph and replayed: ~50 launches + Python bookkeeping become a single
+    graph launch.  The learning rate / Adam bias corrections and the distortion-loss ramp are device
+    scalars refreshed before every replay, so the reference's schedule (`nerf.py:173-184,300-311`)
+    is followed exactly.  Usage::
+
+        step = GraphedTrainStep(scene, "geo", sup_pool, optimizer)
+        for i in range(iters):
+            scene.update_lr(optimizer, conf.geo_optimizer, i / iters)
+            loss = step(progress=i / app_iters)
+    """
+
+    def __init__(self, scene: NeRFScene, phase: str, sup_pool: RaySupervision, optimizer: FusedAdam, warmup: int = 3):
+        assert phase in ("geo", "app") and scene.fused_train
+        self.scene, self.phase, self.pool, self.opt = scene, phase, sup_pool, optimizer
+        dev = scene.device
+        self.ratio = torch.zeros((), device=dev)
+        self._ratio_host = torch.zeros(()).pin_memory()
+        self.net = scene.nerf.geo_mlp if phase == "geo" else scene.nerf.app_mlp
+        sup_pool.use_default_generator = True                 # graph-safe RNG; decorrelate the ranks' batches
+        torch.cuda.manual_seed(int(sup_pool.generator.initial_seed()) + 7919 * parallel.rank())
+        optimizer.enable_graph_mode()
+        scene.set_train()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                         # eager warm-up on a side stream (cuBLAS workspaces, NCCL, allocator)
+            for _ in range(warmup):
+                self._prepare(0.5)
+                self._body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        self._prepare(0.5)
+        with torch.cuda.graph(self.graph):
+            self.loss = self._body()
+        optimizer.step_count = 0                               # warm-up / capture steps do not count
+        optimizer.exp_avg.zero_(); optimizer.exp_avg_sq.zero_()
+
+    def _prepare(self, progress: float):
+        self._ratio_host.fill_(min(progress * 2.0, 1.0))
+        self.ratio.copy_(self._ratio_host, non_blocking=True)
+        self.opt.push_hyper()
+
+    def _body(self):
+        sc = self.scene
+        sc._fused_key = None                                   # always re-pack inside the step (captured)
+        if self.phase == "geo":
+            return sc.train_one_step_geo(self.opt, self.pool, progress=self.ratio)
+        return sc.train_one_step_app(self.opt, self.pool, progress=self.ratio)
+
+    def __call__(self, progress: float = 0.0):
+        self._prepare(progress)
+        self.graph.replay()
+        # the replayed Adam kernel wrote params + fp16 shadow: tell the version-keyed caches
+        p = self.net.params
+        torch._C._increment_version([p])
+        self.net._half_key = (p._version, p.data_ptr())
+        self.scene._fused_key = None
+        return self.loss

@@ -216,3 +216,39 @@ def test_occ_estimator_scene_fits_and_renders():
     assert out["rgb"].shape == (h, w, 3) and torch.isfinite(out["rgb"]).all()
     d_err, c_err = float((out["distance"] - dist).abs().mean()), float((out["rgb"] - rgb).abs().mean())
     assert d_err < 0.05 and c_err < 0.2, (d_err, c_err)
+
+
+def test_graphed_training_fits_like_eager():
+    """The whole optimisation step captured in a CUDA graph (GraphedTrainStep): the fit converges like
+    the eager fit, the schedule is honoured (lr = 0 leaves the parameters untouched), and caches that
+    key on the parameter version see the replayed updates."""
+    from perf_b200 import synthetic
+    from perf_b200.scene import FusedAdam, GraphedTrainStep, NeRFScene, RaySupervision
+    h, w = 64, 128
+    rgb, dist = synthetic.smooth_rgb(h, w, seed=0, device="cuda"), synthetic.box_room_distance(h, w, device="cuda")
+    conf = dict(NeRFScene(n_samples=8).train_conf)
+    conf.update(pixel_loss_batch_size=2048, raw_phase_iter_geo=150, raw_phase_iter_app=100)
+    errs = {}
+    for graph in (False, True):
+        torch.manual_seed(0)
+        sc = NeRFScene(train_conf=conf, n_samples=48, graph_train=graph)
+        pool = RaySupervision.from_panorama(torch.eye(4), rgb, dist, seed=0)
+        sc.fit(pool)
+        out = sc.render_pano(torch.eye(4), h, w)
+        errs[graph] = (float((out["distance"] - dist).abs().mean()), float((out["rgb"] - rgb).abs().mean()))
+    assert errs[True][0] < 0.05 and errs[True][0] < 2.0 * errs[False][0] + 5e-3, errs
+    assert errs[True][1] < 2.0 * errs[False][1] + 1e-2, errs
+    # lr = 0: replay must not move the parameters; lr > 0: it must, and the fp16 shadow follows
+    sc = NeRFScene(train_conf=conf, n_samples=48)
+    pool = RaySupervision.from_panorama(torch.eye(4), rgb, dist, seed=0)
+    opt = FusedAdam(sc.nerf.geo_mlp.params, lr=0.0, module=sc.nerf.geo_mlp)
+    step = GraphedTrainStep(sc, "geo", pool, opt)
+    before = sc.nerf.geo_mlp.params.detach().clone()
+    l0 = float(step(0.3))
+    assert torch.equal(sc.nerf.geo_mlp.params.detach(), before)
+    opt.param_groups[0]["lr"] = 1e-2
+    for _ in range(30):
+        step(0.3)
+    assert not torch.equal(sc.nerf.geo_mlp.params.detach(), before)
+    assert torch.equal(sc.nerf.geo_mlp._half(), sc.nerf.geo_mlp.params.detach().half())
+    assert float(step(0.3)) < l0

@@ -3,7 +3,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from perf_b200 import synthetic, parallel
-from perf_b200.scene import NeRFScene, RaySupervision, FusedAdam
+from perf_b200.scene import NeRFScene, RaySupervision, FusedAdam, GraphedTrainStep
 
 rank, world, local = parallel.init()
 torch.cuda.set_device(local)
@@ -15,7 +15,11 @@ pool = RaySupervision.from_panorama(torch.eye(4), rgb, dist)
 for phase in os.environ.get("PHASES", "geo,app").split(","):
     net = sc.nerf.geo_mlp if phase == "geo" else sc.nerf.app_mlp
     opt = FusedAdam(net.params, lr=1e-3, module=net)
-    step = sc.train_one_step_geo if phase == "geo" else sc.train_one_step_app
+    if os.environ.get("GRAPH", "0") == "1":
+        g = GraphedTrainStep(sc, phase, pool, opt)
+        step = lambda opt_, pool_, progress=0.5: g(progress)
+    else:
+        step = sc.train_one_step_geo if phase == "geo" else sc.train_one_step_app
     for _ in range(5):
         step(opt, pool, progress=0.5)
     torch.cuda.synchronize()
@@ -27,4 +31,4 @@ for phase in os.environ.get("PHASES", "geo,app").split(","):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
     if rank == 0:
-        print(f"[{phase}] fused={sc.fused_train} train step B={B} S={S} world={world}: {ms:.3f} ms/step  {B*S/ms/1e3:.1f} Msamples/s", flush=True)
+        print(f"[{phase}] fused={sc.fused_train} graph={os.environ.get('GRAPH', '0')} train step B={B} S={S} world={world}: {ms:.3f} ms/step  {B*S/ms/1e3:.1f} Msamples/s", flush=True)
