@@ -166,18 +166,20 @@ def bench_train(dev, rank, world, steps=20, warmup=5):
     import torch
     import torch.distributed as dist
     from perf_b200 import synthetic
-    from perf_b200.scene import FusedAdam, NeRFScene, RaySupervision
+    from perf_b200.scene import FusedAdam, GraphedTrainStep, NeRFScene, RaySupervision
     h, w = 512, 1024
     rgb, distance = synthetic.smooth_rgb(h, w, device=dev), synthetic.box_room_distance(h, w, device=dev)
     sc = NeRFScene(n_samples=S, device=dev)
     sc.set_train()
     pool = RaySupervision.from_panorama(torch.eye(4), rgb, distance)
     out = {"rays_per_step_global": 8192, "samples_per_ray": S, "world": world,
-           "note": "forward+backward+Adam per step, strong scaling of the reference's 8192-ray batch; random-init field, synthetic RGB-D"}
+           "note": "forward+backward+all-reduce+Adam per step captured in one CUDA graph; strong scaling of the reference's 8192-ray "
+                   "batch; random-init field, synthetic RGB-D"}
     for phase in ("geo", "app"):
         net = sc.nerf.geo_mlp if phase == "geo" else sc.nerf.app_mlp
         opt = FusedAdam(net.params, lr=1e-3, module=net)
-        step = sc.train_one_step_geo if phase == "geo" else sc.train_one_step_app
+        graphed = GraphedTrainStep(sc, phase, pool, opt)       # the whole step = one CUDA-graph launch
+        step = lambda opt_, pool_, progress=0.5: graphed(progress)
         for _ in range(warmup):
             step(opt, pool, progress=0.5)
         if world > 1:

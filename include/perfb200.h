@@ -238,6 +238,10 @@ int perf_adam_step(float* d_params, const float* d_grads, float* d_exp_avg, floa
                    void* d_params_half /*nullable*/, uint64_t n, float lr, float beta1, float beta2,
                    float eps, uint32_t step /*1-based*/, float grad_scale, void* stream);
 
+/* d_dst[0..n) = h_values[0..n), n <= 8, stream-ordered; the values travel as kernel arguments, so the
+ * host array may be reused immediately (feeds the device-side schedule of a replayed CUDA graph). */
+int perf_set_scalars(float* d_dst, const float* h_values, int n, void* stream);
+
 /* Same update with {lr, 1 - beta1^step, sqrt(1 - beta2^step)} read from DEVICE memory (d_hyper[3]) at
  * run time: the launch can live inside a captured CUDA graph and be replayed with a new schedule. */
 int perf_adam_step_dev(float* d_params, const float* d_grads, float* d_exp_avg, float* d_exp_avg_sq,

@@ -75,6 +75,7 @@ SIGNATURES = {
     "perf_mlp_bwd_out": (i32, [vp, i32, vp, vp, vp, u64, vp]),
     "perf_relu_mask": (i32, [vp, vp, u64, vp]),
     "perf_adam_step": (i32, [vp, vp, vp, vp, vp, u64, f32, f32, f32, f32, u32, f32, vp]),
+    "perf_set_scalars": (i32, [vp, P(f32), i32, vp]),
     "perf_adam_step_dev": (i32, [vp, vp, vp, vp, vp, u64, vp, f32, f32, f32, f32, vp]),
 }
 

@@ -326,6 +326,9 @@ accumulate_along_rays_kernel(const float* __restrict__ w, const float* __restric
     }
 }
 
+struct Scalars8 { float v[8]; };
+__global__ void set_scalars_kernel(float* dst, Scalars8 s, int n) { if ((int)threadIdx.x < n) dst[threadIdx.x] = s.v[threadIdx.x]; }
+
 // ---- fused Adam (torch.optim.Adam semantics, amsgrad=False, weight_decay=0) + fp16 shadow.
 // `hyper` (device, optional): {lr, 1 - beta1^t, sqrt(1 - beta2^t)} read at run time, so a CUDA graph
 // holding this launch can be replayed with a new learning rate / step count.
@@ -515,6 +518,15 @@ int perf_adam_step(float* d_params, const float* d_grads, float* d_exp_avg, floa
     const float bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
     adam_kernel<<<blocks_for(n, 256), 256, 0, S(stream)>>>(d_params, d_grads, d_exp_avg, d_exp_avg_sq, (__half*)d_params_half,
                                                            n, lr, beta1, beta2, eps, bc1, bc2_sqrt, grad_scale, nullptr);
+    PERF_LAUNCH_CHECK();
+    return PERF_OK;
+}
+
+int perf_set_scalars(float* d_dst, const float* h_values, int n, void* stream)
+{
+    PERF_CHECK_ARG(d_dst && h_values && n >= 1 && n <= 8, "perf_set_scalars: need 1..8 values");
+    Scalars8 s; for (int i = 0; i < 8; ++i) s.v[i] = i < n ? h_values[i] : 0.f;   // by-value: no host-buffer lifetime issues
+    set_scalars_kernel<<<1, 32, 0, S(stream)>>>(d_dst, s, n);
     PERF_LAUNCH_CHECK();
     return PERF_OK;
 }

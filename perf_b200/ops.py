@@ -535,3 +535,11 @@ def adam_step_dev(params, grads, exp_avg, exp_avg_sq, hyper: torch.Tensor, param
     with torch.cuda.device(params.device):
         _call(_L().perf_adam_step_dev, _p(params), _p(grads), _p(exp_avg), _p(exp_avg_sq), _p(params_half),
               params.numel(), _p(hyper), beta1, beta2, eps, grad_scale, _stream())
+
+
+def set_scalars(dst: torch.Tensor, values) -> None:
+    """dst[:len(values)] = values (<= 8 floats), stream-ordered, race-free w.r.t. the host (by-value kernel args)."""
+    vals = [float(v) for v in values]
+    arr = (C.c_float * len(vals))(*vals)
+    with torch.cuda.device(dst.device):
+        _call(_L().perf_set_scalars, _p(dst), arr, len(vals), _stream())

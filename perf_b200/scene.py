@@ -209,20 +209,15 @@ class FusedAdam:
         self.step_count = 0
         # graph mode: lr / bias corrections live in a device tensor refreshed from pinned memory before each replay
         self.hyper = None
-        self._hyper_host = None
 
     def enable_graph_mode(self):
         self.hyper = torch.zeros(3, dtype=torch.float32, device=self.param.device)
-        self._hyper_host = torch.zeros(3, dtype=torch.float32).pin_memory()
 
     def push_hyper(self):
         """(graph mode) advance the step count and upload {lr, 1-b1^t, sqrt(1-b2^t)}; call before replay."""
         self.step_count += 1
         t = self.step_count
-        self._hyper_host[0] = self.param_groups[0]["lr"]
-        self._hyper_host[1] = 1.0 - self.betas[0] ** t
-        self._hyper_host[2] = (1.0 - self.betas[1] ** t) ** 0.5
-        self.hyper.copy_(self._hyper_host, non_blocking=True)
+        ops.set_scalars(self.hyper, [self.param_groups[0]["lr"], 1.0 - self.betas[0] ** t, (1.0 - self.betas[1] ** t) ** 0.5])
 
     def zero_grad(self):
         self.param.grad = None
@@ -515,8 +510,7 @@ class GraphedTrainStep:
         assert phase in ("geo", "app") and scene.fused_train
         self.scene, self.phase, self.pool, self.opt = scene, phase, sup_pool, optimizer
         dev = scene.device
-        self.ratio = torch.zeros((), device=dev)
-        self._ratio_host = torch.zeros(()).pin_memory()
+        self.ratio = torch.zeros(1, device=dev)
         self.net = scene.nerf.geo_mlp if phase == "geo" else scene.nerf.app_mlp
         sup_pool.use_default_generator = True                 # graph-safe RNG; decorrelate the ranks' batches
         torch.cuda.manual_seed(int(sup_pool.generator.initial_seed()) + 7919 * parallel.rank())
@@ -538,16 +532,15 @@ class GraphedTrainStep:
         optimizer.exp_avg.zero_(); optimizer.exp_avg_sq.zero_()
 
     def _prepare(self, progress: float):
-        self._ratio_host.fill_(min(progress * 2.0, 1.0))
-        self.ratio.copy_(self._ratio_host, non_blocking=True)
+        ops.set_scalars(self.ratio, [min(progress * 2.0, 1.0)])
         self.opt.push_hyper()
 
     def _body(self):
         sc = self.scene
         sc._fused_key = None                                   # always re-pack inside the step (captured)
         if self.phase == "geo":
-            return sc.train_one_step_geo(self.opt, self.pool, progress=self.ratio)
-        return sc.train_one_step_app(self.opt, self.pool, progress=self.ratio)
+            return sc.train_one_step_geo(self.opt, self.pool, progress=self.ratio[0])
+        return sc.train_one_step_app(self.opt, self.pool, progress=self.ratio[0])
 
     def __call__(self, progress: float = 0.0):
         self._prepare(progress)
