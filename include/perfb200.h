@@ -191,7 +191,15 @@ typedef struct perf_train_buffers {
     void*  d_h2;         /* [S*R,64] fp16 hidden 2 (PHASE_APP only)                         */
     float* d_dist_acc;   /* [R] sum w*t_mid before the background rule                      */
     float* d_distloss;   /* [R] distortion-loss numerator per ray (flatten_eff_distloss * n_rays) */
+    /* Ray splitting for small batches (optional, both NULL = off): the forward may cut every ray into
+     * `segments` pieces handled by different threads; then d_weights / d_trans hold segment-LOCAL values
+     * (T = 1 at the segment start) and d_seg_trans [PERF_MAX_SEGMENTS * R] the transmittance at each
+     * segment start (row = segment * R + ray).  The forward writes the count it chose to *h_segments_out;
+     * pass the same struct (and that count) to perf_train_backward_composite. */
+    float*    d_seg_trans;
+    uint32_t* h_segments_out;
 } perf_train_buffers;
+#define PERF_MAX_SEGMENTS 16
 
 /* Forward of a training step: like perf_render_rays (PERF_FLAG_TRAINING semantics: jitter, training
  * background rule) and additionally fills `buf`. */
@@ -202,7 +210,7 @@ int perf_train_forward(const perf_render_args* args, const float* d_rays_o, cons
  * PHASE_GEO: d_out [S*R]   = dL/d(raw density logit)   (trunc_exp backward included)
  * PHASE_APP: d_out [S*R,3] = dL/d(colour pre-sigmoid)  (weights are detached, nerf_renderer.py:183)
  * d_g_* may be NULL (zero gradient).  d_distance_out: the forward's distance output (ReLU mask). */
-int perf_train_backward_composite(int phase, uint32_t n_samples, float near, float far, uint64_t R,
+int perf_train_backward_composite(int phase, uint32_t n_samples, uint32_t segments, float near, float far, uint64_t R,
                                   const float* d_jitter, const float* d_bg_noise, const perf_train_buffers* buf,
                                   const float* d_g_rgb, const float* d_g_distance, const float* d_g_opacity,
                                   const float* d_g_distloss, const float* d_distance_out, const float* d_opacity_out,

@@ -38,9 +38,13 @@ class RenderArgs(C.Structure):
                 ("d_jitter", vp), ("d_bg_noise", vp), ("d_rgb", vp), ("d_distance", vp), ("d_opacity", vp), ("image_width", u32)]
 
 
+P_u32 = C.POINTER(u32)
+PERF_MAX_SEGMENTS = 16
+
+
 class TrainBuffers(C.Structure):
     _fields_ = [("d_sigma", vp), ("d_weights", vp), ("d_trans", vp), ("d_rgb", vp), ("d_feat", vp), ("d_h1", vp),
-                ("d_h2", vp), ("d_dist_acc", vp), ("d_distloss", vp)]
+                ("d_h2", vp), ("d_dist_acc", vp), ("d_distloss", vp), ("d_seg_trans", vp), ("h_segments_out", P_u32)]
 
 
 PERF_PHASE_GEO, PERF_PHASE_APP = 1, 2
@@ -68,7 +72,7 @@ SIGNATURES = {
     "perf_render_packed": (i32, [P(RenderArgs), vp, vp, u64, vp, vp, vp, vp]),
     "perf_render_pano": (i32, [P(RenderArgs), P(f32), i32, i32, i32, i32, vp]),
     "perf_train_forward": (i32, [P(RenderArgs), vp, vp, u64, i32, P(TrainBuffers), vp]),
-    "perf_train_backward_composite": (i32, [i32, u32, f32, f32, u64, vp, vp, P(TrainBuffers), vp, vp, vp, vp, vp, vp, vp, vp]),
+    "perf_train_backward_composite": (i32, [i32, u32, u32, f32, f32, u64, vp, vp, P(TrainBuffers), vp, vp, vp, vp, vp, vp, vp, vp]),
     "perf_hashgrid_bwd_rays": (i32, [P(GridCfg), P(f32), vp, vp, vp, u64, u32, f32, f32, vp, vp, vp]),
     "perf_occ_count": (i32, [vp, P(i32), P(f32), vp, vp, vp, u64, f32, f32, f32, vp, vp]),
     "perf_occ_write": (i32, [vp, P(i32), P(f32), vp, vp, vp, u64, f32, f32, f32, vp, vp, vp, vp, vp]),

@@ -49,6 +49,12 @@ struct RenderArgs {
     uint4*        s_h2;         // [S*R, 64] fp16 (colour phase only)
     float*        s_dacc;       // [R] distance accumulate BEFORE the background rule
     float*        s_dl;         // [R] distortion-loss numerator of the ray
+    // ray splitting (explicit rays, fixed S): every ray is cut into `seg` consecutive segments of
+    // S/seg samples handled by `seg` different threads of the tile (tile = 128/seg rays); the segment
+    // results are combined with the transmittance product rule.  Fills the GPU for small ray batches
+    // (an 8192-ray training batch is only 64 tiles of 128 rays, but 512 tiles of 16 rays x 8 segments).
+    uint32_t      seg;          // power of two, divides S and 128; 1 = off
+    float*        s_toff;       // [seg * R] transmittance at the start of each segment (SAVE, seg > 1)
 };
 
 constexpr int RS_A     = 0;                         // 16 KB: A_geo | A_app, later H (K=64)
@@ -449,7 +455,10 @@ __global__ void __launch_bounds__(TILE, 4) render_march_kernel(const __grid_cons
     const bool patch = PANO || a.W > 0;
     const int rows = patch ? (int)(a.R / (uint64_t)a.W) : 0;
     const uint32_t tiles_x = patch ? (uint32_t)((a.W + 15) / 16) : 0u;
-    const uint64_t n_tiles = patch ? (uint64_t)tiles_x * (uint64_t)((rows + 7) / 8) : (a.R + TILE - 1) / TILE;
+    const uint32_t seg = (PANO || patch || a.pk_offsets != nullptr || a.seg == 0) ? 1u : a.seg;
+    const uint32_t rpt = TILE / seg, kps = S / seg;                 // rays per tile, samples per segment
+    const uint32_t my_seg = (uint32_t)tid / rpt;
+    const uint64_t n_tiles = patch ? (uint64_t)tiles_x * (uint64_t)((rows + 7) / 8) : (a.R + rpt - 1) / rpt;
 
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         // ---- this thread's ray
@@ -480,7 +489,7 @@ __global__ void __launch_bounds__(TILE, 4) render_march_kernel(const __grid_cons
                 valid = prow < rows && pcol < a.W;
                 ray = (uint64_t)prow * (uint64_t)a.W + (uint64_t)pcol;
             } else {
-                ray = tile * TILE + tid;
+                ray = tile * rpt + (uint32_t)tid % rpt;
                 valid = ray < a.R;
             }
             if (valid) {
@@ -495,7 +504,7 @@ __global__ void __launch_bounds__(TILE, 4) render_march_kernel(const __grid_cons
         float dl_uni = 0.f, dl_bi = 0.f;                      // distortion loss pieces (SAVE only)
         // packed mode: every thread walks ITS ray's samples; the tile iterates to the longest ray
         // (neighbouring rays cross the same occupied shells, so lengths inside a tile are similar)
-        uint32_t n_iter = S, my_count = S;
+        uint32_t n_iter = kps, my_count = S;
         int64_t pk_base = 0;
         if (!PANO && a.pk_offsets != nullptr) {
             my_count = 0;
@@ -508,7 +517,8 @@ __global__ void __launch_bounds__(TILE, 4) render_march_kernel(const __grid_cons
             n_iter = max(max(s_max[0], s_max[1]), max(s_max[2], s_max[3]));
         }
 #pragma unroll 1
-        for (uint32_t k = 0; k < n_iter; ++k) {
+        for (uint32_t kk = 0; kk < n_iter; ++kk) {
+            const uint32_t k = my_seg * kps + kk;                 // seg == 1: k == kk
             const bool live = valid && k < my_count;
             float ts, te;
             if (!PANO && a.pk_offsets != nullptr) {
@@ -553,7 +563,35 @@ __global__ void __launch_bounds__(TILE, 4) render_march_kernel(const __grid_cons
             if constexpr (SIMT) __syncthreads();
         }
 
-        if (valid) {
+        bool writer = valid;
+        if (seg > 1) {
+            // combine the `seg` partial composites of every ray (each computed as if T = 1 at the segment
+            // start): w = Toff w', Wx = Wpre + Toff Wx', ... ; scratch = the (now idle) feature tiles
+            float* part = reinterpret_cast<float*>(sA);
+            __syncthreads();
+            part[0 * TILE + tid] = sum_sd; part[1 * TILE + tid] = acc_w; part[2 * TILE + tid] = acc_d;
+            part[3 * TILE + tid] = acc_r;  part[4 * TILE + tid] = acc_g; part[5 * TILE + tid] = acc_b;
+            part[6 * TILE + tid] = dl_uni; part[7 * TILE + tid] = dl_bi;
+            __syncthreads();
+            writer = valid && my_seg == 0;
+            if (writer) {
+                float cum_sd = 0.f, W = 0.f, D = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, du = 0.f, db = 0.f;
+                for (uint32_t sgi = 0; sgi < seg; ++sgi) {
+                    const int t = (int)(sgi * rpt) + tid;         // thread that handled segment sgi of my ray
+                    const float toff = expf(-cum_sd);
+                    if (SAVE != 0) a.s_toff[(uint64_t)sgi * a.R + ray] = toff;
+                    const float pW = part[1 * TILE + t], pD = part[2 * TILE + t];
+                    du = fmaf(toff * toff, part[6 * TILE + t], du);
+                    db += toff * (W * pD - D * pW) + toff * toff * part[7 * TILE + t];
+                    W = fmaf(toff, pW, W); D = fmaf(toff, pD, D);
+                    cr = fmaf(toff, part[3 * TILE + t], cr); cg = fmaf(toff, part[4 * TILE + t], cg); cb = fmaf(toff, part[5 * TILE + t], cb);
+                    cum_sd += part[0 * TILE + t];
+                }
+                acc_w = W; acc_d = D; acc_r = cr; acc_g = cg; acc_b = cb; dl_uni = du; dl_bi = db;
+            }
+            __syncthreads();                                      // scratch is rewritten by the next tile's features
+        }
+        if (writer) {
             const float one_m = 1.f - acc_w;
             float dist = acc_d, r = acc_r, g = acc_g, b = acc_b;
             if constexpr (SAVE != 0) { a.s_dacc[ray] = acc_d; a.s_dl[ray] = dl_uni * (1.f / 3.f) + 2.f * dl_bi; }
@@ -606,7 +644,10 @@ static int launch_render(const perf_render_args* args, RenderArgs& a, bool pano,
     if (scan) n_work = (a.R + a.rays_per_unit - 1) / a.rays_per_unit;
     else if (pano) n_work = (uint64_t)((a.W + 15) / 16) * (uint64_t)(((int)(a.R / (uint64_t)a.W) + 7) / 8);
     else if (a.W > 0) n_work = (uint64_t)((a.W + 15) / 16) * (uint64_t)(((int)(a.R / (uint64_t)a.W) + 7) / 8);
-    else n_work = (a.R + TILE - 1) / TILE;
+    else {
+        const uint32_t rpt = TILE / (a.seg ? a.seg : 1u);
+        n_work = (a.R + rpt - 1) / rpt;
+    }
     const unsigned grid = (unsigned)(n_work < (uint64_t)num_sms() * 4 ? n_work : (uint64_t)num_sms() * 4);
 #define PERF_RENDER_LAUNCH(...) do { \
         auto k = __VA_ARGS__; \
@@ -677,6 +718,14 @@ int perf_train_forward(const perf_render_args* args, const float* d_rays_o, cons
     a.s_sigma = buf->d_sigma; a.s_w = buf->d_weights; a.s_trans = buf->d_trans; a.s_rgb = (__half*)buf->d_rgb;
     a.s_feat = (uint4*)buf->d_feat; a.s_h1 = (uint4*)buf->d_h1; a.s_h2 = (uint4*)buf->d_h2;
     a.s_dacc = buf->d_dist_acc; a.s_dl = buf->d_distloss;
+    // split rays into segments until the tiles fill the machine (4 CTAs / SM), if the caller gave room
+    a.seg = 1; a.s_toff = buf->d_seg_trans;
+    if (buf->d_seg_trans != nullptr) {
+        const uint64_t slots = (uint64_t)num_sms() * 4;
+        while (a.seg < PERF_MAX_SEGMENTS && args->n_samples % (a.seg * 2) == 0 && (R * a.seg + TILE - 1) / TILE < slots) a.seg *= 2;
+    }
+    PERF_CHECK_ARG(buf->h_segments_out != nullptr || a.seg == 1, "d_seg_trans given without h_segments_out");
+    if (buf->h_segments_out) *buf->h_segments_out = a.seg;
     perf_render_args t = *args; t.flags |= PERF_FLAG_TRAINING;
     return launch_render(&t, a, false, (cudaStream_t)stream, phase);
 }

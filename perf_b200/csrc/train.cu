@@ -5,7 +5,7 @@
 namespace perf {
 
 struct CompBwdArgs {
-    uint32_t S; float near, far; uint64_t R;
+    uint32_t S, seg; float near, far; uint64_t R; const float* toff;
     const float* jitter; const float* bg_noise;
     const float *sigma, *w, *T; const __half* rgb;
     const float *dist_acc;
@@ -29,9 +29,10 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(const CompBwdArgs a)
     if constexpr (PHASE == PERF_PHASE_APP) {
         float gr = 0.f, gg = 0.f, gb = 0.f;
         if (a.g_rgb) { gr = a.g_rgb[3 * ray]; gg = a.g_rgb[3 * ray + 1]; gb = a.g_rgb[3 * ray + 2]; }
+        const uint32_t kps = S / a.seg;
         for (uint32_t k = 0; k < S; ++k) {
             const uint64_t row = (uint64_t)k * a.R + ray;
-            const float w = a.w[row];
+            const float w = a.w[row] * (a.seg > 1 ? a.toff[(uint64_t)(k / kps) * a.R + ray] : 1.f);
             const uint2 c = *reinterpret_cast<const uint2*>(a.rgb + row * 4);
             const float2 c01 = unpack_half2(c.x), c2 = unpack_half2(c.y);
             // colours = sum w.detach() * rgb; rgb = sigmoid(z): dz = g * w * y (1 - y)
@@ -48,9 +49,11 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(const CompBwdArgs a)
         const float gO = (a.g_op ? a.g_op[ray] : 0.f) - gd * c;
         const float gdl = a.g_dl ? a.g_dl[ray] : 0.f;
         float Wsuf = 0.f, WMsuf = 0.f, suf_wg = 0.f;
+        const uint32_t kps = S / a.seg;
         for (uint32_t kk = S; kk-- > 0;) {
             const uint64_t row = (uint64_t)kk * a.R + ray;
-            const float w = a.w[row], T = a.T[row], sig = a.sigma[row];
+            const float toff = a.seg > 1 ? a.toff[(uint64_t)(kk / kps) * a.R + ray] : 1.f;     // segment-local -> global
+            const float w = a.w[row] * toff, T = a.T[row] * toff, sig = a.sigma[row];
             const float ts = __fadd_rn(a.near, __fmul_rn(__fadd_rn((float)kk, jit), step));
             const float te = __fadd_rn(a.near, __fmul_rn(__fadd_rn((float)(kk + 1), jit), step));
             const float m = __fadd_rn(ts, te) * 0.5f, dt = __fsub_rn(te, ts);
@@ -255,7 +258,7 @@ using namespace perf;
 extern "C" {
 #pragma GCC visibility push(default)
 
-int perf_train_backward_composite(int phase, uint32_t n_samples, float near, float far, uint64_t R,
+int perf_train_backward_composite(int phase, uint32_t n_samples, uint32_t segments, float near, float far, uint64_t R,
                                   const float* d_jitter, const float* d_bg_noise, const perf_train_buffers* buf,
                                   const float* d_g_rgb, const float* d_g_distance, const float* d_g_opacity,
                                   const float* d_g_distloss, const float* d_distance_out, const float* d_opacity_out,
@@ -265,7 +268,8 @@ int perf_train_backward_composite(int phase, uint32_t n_samples, float near, flo
     PERF_CHECK_ARG(phase == PERF_PHASE_GEO || phase == PERF_PHASE_APP, "bad phase");
     PERF_CHECK_ARG(n_samples >= 1 && far > near, "bad sampling range");
     CompBwdArgs a; memset(&a, 0, sizeof(a));
-    a.S = n_samples; a.near = near; a.far = far; a.R = R; a.jitter = d_jitter; a.bg_noise = d_bg_noise;
+    PERF_CHECK_ARG(segments >= 1 && n_samples % segments == 0 && (segments == 1 || buf->d_seg_trans), "bad segment count %u", segments);
+    a.S = n_samples; a.seg = segments; a.toff = buf->d_seg_trans; a.near = near; a.far = far; a.R = R; a.jitter = d_jitter; a.bg_noise = d_bg_noise;
     a.sigma = buf->d_sigma; a.w = buf->d_weights; a.T = buf->d_trans; a.rgb = (const __half*)buf->d_rgb; a.dist_acc = buf->d_dist_acc;
     a.g_rgb = d_g_rgb; a.g_dist = d_g_distance; a.g_op = d_g_opacity; a.g_dl = d_g_distloss;
     a.dist_out = d_distance_out; a.op_out = d_opacity_out; a.out = d_out;

@@ -411,7 +411,8 @@ class FusedTrainContext:
             f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
             f16 = lambda *s: torch.empty(*s, dtype=torch.float16, device=dev)
             b = {"sigma": f32(N), "w": f32(N), "T": f32(N), "feat": f16(N, 32), "h1": f16(N, 64),
-                 "dacc": f32(R), "dl": f32(R), "rgb": None, "h2": None}
+                 "dacc": f32(R), "dl": f32(R), "rgb": None, "h2": None,
+                 "toff": f32(_lib.PERF_MAX_SEGMENTS * R), "segments": C.c_uint32(1)}
             if phase == _lib.PERF_PHASE_APP:
                 b["rgb"], b["h2"] = f16(N, 4), f16(N, 64)
             self._bufs = {key: b}                                  # keep only the latest shape
@@ -421,7 +422,7 @@ class FusedTrainContext:
     def c_buffers(b) -> "_lib.TrainBuffers":
         ptr = lambda t: None if t is None else t.data_ptr()
         return _lib.TrainBuffers(ptr(b["sigma"]), ptr(b["w"]), ptr(b["T"]), ptr(b["rgb"]), ptr(b["feat"]), ptr(b["h1"]),
-                                 ptr(b["h2"]), ptr(b["dacc"]), ptr(b["dl"]))
+                                 ptr(b["h2"]), ptr(b["dacc"]), ptr(b["dl"]), ptr(b["toff"]), C.pointer(b["segments"]))
 
 
 def mlp_backward_half(mlp: MLPConfig, weights_half: torch.Tensor, feat, h1, h2, dz: torch.Tensor,
@@ -497,7 +498,7 @@ class _FusedTrainStep(torch.autograd.Function):
         g_rgb, g_dist, g_op, g_dl = c(g_rgb), c(g_dist), c(g_op), c(g_dl)
         cb = FusedTrainContext.c_buffers(b)
         with torch.cuda.device(dev):
-            _call(_L().perf_train_backward_composite, phase, S, tc.near, tc.far, R, _p(jitter), _p(bg_noise), C.byref(cb),
+            _call(_L().perf_train_backward_composite, phase, S, int(b["segments"].value), tc.near, tc.far, R, _p(jitter), _p(bg_noise), C.byref(cb),
                   _p(g_rgb), _p(g_dist), _p(g_op), _p(g_dl), _p(dist), _p(op), _p(dz), _stream())
         half = tc.geo_half if geo else tc.app_half
         # ONE flat gradient in the parameter layout [MLP | grid]: the GEMMs and the scatter write into it
