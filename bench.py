@@ -156,7 +156,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": "port",
                              "sample": f"{n_rays} rays x {S} samples of the benchmark panorama per step (oracle/render.py)"},
             "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def bench_train(dev, rank, world, steps=20, warmup=5):
@@ -300,10 +300,30 @@ def run_ours(args, rank, world, local_rank):
     if cpu_v is not None:
         line["cpu_baseline"] = {"value": cpu_v, "unit": "Msamples/s", "cores": cores, "kind": "port",
                                 "sample": f"4096 rays x {S} samples (row {H // 2} of the panorama), oracle/render.py mixed-precision restatement, {cpu_s:.1f} s"}
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Send everything libraries print to fd 1 (NCCL's version banner, ...) to stderr until emit()."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    """The ONE JSON line of the contract, on the real stdout."""
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
     print(json.dumps(line), flush=True)
 
 
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
