@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(const CompBwdArgs a)
         float gr = 0.f, gg = 0.f, gb = 0.f;
         if (a.g_rgb) { gr = a.g_rgb[3 * ray]; gg = a.g_rgb[3 * ray + 1]; gb = a.g_rgb[3 * ray + 2]; }
         const uint32_t kps = S / a.seg;
+#pragma unroll 4
         for (uint32_t k = 0; k < S; ++k) {
             const uint64_t row = (uint64_t)k * a.R + ray;
             const float w = a.w[row] * (a.seg > 1 ? a.toff[(uint64_t)(k / kps) * a.R + ray] : 1.f);
@@ -50,6 +51,7 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(const CompBwdArgs a)
         const float gdl = a.g_dl ? a.g_dl[ray] : 0.f;
         float Wsuf = 0.f, WMsuf = 0.f, suf_wg = 0.f;
         const uint32_t kps = S / a.seg;
+#pragma unroll 4
         for (uint32_t kk = S; kk-- > 0;) {
             const uint64_t row = (uint64_t)kk * a.R + ray;
             const float toff = a.seg > 1 ? a.toff[(uint64_t)(kk / kps) * a.R + ray] : 1.f;     // segment-local -> global
@@ -200,6 +202,10 @@ __global__ void __launch_bounds__(128) hashgrid_bwd_march_kernel(const __grid_co
     const int l = blockIdx.y;
     const uint64_t ray = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (ray >= a.R) return;
+    // blockIdx.z: piece of the ray walked by this thread (more threads, shorter dependent loops;
+    // costs one extra flush per piece)
+    const uint32_t k_per = (a.S + gridDim.z - 1) / gridDim.z;
+    const uint32_t k_lo = blockIdx.z * k_per, k_hi = min(a.S, k_lo + k_per);
     const float step = __fdiv_rn(__fsub_rn(a.far, a.near), (float)a.S);
     const float jit = a.jitter ? a.jitter[ray] : 0.f;
     const float ox = a.rays_o[3 * ray], oy = a.rays_o[3 * ray + 1], oz = a.rays_o[3 * ray + 2];
@@ -223,7 +229,8 @@ __global__ void __launch_bounds__(128) hashgrid_bwd_march_kernel(const __grid_co
             acc[k] = make_float2(0.f, 0.f);
         }
     };
-    for (uint32_t ks = 0; ks < a.S; ++ks) {
+#pragma unroll 2
+    for (uint32_t ks = k_lo; ks < k_hi; ++ks) {
         const float2 g = *reinterpret_cast<const float2*>(a.dfeat + ((uint64_t)ks * a.R + ray) * stride + 2 * l);
         if (g.x == 0.f && g.y == 0.f) continue;
         const float ts = __fadd_rn(a.near, __fmul_rn(__fadd_rn((float)ks, jit), step));
@@ -301,7 +308,10 @@ int perf_hashgrid_bwd_rays(const perf_grid_cfg* cfg, const float* aabb6, const f
     if (N == 0) return PERF_OK;
     // coarse levels: per-ray marching with register accumulation per cell; fine levels: direct atomics
     const uint32_t n_agg = a.lt.n_levels < 8 ? a.lt.n_levels : 8;
-    dim3 g_agg((unsigned)((R + 127) / 128), n_agg);
+    // enough (ray, level, piece) threads to fill the machine; pieces of >= 16 samples
+    unsigned pieces = 1;
+    while (pieces < 8 && (uint64_t)R * n_agg * pieces < (uint64_t)num_sms() * 2048 && n_samples / (pieces * 2) >= 16) pieces *= 2;
+    dim3 g_agg((unsigned)((R + 127) / 128), n_agg, pieces);
     hashgrid_bwd_march_kernel<<<g_agg, 128, 0, (cudaStream_t)stream>>>(a);
     PERF_LAUNCH_CHECK();
     if (a.lt.n_levels > n_agg) {

@@ -164,8 +164,9 @@ class RaySupervision:
         # sphere into the same warp, so their hash-grid gathers share cache lines at the coarse levels.
         # The batch is the same multiset of rays torch.randint drew (sup_info.py:253-257); only its order changes.
         yy, xx = torch.meshgrid(torch.arange(h, device=rgb.device), torch.arange(w, device=rgb.device), indexing="ij")
-        key = torch.zeros(h, w, dtype=torch.int64, device=rgb.device)
-        for b in range(16):
+        key = torch.zeros(h, w, dtype=torch.int32, device=rgb.device)   # int32: half the radix-sort passes of int64
+        xx, yy = xx.to(torch.int32), yy.to(torch.int32)
+        for b in range(15):                                              # panoramas up to 32768 x 32768
             key |= ((xx >> b) & 1) << (2 * b)
             key |= ((yy >> b) & 1) << (2 * b + 1)
         pool.locality_key = key.reshape(-1)
