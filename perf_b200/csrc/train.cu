@@ -30,7 +30,6 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(const CompBwdArgs a)
         float gr = 0.f, gg = 0.f, gb = 0.f;
         if (a.g_rgb) { gr = a.g_rgb[3 * ray]; gg = a.g_rgb[3 * ray + 1]; gb = a.g_rgb[3 * ray + 2]; }
         const uint32_t kps = S / a.seg;
-#pragma unroll 4
         for (uint32_t k = 0; k < S; ++k) {
             const uint64_t row = (uint64_t)k * a.R + ray;
             const float w = a.w[row] * (a.seg > 1 ? a.toff[(uint64_t)(k / kps) * a.R + ray] : 1.f);
@@ -51,7 +50,6 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(const CompBwdArgs a)
         const float gdl = a.g_dl ? a.g_dl[ray] : 0.f;
         float Wsuf = 0.f, WMsuf = 0.f, suf_wg = 0.f;
         const uint32_t kps = S / a.seg;
-#pragma unroll 4
         for (uint32_t kk = S; kk-- > 0;) {
             const uint64_t row = (uint64_t)kk * a.R + ray;
             const float toff = a.seg > 1 ? a.toff[(uint64_t)(kk / kps) * a.R + ray] : 1.f;     // segment-local -> global
