@@ -299,7 +299,8 @@ def run_ours(args, rank, world, local_rank):
         line["train"] = train
     if cpu_v is not None:
         line["cpu_baseline"] = {"value": cpu_v, "unit": "Msamples/s", "cores": cores, "kind": "port",
-                                "sample": f"4096 rays x {S} samples (row {H // 2} of the panorama), oracle/render.py mixed-precision restatement, {cpu_s:.1f} s"}
+                                "sample": f"4096 rays x {S} samples (row {H // 2} of the panorama), oracle/render.py mixed-precision restatement, {cpu_s:.1f} s; "
+                                          f"threads capped at 16 of {os.cpu_count()} (the oracle is many small torch ops and slows down beyond that)"}
     emit(line)
 
 
