@@ -94,3 +94,25 @@ def test_product_does_not_import_oracle():
         for f in files:
             if f.endswith(".py"):
                 assert "import oracle" not in open(os.path.join(dirpath, f)).read(), f
+
+
+def test_level_table_matches_oracle_property():
+    """Randomised configurations (hypothesis): the library's host-side level table (fp32 scale bits,
+    resolution, size, offset, hashed flag) equals the oracle's restatement of tcnn's constructor."""
+    from hypothesis import given, settings, strategies as st
+    from perf_b200.config import GridConfig
+
+    @settings(max_examples=60, deadline=None)
+    @given(n_levels=st.integers(1, 16), log2t=st.integers(8, 22), base=st.sampled_from([4, 8, 16, 32]),
+           scale=st.floats(1.0625, 2.0, allow_nan=False, width=32))
+    def check(n_levels, log2t, base, scale):
+        cfg = OGrid(n_levels=n_levels, log2_hashmap_size=log2t, base_resolution=base, per_level_scale=float(np.float32(scale)))
+        want = level_table(cfg)
+        if want[-1].offset + want[-1].size >= 2 ** 31:
+            return
+        lv, n = GridConfig(n_levels, 2, log2t, base, float(np.float32(scale))).levels()
+        assert n == want[-1].offset + want[-1].size
+        for a, b in zip(lv, want):
+            assert np.float32(a.scale) == b.scale
+            assert (a.resolution, a.size, a.offset, bool(a.hashed)) == (b.resolution, b.size, b.offset, b.hashed)
+    check()
