@@ -125,7 +125,9 @@ def cpu_oracle_sample(n_rays, threads=None):
     field = oracle.Field(net(oracle.field.GEO_MLP), net(oracle.field.APP_MLP))
     o, d = oracle.gen_pano_rays(bench_pose(), H, W)
     # rays from the middle rows (the poles are degenerate)
-    o, d = o[H // 2].reshape(-1, 3)[:n_rays], d[H // 2].reshape(-1, 3)[:n_rays]
+    rows_needed = (n_rays + W - 1) // W
+    o, d = o[H // 2:H // 2 + rows_needed].reshape(-1, 3)[:n_rays], d[H // 2:H // 2 + rows_needed].reshape(-1, 3)[:n_rays]
+    n_rays = o.shape[0]
     t0 = time.perf_counter()
     with torch.no_grad():
         out = oracle.render_rays(field, o, d, S, mixed=True, accum=torch.float32)
@@ -313,7 +315,7 @@ def run_ours(args, rank, world, local_rank):
         line["train"] = train
     if cpu_v is not None:
         line["cpu_baseline"] = {"value": cpu_v, "unit": "Msamples/s", "cores": cores, "kind": "port",
-                                "sample": f"4096 rays x {S} samples (row {H // 2} of the panorama), oracle/render.py mixed-precision restatement, {cpu_s:.1f} s; "
+                                "sample": f"4096 rays x {S} samples (rows {H // 2}-{H // 2 + 1} of the panorama), oracle/render.py mixed-precision restatement, {cpu_s:.1f} s; "
                                           f"threads capped at 16 of {os.cpu_count()} (the oracle is many small torch ops and slows down beyond that)"}
     emit(line)
 
