@@ -42,13 +42,19 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every .cu under csrc/ into perf_b200/libperfb200.so.  Returns the path."""
     if not force and not is_stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + sources() + ["-o", LIB + ".tmp"]
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
-    os.replace(LIB + ".tmp", LIB)
-    if verbose:
-        print(proc.stderr)
+    import fcntl
+    with open(os.path.join(HERE, ".build.lock"), "w") as lock:      # several ranks may import at once
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not is_stale():                            # another process built it meanwhile
+            return LIB
+        tmp = f"{LIB}.{os.getpid()}.tmp"
+        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + sources() + ["-o", tmp]
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+        os.replace(tmp, LIB)
+        if verbose:
+            print(proc.stderr)
     return LIB
 
 
