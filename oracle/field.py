@@ -38,7 +38,7 @@ def network_forward(x01: torch.Tensor, params: torch.Tensor, grid: GridConfig,
     p = params.detach().float()
     if mixed:
         p = p.half().float()
-    feat = encode(x01, p[n_mlp:], grid, out_half=mixed, exact_fma=(accum == torch.float64))
+    feat = encode(x01, p[n_mlp:], grid, out_half=mixed, exact_fma=(accum == torch.float64), blend="half" if mixed else "fp32")
     return mlp_forward(feat, split_params(p[:n_mlp], mlp), mlp, mixed=mixed, accum=accum)
 
 

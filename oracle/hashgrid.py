@@ -12,10 +12,12 @@ Every upstream-derived rule lives in exactly one named function here:
 ``grid_index`` (dense stride walk, xor-prime hash, ``% hashmap_size``),
 ``encode`` (8-corner trilinear blend, corner order bit0=x, level-major output).
 
-Stated deviation from upstream: tcnn blends in ``__half``; we blend in fp32
-(`fmaf` chain in corner order 0..7) and round the finished feature to fp16 only when
-``out_half=True``.  The CUDA kernels do exactly the same, so oracle and kernel are
-comparable to the bit.
+Blend arithmetic: ``blend="half"`` is tcnn's own for ``__half`` parameters --
+``result = fma((half)weight_k, value_k, result)`` over corners k = 0..7 with ONE fp16
+rounding per fma, starting from zero -- and is what the CUDA kernels implement (HFMA2),
+so oracle and kernel are comparable to the bit.  ``blend="fp32"`` (fp32 `fmaf` chain,
+optionally rounded to fp16 at the end) is the plain-precision reference used by the
+``mixed=False`` field and by gradient checks.
 """
 from __future__ import annotations
 
@@ -152,21 +154,42 @@ def _corner_weights_indices(x01: torch.Tensor, lvl: Level, smoothstep: bool):
     return out
 
 
+def _round_half_exact(x64: torch.Tensor) -> torch.Tensor:
+    """fp64 -> fp16 with ONE correct rounding (numpy converts directly; torch goes through fp32)."""
+    return torch.from_numpy(x64.numpy().astype(np.float16))
+
+
 def encode(x01: torch.Tensor, table: torch.Tensor, cfg: GridConfig = GridConfig(),
-           out_half: bool = False, exact_fma: bool = True) -> torch.Tensor:
+           out_half: bool = False, exact_fma: bool = True, blend: str = "fp32") -> torch.Tensor:
     """Hash-grid encode.  ``x01`` [N,3] fp32 in [0,1]; ``table`` [n_entries, F] (any float
     dtype; values are used as fp32).  Returns [N, L*F] fp32, level-major
-    (``[l0f0, l0f1, l1f0, ...]``); with ``out_half`` the values are rounded to fp16
-    (tcnn's encoded output dtype) and returned as fp32.  ``exact_fma=False`` blends with plain
-    fp32 ``acc + w*v`` (two roundings) -- the fast variant used when the oracle is *timed* as the
-    CPU baseline; results differ from the exact chain by <= 1 fp32 ulp per corner."""
-    assert x01.dim() == 2 and x01.shape[1] == 3
+    (``[l0f0, l0f1, l1f0, ...]``).
+
+    ``blend="half"``: tcnn's fp16 fma chain (table values and weights rounded to fp16, one
+    fp16 rounding per corner); the result is fp16-valued.  ``blend="fp32"``: fp32 fmaf chain;
+    with ``out_half`` the finished feature is rounded to fp16.  ``exact_fma=False`` selects
+    the fast variants used when the oracle is *timed* as the CPU baseline (fp32 intermediates
+    instead of fp64: identical except on rounding ties)."""
+    assert x01.dim() == 2 and x01.shape[1] == 3 and blend in ("fp32", "half")
     F = cfg.n_features_per_level
     table = table.reshape(-1, F).float()
     x01 = x01.float()
     feats = []
     for lvl in level_table(cfg):
-        if exact_fma:
+        if blend == "half":
+            corners = _corner_weights_indices(x01, lvl, cfg.interpolation == "Smoothstep")
+            if exact_fma and not table.requires_grad:
+                acc = torch.zeros(x01.shape[0], F, dtype=torch.float64)
+                for wt, idx in corners:
+                    acc = _round_half_exact(wt.half().double()[:, None] * table[idx].half().double() + acc).double()
+                feats.append(acc.float())
+            else:
+                # differentiable / fast variant: fp32 intermediate, fp16 rounding as a straight-through cast
+                acc = torch.zeros(x01.shape[0], F)
+                for wt, idx in corners:
+                    acc = (wt.half().float()[:, None] * table[idx].half().float() + acc).half().float()
+                feats.append(acc)
+        elif exact_fma:
             acc = torch.zeros(x01.shape[0], F, dtype=torch.float64)
             for wt, idx in _corner_weights_indices(x01, lvl, cfg.interpolation == "Smoothstep"):
                 # fp32 fmaf(weight, value, acc): exact product + add in fp64, one fp32 rounding

@@ -8,7 +8,8 @@ density net 32 -> 64 ReLU -> 1 (no output activation), colour net
 ``[out, in]``; the last matrix is padded to 16 output rows of which only the first
 ``n_output_dims`` are meaningful.
 
-Precision contract (``mixed=True``, what the CUDA path implements): operands are
+Precision contract (``mixed=True``, what the CUDA path implements; the encode feeding it
+uses tcnn's fp16 blend, see ``oracle/hashgrid.py``): operands are
 fp16 (input features, weights, hidden activations after ReLU), every dot product is
 accumulated wider (tcnn: fp16 accumulators; ours: fp32 in TMEM -- stated deviation,
 strictly more accurate), the output pre-activation is rounded to fp16, the output

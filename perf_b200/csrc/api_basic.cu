@@ -179,10 +179,7 @@ hashgrid_fwd_kernel(LevelTable lt, const uint32_t* __restrict__ table, const flo
             uint32_t v[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) v[k] = __ldg(table + c.idx[k]);
-            float f0 = 0.f, f1 = 0.f;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) { float2 t = unpack_half2(v[k]); f0 = fmaf(c.w[k], t.x, f0); f1 = fmaf(c.w[k], t.y, f1); }
-            packed[l] = pack_half2(f0, f1);
+            packed[l] = blend8_half(c.w, v);
         }
     }
     uint32_t* dst = feat + i * lt.n_levels;

@@ -141,6 +141,17 @@ __device__ __forceinline__ float2 unpack_half2(uint32_t u)
 }
 __device__ __forceinline__ float round_half(float v) { return __half2float(__float2half_rn(v)); }
 
+// Trilinear blend of one level, exactly as tcnn's kernel_grid does it for __half parameters:
+// result = fma((half)weight_k, value_k, result) for corners k = 0..7, one fp16 rounding per fma
+// (HFMA2 on the feature pair), starting from zero.  Mirrored by oracle/hashgrid.py::encode(blend="half").
+__device__ __forceinline__ uint32_t blend8_half(const float (&w)[8], const uint32_t (&v)[8])
+{
+    __half2 acc = __float2half2_rn(0.f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc = __hfma2(__float2half2_rn(w[k]), *reinterpret_cast<const __half2*>(&v[k]), acc);
+    return *reinterpret_cast<uint32_t*>(&acc);
+}
+
 // ---------------------------------------------------------------- device: tcgen05 / mbarrier PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

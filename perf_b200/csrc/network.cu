@@ -83,10 +83,7 @@ __global__ void __launch_bounds__(TILE, 4) network_fwd_kernel(const __grid_const
                 uint32_t v[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) v[k] = __ldg(a.table + c.idx[k]);
-                float f0 = 0.f, f1 = 0.f;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) { const float2 t = unpack_half2(v[k]); f0 = fmaf(c.w[k], t.x, f0); f1 = fmaf(c.w[k], t.y, f1); }
-                packed[l] = pack_half2(f0, f1);
+                packed[l] = blend8_half(c.w, v);
             }
         } else {
 #pragma unroll

@@ -159,14 +159,10 @@ __device__ __forceinline__ void encode_group(const RenderArgs& a, const RenderSm
         uint2 v[8];
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) v[kk] = __ldg(a.table + c.idx[kk]);
-        float g0 = 0.f, g1 = 0.f, a0 = 0.f, a1 = 0.f;
+        uint32_t vg[8], va[8];
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-            const float2 tg = unpack_half2(v[kk].x), ta = unpack_half2(v[kk].y);
-            g0 = fmaf(c.w[kk], tg.x, g0); g1 = fmaf(c.w[kk], tg.y, g1);
-            a0 = fmaf(c.w[kk], ta.x, a0); a1 = fmaf(c.w[kk], ta.y, a1);
-        }
-        pg[ll] = pack_half2(g0, g1); pa[ll] = pack_half2(a0, a1);
+        for (int kk = 0; kk < 8; ++kk) { vg[kk] = v[kk].x; va[kk] = v[kk].y; }
+        pg[ll] = blend8_half(c.w, vg); pa[ll] = blend8_half(c.w, va);
     }
     *reinterpret_cast<uint4*>(sm.sAg + (q * TILE + tid) * 16) = make_uint4(pg[0], pg[1], pg[2], pg[3]);
     *reinterpret_cast<uint4*>(sm.sAa + (q * TILE + tid) * 16) = make_uint4(pa[0], pa[1], pa[2], pa[3]);

@@ -81,7 +81,7 @@ def test_network_fwd_matches_oracle(ops, golden_field, net, simt):
     n_mlp = flat_param_count(ocfg)
     ph = params.half()
     want = network_forward(x, params, O_GRID, ocfg, mixed=True)
-    feat_want = encode(x, ph.float()[n_mlp:], O_GRID, out_half=True)
+    feat_want = encode(x, ph.float()[n_mlp:], O_GRID, blend="half")
     out, feat, h1, h2 = ops.network_fwd(ph.cuda(), x.cuda(), PERF_GRID, pcfg, save=True, simt=simt)
     assert_close_half(feat, feat_want, "feat", atol=1e-3, frac_exact=0.995)
     hs = mlp_hidden(feat_want, split_params(ph.float()[:n_mlp], ocfg), ocfg)
@@ -106,7 +106,7 @@ def test_network_autograd_matches_oracle_autograd(ops, golden_field, net):
     dout = torch.randn(N, ocfg.n_out, generator=g)
     n_mlp = flat_param_count(ocfg)
     p_ref = params.clone().requires_grad_(True)
-    feat = encode(x, p_ref[n_mlp:], O_GRID, out_half=True)
+    feat = encode(x, p_ref[n_mlp:], O_GRID, blend="half")
     y = mlp_forward(feat, split_params(p_ref[:n_mlp], ocfg), ocfg, mixed=True)
     (y * dout).sum().backward()
     p = params.cuda().requires_grad_(True)

@@ -29,9 +29,9 @@ def oracle_train_forward(field, p_geo, p_app, o, d, S, jitter, noise):
     x01 = ((pos + 1) / 2).reshape(-1, 3)
     sel = ((x01 > 0) & (x01 < 1)).all(-1)
     ng, na = flat_param_count(O_GEO), flat_param_count(O_APP)
-    raw = mlp_forward(encode(x01, p_geo[ng:], O_GRID, out_half=True), split_params(p_geo[:ng], O_GEO), O_GEO, mixed=True)
+    raw = mlp_forward(encode(x01, p_geo[ng:], O_GRID, blend="half"), split_params(p_geo[:ng], O_GEO), O_GEO, mixed=True)
     sig = (torch.exp(raw[:, 0]) * sel).reshape(-1, S)
-    rgb = (mlp_forward(encode(x01, p_app[na:], O_GRID, out_half=True), split_params(p_app[:na], O_APP), O_APP, mixed=True)
+    rgb = (mlp_forward(encode(x01, p_app[na:], O_GRID, blend="half"), split_params(p_app[:na], O_APP), O_APP, mixed=True)
            * sel[:, None]).reshape(-1, S, 3)
     w, T, _ = oracle.render_weight_from_density(ts, te, sig)
     op = w.sum(-1, keepdim=True)
