@@ -28,8 +28,8 @@ def _init_params(grid: GridConfig, mlp, seed: int) -> torch.Tensor:
                  + [(mlp.padded_out, mlp.n_neurons)]
         for o, i in shapes:
             lim = (6.0 / (o + i)) ** 0.5
-            parts.append((torch.rand(o * i, generator=g) * 2 - 1) * lim)
-    parts.append((torch.rand(grid.n_entries * grid.n_features_per_level, generator=g) * 2 - 1) * 1e-4)
+            parts.append((torch.rand(o * i, generator=g, device="cpu") * 2 - 1) * lim)
+    parts.append((torch.rand(grid.n_entries * grid.n_features_per_level, generator=g, device="cpu") * 2 - 1) * 1e-4)
     return torch.cat(parts)
 
 

@@ -229,3 +229,25 @@ def test_occ_estimator_shim_end_to_end(ops, golden_field):
     from perf_b200.shims import nerfacc
     w, T, _ = nerfacc.render_weight_from_density(ts, te, sig, ray_indices=ri, n_rays=R)
     np.testing.assert_allclose(w.cpu().numpy(), w0.numpy(), rtol=1e-4, atol=1e-6)
+
+
+def test_shims_under_cuda_default_tensor_type(golden_field):
+    """The reference's main() makes CUDA the default tensor type (core_exp_runner.py:266); the plugin
+    modules must construct and run in that regime (parameters land on the GPU like tcnn's)."""
+    import perf_b200.shims.tinycudann as tcnn
+    from perf_b200.field import ENCODING_CONFIG, GEO_NETWORK_CONFIG
+    from perf_b200.shims.nerfacc.estimators.occ_grid import OccGridEstimator
+    torch.set_default_device("cuda")
+    try:
+        net = tcnn.NetworkWithInputEncoding(3, 1, ENCODING_CONFIG, GEO_NETWORK_CONFIG)
+        assert net.params.is_cuda and net.params.dtype == torch.float32
+        y = net(torch.rand(100, 3))
+        assert y.is_cuda and y.dtype == torch.float16 and y.shape == (100, 1)
+        est = OccGridEstimator(roi_aabb=torch.tensor([-1., -1., -1., 1., 1., 1.]), resolution=16, levels=1)
+        assert est.binaries.is_cuda
+        est.binaries |= True
+        ri, ts, te = est.sampling(torch.zeros(4, 3), torch.nn.functional.normalize(torch.rand(4, 3), dim=-1), near_plane=0., far_plane=1.5,
+                                  render_step_size=0.05, stratified=True)
+        assert ri.numel() > 0
+    finally:
+        torch.set_default_device("cpu")
