@@ -166,3 +166,31 @@ def test_distloss_matches_quadratic_definition():
     brute = ((w[:, :, None] * w[:, None, :] * (m[:, :, None] - m[:, None, :]).abs()).sum()
              + (w * w * iv).sum() / 3) / R
     assert torch.allclose(fast, brute, atol=1e-6)
+
+
+def test_host_fixed_sampler_equals_oracle():
+    """perf_b200.scene.FixedSampleEstimator (host-side torch code feeding the modular path) produces
+    the oracle's intervals bit for bit, packed ray-major."""
+    from perf_b200.scene import FixedSampleEstimator
+    g = torch.Generator().manual_seed(9)
+    R, S = 13, 24
+    jit = torch.rand(R, generator=g)
+    est = FixedSampleEstimator(S, 1e-2, 1.0)
+    o = torch.zeros(R, 3)
+    for stratified, j in ((False, None), (True, jit)):
+        ri, ts, te = est.sampling(o, o, stratified=stratified, jitter=j)
+        ts0, te0 = oracle.fixed_samples(R, S, 1e-2, 1.0, j)
+        assert torch.equal(ts, ts0.reshape(-1)) and torch.equal(te, te0.reshape(-1))
+        assert torch.equal(ri, torch.arange(R).repeat_interleave(S))
+
+
+def test_config_loader_overrides(tmp_path):
+    from perf_b200.config import load_config
+    (tmp_path / "device").mkdir()
+    (tmp_path / "device" / "local.yaml").write_text("base_exp_dir: /tmp/exp\n")
+    (tmp_path / "nerf.yaml").write_text("defaults:\n  - device: local\n  - _self_\nmode: train\nscene:\n  estimator_type: occ\n"
+                                        "  train_conf:\n    geo_optimizer:\n      peak_lr: 1e-2\n    pixel_loss_batch_size: 8192\n")
+    c = load_config(str(tmp_path), "nerf", ["mode=render_dense", "scene.train_conf.pixel_loss_batch_size=1024", "scene.new.key=0.5"])
+    assert c.mode == "render_dense" and c.device.base_exp_dir == "/tmp/exp"
+    assert c.scene.train_conf.geo_optimizer.peak_lr == 1e-2 and isinstance(c.scene.train_conf.geo_optimizer.peak_lr, float)
+    assert c.scene.train_conf.pixel_loss_batch_size == 1024 and c.scene.new.key == 0.5

@@ -95,3 +95,49 @@ def test_distloss_shim_matches_oracle():
     assert torch.allclose(c, b, atol=1e-6)
     a.backward()
     assert torch.isfinite(w.grad).all()
+
+
+class _Opt:
+    def __init__(self):
+        self.param_groups = [{"lr": 0.0}]
+
+
+def test_lr_schedule_matches_reference(reference_modules):
+    """`NeRFScene.update_lr` (nerf.py:300-311) of the reference vs ours over the whole schedule,
+    with the optimiser settings of configs/nerf.yaml read by our hydra-less loader."""
+    from perf_b200.config import load_config
+    from perf_b200.scene import NeRFScene as Ours
+    _, _, nerf_scene = reference_modules
+    conf = load_config(os.path.join(REF, "configs"), "nerf")
+    oc = conf.scene.train_conf.geo_optimizer
+    assert (oc.init_lr, oc.peak_lr, oc.peak_at, oc.lr_alpha) == (0.0, 1e-2, 0.2, 1e-2)
+    assert conf.scene.estimator_type == "occ" and conf.scene.train_conf.pixel_loss_batch_size == 8192
+    assert conf.device.base_exp_dir == "."
+    a, b = _Opt(), _Opt()
+    for i in range(0, 3000, 37):
+        nerf_scene.NeRFScene.update_lr(None, a, oc, i / 3000)
+        Ours.update_lr(None, b, oc, i / 3000)
+        assert abs(a.param_groups[0]["lr"] - b.param_groups[0]["lr"]) < 1e-12
+
+
+def test_gen_occ_grid_and_batch_sampler_match_reference(reference_modules):
+    """`SupInfoPool.gen_occ_grid` (sup_info.py:304-330) and the to_bounded_rays constants
+    (nerf.py:313-319): the reference's functions run on a stand-in `self` vs our RaySupervision."""
+    from types import SimpleNamespace
+    from modules.dataset import sup_info
+    from utils.camera_utils import Rays as RefRays
+    from perf_b200.scene import RaySupervision, Rays, NeRFScene as Ours
+    g = torch.Generator().manual_seed(0)
+    n = 5000
+    o = (torch.rand(n, 3, generator=g) - .5) * .2
+    d = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1)
+    dist = torch.rand(n, 1, generator=g) * .8 + .05
+    fake = SimpleNamespace(all_sup_rays=RefRays(o, d), all_sup_distances=dist)
+    ref_grid, ref_pts = sup_info.SupInfoPool.gen_occ_grid(fake, res=32)
+    pool = RaySupervision(Rays(o, d), torch.rand(n, 3, generator=g), dist)
+    grid, pts = pool.gen_occ_grid(32)
+    assert torch.equal(grid, ref_grid) and torch.equal(pts, ref_pts)
+    _, _, nerf_scene = reference_modules
+    br_ref = nerf_scene.NeRFScene.to_bounded_rays(None, RefRays(o, d))
+    br = Ours.to_bounded_rays(None, Rays(o, d))
+    assert torch.equal(br.near, br_ref.near) and torch.equal(br.far, br_ref.far)
