@@ -137,6 +137,17 @@ __device__ __forceinline__ void ray_scan(float (&val)[NV], float (&excl)[NV], ui
     }
 }
 
+// Pixel-patch tiling of a 128-thread tile: a warp covers PATCH_WW x PATCH_WH pixels, the CTA's four
+// warps are arranged PATCH_WX x PATCH_WY.
+#ifndef PATCH_WW
+#define PATCH_WW 8
+#define PATCH_WH 4
+#define PATCH_WX 2
+#define PATCH_WY 2
+#endif
+constexpr int PATCH_W = PATCH_WW * PATCH_WX, PATCH_H = PATCH_WH * PATCH_WY;
+static_assert(PATCH_WW * PATCH_WH == 32 && PATCH_WX * PATCH_WY == 4, "a warp is 32 pixels, a tile 4 warps");
+
 struct RenderSmem {
     uint8_t *sA, *sAg, *sAa, *sW1g, *sW1a, *sW2a;
     float *sWoutG, *sWoutA;
@@ -450,11 +461,11 @@ __global__ void __launch_bounds__(TILE, 4) render_march_kernel(const __grid_cons
     // tiles are 16x8 pixel patches; otherwise 128 consecutive rays
     const bool patch = PANO || a.W > 0;
     const int rows = patch ? (int)(a.R / (uint64_t)a.W) : 0;
-    const uint32_t tiles_x = patch ? (uint32_t)((a.W + 15) / 16) : 0u;
+    const uint32_t tiles_x = patch ? (uint32_t)((a.W + PATCH_W - 1) / PATCH_W) : 0u;
     const uint32_t seg = (PANO || patch || a.pk_offsets != nullptr || a.seg == 0) ? 1u : a.seg;
     const uint32_t rpt = TILE / seg, kps = S / seg;                 // rays per tile, samples per segment
     const uint32_t my_seg = (uint32_t)tid / rpt;
-    const uint64_t n_tiles = patch ? (uint64_t)tiles_x * (uint64_t)((rows + 7) / 8) : (a.R + rpt - 1) / rpt;
+    const uint64_t n_tiles = patch ? (uint64_t)tiles_x * (uint64_t)((rows + PATCH_H - 1) / PATCH_H) : (a.R + rpt - 1) / rpt;
 
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         // ---- this thread's ray
@@ -462,8 +473,8 @@ __global__ void __launch_bounds__(TILE, 4) render_march_kernel(const __grid_cons
         float ox = 0.f, oy = 0.f, oz = 0.f, dx = 1.f, dy = 0.f, dz = 0.f, jit = 0.f;
         if constexpr (PANO) {
             const int ty = (int)(tile / tiles_x), tx = (int)(tile % tiles_x);
-            const int prow = ty * 8 + (warp >> 1) * 4 + (lane >> 3);          // row inside the window
-            const int pcol = tx * 16 + (warp & 1) * 8 + (lane & 7);
+            const int prow = ty * PATCH_H + (warp / PATCH_WX) * PATCH_WH + lane / PATCH_WW;   // row inside the window
+            const int pcol = tx * PATCH_W + (warp % PATCH_WX) * PATCH_WW + lane % PATCH_WW;
             valid = prow < rows && pcol < a.W;
             ray = (uint64_t)prow * (uint64_t)a.W + (uint64_t)pcol;
             if (valid) {
@@ -481,7 +492,8 @@ __global__ void __launch_bounds__(TILE, 4) render_march_kernel(const __grid_cons
         } else {
             if (patch) {
                 const int ty = (int)(tile / tiles_x), tx = (int)(tile % tiles_x);
-                const int prow = ty * 8 + (warp >> 1) * 4 + (lane >> 3), pcol = tx * 16 + (warp & 1) * 8 + (lane & 7);
+                const int prow = ty * PATCH_H + (warp / PATCH_WX) * PATCH_WH + lane / PATCH_WW;
+                const int pcol = tx * PATCH_W + (warp % PATCH_WX) * PATCH_WW + lane % PATCH_WW;
                 valid = prow < rows && pcol < a.W;
                 ray = (uint64_t)prow * (uint64_t)a.W + (uint64_t)pcol;
             } else {
@@ -638,8 +650,7 @@ static int launch_render(const perf_render_args* args, RenderArgs& a, bool pano,
     const bool scan = (args->flags & PERF_FLAG_SCAN_KERNEL) != 0;
     uint64_t n_work;
     if (scan) n_work = (a.R + a.rays_per_unit - 1) / a.rays_per_unit;
-    else if (pano) n_work = (uint64_t)((a.W + 15) / 16) * (uint64_t)(((int)(a.R / (uint64_t)a.W) + 7) / 8);
-    else if (a.W > 0) n_work = (uint64_t)((a.W + 15) / 16) * (uint64_t)(((int)(a.R / (uint64_t)a.W) + 7) / 8);
+    else if (pano || a.W > 0) n_work = (uint64_t)((a.W + PATCH_W - 1) / PATCH_W) * (uint64_t)(((int)(a.R / (uint64_t)a.W) + PATCH_H - 1) / PATCH_H);
     else {
         const uint32_t rpt = TILE / (a.seg ? a.seg : 1u);
         n_work = (a.R + rpt - 1) / rpt;
@@ -648,7 +659,8 @@ static int launch_render(const perf_render_args* args, RenderArgs& a, bool pano,
 #define PERF_RENDER_LAUNCH(...) do { \
         auto k = __VA_ARGS__; \
         static thread_local int attr_dev = -1; int dev_ = 0; PERF_CUDA(cudaGetDevice(&dev_)); \
-        if (attr_dev != dev_) { PERF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_TOTAL)); attr_dev = dev_; } \
+        if (attr_dev != dev_) { PERF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_TOTAL)); \
+            attr_dev = dev_; } \
         k<<<grid, TILE, RS_TOTAL, stream>>>(a); } while (0)
     const bool fast = fast_addressing_ok(a.lt, 4) && (args->flags & PERF_FLAG_GENERIC_ADDR) == 0;   // PeRF's grid: 4 dense + 12 hashed levels
     if (save != 0) {
