@@ -218,10 +218,16 @@ class _NetworkFunction(torch.autograd.Function):
     def backward(ctx, dout):
         x01, params_half, feat, h1, h2, out = ctx.saved_tensors
         grid, mlp = ctx.grid, ctx.mlp
-        d_w, dfeat = mlp_backward(mlp, params_half[:mlp.n_params], feat, h1,
-                                  h2 if mlp.n_hidden_layers == 2 else None, out, dout)
-        d_table = hashgrid_bwd(x01, dfeat, grid)
-        return torch.cat([d_w, d_table.reshape(-1)]), None, None, None, None
+        dz = dout.float()
+        if mlp.output_activation == "Sigmoid":
+            y = out.float()
+            dz = dz * y * (1.0 - y)
+        # one flat gradient in the parameter layout [MLP | grid]; fp16 tensor-core GEMMs for the MLP part
+        grad = torch.zeros(mlp.n_params + 2 * grid.n_entries, dtype=torch.float32, device=dz.device)
+        _, dfeat = mlp_backward_half(mlp, params_half[:mlp.n_params], feat, h1, h2 if mlp.n_hidden_layers == 2 else None,
+                                     dz.contiguous(), grad_out=grad[:mlp.n_params])
+        hashgrid_bwd(x01, dfeat, grid, out=grad[mlp.n_params:].view(-1, 2))
+        return grad, None, None, None, None
 
 
 def network_apply(params: torch.Tensor, x01: torch.Tensor, grid: GridConfig, mlp: MLPConfig,
