@@ -37,13 +37,14 @@ int build_level_table(const perf_grid_cfg* cfg, LevelTable* out, uint64_t* n_ent
     PERF_CHECK_ARG(cfg->base_resolution >= 1 && cfg->per_level_scale >= 1.0f, "bad base_resolution / per_level_scale");
     LevelTable lt; memset(&lt, 0, sizeof(lt));
     lt.n_levels = cfg->n_levels; lt.smoothstep = cfg->interpolation;
-    const float log2s = log2f(cfg->per_level_scale);
+    // tcnn: scale = exp2f(l * log2f(s)) * base - 1 in fp32 ON THE DEVICE; libm / CUDA exp2f differ by
+    // an ulp, so the product is defined here in fp64 with ONE rounding to fp32 (libm-independent;
+    // mirrored by oracle/hashgrid.py::grid_scale and property-tested in tests/test_abi.py)
+    const float log2s = (float)log2((double)cfg->per_level_scale);
     uint64_t offset = 0;
     for (uint32_t l = 0; l < cfg->n_levels; ++l) {
         volatile float x = (float)l * log2s;
-        volatile float e = exp2f(x);
-        volatile float m = e * (float)cfg->base_resolution;
-        const float scale = m - 1.0f;
+        const float scale = (float)(exp2((double)x) * (double)cfg->base_resolution - 1.0);
         const uint32_t res = (uint32_t)ceilf(scale) + 1u;
         const uint64_t max_params = 0xFFFFFFFFull / 2;
         uint64_t dense = ((double)res * res * res > (double)max_params) ? max_params : (uint64_t)res * res * res;

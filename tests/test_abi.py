@@ -102,7 +102,7 @@ def test_level_table_matches_oracle_property():
     from hypothesis import given, settings, strategies as st
     from perf_b200.config import GridConfig
 
-    @settings(max_examples=60, deadline=None)
+    @settings(max_examples=300, deadline=None)
     @given(n_levels=st.integers(1, 16), log2t=st.integers(8, 22), base=st.sampled_from([4, 8, 16, 32]),
            scale=st.floats(1.0625, 2.0, allow_nan=False, width=32))
     def check(n_levels, log2t, base, scale):
