@@ -195,41 +195,66 @@ hashgrid_fwd_kernel(LevelTable lt, const uint32_t* __restrict__ table, const flo
 }
 
 // ---- hash-grid backward (tcnn kernel_grid_backward): dtable[idx] += w * dfeat, float2 atomics.
-// One thread per (sample, level): neighbouring threads of a warp work on the same level of
-// neighbouring samples, which keeps the atomics of a warp inside one level's table.
+// One thread per (sample, level): the threads of a warp work on the same level of neighbouring
+// samples.  MERGE (coarse levels): samples arrive ray-major, so neighbouring lanes usually sit in the
+// SAME cell (a level-0 cell holds ~17 consecutive samples of a ray); runs of equal cells are summed
+// with a segmented warp scan and only the last lane of a run issues the 8 atomics -- this removes
+// most of the same-address traffic on the few coarse cells every ray crosses near the camera.
+template <bool MERGE>
 __global__ void __launch_bounds__(256)
-hashgrid_bwd_kernel(LevelTable lt, const float* __restrict__ x01, const float* __restrict__ dfeat,
+hashgrid_bwd_kernel(LevelTable lt, int level0, const float* __restrict__ x01, const float* __restrict__ dfeat,
                     uint64_t N, float2* __restrict__ dtable)
 {
-    const int l = blockIdx.y;
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    const float2 g = *reinterpret_cast<const float2*>(dfeat + i * (2 * lt.n_levels) + 2 * l);
-    if (g.x == 0.f && g.y == 0.f) return;
-    const float x = x01[3 * i], y = x01[3 * i + 1], z = x01[3 * i + 2];
-    // level index must be a compile-time-like constant for the by-value table: copy the fields
-    LevelTable const& t = lt;
-    Corner8 c;
-    {
-        // dynamic l: index the parameter arrays directly (constant bank, dynamic index is fine)
-        const float scale = t.scale[l];
-        const uint32_t res = t.res[l], size = t.size[l], off = t.offset[l];
-        const bool hashed = (t.hashed_mask >> l) & 1u, pow2 = (t.pow2_mask >> l) & 1u;
-        float px = fmaf(scale, x, 0.5f), py = fmaf(scale, y, 0.5f), pz = fmaf(scale, z, 0.5f);
-        float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
-        uint32_t gx = (uint32_t)(int)fx, gy = (uint32_t)(int)fy, gz = (uint32_t)(int)fz;
-        float wx = px - fx, wy = py - fy, wz = pz - fz;
-        if (t.smoothstep) { wx = wx * wx * (3.f - 2.f * wx); wy = wy * wy * (3.f - 2.f * wy); wz = wz * wz * (3.f - 2.f * wz); }
-        const float ox = 1.f - wx, oy = 1.f - wy, oz = 1.f - wz;
+    const int l = level0 + blockIdx.y, lane = threadIdx.x & 31;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < N;
+    float2 g = make_float2(0.f, 0.f);
+    float x = 0.5f, y = 0.5f, z = 0.5f;
+    if (live) {
+        g = *reinterpret_cast<const float2*>(dfeat + i * (2 * lt.n_levels) + 2 * l);
+        x = x01[3 * i]; y = x01[3 * i + 1]; z = x01[3 * i + 2];
+    }
+    const bool active = live && (g.x != 0.f || g.y != 0.f);
+    if (!MERGE && !active) return;
+    const float scale = lt.scale[l];
+    const uint32_t res = lt.res[l], size = lt.size[l], off = lt.offset[l];
+    const bool hashed = (lt.hashed_mask >> l) & 1u, pow2 = (lt.pow2_mask >> l) & 1u;
+    const float px = fmaf(scale, x, 0.5f), py = fmaf(scale, y, 0.5f), pz = fmaf(scale, z, 0.5f);
+    const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+    const uint32_t gx = (uint32_t)(int)fx, gy = (uint32_t)(int)fy, gz = (uint32_t)(int)fz;
+    float wx = px - fx, wy = py - fy, wz = pz - fz;
+    if (lt.smoothstep) { wx = wx * wx * (3.f - 2.f * wx); wy = wy * wy * (3.f - 2.f * wy); wz = wz * wz * (3.f - 2.f * wz); }
+    const float ox = 1.f - wx, oy = 1.f - wy, oz = 1.f - wz;
+    float2 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float w = active ? __fmul_rn(__fmul_rn((k & 1) ? wx : ox, (k & 2) ? wy : oy), (k & 4) ? wz : oz) : 0.f;
+        v[k] = make_float2(w * g.x, w * g.y);
+    }
+    bool tail = true;
+    if constexpr (MERGE) {
+        const uint32_t pgx = __shfl_up_sync(0xffffffffu, gx, 1), pgy = __shfl_up_sync(0xffffffffu, gy, 1), pgz = __shfl_up_sync(0xffffffffu, gz, 1);
+        const bool pact = __shfl_up_sync(0xffffffffu, (int)active, 1) != 0;
+        const bool head = lane == 0 || !active || !pact || pgx != gx || pgy != gy || pgz != gz;
+        const uint32_t heads = __ballot_sync(0xffffffffu, head);
+        const int seg_start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+#pragma unroll
+        for (int offs = 1; offs < 32; offs <<= 1) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float tx = __shfl_up_sync(0xffffffffu, v[k].x, offs), ty = __shfl_up_sync(0xffffffffu, v[k].y, offs);
+                if (lane - offs >= seg_start) { v[k].x += tx; v[k].y += ty; }
+            }
+        }
+        tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+    }
+    if (active && tail) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            c.w[k] = __fmul_rn(__fmul_rn((k & 1) ? wx : ox, (k & 2) ? wy : oy), (k & 4) ? wz : oz);
-            c.idx[k] = off + level_index(gx + (k & 1), gy + ((k >> 1) & 1), gz + ((k >> 2) & 1), hashed, pow2, res, size);
+            const uint32_t idx = off + level_index(gx + (k & 1), gy + ((k >> 1) & 1), gz + ((k >> 2) & 1), hashed, pow2, res, size);
+            atomicAdd(dtable + idx, v[k]);
         }
     }
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-        atomicAdd(dtable + c.idx[k], make_float2(c.w[k] * g.x, c.w[k] * g.y));
 }
 
 // ---- packed composite kernels (nerfacc semantics): one warp per ray, lanes over its samples.
@@ -462,9 +487,14 @@ int perf_hashgrid_bwd(const perf_grid_cfg* cfg, const float* d_x01, const float*
     LevelTable lt; int rc = build_level_table(cfg, &lt, nullptr); if (rc) return rc;
     PERF_CHECK_ARG((uintptr_t)d_dtable % 8 == 0 && (uintptr_t)d_dfeat % 8 == 0, "misaligned dtable/dfeat");
     if (N == 0) return PERF_OK;
-    dim3 grid(blocks_for(N, 256), lt.n_levels);
-    hashgrid_bwd_kernel<<<grid, 256, 0, S(stream)>>>(lt, d_x01, d_dfeat, N, (float2*)d_dtable);
+    // levels whose cells span several consecutive samples of a ray: merge runs; the rest: direct atomics
+    const uint32_t n_merge = lt.n_levels < 6 ? lt.n_levels : 6;
+    hashgrid_bwd_kernel<true><<<dim3(blocks_for(N, 256), n_merge), 256, 0, S(stream)>>>(lt, 0, d_x01, d_dfeat, N, (float2*)d_dtable);
     PERF_LAUNCH_CHECK();
+    if (lt.n_levels > n_merge) {
+        hashgrid_bwd_kernel<false><<<dim3(blocks_for(N, 256), lt.n_levels - n_merge), 256, 0, S(stream)>>>(lt, (int)n_merge, d_x01, d_dfeat, N, (float2*)d_dtable);
+        PERF_LAUNCH_CHECK();
+    }
     return PERF_OK;
 }
 
