@@ -113,10 +113,9 @@ relu_mask_kernel(uint4* __restrict__ dh, const uint4* __restrict__ h, uint64_t n
 }
 
 // ---- grid-gradient scatter, rows sample-major, positions recomputed from the rays.
-// One thread per (row, level); lanes are neighbouring rays at the same sample index.  Lanes whose
-// sample sits in the same cell as the previous lane's form a run; the run is summed with warp
-// shuffles and its last lane issues the 8 float2 atomics (near the camera ALL rays share the coarse
-// cells: without this the same 8 addresses receive tens of thousands of atomics).
+// Fine levels: one thread per (row, level), direct float2 atomics (lanes are neighbouring rays at the same
+// sample index: at these resolutions they sit in different cells).  Coarse levels: see
+// hashgrid_bwd_march_kernel below.
 struct GridBwdRaysArgs {
     LevelTable lt;
     float aabb_min[3], aabb_ext[3];
@@ -125,10 +124,9 @@ struct GridBwdRaysArgs {
     const float* dfeat; float2* dtable;
 };
 
-template <bool AGG>
 __global__ void __launch_bounds__(256) hashgrid_bwd_rays_kernel(const __grid_constant__ GridBwdRaysArgs a)
 {
-    const int l = blockIdx.y, lane = threadIdx.x & 31;
+    const int l = blockIdx.y;
     const uint64_t N = a.R * a.S;
     const uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = row < N;
@@ -163,25 +161,7 @@ __global__ void __launch_bounds__(256) hashgrid_bwd_rays_kernel(const __grid_con
         const float w = active ? __fmul_rn(__fmul_rn((k & 1) ? wx : ox, (k & 2) ? wy : oy), (k & 4) ? wz : oz) : 0.f;
         v[k] = make_float2(w * g.x, w * g.y);
     }
-    bool tail = true;
-    if constexpr (AGG) {
-        // run = maximal group of consecutive lanes in the same cell (inactive lanes never join)
-        const uint32_t pgx = __shfl_up_sync(0xffffffffu, gx, 1), pgy = __shfl_up_sync(0xffffffffu, gy, 1), pgz = __shfl_up_sync(0xffffffffu, gz, 1);
-        const bool pact = __shfl_up_sync(0xffffffffu, (int)active, 1) != 0;
-        const bool head = lane == 0 || !active || !pact || pgx != gx || pgy != gy || pgz != gz;
-        const uint32_t heads = __ballot_sync(0xffffffffu, head);
-        const int seg_start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
-#pragma unroll
-        for (int offs = 1; offs < 32; offs <<= 1) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const float tx = __shfl_up_sync(0xffffffffu, v[k].x, offs), ty = __shfl_up_sync(0xffffffffu, v[k].y, offs);
-                if (lane - offs >= seg_start) { v[k].x += tx; v[k].y += ty; }
-            }
-        }
-        tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
-    }
-    if (active && tail) {
+    if (active) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const uint32_t idx = off + level_index(gx + (k & 1), gy + ((k >> 1) & 1), gz + ((k >> 2) & 1), hashed, pow2, res, size);
@@ -321,7 +301,7 @@ int perf_hashgrid_bwd_rays(const perf_grid_cfg* cfg, const float* aabb6, const f
         b.lt.hashed_mask = a.lt.hashed_mask >> n_agg; b.lt.pow2_mask = a.lt.pow2_mask >> n_agg;
         b.dfeat = a.dfeat + 2 * n_agg;                       // column window; row stride stays 2 * n_levels
         dim3 g_rest((unsigned)((N + 255) / 256), a.lt.n_levels - n_agg);
-        hashgrid_bwd_rays_kernel<false><<<g_rest, 256, 0, (cudaStream_t)stream>>>(b);
+        hashgrid_bwd_rays_kernel<<<g_rest, 256, 0, (cudaStream_t)stream>>>(b);
         PERF_LAUNCH_CHECK();
     }
     return PERF_OK;

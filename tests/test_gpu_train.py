@@ -54,7 +54,6 @@ def test_train_step_gradient_matches_oracle(golden_field, phase):
     gt_d, gt_c = torch.rand(R, 1, generator=g) * .8, torch.rand(R, 3, generator=g)
     jitter = torch.rand(R, generator=g)
     # the scene draws its random numbers from torch's CUDA generator: bg colour, then distance noise
-    sc.estimator.sampling_jitter = jitter
     orig = sc.estimator.sampling
     sc.estimator.sampling = lambda *a, **k: orig(*a, **{**k, "jitter": jitter.cuda()})
     torch.manual_seed(5)

@@ -1,7 +1,7 @@
 #!/bin/bash
 # launch-level profile of the fused training step (eager, so every kernel is listed)
 mkdir -p gpurun_out
-PHASES=${PHASES:-geo} NSTEPS=2 GRAPH=0 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/train_launches.csv python tools/train_bench.py > gpurun_out/train_ncu.log 2>&1
+PHASES=${PHASES:-geo} NSTEPS=2 GRAPH=0 FUSED=${FUSED:-1} timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/train_launches.csv python tools/train_bench.py > gpurun_out/train_ncu.log 2>&1
 python - <<'PY'
 import csv, collections
 rows = [r for r in csv.reader(open('gpurun_out/train_launches.csv')) if len(r) > 14 and r[0].isdigit()]
