@@ -14,8 +14,8 @@ JSON keys beyond the base contract:
   roofline      dominant kernel (render_march_kernel): ALGORITHMIC bytes = 1024 B/sample (16 levels x 8
                 corners x 2 features x 2 B x 2 fields) / CUDA-event time, against the
                 measured HBM copy bandwidth in MEASURED_PEAKS.json.
-  cpu_baseline  the oracle (oracle/render.py, fp32 accumulate) timed on this box's host cores on
-                a bounded sample of the same rays.
+  cpu_baseline  the oracle's plain-C / OpenMP port (oracle/cpath.c) on all host threads on a bounded
+                sample of the same rays; the PyTorch port (oracle/render.py) is reported beside it.
   e2e           same metric through the public API with a host pose in and host images out.
 """
 from __future__ import annotations
@@ -136,19 +136,44 @@ def cpu_oracle_sample(n_rays, threads=None):
     return n_rays * S / dt / 1e6, dt, torch.get_num_threads()
 
 
+def cpu_c_port_sample(n_rays):
+    """The plain-C / OpenMP restatement (oracle/cpath.c) on all host threads, on `n_rays` rays of the
+    benchmark panorama (middle rows).  Returns (Msamples/s, seconds, threads)."""
+    import torch
+    import oracle
+    from oracle import cpath
+    g = torch.Generator().manual_seed(SEED)
+    n_e = oracle.hashgrid.n_table_entries(oracle.field.PERF_GRID)
+
+    def net(mlp):
+        w = (torch.rand(oracle.mlp.flat_param_count(mlp), generator=g) * 2 - 1) * 0.3
+        t = (torch.rand(2 * n_e, generator=g) * 2 - 1) * 0.5
+        return torch.cat([w, t])
+    field = oracle.Field(net(oracle.field.GEO_MLP), net(oracle.field.APP_MLP))
+    o, d = oracle.gen_pano_rays(bench_pose(), H, W)
+    rows_needed = (n_rays + W - 1) // W
+    r0 = (H - rows_needed) // 2
+    o, d = o[r0:r0 + rows_needed].reshape(-1, 3)[:n_rays], d[r0:r0 + rows_needed].reshape(-1, 3)[:n_rays]
+    cpath.render_rays(field, o[:256], d[:256], S)                     # build + warm up
+    t0 = time.perf_counter()
+    cpath.render_rays(field, o, d, S)
+    dt = time.perf_counter() - t0
+    return o.shape[0] * S / dt / 1e6, dt, cpath.max_threads()
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path = the oracle port (the
     reference's third-party CUDA deps cannot be installed here and have no CPU path), host cores,
     bounded sample per step."""
     if rank != 0:
         return
-    n_rays = 4096                                     # 524 288 samples per step
+    n_rays = 65536                                    # 8.4 M samples per step, all host threads (C / OpenMP port)
     for _ in range(args.warmup):
-        cpu_oracle_sample(n_rays)
+        cpu_c_port_sample(n_rays)
     ts = []
     cores = 1
     for _ in range(args.steps):
-        v, dt, cores = cpu_oracle_sample(n_rays)
+        v, dt, cores = cpu_c_port_sample(n_rays)
         ts.append(dt)
     ms = 1e3 * sum(ts) / len(ts)
     value = n_rays * S / (ms / 1e3) / 1e6
@@ -157,7 +182,7 @@ def run_reference(args, rank, world):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": "port",
-                             "sample": f"{n_rays} rays x {S} samples of the benchmark panorama per step (oracle/render.py)"},
+                             "sample": f"{n_rays} rays x {S} samples of the benchmark panorama per step (oracle/cpath.c, OpenMP)"},
             "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -285,7 +310,8 @@ def run_ours(args, rank, world, local_rank):
         traffic = (t["dram_bytes_read"] + t["dram_bytes_write"]) if world == 1 else None
     except Exception:
         pass
-    cpu_v, cpu_s, cores = cpu_oracle_sample(4096) if world == 1 else (None, None, None)
+    cpu_v, cpu_s, cores = cpu_oracle_sample(4096) if world == 1 else (None, None, None)     # PyTorch port (+ parity reference)
+    c_v, c_s, c_cores = cpu_c_port_sample(65536) if world == 1 else (None, None, None)          # C / OpenMP port, all threads
     line = {"metric": "Msamples/sec (rays x samples)", "value": value, "unit": "Msamples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic (seeded random-init field, no checkpoints exist)",
@@ -314,9 +340,11 @@ def run_ours(args, rank, world, local_rank):
     if train is not None:
         line["train"] = train
     if cpu_v is not None:
-        line["cpu_baseline"] = {"value": cpu_v, "unit": "Msamples/s", "cores": cores, "kind": "port",
-                                "sample": f"4096 rays x {S} samples (rows {H // 2}-{H // 2 + 1} of the panorama), oracle/render.py mixed-precision restatement, {cpu_s:.1f} s; "
-                                          f"threads capped at 16 of {os.cpu_count()} (the oracle is many small torch ops and slows down beyond that)"}
+        line["cpu_baseline"] = {"value": c_v, "unit": "Msamples/s", "cores": c_cores, "kind": "port",
+                                "sample": f"65536 rays x {S} samples (middle rows of the panorama), oracle/cpath.c = plain-C / OpenMP restatement, "
+                                          f"all {c_cores} host threads, {c_s:.1f} s",
+                                "pytorch_port": {"value": cpu_v, "cores": cores, "sample": f"4096 rays x {S} samples, oracle/render.py, {cpu_s:.1f} s; threads "
+                                                 f"capped at 16 of {os.cpu_count()} (many small torch ops: slower beyond that)"}}
     emit(line)
 
 

@@ -1,7 +1,9 @@
 """CPU oracle for the PeRF per-ray hot path.  TEST INFRASTRUCTURE ONLY.
 
 This package is a plain-PyTorch (CPU, no custom code paths) restatement of the
-arithmetic PeRF's renderer performs per ray:
+arithmetic PeRF's renderer performs per ray (plus ``cpath.c``/``cpath.py``: the same eval
+path in plain C + OpenMP, cross-checked against the PyTorch restatement in
+``tests/test_oracle.py`` and used as the multi-threaded CPU baseline in ``bench.py``):
 
     equirect ray-gen  ->  fixed-S point sampling  ->  multi-resolution hash-grid
     encode + 64-wide MLP (density field, colour field)  ->  alpha composite

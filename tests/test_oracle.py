@@ -194,3 +194,19 @@ def test_config_loader_overrides(tmp_path):
     assert c.mode == "render_dense" and c.device.base_exp_dir == "/tmp/exp"
     assert c.scene.train_conf.geo_optimizer.peak_lr == 1e-2 and isinstance(c.scene.train_conf.geo_optimizer.peak_lr, float)
     assert c.scene.train_conf.pixel_loss_batch_size == 1024 and c.scene.new.key == 0.5
+
+
+def test_c_port_matches_pytorch_oracle(golden_field):
+    """oracle/cpath.c (the OpenMP CPU baseline of bench.py) against the PyTorch oracle: same mixed
+    precision contract, so the composited pixels agree to fp16-rounding noise."""
+    from oracle import cpath
+    g = torch.Generator().manual_seed(8)
+    R, S = 96, 48
+    o = (torch.rand(R, 3, generator=g) - .5) * .3
+    d = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1)
+    o[:3] = 3.0                                                  # rays outside the box: pure background
+    want = oracle.render_rays(golden_field, o, d, S, mixed=True)
+    got = cpath.render_rays(golden_field, o, d, S, n_threads=4)
+    for k, tol in (("rgb", 2e-3), ("distance", 2e-3), ("opacities", 2e-3)):
+        assert (got[k] - want[k]).abs().max() <= tol, (k, float((got[k] - want[k]).abs().max()))
+    assert torch.equal(got["rgb"][:3], torch.full((3, 3), 0.5)) and cpath.max_threads() >= 1
