@@ -154,11 +154,12 @@ def cpu_c_port_sample(n_rays):
     rows_needed = (n_rays + W - 1) // W
     r0 = (H - rows_needed) // 2
     o, d = o[r0:r0 + rows_needed].reshape(-1, 3)[:n_rays], d[r0:r0 + rows_needed].reshape(-1, 3)[:n_rays]
-    cpath.render_rays(field, o[:256], d[:256], S)                     # build + warm up
+    n_thr = len(os.sched_getaffinity(0))                              # explicit: torchrun exports OMP_NUM_THREADS=1
+    cpath.render_rays(field, o[:256], d[:256], S, n_threads=n_thr)    # build + warm up
     t0 = time.perf_counter()
-    cpath.render_rays(field, o, d, S)
+    cpath.render_rays(field, o, d, S, n_threads=n_thr)
     dt = time.perf_counter() - t0
-    return o.shape[0] * S / dt / 1e6, dt, cpath.max_threads()
+    return o.shape[0] * S / dt / 1e6, dt, n_thr
 
 
 def run_reference(args, rank, world):
