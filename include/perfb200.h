@@ -110,6 +110,22 @@ int perf_hashgrid_fwd(const perf_grid_cfg* cfg, const void* d_table, const float
 int perf_hashgrid_bwd(const perf_grid_cfg* cfg, const float* d_x01, const float* d_dfeat,
                       uint64_t N, float* d_dtable, void* stream);
 
+/* Hash-grid backward w.r.t. the INPUT positions: d_dx [N,3] fp32 = sum_f dfeat_f * d feat_f / d x01
+ * (Linear and Smoothstep).  d_table_half: fp16 [n_entries,2]; d_dfeat [N, L*2] fp32.
+ * Replaces tcnn kernel_grid_backward_input, reached by tcnn.Encoding when its input requires grad
+ * (modules/geo_predictors/pano_joint_predictor.py:30-41,48-52; pano_geo_refiner.py:19). */
+int perf_hashgrid_bwd_input(const perf_grid_cfg* cfg, const void* d_table_half, const float* d_x01,
+                            const float* d_dfeat, uint64_t N, float* d_dx, void* stream);
+/* Double backward of perf_hashgrid_bwd_input: with d_ddx [N,3] = d(loss)/d(d_dx), writes the gradient
+ * w.r.t. dfeat (d_ddfeat [N, L*2] fp32, overwritten), accumulates the gradient w.r.t. the table
+ * (d_dtable [n_entries,2] fp32 +=, caller zeroes) and w.r.t. x01 (d_dx2 [N,3] fp32 +=, caller zeroes).
+ * Any of the three outputs may be NULL.  Replaces tcnn kernel_grid_backward_input_backward_dLdoutput /
+ * _backward_grid / _backward_input, i.e. what torch.autograd.grad(distance, directions,
+ * create_graph=True) followed by loss.backward() runs (pano_joint_predictor.py:58-64). */
+int perf_hashgrid_bwd_bwd_input(const perf_grid_cfg* cfg, const void* d_table_half, const float* d_x01,
+                                const float* d_dfeat, const float* d_ddx, uint64_t N,
+                                float* d_ddfeat, float* d_dtable, float* d_dx2, void* stream);
+
 /* Network forward = encode + MLP fused (tcnn NetworkWithInputEncoding.forward;
  * ngp_nerf.py:142,158).  d_x01 [N,3] fp32; d_params_half: fp16 flat params (MLP | grid);
  * d_out [N, n_out] fp16.  Optional saves for the backward pass (NULL to skip):

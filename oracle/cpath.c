@@ -127,7 +127,12 @@ int oracle_render_rays(const float* geo_params, const float* app_params, const f
     half* g16 = (half*)malloc(n_geo * sizeof(half));
     half* a16 = (half*)malloc(n_app * sizeof(half));
     if (!g16 || !a16) { free(g16); free(a16); return -1; }
+#ifdef _OPENMP
+    if (n_threads > 0) omp_set_num_threads(n_threads);
+#endif
+#pragma omp parallel for schedule(static)
     for (size_t i = 0; i < n_geo; ++i) g16[i] = f2h(geo_params[i]);     /* params.to(half) */
+#pragma omp parallel for schedule(static)
     for (size_t i = 0; i < n_app; ++i) a16[i] = f2h(app_params[i]);
     const half *gT = g16 + n_geo_mlp, *aT = a16 + n_app_mlp;
     float* gW1 = transpose_to_float(g16, HID, 32);
@@ -138,9 +143,6 @@ int oracle_render_rays(const float* geo_params, const float* app_params, const f
     for (int k = 0; k < 3 * HID; ++k) aWo[k] = h2f(a16[64 * 32 + 64 * 64 + k]);
     if (!gW1 || !aW1 || !aW2) { free(g16); free(a16); free(gW1); free(aW1); free(aW2); return -1; }
     const float step = (far - near) / (float)S;
-#ifdef _OPENMP
-    if (n_threads > 0) omp_set_num_threads(n_threads);
-#endif
 #pragma omp parallel for schedule(dynamic, 16)
     for (long r = 0; r < R; ++r) {
         const float* o = rays_o + 3 * r; const float* d = rays_d + 3 * r;

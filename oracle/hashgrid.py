@@ -217,3 +217,70 @@ def encode_backward_table(x01: torch.Tensor, dfeat: torch.Tensor,
         for wt, idx in _corner_weights_indices(x01, lvl, cfg.interpolation == "Smoothstep"):
             grad.index_add_(0, idx, wt.double()[:, None] * d)
     return grad.float()
+
+
+def encode_autograd(x01: torch.Tensor, table: torch.Tensor, cfg: GridConfig = GridConfig(),
+                    fp32_positions: bool = False) -> torch.Tensor:
+    """Hash-grid encode as a plain differentiable fp64 torch expression: autograd through it gives the
+    oracle for the gradients w.r.t. the INPUT positions (tcnn ``kernel_grid_backward_input``) and for
+    their double backward (``kernel_grid_backward_input_backward_grid / _backward_dLdoutput /
+    _backward_input``), which `SphereDistanceField.forward(requires_grad=True)` uses
+    (`/root/reference/modules/geo_predictors/pano_joint_predictor.py:48-68`).
+
+    ``x01`` [N,3] (grad flows), ``table`` [n_entries, F] (grad flows; pass fp16-rounded values to match
+    the kernels, which read the fp16 shadow).  The cell of every sample is taken from the fp32
+    ``pos_fract`` (bit-identical to the kernels); inside the cell the fractional position is
+    ``scale*x + 0.5 - cell`` in fp64, whose derivative w.r.t. x is ``scale`` (tcnn: ``floor`` has no
+    gradient).  Smoothstep: ``s = w^2 (3 - 2w)``, so ``ds/dw = 6w(1-w)`` and ``d2s/dw2 = 6 - 12w``.
+
+    ``fp32_positions``: take the VALUE of the fractional position from the fp32 ``pos_fract`` as tcnn and
+    the kernels do (at scale 2047 an fp32 position carries ~3e-5 of absolute error, which the smoothstep
+    derivative amplifies to ~1e-4 relative) while keeping ``d w / d x = scale``.  This is the mode the
+    kernels are compared in; the pure-fp64 mode is the one ``gradcheck`` can differentiate numerically."""
+    F = cfg.n_features_per_level
+    table = table.reshape(-1, F).double()
+    xd = x01.double()
+    feats = []
+    for lvl in level_table(cfg):
+        g, w32 = pos_fract(x01.detach().float(), lvl.scale)
+        if fp32_positions:
+            w = w32.double() + (xd - xd.detach()) * float(lvl.scale)
+        else:
+            g_signed = torch.floor((x01.detach().float().double() * float(lvl.scale) + 0.5).float()).double()
+            w = xd * float(lvl.scale) + 0.5 - g_signed
+        if cfg.interpolation == "Smoothstep":
+            w = w * w * (3.0 - 2.0 * w)
+        acc = torch.zeros(x01.shape[0], F, dtype=torch.float64)
+        for c in range(8):
+            wt = torch.ones_like(w[..., 0])
+            gc = g.clone()
+            for dim in range(3):
+                if c & (1 << dim):
+                    wt = wt * w[..., dim]
+                    gc[..., dim] = (g[..., dim] + 1) & _U32
+                else:
+                    wt = wt * (1.0 - w[..., dim])
+            acc = acc + wt[:, None] * table[grid_index(gc, lvl) + lvl.offset]
+        feats.append(acc)
+    return torch.cat(feats, dim=1)
+
+
+def encode_input_grad(x01: torch.Tensor, table: torch.Tensor, dfeat: torch.Tensor,
+                      cfg: GridConfig = GridConfig(), create_graph: bool = False, fp32_positions: bool = False):
+    """d(loss)/d(x01) [N,3] fp64 = sum_f dfeat_f * d feat_f / d x01 (tcnn ``kernel_grid_backward_input``),
+    by autograd through :func:`encode_autograd`."""
+    x = x01.double() if x01.requires_grad else x01.detach().double().requires_grad_(True)
+    y = encode_autograd(x, table, cfg, fp32_positions)
+    return torch.autograd.grad(y, x, grad_outputs=dfeat.double(), create_graph=create_graph)[0]
+
+
+def encode_input_grad_backward(x01: torch.Tensor, table: torch.Tensor, dfeat: torch.Tensor, ddx: torch.Tensor,
+                               cfg: GridConfig = GridConfig(), fp32_positions: bool = False):
+    """Double backward of :func:`encode_input_grad`: gradients of ``(dx * ddx).sum()`` w.r.t.
+    ``(dfeat, table, x01)`` (tcnn ``kernel_grid_backward_input_backward_dLdoutput / _grid / _input``)."""
+    x = x01.detach().double().requires_grad_(True)
+    t = table.detach().double().requires_grad_(True)
+    g = dfeat.detach().double().requires_grad_(True)
+    y = encode_autograd(x, t, cfg, fp32_positions)
+    dx = torch.autograd.grad(y, x, grad_outputs=g, create_graph=True)[0]
+    return torch.autograd.grad((dx * ddx.double()).sum(), (g, t, x), allow_unused=True)

@@ -63,6 +63,8 @@ SIGNATURES = {
     "perf_raygen_pers": (i32, [P(f32), f32, i32, i32, vp, vp, vp]),
     "perf_hashgrid_fwd": (i32, [P(GridCfg), vp, vp, u64, vp, vp]),
     "perf_hashgrid_bwd": (i32, [P(GridCfg), vp, vp, u64, vp, vp]),
+    "perf_hashgrid_bwd_input": (i32, [P(GridCfg), vp, vp, vp, u64, vp, vp]),
+    "perf_hashgrid_bwd_bwd_input": (i32, [P(GridCfg), vp, vp, vp, vp, u64, vp, vp, vp, vp]),
     "perf_network_fwd": (i32, [P(GridCfg), P(MlpCfg), vp, vp, u64, vp, vp, vp, vp, u32, vp]),
     "perf_mlp_fwd": (i32, [P(MlpCfg), vp, vp, u64, vp, vp, vp, u32, vp]),
     "perf_weights_from_density": (i32, [vp, vp, vp, vp, u64, u64, vp, vp, vp, vp]),

@@ -43,7 +43,7 @@ struct Corner8 {
     float    w[8];       // trilinear weight, corner c: bit0=x, bit1=y, bit2=z
 };
 
-__device__ __forceinline__ uint32_t level_index(uint32_t gx, uint32_t gy, uint32_t gz,
+__host__ __device__ __forceinline__ uint32_t level_index(uint32_t gx, uint32_t gy, uint32_t gz,
                                                 bool hashed, bool pow2, uint32_t res, uint32_t size)
 {
     uint32_t idx;

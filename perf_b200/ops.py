@@ -118,6 +118,34 @@ def hashgrid_bwd(x01: torch.Tensor, dfeat: torch.Tensor, grid: GridConfig = PERF
     return out
 
 
+def hashgrid_bwd_input(table_half: torch.Tensor, x01: torch.Tensor, dfeat: torch.Tensor, grid: GridConfig = PERF_GRID) -> torch.Tensor:
+    """d(loss)/d(x01) [N,3] fp32 of the encode (Linear or Smoothstep); ``dfeat`` [N, L*2] fp32."""
+    table_half, x01, dfeat = _chk(table_half, torch.float16, "table"), _chk(x01, torch.float32, "x01"), _chk(dfeat, torch.float32, "dfeat")
+    dx = torch.empty_like(x01)
+    if x01.shape[0] == 0:
+        return dx
+    with torch.cuda.device(x01.device):
+        _call(_L().perf_hashgrid_bwd_input, grid.c(), _p(table_half), _p(x01), _p(dfeat), x01.shape[0], _p(dx), _stream())
+    return dx
+
+
+def hashgrid_bwd_bwd_input(table_half: torch.Tensor, x01: torch.Tensor, dfeat: torch.Tensor, ddx: torch.Tensor,
+                           grid: GridConfig = PERF_GRID, want=(True, True, True)):
+    """Double backward of :func:`hashgrid_bwd_input`.  ``ddx`` [N,3] = d(loss)/d(dx).  Returns
+    ``(d_dfeat [N, L*2], d_table [n_entries, 2], d_x01 [N,3])`` fp32, ``None`` where ``want`` is False."""
+    table_half, x01 = _chk(table_half, torch.float16, "table"), _chk(x01, torch.float32, "x01")
+    dfeat, ddx = _chk(dfeat, torch.float32, "dfeat"), _chk(ddx, torch.float32, "ddx")
+    N, dev = x01.shape[0], x01.device
+    ddfeat = torch.empty(N, grid.n_features, dtype=torch.float32, device=dev) if want[0] else None
+    dtable = torch.zeros(grid.n_entries, 2, dtype=torch.float32, device=dev) if want[1] else None
+    dx2 = torch.zeros(N, 3, dtype=torch.float32, device=dev) if want[2] else None
+    if N and any(want):
+        with torch.cuda.device(dev):
+            _call(_L().perf_hashgrid_bwd_bwd_input, grid.c(), _p(table_half), _p(x01), _p(dfeat), _p(ddx), N,
+                  _p(ddfeat), _p(dtable), _p(dx2), _stream())
+    return ddfeat, dtable, dx2
+
+
 def hashgrid_bwd_rays(rays_o, rays_d, jitter, n_samples: int, near: float, far: float, dfeat: torch.Tensor,
                       aabb=(-1., -1., -1., 1., 1., 1.), grid: GridConfig = PERF_GRID, out: Optional[torch.Tensor] = None):
     """d(table) from sample-major rows (row = k * R + ray) whose positions are recomputed from the
@@ -236,20 +264,58 @@ def network_apply(params: torch.Tensor, x01: torch.Tensor, grid: GridConfig, mlp
 
 
 class _EncodingFunction(torch.autograd.Function):
-    """tcnn.Encoding: feat = encode(x01; params), differentiable w.r.t. ``params`` only."""
+    """tcnn.Encoding: feat = encode(x01; params), differentiable w.r.t. ``params`` and -- when the
+    positions require grad -- w.r.t. ``x01``, once more differentiable through that input gradient
+    (tcnn's ``_module_function`` / ``_module_function_backward`` pair; what
+    `pano_joint_predictor.py:58-64` needs for ``autograd.grad(distance, directions, create_graph=True)``)."""
 
     @staticmethod
     def forward(ctx, params, x01, grid):
-        x01 = x01.detach().float().contiguous()
-        feat = hashgrid_fwd(params_to_half(params.detach()).view(-1, 2), x01, grid)
-        ctx.save_for_backward(x01)
-        ctx.grid = grid
+        xd = x01.detach().float().contiguous()
+        half = params_to_half(params.detach()).view(-1, 2)
+        feat = hashgrid_fwd(half, xd, grid)
+        ctx.save_for_backward(params, x01)
+        ctx.grid, ctx.half = grid, half
         return feat
 
     @staticmethod
     def backward(ctx, dfeat):
-        (x01,) = ctx.saved_tensors
-        return hashgrid_bwd(x01, dfeat.float().contiguous(), ctx.grid).reshape(-1), None, None
+        params, x01 = ctx.saved_tensors
+        if not ctx.needs_input_grad[1]:
+            dparams = hashgrid_bwd(x01.detach().float().contiguous(), dfeat.float().contiguous(), ctx.grid).reshape(-1) \
+                if ctx.needs_input_grad[0] else None
+            return dparams, None, None
+        dparams, dx = _EncodingBackward.apply(params, x01, dfeat, ctx.half, ctx.grid, ctx.needs_input_grad[0])
+        return (dparams if ctx.needs_input_grad[0] else None), dx.to(x01.dtype), None
+
+
+class _EncodingBackward(torch.autograd.Function):
+    """(d_params, d_x01) of the encode as a differentiable node: its own backward is the double
+    backward w.r.t. the INPUT gradient only (as in tcnn, gradients flowing into ``d_params`` are
+    not propagated)."""
+
+    @staticmethod
+    def forward(ctx, params, x01, dfeat, half, grid, want_params):
+        xd, g = x01.detach().float().contiguous(), dfeat.detach().float().contiguous()
+        dx = hashgrid_bwd_input(half, xd, g, grid)
+        dparams = hashgrid_bwd(xd, g, grid).reshape(-1) if want_params else torch.zeros((), device=xd.device)
+        ctx.save_for_backward(xd, g)
+        ctx.grid, ctx.half, ctx.x_dtype, ctx.g_dtype = grid, half, x01.dtype, dfeat.dtype
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(dparams)
+        return dparams, dx
+
+    @staticmethod
+    def backward(ctx, _unused, ddx):
+        if ddx is None:
+            return None, None, None, None, None, None
+        xd, g = ctx.saved_tensors
+        want = (ctx.needs_input_grad[2], ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        ddfeat, dtable, dx2 = hashgrid_bwd_bwd_input(ctx.half, xd, g, ddx.float().contiguous(), ctx.grid, want)
+        return (None if dtable is None else dtable.reshape(-1),
+                None if dx2 is None else dx2.to(ctx.x_dtype),
+                None if ddfeat is None else ddfeat.to(ctx.g_dtype),
+                None, None, None)
 
 
 def encoding_apply(params: torch.Tensor, x01: torch.Tensor, grid: GridConfig) -> torch.Tensor:

@@ -5,7 +5,9 @@ Implements what PeRF calls (`/root/reference/modules/fields/ngp_nerf.py:96-134,1
 ``NetworkWithInputEncoding(n_input_dims, n_output_dims, encoding_config, network_config, seed)``
 and ``Encoding(n_input_dims, encoding_config, seed, dtype)`` -- ``torch.nn.Module``s with ONE flat
 fp32 ``params`` Parameter in tcnn's layout ``[MLP matrices | grid level 0..L-1]`` (checkpoint
-compatible), fp16 outputs, gradients w.r.t. ``params``.  Anything else raises at construction.
+compatible), fp16 outputs, gradients w.r.t. ``params``; ``Encoding`` (Linear or Smoothstep) is also
+differentiable w.r.t. its input positions, and once more through that input gradient
+(`pano_joint_predictor.py:58-64`).  Anything else raises at construction.
 """
 from __future__ import annotations
 
@@ -47,11 +49,12 @@ class _Base(torch.nn.Module):
         return self._half_cache
 
     @staticmethod
-    def _check_input(x: torch.Tensor, n_in: int) -> torch.Tensor:
+    def _check_input(x: torch.Tensor, n_in: int, input_grad: bool = False) -> torch.Tensor:
         if x.dim() != 2 or x.shape[1] != n_in:
             raise ValueError(f"expected input of shape [N, {n_in}], got {tuple(x.shape)}")
-        if x.requires_grad:
-            raise NotImplementedError("perf_b200 tinycudann: gradients w.r.t. the input positions are not implemented")
+        if x.requires_grad and not input_grad:
+            raise NotImplementedError("perf_b200 tinycudann: NetworkWithInputEncoding has no gradients w.r.t. the input "
+                                      "positions (PeRF never asks for them); tcnn.Encoding has")
         return x
 
 
@@ -85,7 +88,7 @@ class Encoding(_Base):
         self.params = torch.nn.Parameter(_init_params(self.grid, None, seed).to(torch.empty(0).device))
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        x = self._check_input(x, self.n_input_dims)
+        x = self._check_input(x, self.n_input_dims, input_grad=True)
         return ops.encoding_apply(self.params, x, self.grid).to(self.dtype)
 
 

@@ -1,0 +1,62 @@
+"""TEST HARNESS: compiles perf_b200/csrc/encoding_grad.cu with -DPERF_HOST_HARNESS (plus api_basic.cu for the
+level-table builder) into tests/_build/libperf_host_harness.so, a SEPARATE shared object whose two extra
+entry points run the kernels' __host__ __device__ bodies over host arrays.  It lets the CPU test-suite check
+the arithmetic of the CUDA source against the oracle; the product library (perf_b200/libperfb200.so) is built
+without the macro and has no host path."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(os.path.dirname(HERE), "perf_b200", "csrc")
+OUT = os.path.join(HERE, "_build", "libperf_host_harness.so")
+SOURCES = [os.path.join(CSRC, "api_basic.cu"), os.path.join(CSRC, "encoding_grad.cu")]
+_LIB = None
+
+
+def build() -> str:
+    from perf_b200.build import _nvcc
+    deps = SOURCES + [os.path.join(CSRC, "common.cuh")]
+    if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
+        os.makedirs(os.path.dirname(OUT), exist_ok=True)
+        tmp = f"{OUT}.{os.getpid()}.tmp"
+        cmd = [_nvcc(), "-DPERF_HOST_HARNESS", "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "--shared",
+               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"] + SOURCES + ["-o", tmp]
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+        os.replace(tmp, OUT)
+    return OUT
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+    return _LIB
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def bwd_input(grid_cfg, table_half: np.ndarray, x01: np.ndarray, dfeat: np.ndarray) -> np.ndarray:
+    """grid_cfg: perf_b200.config.GridConfig; table_half [n,2] float16; x01 [N,3] f32; dfeat [N,2L] f32."""
+    n = x01.shape[0]
+    dx = np.zeros((n, 3), np.float32)
+    rc = lib().perf_host_hashgrid_bwd_input(C.byref(grid_cfg.c()), _p(table_half), _p(x01), _p(dfeat), C.c_uint64(n), _p(dx))
+    assert rc == 0, rc
+    return dx
+
+
+def bwd_bwd_input(grid_cfg, table_half, x01, dfeat, ddx):
+    n = x01.shape[0]
+    ddfeat = np.zeros((n, grid_cfg.n_features), np.float32)
+    dtable = np.zeros((grid_cfg.n_entries, 2), np.float32)
+    dx2 = np.zeros((n, 3), np.float32)
+    rc = lib().perf_host_hashgrid_bwd_bwd_input(C.byref(grid_cfg.c()), _p(table_half), _p(x01), _p(dfeat), _p(ddx), C.c_uint64(n),
+                                                _p(ddfeat), _p(dtable), _p(dx2))
+    assert rc == 0, rc
+    return ddfeat, dtable, dx2
