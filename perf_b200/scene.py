@@ -331,6 +331,13 @@ class NeRFScene:
             return {**out, "is_valid": True}
         return self.fused.render_pano(pose, height, width, self.estimator.n_samples, row0=row0, rows=rows)
 
+    @torch.no_grad()
+    def get_pano_visibility_mask(self, sup_pool, rays: Rays):
+        """`nerf.py:320-358`: render the distance of ``rays`` [H,W,3], un-project, and ask every registered
+        panorama whether it sees that surface point (1 visible, 0 invisible; ``SupInfoPool.pano_visibility_mask``)."""
+        distance = self.render(rays, query_keys=["distance"])["distance"].squeeze()
+        return sup_pool.pano_visibility_mask(rays, distance)
+
     def _render_once_fused(self, rays: Rays, geo_inference: bool, app_inference: bool):
         """Training-mode render as ONE forward kernel; gradients reach the network that is not in
         inference mode.  Same outputs as the modular path except the per-sample tensors: instead of
