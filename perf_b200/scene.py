@@ -491,7 +491,14 @@ class NeRFScene:
         return {"render": self.renderer.state_dict(), "nerf": self.nerf.state_dict(), "estimator": self.estimator.state_dict()}
 
     def load_state_dict(self, state_dict):
+        """`nerf.py:368-372`.  A checkpoint written with another sampler (e.g. the reference's occupancy grid loaded
+        into a fixed-S scene) restores the field and skips the estimator buffers that do not apply."""
+        if "render" in state_dict:
+            self.renderer.load_state_dict(state_dict["render"])
         self.nerf.load_state_dict(state_dict["nerf"])
+        est = state_dict.get("estimator", {})
+        if est and set(est) == set(self.estimator.state_dict()):
+            self.estimator.load_state_dict(est)
         self._fused_key = None
 
     def set_train(self):
