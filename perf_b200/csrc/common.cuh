@@ -59,7 +59,15 @@ __host__ __device__ __forceinline__ uint32_t level_index(uint32_t gx, uint32_t g
     return idx;
 }
 
-__device__ __forceinline__ void level_corners(const LevelTable& lt, int l, float x, float y, float z, Corner8& c)
+// round-to-nearest multiply that the compiler may not contract into an fma (device); plain IEEE multiply
+// when the same source is compiled for the host by tests/host_harness.py
+#ifdef __CUDA_ARCH__
+#define PERF_FMUL_RN(a, b) __fmul_rn((a), (b))
+#else
+#define PERF_FMUL_RN(a, b) ((a) * (b))
+#endif
+
+__host__ __device__ __forceinline__ void level_corners(const LevelTable& lt, int l, float x, float y, float z, Corner8& c)
 {
     const float scale = lt.scale[l];
     const uint32_t res = lt.res[l], size = lt.size[l], off = lt.offset[l];
@@ -75,7 +83,7 @@ __device__ __forceinline__ void level_corners(const LevelTable& lt, int l, float
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         // weight = ((1 * ax) * ay) * az in this order (oracle/hashgrid.py::_corner_weights_indices)
-        float w = __fmul_rn(__fmul_rn((k & 1) ? wx : ox, (k & 2) ? wy : oy), (k & 4) ? wz : oz);
+        float w = PERF_FMUL_RN(PERF_FMUL_RN((k & 1) ? wx : ox, (k & 2) ? wy : oy), (k & 4) ? wz : oz);
         c.w[k] = w;
         c.idx[k] = off + level_index(gx + (k & 1), gy + ((k >> 1) & 1), gz + ((k >> 2) & 1), hashed, pow2, res, size);
     }
@@ -86,7 +94,7 @@ __device__ __forceinline__ void level_corners(const LevelTable& lt, int l, float
 // lie in [0,1] (callers clamp masked-out samples) and interpolation is Linear.  Produces exactly
 // the indices / weights of level_corners() under those preconditions -- no divisions, no branches.
 template <bool HASHED>
-__device__ __forceinline__ void level_corners_fast(const LevelTable& lt, int l, float x, float y, float z, Corner8& c)
+__host__ __device__ __forceinline__ void level_corners_fast(const LevelTable& lt, int l, float x, float y, float z, Corner8& c)
 {
     const float scale = lt.scale[l];
     const uint32_t res = lt.res[l], size = lt.size[l], off = lt.offset[l];
@@ -95,9 +103,9 @@ __device__ __forceinline__ void level_corners_fast(const LevelTable& lt, int l, 
     const uint32_t gx = (uint32_t)(int)fx, gy = (uint32_t)(int)fy, gz = (uint32_t)(int)fz;
     const float wx = px - fx, wy = py - fy, wz = pz - fz;
     const float ox = 1.0f - wx, oy = 1.0f - wy, oz = 1.0f - wz;
-    const float wxy[4] = {__fmul_rn(ox, oy), __fmul_rn(wx, oy), __fmul_rn(ox, wy), __fmul_rn(wx, wy)};
+    const float wxy[4] = {PERF_FMUL_RN(ox, oy), PERF_FMUL_RN(wx, oy), PERF_FMUL_RN(ox, wy), PERF_FMUL_RN(wx, wy)};
 #pragma unroll
-    for (int k = 0; k < 8; ++k) c.w[k] = __fmul_rn(wxy[k & 3], (k & 4) ? wz : oz);
+    for (int k = 0; k < 8; ++k) c.w[k] = PERF_FMUL_RN(wxy[k & 3], (k & 4) ? wz : oz);
     if constexpr (HASHED) {
         const uint32_t mask = size - 1u;
         const uint32_t hy0 = gy * 2654435761u, hy1 = hy0 + 2654435761u;

@@ -1,0 +1,32 @@
+// TEST HARNESS (compiled only by tests/host_harness.py into tests/_build/, never into libperfb200.so):
+// host entry points that run the __host__ __device__ addressing helpers of perf_b200/csrc/common.cuh over
+// host arrays, so the CPU test-suite can compare the generic and the specialised ("fast") hash-grid
+// addressing with each other and with the oracle for arbitrary grid configurations.
+#include "../perf_b200/csrc/common.cuh"
+
+using namespace perf;
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+// mode 0: level_corners (generic); mode 1: level_corners_fast<HASHED> with HASHED taken from the level table.
+// Returns 1 in *fast_ok when fast_addressing_ok(lt, n_dense) holds.  idx [N,8] uint32, w [N,8] float.
+int perf_host_level_corners(const perf_grid_cfg* cfg, int level, int mode, uint32_t n_dense, const float* x01, uint64_t N,
+                            uint32_t* idx, float* w, int* fast_ok)
+{
+    LevelTable lt; int rc = build_level_table(cfg, &lt, nullptr); if (rc) return rc;
+    if (fast_ok) *fast_ok = fast_addressing_ok(lt, n_dense) ? 1 : 0;
+    if (level < 0 || level >= (int)lt.n_levels) return PERF_EINVAL;
+    const bool hashed = (lt.hashed_mask >> level) & 1u;
+    for (uint64_t i = 0; i < N; ++i) {
+        Corner8 c;
+        if (mode == 0) level_corners(lt, level, x01[3 * i], x01[3 * i + 1], x01[3 * i + 2], c);
+        else if (hashed) level_corners_fast<true>(lt, level, x01[3 * i], x01[3 * i + 1], x01[3 * i + 2], c);
+        else level_corners_fast<false>(lt, level, x01[3 * i], x01[3 * i + 1], x01[3 * i + 2], c);
+        for (int k = 0; k < 8; ++k) { idx[8 * i + k] = c.idx[k]; w[8 * i + k] = c.w[k]; }
+    }
+    return PERF_OK;
+}
+
+#pragma GCC visibility pop
+}

@@ -12,7 +12,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(HERE), "perf_b200", "csrc")
 OUT = os.path.join(HERE, "_build", "libperf_host_harness.so")
-SOURCES = [os.path.join(CSRC, "api_basic.cu"), os.path.join(CSRC, "encoding_grad.cu")]
+SOURCES = [os.path.join(CSRC, "api_basic.cu"), os.path.join(CSRC, "encoding_grad.cu"), os.path.join(HERE, "host_harness.cu")]
 _LIB = None
 
 
@@ -23,7 +23,7 @@ def build() -> str:
         os.makedirs(os.path.dirname(OUT), exist_ok=True)
         tmp = f"{OUT}.{os.getpid()}.tmp"
         cmd = [_nvcc(), "-DPERF_HOST_HARNESS", "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "--shared",
-               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"] + SOURCES + ["-o", tmp]
+               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xcompiler", "-ffp-contract=off"] + SOURCES + ["-o", tmp]
         proc = subprocess.run(cmd, capture_output=True, text=True)
         if proc.returncode != 0:
             raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
@@ -60,3 +60,13 @@ def bwd_bwd_input(grid_cfg, table_half, x01, dfeat, ddx):
                                                 _p(ddfeat), _p(dtable), _p(dx2))
     assert rc == 0, rc
     return ddfeat, dtable, dx2
+
+
+def level_corners(grid_cfg, level: int, x01: np.ndarray, fast: bool, n_dense: int = 4):
+    """(idx [N,8] uint32, w [N,8] f32, fast_ok) from level_corners (generic) or level_corners_fast."""
+    n = x01.shape[0]
+    idx, w, ok = np.zeros((n, 8), np.uint32), np.zeros((n, 8), np.float32), C.c_int(0)
+    rc = lib().perf_host_level_corners(C.byref(grid_cfg.c()), int(level), int(bool(fast)), C.c_uint32(n_dense), _p(x01), C.c_uint64(n),
+                                       _p(idx), _p(w), C.byref(ok))
+    assert rc == 0, rc
+    return idx, w, bool(ok.value)

@@ -1,0 +1,79 @@
+"""Hash-grid addressing of perf_b200/csrc/common.cuh, compiled for the host (tests/host_harness.py):
+the generic `level_corners` against the oracle for arbitrary grid configurations, and the specialised
+branch-free `level_corners_fast` against the generic one wherever `fast_addressing_ok` admits it."""
+import numpy as np
+import pytest
+import torch
+from hypothesis import given, settings, strategies as st
+
+import host_harness as hh
+from oracle.hashgrid import GridConfig as OGrid, _corner_weights_indices, level_table
+from perf_b200.config import GridConfig
+
+
+def _points(n, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(n, 3, generator=g)
+    x[:8] = torch.tensor([[0., 0., 0.], [1., 1., 1.], [0.5, 0.5, 0.5], [1., 0., 0.5], [1e-7, 0.999999, 0.25],
+                          [0.9999999, 0.9999999, 0.9999999], [0., 1., 0.], [0.33333334, 0.6666667, 1.0]])
+    return x
+
+
+def _oracle(cfg, level, x):
+    lvl = level_table(cfg)[level]
+    corners = _corner_weights_indices(x, lvl, cfg.interpolation == "Smoothstep")
+    idx = torch.stack([c[1] for c in corners], 1).numpy().astype(np.uint32)
+    w = torch.stack([c[0] for c in corners], 1).numpy()
+    return idx, w
+
+
+@settings(max_examples=60, deadline=None)
+@given(n_levels=st.integers(1, 16), log2_t=st.integers(4, 22), base=st.integers(1, 64),
+       scale=st.floats(1.0, 2.5, width=32), smooth=st.booleans(), seed=st.integers(0, 2 ** 16))
+def test_generic_addressing_matches_oracle(n_levels, log2_t, base, scale, smooth, seed):
+    interp = "Smoothstep" if smooth else "Linear"
+    ocfg = OGrid(n_levels=n_levels, log2_hashmap_size=log2_t, base_resolution=base, per_level_scale=float(scale), interpolation=interp)
+    lv = level_table(ocfg)
+    if lv[-1].offset + lv[-1].size >= 2 ** 31:                 # the library refuses grids this large
+        return
+    pcfg = GridConfig(n_levels, 2, log2_t, base, float(scale), interp)
+    x = _points(64, seed)
+    for level in sorted({0, n_levels // 2, n_levels - 1}):
+        idx, w, _ = hh.level_corners(pcfg, level, x.numpy(), fast=False)
+        o_idx, o_w = _oracle(ocfg, level, x)
+        assert np.array_equal(idx, o_idx), (level, "indices")
+        assert np.array_equal(w, o_w), (level, "weights")
+
+
+@settings(max_examples=60, deadline=None)
+@given(log2_t=st.integers(12, 22), base=st.integers(4, 32), scale=st.floats(1.25, 2.0, width=32), seed=st.integers(0, 2 ** 16))
+def test_fast_addressing_equals_generic_where_admitted(log2_t, base, scale, seed):
+    """For every 16-level Linear grid: whenever the host-side gate admits the specialised path for some number
+    of leading dense levels, it produces exactly the generic indices and weights on [0,1]^3."""
+    ocfg = OGrid(n_levels=16, log2_hashmap_size=log2_t, base_resolution=base, per_level_scale=float(scale))
+    lv = level_table(ocfg)
+    if lv[-1].offset + lv[-1].size >= 2 ** 31:
+        return
+    pcfg = GridConfig(16, 2, log2_t, base, float(scale), "Linear")
+    x = _points(64, seed).numpy()
+    n_dense = sum(1 for l in lv if not l.hashed)
+    admitted = hh.level_corners(pcfg, 0, x[:1], fast=True, n_dense=n_dense)[2]
+    pow2_hashed = all((l.size & (l.size - 1)) == 0 for l in lv if l.hashed)
+    assert admitted == pow2_hashed                              # the gate is exactly "dense prefix + pow2 hashed tail"
+    if not admitted:
+        return
+    for level in range(16):
+        a = hh.level_corners(pcfg, level, x, fast=False)
+        b = hh.level_corners(pcfg, level, x, fast=True, n_dense=n_dense)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), level
+
+
+def test_perf_grid_is_admitted_with_four_dense_levels():
+    pcfg = GridConfig(16, 2, 18, 16, 1.4472692012786865, "Linear")
+    x = _points(256, 1).numpy()
+    assert hh.level_corners(pcfg, 0, x[:1], fast=True, n_dense=4)[2]
+    assert not hh.level_corners(pcfg, 0, x[:1], fast=True, n_dense=3)[2]
+    assert not hh.level_corners(GridConfig(16, 2, 18, 16, 1.4472692012786865, "Smoothstep"), 0, x[:1], fast=True, n_dense=4)[2]
+    for level in range(16):
+        a, b = hh.level_corners(pcfg, level, x, fast=False), hh.level_corners(pcfg, level, x, fast=True)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
