@@ -138,6 +138,44 @@ inline bool fast_addressing_ok(const LevelTable& lt, uint32_t n_dense)
     return true;
 }
 
+// Scatter of one level's 8 corner contributions (float2 each) into an fp32 gradient table.
+// V4: the two x-neighbours of a corner pair sit in the same 16-byte slot whenever their indices differ in bit 0
+// only (always for a hashed level when the cell's x coordinate is even, and for a dense level when the index
+// is even): one 16-byte vector atomic then replaces two 8-byte ones.  `dtable` must be 16-byte aligned for V4.
+// (Host compilation = tests/host_harness.py: plain adds, one thread.)
+__host__ __device__ __forceinline__ void grad_add2(float2* p, float2 v)
+{
+#ifdef __CUDA_ARCH__
+    atomicAdd(p, v);
+#else
+    p->x += v.x; p->y += v.y;
+#endif
+}
+__host__ __device__ __forceinline__ void grad_add4(float4* p, float4 v)
+{
+#ifdef __CUDA_ARCH__
+    atomicAdd(p, v);
+#else
+    p->x += v.x; p->y += v.y; p->z += v.z; p->w += v.w;
+#endif
+}
+template <bool V4>
+__host__ __device__ __forceinline__ void scatter8(float2* __restrict__ dtable, const uint32_t (&idx)[8], const float2 (&v)[8])
+{
+#pragma unroll
+    for (int k = 0; k < 8; k += 2) {
+        const uint32_t i0 = idx[k], i1 = idx[k + 1];
+        if (V4 && ((i0 ^ i1) == 1u)) {
+            const bool swap = (i0 & 1u) != 0u;
+            const float2 lo = swap ? v[k + 1] : v[k], hi = swap ? v[k] : v[k + 1];
+            grad_add4(reinterpret_cast<float4*>(dtable + (i0 & ~1u)), make_float4(lo.x, lo.y, hi.x, hi.y));
+        } else {
+            grad_add2(dtable + i0, v[k]);
+            grad_add2(dtable + i1, v[k + 1]);
+        }
+    }
+}
+
 __device__ __forceinline__ uint32_t pack_half2(float a, float b)
 {
     __half2 h = __floats2half2_rn(a, b);

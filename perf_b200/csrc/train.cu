@@ -1,5 +1,6 @@
 // train.cu -- backward half of the fused training step: composite backward (thread = ray, marching
 // back along the saved samples) and the grid-gradient scatter for ray-ordered samples.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace perf {
@@ -124,6 +125,7 @@ struct GridBwdRaysArgs {
     const float* dfeat; float2* dtable;
 };
 
+template <bool V4>
 __global__ void __launch_bounds__(256) hashgrid_bwd_rays_kernel(const __grid_constant__ GridBwdRaysArgs a)
 {
     const int l = blockIdx.y;
@@ -162,11 +164,11 @@ __global__ void __launch_bounds__(256) hashgrid_bwd_rays_kernel(const __grid_con
         v[k] = make_float2(w * g.x, w * g.y);
     }
     if (active) {
+        uint32_t idx[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const uint32_t idx = off + level_index(gx + (k & 1), gy + ((k >> 1) & 1), gz + ((k >> 2) & 1), hashed, pow2, res, size);
-            atomicAdd(a.dtable + idx, v[k]);
-        }
+        for (int k = 0; k < 8; ++k)
+            idx[k] = off + level_index(gx + (k & 1), gy + ((k >> 1) & 1), gz + ((k >> 2) & 1), hashed, pow2, res, size);
+        scatter8<V4>(a.dtable, idx, v);
     }
 }
 
@@ -301,7 +303,11 @@ int perf_hashgrid_bwd_rays(const perf_grid_cfg* cfg, const float* aabb6, const f
         b.lt.hashed_mask = a.lt.hashed_mask >> n_agg; b.lt.pow2_mask = a.lt.pow2_mask >> n_agg;
         b.dfeat = a.dfeat + 2 * n_agg;                       // column window; row stride stays 2 * n_levels
         dim3 g_rest((unsigned)((N + 255) / 256), a.lt.n_levels - n_agg);
-        hashgrid_bwd_rays_kernel<<<g_rest, 256, 0, (cudaStream_t)stream>>>(b);
+        // experimental (off by default, measured in round 2): 16-byte vector atomics for x-neighbour pairs
+        const char* env_v4 = getenv("PERF_B200_SCATTER_V4");
+        const bool want_v4 = env_v4 && env_v4[0] == '1';
+        if (want_v4 && (uintptr_t)b.dtable % 16 == 0) hashgrid_bwd_rays_kernel<true><<<g_rest, 256, 0, (cudaStream_t)stream>>>(b);
+        else hashgrid_bwd_rays_kernel<false><<<g_rest, 256, 0, (cudaStream_t)stream>>>(b);
         PERF_LAUNCH_CHECK();
     }
     return PERF_OK;

@@ -28,5 +28,17 @@ int perf_host_level_corners(const perf_grid_cfg* cfg, int level, int mode, uint3
     return PERF_OK;
 }
 
+// scatter8<V4> over N rows of (idx[8], v[8] float2) into dtable (float2 entries, 16-byte aligned for v4 != 0)
+int perf_host_scatter8(int v4, const uint32_t* idx, const float* v, uint64_t N, float* dtable)
+{
+    if (v4 && ((uintptr_t)dtable % 16) != 0) return PERF_EINVAL;
+    for (uint64_t i = 0; i < N; ++i) {
+        uint32_t id[8]; float2 val[8];
+        for (int k = 0; k < 8; ++k) { id[k] = idx[8 * i + k]; val[k] = make_float2(v[16 * i + 2 * k], v[16 * i + 2 * k + 1]); }
+        if (v4) scatter8<true>((float2*)dtable, id, val); else scatter8<false>((float2*)dtable, id, val);
+    }
+    return PERF_OK;
+}
+
 #pragma GCC visibility pop
 }

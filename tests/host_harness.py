@@ -70,3 +70,14 @@ def level_corners(grid_cfg, level: int, x01: np.ndarray, fast: bool, n_dense: in
                                        _p(idx), _p(w), C.byref(ok))
     assert rc == 0, rc
     return idx, w, bool(ok.value)
+
+
+def scatter8(idx: np.ndarray, v: np.ndarray, n_entries: int, v4: bool) -> np.ndarray:
+    """scatter8<V4> of common.cuh: idx [N,8] uint32, v [N,8,2] f32 -> dtable [n_entries,2] f32."""
+    raw = np.zeros(2 * n_entries + 4, np.float32)
+    shift = (-raw.ctypes.data % 16) // 4                       # 16-byte aligned view
+    dtable = raw[shift:shift + 2 * n_entries].reshape(n_entries, 2)
+    rc = lib().perf_host_scatter8(int(v4), _p(np.ascontiguousarray(idx, np.uint32)), _p(np.ascontiguousarray(v, np.float32)),
+                                  C.c_uint64(idx.shape[0]), _p(dtable))
+    assert rc == 0, rc
+    return dtable.copy()

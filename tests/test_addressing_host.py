@@ -77,3 +77,35 @@ def test_perf_grid_is_admitted_with_four_dense_levels():
     for level in range(16):
         a, b = hh.level_corners(pcfg, level, x, fast=False), hh.level_corners(pcfg, level, x, fast=True)
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_vector_atomic_scatter_pairs_equal_plain_scatter():
+    """scatter8<V4> (x-neighbour pairs in one 16-byte slot -> one vector add) against scatter8<false> and numpy, on
+    index patterns covering: aligned pair in both orders, unaligned neighbours (odd, odd+1), equal indices, far apart,
+    and real level addressing of the PeRF grid."""
+    rng = np.random.default_rng(0)
+    n_entries = 4096
+    rows = []
+    for _ in range(500):
+        base = rng.integers(0, n_entries // 2 - 2, size=4) * 2
+        kind = rng.integers(0, 5, size=4)
+        pairs = []
+        for b, kd in zip(base, kind):
+            pairs += {0: [b, b + 1], 1: [b + 1, b], 2: [b + 1, b + 2], 3: [b, b], 4: [b, (b + 1000) % n_entries]}[int(kd)]
+        rows.append(pairs)
+    idx = np.array(rows, np.uint32)
+    v = rng.standard_normal((len(rows), 8, 2)).astype(np.float32)
+    want = np.zeros((n_entries, 2), np.float64)
+    np.add.at(want, idx.reshape(-1), v.reshape(-1, 2).astype(np.float64))
+    plain, vec = hh.scatter8(idx, v, n_entries, v4=False), hh.scatter8(idx, v, n_entries, v4=True)
+    np.testing.assert_allclose(plain, want, atol=1e-5)
+    np.testing.assert_allclose(vec, want, atol=1e-5)
+    # real addressing: every level of the PeRF grid
+    pcfg = GridConfig(16, 2, 18, 16, 1.4472692012786865, "Linear")
+    x = _points(512, 3).numpy()
+    for level in (0, 3, 4, 9, 15):
+        idx, w, _ = hh.level_corners(pcfg, level, x, fast=False)
+        val = np.stack([w, -w], -1).astype(np.float32)
+        a, b = hh.scatter8(idx, val, pcfg.n_entries, v4=False), hh.scatter8(idx, val, pcfg.n_entries, v4=True)
+        np.testing.assert_allclose(a, b, atol=1e-6)
+        assert abs(float(b[:, 0].sum()) - len(x)) < 1e-2          # the 8 weights of a sample sum to 1

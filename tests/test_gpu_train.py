@@ -1,5 +1,7 @@
 """GPU tests of the training path (differentiable render -> losses -> backward -> fused Adam)
 through the host mirror of NeRFScene, against the oracle's autograd and torch.optim.Adam."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -251,3 +253,23 @@ def test_graphed_training_fits_like_eager():
     assert not torch.equal(sc.nerf.geo_mlp.params.detach(), before)
     assert torch.equal(sc.nerf.geo_mlp._half(), sc.nerf.geo_mlp.params.detach().half())
     assert float(step(0.3)) < l0
+
+
+@pytest.mark.skipif(os.environ.get("PERF_B200_EXPERIMENTAL") != "1", reason="experimental variant (DESIGN.md 8.1): set PERF_B200_EXPERIMENTAL=1")
+def test_vector_atomic_scatter_variant_matches_default():
+    """PERF_B200_SCATTER_V4=1 (16-byte vector atomics for x-neighbour pairs in the fine-level grid scatter)
+    accumulates the same gradient table as the default 8-byte atomics."""
+    from perf_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    R, S = 4096, 32
+    o = ((torch.rand(R, 3, generator=g) - 0.5) * 0.2).cuda()
+    d = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1).cuda()
+    dfeat = torch.randn(R * S, 32, generator=g).cuda()
+    os.environ.pop("PERF_B200_SCATTER_V4", None)
+    want = ops.hashgrid_bwd_rays(o, d, None, S, 1e-2, 1.0, dfeat)
+    os.environ["PERF_B200_SCATTER_V4"] = "1"
+    try:
+        got = ops.hashgrid_bwd_rays(o, d, None, S, 1e-2, 1.0, dfeat)
+    finally:
+        os.environ.pop("PERF_B200_SCATTER_V4", None)
+    assert (got - want).abs().max() <= 1e-4 * want.abs().max()
