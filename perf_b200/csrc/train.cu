@@ -303,9 +303,10 @@ int perf_hashgrid_bwd_rays(const perf_grid_cfg* cfg, const float* aabb6, const f
         b.lt.hashed_mask = a.lt.hashed_mask >> n_agg; b.lt.pow2_mask = a.lt.pow2_mask >> n_agg;
         b.dfeat = a.dfeat + 2 * n_agg;                       // column window; row stride stays 2 * n_levels
         dim3 g_rest((unsigned)((N + 255) / 256), a.lt.n_levels - n_agg);
-        // experimental (off by default, measured in round 2): 16-byte vector atomics for x-neighbour pairs
+        // 16-byte vector atomics for x-neighbour pairs (REDG.E.ADD.F32x4): 0.659 -> 0.586 ms for the two scatter
+        // launches of an 8192 x 128 step on a B200 (tools/ab_scatter_v4.py); PERF_B200_SCATTER_V4=0 restores the 8-byte path
         const char* env_v4 = getenv("PERF_B200_SCATTER_V4");
-        const bool want_v4 = env_v4 && env_v4[0] == '1';
+        const bool want_v4 = !(env_v4 && env_v4[0] == '0');
         if (want_v4 && (uintptr_t)b.dtable % 16 == 0) hashgrid_bwd_rays_kernel<true><<<g_rest, 256, 0, (cudaStream_t)stream>>>(b);
         else hashgrid_bwd_rays_kernel<false><<<g_rest, 256, 0, (cudaStream_t)stream>>>(b);
         PERF_LAUNCH_CHECK();

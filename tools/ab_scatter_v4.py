@@ -1,5 +1,5 @@
-"""A/B of the fine-level grid scatter: default 8-byte atomics vs PERF_B200_SCATTER_V4=1 (16-byte vector atomics
-for x-neighbour pairs).  Same inputs as one 8192 x 128 training step; prints ms per call and the max difference."""
+"""A/B of the fine-level grid scatter: 8-byte atomics (PERF_B200_SCATTER_V4=0) vs 16-byte vector atomics for
+x-neighbour pairs (the default since this measurement: 0.659 -> 0.586 ms on a B200).  Same inputs as one 8192 x 128 training step; prints ms per call and the max difference."""
 import os
 import sys
 
@@ -18,10 +18,7 @@ out = torch.zeros(ops.PERF_GRID.n_entries, 2, device="cuda")
 
 
 def run(v4, iters=20):
-    if v4:
-        os.environ["PERF_B200_SCATTER_V4"] = "1"
-    else:
-        os.environ.pop("PERF_B200_SCATTER_V4", None)
+    os.environ["PERF_B200_SCATTER_V4"] = "1" if v4 else "0"
     for _ in range(3):
         ops.hashgrid_bwd_rays(o, d, jit, S, 1e-2, 1.0, dfeat, out=out.zero_())
     torch.cuda.synchronize()
