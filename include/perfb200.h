@@ -126,6 +126,15 @@ int perf_hashgrid_bwd_bwd_input(const perf_grid_cfg* cfg, const void* d_table_ha
                                 const float* d_dfeat, const float* d_ddx, uint64_t N,
                                 float* d_ddfeat, float* d_dtable, float* d_dx2, void* stream);
 
+/* MLP backward from the saved fp16 activations, one tcgen05 kernel (tcnn FullyFusedMLP backward for the two
+ * PeRF networks, ngp_nerf.py:107-113,127-133).  d_feat [N,32], d_h1 [N,64], d_h2 [N,64] (two hidden layers,
+ * else NULL): fp16 saves of perf_network_fwd / perf_train_forward; d_dz [N,n_out] fp32 = gradient w.r.t. the
+ * output pre-activation (n_out <= 3).  d_dweights: fp32 gradient of the flat MLP params, ACCUMULATED (caller
+ * zeroes); d_dfeat [N,32] fp32 overwritten.  flags: PERF_FLAG_SIMT_MLP selects the CUDA-core twin.
+ * EXPERIMENTAL in round 1 (not yet run on a GPU): the default training path does not call it. */
+int perf_mlp_bwd(const perf_mlp_cfg* mlp, const void* d_weights_half, const void* d_feat, const void* d_h1, const void* d_h2,
+                 const float* d_dz, uint64_t N, float* d_dweights, float* d_dfeat, uint32_t flags, void* stream);
+
 /* Network forward = encode + MLP fused (tcnn NetworkWithInputEncoding.forward;
  * ngp_nerf.py:142,158).  d_x01 [N,3] fp32; d_params_half: fp16 flat params (MLP | grid);
  * d_out [N, n_out] fp16.  Optional saves for the backward pass (NULL to skip):

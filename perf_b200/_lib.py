@@ -78,6 +78,7 @@ SIGNATURES = {
     "perf_hashgrid_bwd_rays": (i32, [P(GridCfg), P(f32), vp, vp, vp, u64, u32, f32, f32, vp, vp, vp]),
     "perf_occ_count": (i32, [vp, P(i32), P(f32), vp, vp, vp, u64, f32, f32, f32, vp, vp]),
     "perf_occ_write": (i32, [vp, P(i32), P(f32), vp, vp, vp, u64, f32, f32, f32, vp, vp, vp, vp, vp]),
+    "perf_mlp_bwd": (i32, [P(MlpCfg), vp, vp, vp, vp, vp, u64, vp, vp, u32, vp]),
     "perf_mlp_bwd_out": (i32, [vp, i32, vp, vp, vp, u64, vp]),
     "perf_relu_mask": (i32, [vp, vp, u64, vp]),
     "perf_adam_step": (i32, [vp, vp, vp, vp, vp, u64, f32, f32, f32, f32, u32, f32, vp]),

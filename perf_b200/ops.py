@@ -7,6 +7,7 @@ CPU path: a non-CUDA tensor raises.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -505,6 +506,8 @@ def mlp_backward_half(mlp: MLPConfig, weights_half: torch.Tensor, feat, h1, h2, 
     Returns (d_weights_flat fp32 [mlp.n_params] -- written into ``grad_out`` when given --, dfeat fp32 [N,32])."""
     N, dev = dz.shape[0], dz.device
     W = weights_half
+    if os.environ.get("PERF_B200_TC_MLP_BWD") == "1":         # experimental single-kernel backward (csrc/mlp_bwd.cu)
+        return mlp_backward_fused(mlp, weights_half, feat, h1, h2, dz, grad_out)
     w1 = W[:64 * 32].view(64, 32)
     p = 64 * 32
     w2 = None
@@ -529,6 +532,24 @@ def mlp_backward_half(mlp: MLPConfig, weights_half: torch.Tensor, feat, h1, h2, 
             _call(_L().perf_relu_mask, _p(dh), _p(h1), N * 64, _stream())
     g_w1.copy_(torch.mm(dh.t(), feat, out_dtype=torch.float32))
     dfeat = torch.mm(dh, w1, out_dtype=torch.float32)
+    return grad_out, dfeat
+
+
+def mlp_backward_fused(mlp: MLPConfig, weights_half: torch.Tensor, feat, h1, h2, dz: torch.Tensor,
+                       grad_out: Optional[torch.Tensor] = None, simt: bool = False):
+    """Same contract as :func:`mlp_backward_half`, as ONE tcgen05 kernel (perf_mlp_bwd).  EXPERIMENTAL: written
+    at the end of round 1 without GPU time to validate it; only reached with PERF_B200_TC_MLP_BWD=1."""
+    N, dev = dz.shape[0], dz.device
+    if grad_out is None:
+        grad_out = torch.zeros(mlp.n_params, dtype=torch.float32, device=dev)
+    else:
+        grad_out[:mlp.n_params].zero_()
+    dfeat = torch.empty(N, 32, dtype=torch.float32, device=dev)
+    dz = _chk(dz.reshape(N, mlp.n_out), torch.float32, "dz")
+    with torch.cuda.device(dev):
+        _call(_L().perf_mlp_bwd, mlp.c(), _p(_chk(weights_half, torch.float16, "weights")), _p(_chk(feat, torch.float16, "feat")),
+              _p(_chk(h1, torch.float16, "h1")), _p(None if h2 is None else _chk(h2, torch.float16, "h2")), _p(dz), N,
+              _p(grad_out), _p(dfeat), _lib.PERF_FLAG_SIMT_MLP if simt else 0, _stream())
     return grad_out, dfeat
 
 

@@ -271,3 +271,34 @@ def test_vector_atomic_scatter_matches_scalar_pairs():
         os.environ.pop("PERF_B200_SCATTER_V4", None)
     got = ops.hashgrid_bwd_rays(o, d, None, S, 1e-2, 1.0, dfeat)
     assert float(want.abs().max()) > 0 and (got - want).abs().max() <= 1e-4 * want.abs().max()
+
+
+@pytest.mark.skipif(os.environ.get("PERF_B200_EXPERIMENTAL") != "1",
+                    reason="experimental kernel (csrc/mlp_bwd.cu, written without GPU time in round 1): set PERF_B200_EXPERIMENTAL=1")
+@pytest.mark.parametrize("two_hidden", [False, True], ids=["density", "colour"])
+@pytest.mark.parametrize("simt", [True, False], ids=["simt", "tcgen05"])
+def test_single_kernel_mlp_backward_matches_gemm_path(two_hidden, simt):
+    """perf_mlp_bwd (one tcgen05 kernel; CUDA-core twin on the same shared-memory images) against the default
+    path (cuBLAS fp16 GEMMs + perf_mlp_bwd_out / perf_relu_mask) on the same saved activations."""
+    from perf_b200 import ops
+    from perf_b200.config import APP_MLP, GEO_MLP
+    mlp = APP_MLP if two_hidden else GEO_MLP
+    g = torch.Generator().manual_seed(7)
+    N = 128 * 37 + 53                                              # ragged last tile
+    W = ((torch.rand(mlp.n_params, generator=g) * 2 - 1) * 0.3).half().cuda()
+    feat = ((torch.rand(N, 32, generator=g) * 2 - 1) * 0.5).half().cuda()
+    w1 = W[:2048].view(64, 32)
+    h1 = torch.relu(feat.float() @ w1.float().t()).half()
+    h2 = None
+    if two_hidden:
+        h2 = torch.relu(h1.float() @ W[2048:2048 + 4096].view(64, 64).float().t()).half()
+    dz = (torch.randn(N, mlp.n_out, generator=g) * 0.1).cuda()
+    os.environ.pop("PERF_B200_TC_MLP_BWD", None)
+    want_w, want_f = ops.mlp_backward_half(mlp, W, feat, h1, h2, dz)
+    got_w, got_f = ops.mlp_backward_fused(mlp, W, feat, h1, h2, dz, simt=simt)
+    torch.cuda.synchronize()
+    n_real = 2048 + (4096 if two_hidden else 0)
+    assert (got_f - want_f).abs().max() <= 2e-3 * want_f.abs().max() + 1e-6
+    assert (got_w[:n_real] - want_w[:n_real]).abs().max() <= 2e-3 * want_w[:n_real].abs().max()
+    wo_g, wo_w = got_w[n_real:].view(16, 64)[:mlp.n_out], want_w[n_real:].view(16, 64)[:mlp.n_out]
+    assert (wo_g - wo_w).abs().max() <= 2e-3 * wo_w.abs().max()
