@@ -21,7 +21,6 @@ ordinary torch; the batches it hands out feed the CUDA training step.
 """
 from __future__ import annotations
 
-from typing import Optional
 
 import numpy as np
 import torch
