@@ -20,38 +20,38 @@ APP_NETWORK_CONFIG = {"otype": "FullyFusedMLP", "activation": "ReLU", "output_ac
                       "n_neurons": 64, "n_hidden_layers": 2}                            # ngp_nerf.py:127-133
 
 
-class _TruncExp(torch.autograd.Function):
-    """`ngp_nerf.py:24-40`: forward exp(x) in fp32, backward g * exp(clamp(x, max=15))."""
+class _ExpWithCappedSlope(torch.autograd.Function):
+    """The density activation of `ngp_nerf.py:24-40`: exp(raw) evaluated in fp32; its derivative is taken as
+    exp(min(raw, 15)) so that one exploding logit cannot blow up the step (the fused kernels apply the same
+    cap: ``composite_bwd_kernel``, ``fminf(sigma, e^15)``)."""
 
     @staticmethod
-    def forward(ctx, x):
-        x = x.float()
-        ctx.save_for_backward(x)
-        return torch.exp(x)
+    def forward(ctx, raw):
+        raw32 = raw.float()
+        ctx.save_for_backward(raw32)
+        return raw32.exp()
 
     @staticmethod
-    def backward(ctx, g):
-        (x,) = ctx.saved_tensors
-        return g * torch.exp(torch.clamp(x, max=15))
+    def backward(ctx, grad_sigma):
+        (raw32,) = ctx.saved_tensors
+        return grad_sigma * raw32.clamp(max=15.0).exp()
 
 
-trunc_exp = _TruncExp.apply
+trunc_exp = _ExpWithCappedSlope.apply
 
 
 class NGPNeRF(torch.nn.Module):
     def __init__(self, aabb: Union[torch.Tensor, List[float]], num_dim: int = 3, seed: int = 1337):
         super().__init__()
-        if not isinstance(aabb, torch.Tensor):
-            aabb = torch.tensor(aabb, dtype=torch.float32)
-        self.register_buffer("aabb", aabb)
         self.num_dim = num_dim
+        self.register_buffer("aabb", torch.as_tensor(aabb, dtype=torch.float32).clone())      # [min xyz | max xyz]
         self.geo_mlp = tcnn.NetworkWithInputEncoding(num_dim, 1, ENCODING_CONFIG, GEO_NETWORK_CONFIG, seed=seed)
         self.app_mlp = tcnn.NetworkWithInputEncoding(num_dim, 3, ENCODING_CONFIG, APP_NETWORK_CONFIG, seed=seed + 1)
 
     def _normalise(self, x):
-        aabb_min, aabb_max = torch.split(self.aabb, self.num_dim, dim=-1)
-        x = (x - aabb_min) / (aabb_max - aabb_min)
-        return x, ((x > 0.0) & (x < 1.0)).all(dim=-1)
+        lo, hi = self.aabb[:self.num_dim], self.aabb[self.num_dim:]
+        unit = (x - lo) / (hi - lo)
+        return unit, ((unit > 0.0) & (unit < 1.0)).all(dim=-1)
 
     def query_density(self, x: torch.Tensor) -> torch.Tensor:
         """`ngp_nerf.py:136-150`: sigma = trunc_exp(geo_mlp(x01)) * selector, shape [..., 1] fp32."""
