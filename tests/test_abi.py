@@ -116,3 +116,26 @@ def test_level_table_matches_oracle_property():
             assert np.float32(a.scale) == b.scale
             assert (a.resolution, a.size, a.offset, bool(a.hashed)) == (b.resolution, b.size, b.offset, b.hashed)
     check()
+
+
+def test_header_is_plain_c_and_a_c_host_links(tmp_path):
+    """The boundary is a C ABI: include/perfb200.h compiles as strict C99 and examples/render_pano_host.c (a host
+    that uses nothing but the header and the CUDA runtime) compiles and links against libperfb200.so."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = os.path.join(root, "include", "perfb200.h")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr], check=True)
+    cuda = "/usr/local/cuda"
+    if not os.path.exists(os.path.join(cuda, "include", "cuda_runtime_api.h")):
+        pytest.skip("no CUDA toolkit headers")
+    from perf_b200.build import build
+    lib_dir = os.path.dirname(build())
+    exe = str(tmp_path / "render_pano_host")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(root, "include"), "-I", os.path.join(cuda, "include"),
+                    os.path.join(root, "examples", "render_pano_host.c"), "-L", lib_dir, "-lperfb200",
+                    "-L", os.path.join(cuda, "lib64"), "-lcudart", "-lm", f"-Wl,-rpath,{lib_dir}", "-o", exe], check=True)
+    usage = subprocess.run([exe], capture_output=True, text=True)
+    assert usage.returncode == 2 and "usage" in usage.stderr
