@@ -136,4 +136,6 @@ class WildDataset(Dataset):                                                     
             raise ValueError(f"{self.ref_distance_path}: shape {tuple(self.ref_distance.shape)} does not match the image "
                              f"({self.height}, {self.width})")
         self.normalization()
-        self.save_ref_geometry()
+        from . import parallel
+        if parallel.rank() == 0:                                               # under torchrun every rank builds the dataset
+            self.save_ref_geometry()
