@@ -102,10 +102,11 @@ class Dataset:                                                                  
         self.ref_distance /= scale
 
     def save_ref_geometry(self):                                                             # dataset.py:103-119
-        if self.ref_distance_path is not None:
-            np.save(self.ref_distance_path, self.ref_distance.cpu().numpy())
-        if self.ref_normal_path is not None:
-            np.save(self.ref_normal_path, self.ref_normal.cpu().numpy())
+        for path, value in ((self.ref_distance_path, self.ref_distance), (self.ref_normal_path, self.ref_normal)):
+            if path is not None:                                              # atomic: other ranks may be reading it
+                tmp = f"{path}.{os.getpid()}.tmp.npy"
+                np.save(tmp, value.cpu().numpy())
+                os.replace(tmp, path)
         pts = self.ref_point_cloud().cpu().numpy().reshape(-1, 3)
         assert self.ref_geometry_path is not None and self.ref_geometry_path[-4:] == ".ply"
         write_point_cloud_ply(self.ref_geometry_path, pts, None if self.image is None else self.image.reshape(-1, 3).cpu().numpy())
