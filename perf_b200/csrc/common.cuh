@@ -63,8 +63,14 @@ __host__ __device__ __forceinline__ uint32_t level_index(uint32_t gx, uint32_t g
 // when the same source is compiled for the host by tests/host_harness.py
 #ifdef __CUDA_ARCH__
 #define PERF_FMUL_RN(a, b) __fmul_rn((a), (b))
+#define PERF_FADD_RN(a, b) __fadd_rn((a), (b))
+#define PERF_FSUB_RN(a, b) __fsub_rn((a), (b))
+#define PERF_FDIV_RN(a, b) __fdiv_rn((a), (b))
 #else
 #define PERF_FMUL_RN(a, b) ((a) * (b))
+#define PERF_FADD_RN(a, b) ((a) + (b))
+#define PERF_FSUB_RN(a, b) ((a) - (b))
+#define PERF_FDIV_RN(a, b) ((a) / (b))
 #endif
 
 __host__ __device__ __forceinline__ void level_corners(const LevelTable& lt, int l, float x, float y, float z, Corner8& c)

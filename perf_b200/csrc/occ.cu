@@ -16,23 +16,23 @@ struct OccArgs {
     int64_t* ray_indices; float *t_starts, *t_ends;
 };
 
+// One ray.  __host__ __device__: tests/host_harness.py compiles this file with -DPERF_HOST_HARNESS into a separate
+// test-only object and runs the same body over host arrays against oracle/occ_sampler.py.
 template <bool WRITE>
-__global__ void __launch_bounds__(128) occ_march_kernel(const OccArgs a)
+__host__ __device__ __forceinline__ void occ_march_ray(const OccArgs& a, uint64_t ray)
 {
-    const uint64_t ray = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (ray >= a.R) return;
     const float o[3] = {a.rays_o[3 * ray], a.rays_o[3 * ray + 1], a.rays_o[3 * ray + 2]};
     const float d[3] = {a.rays_d[3 * ray], a.rays_d[3 * ray + 1], a.rays_d[3 * ray + 2]};
     float tn = -INFINITY, tf = INFINITY;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        const float inv = __fdiv_rn(1.0f, fabsf(d[i]) < 1e-12f ? 1e-12f : d[i]);
-        const float t0 = __fmul_rn(__fsub_rn(a.amin[i], o[i]), inv), t1 = __fmul_rn(__fsub_rn(a.amax[i], o[i]), inv);
+        const float inv = PERF_FDIV_RN(1.0f, fabsf(d[i]) < 1e-12f ? 1e-12f : d[i]);
+        const float t0 = PERF_FMUL_RN(PERF_FSUB_RN(a.amin[i], o[i]), inv), t1 = PERF_FMUL_RN(PERF_FSUB_RN(a.amax[i], o[i]), inv);
         tn = fmaxf(tn, fminf(t0, t1)); tf = fminf(tf, fmaxf(t0, t1));
     }
     tn = fmaxf(tn, a.near); tf = fminf(tf, a.far);
     const float u = a.jitter ? a.jitter[ray] : 0.f;
-    const float half_step = __fmul_rn(0.5f, a.step);
+    const float half_step = PERF_FMUL_RN(0.5f, a.step);
     int64_t pos = WRITE ? a.offsets[ray] : 0;
     int32_t n = 0;
     if (tf >= tn) {
@@ -40,25 +40,32 @@ __global__ void __launch_bounds__(128) occ_march_kernel(const OccArgs a)
         float kf = floorf((tn - a.near) / a.step - u - 0.5f) - 2.0f;
         uint32_t k = kf > 0.f ? (uint32_t)kf : 0u;
         for (;; ++k) {
-            const float ts = __fadd_rn(a.near, __fmul_rn(__fadd_rn((float)k, u), a.step));
-            const float mid = __fadd_rn(ts, half_step);
+            const float ts = PERF_FADD_RN(a.near, PERF_FMUL_RN(PERF_FADD_RN((float)k, u), a.step));
+            const float mid = PERF_FADD_RN(ts, half_step);
             if (mid > tf) break;
             if (mid < tn) continue;
             int c[3];
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-                const float p = __fadd_rn(o[i], __fmul_rn(d[i], mid));
+                const float p = PERF_FADD_RN(o[i], PERF_FMUL_RN(d[i], mid));
                 const int res = i == 0 ? a.rx : (i == 1 ? a.ry : a.rz);
-                int ci = (int)floorf(__fmul_rn(__fdiv_rn(__fsub_rn(p, a.amin[i]), a.aext[i]), (float)res));
+                int ci = (int)floorf(PERF_FMUL_RN(PERF_FDIV_RN(PERF_FSUB_RN(p, a.amin[i]), a.aext[i]), (float)res));
                 c[i] = ci < 0 ? 0 : (ci > res - 1 ? res - 1 : ci);
             }
             if (a.binaries[((int64_t)c[0] * a.ry + c[1]) * a.rz + c[2]]) {
-                if (WRITE) { a.ray_indices[pos] = (int64_t)ray; a.t_starts[pos] = ts; a.t_ends[pos] = __fadd_rn(ts, a.step); ++pos; }
+                if (WRITE) { a.ray_indices[pos] = (int64_t)ray; a.t_starts[pos] = ts; a.t_ends[pos] = PERF_FADD_RN(ts, a.step); ++pos; }
                 ++n;
             }
         }
     }
     if (!WRITE) a.counts[ray] = n;
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(128) occ_march_kernel(const OccArgs a)
+{
+    const uint64_t ray = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ray < a.R) occ_march_ray<WRITE>(a, ray);
 }
 
 }  // namespace perf
@@ -104,6 +111,19 @@ int perf_occ_write(const uint8_t* d_binaries, const int* h_res3, const float* h_
     PERF_LAUNCH_CHECK();
     return PERF_OK;
 }
+
+#ifdef PERF_HOST_HARNESS
+/* TEST HARNESS ONLY (never compiled into libperfb200.so): the per-ray body over HOST arrays.  pass 0 = count, 1 = write. */
+int perf_host_occ_march(int pass, const uint8_t* h_binaries, const int* h_res3, const float* h_aabb6, const float* h_rays_o,
+                        const float* h_rays_d, const float* h_jitter, uint64_t R, float near, float far, float step,
+                        int32_t* h_counts, const int64_t* h_offsets, int64_t* h_ray_indices, float* h_t_starts, float* h_t_ends)
+{
+    OccArgs a; int rc = fill(a, h_binaries, h_res3, h_aabb6, h_rays_o, h_rays_d, h_jitter, R, near, far, step); if (rc) return rc;
+    a.counts = h_counts; a.offsets = h_offsets; a.ray_indices = h_ray_indices; a.t_starts = h_t_starts; a.t_ends = h_t_ends;
+    for (uint64_t r = 0; r < R; ++r) { if (pass == 0) occ_march_ray<false>(a, r); else occ_march_ray<true>(a, r); }
+    return PERF_OK;
+}
+#endif
 
 #pragma GCC visibility pop
 }

@@ -12,7 +12,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(HERE), "perf_b200", "csrc")
 OUT = os.path.join(HERE, "_build", "libperf_host_harness.so")
-SOURCES = [os.path.join(CSRC, "api_basic.cu"), os.path.join(CSRC, "encoding_grad.cu"), os.path.join(HERE, "host_harness.cu")]
+SOURCES = [os.path.join(CSRC, "api_basic.cu"), os.path.join(CSRC, "encoding_grad.cu"), os.path.join(CSRC, "occ.cu"),
+           os.path.join(HERE, "host_harness.cu")]
 _LIB = None
 
 
@@ -81,3 +82,22 @@ def scatter8(idx: np.ndarray, v: np.ndarray, n_entries: int, v4: bool) -> np.nda
                                   C.c_uint64(idx.shape[0]), _p(dtable))
     assert rc == 0, rc
     return dtable.copy()
+
+
+def occ_sample(binaries: np.ndarray, aabb, rays_o: np.ndarray, rays_d: np.ndarray, near: float, far: float, step: float, jitter=None):
+    """occ_march_ray of csrc/occ.cu (count pass, exclusive scan, write pass) -> (ray_indices, t_starts, t_ends)."""
+    R = rays_o.shape[0]
+    bin8 = np.ascontiguousarray(binaries, np.uint8)
+    res3 = (C.c_int * 3)(*binaries.shape)
+    a6 = (C.c_float * 6)(*[float(v) for v in aabb])
+    o, d = np.ascontiguousarray(rays_o, np.float32), np.ascontiguousarray(rays_d, np.float32)
+    j = None if jitter is None else np.ascontiguousarray(jitter, np.float32)
+    counts = np.zeros(R, np.int32)
+    f = lib().perf_host_occ_march
+    args = (_p(bin8), res3, a6, _p(o), _p(d), _p(j), C.c_uint64(R), C.c_float(near), C.c_float(far), C.c_float(step))
+    assert f(0, *args, _p(counts), None, None, None, None) == 0
+    offsets = np.concatenate([[0], np.cumsum(counts, dtype=np.int64)]).astype(np.int64)
+    n = int(offsets[-1])
+    ri, ts, te = np.zeros(max(n, 1), np.int64), np.zeros(max(n, 1), np.float32), np.zeros(max(n, 1), np.float32)
+    assert f(1, *args, None, _p(offsets), _p(ri), _p(ts), _p(te)) == 0
+    return ri[:n], ts[:n], te[:n]
