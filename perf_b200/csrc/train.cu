@@ -125,26 +125,26 @@ struct GridBwdRaysArgs {
     const float* dfeat; float2* dtable;
 };
 
+// One (row, level) of the fine-level scatter.  __host__ __device__ like the other per-thread bodies of this file:
+// tests/host_harness.py runs them over host arrays (single thread, plain adds) against the oracle.
 template <bool V4>
-__global__ void __launch_bounds__(256) hashgrid_bwd_rays_kernel(const __grid_constant__ GridBwdRaysArgs a)
+__host__ __device__ __forceinline__ void bwd_rays_row_level(const GridBwdRaysArgs& a, uint64_t row, int l)
 {
-    const int l = blockIdx.y;
     const uint64_t N = a.R * a.S;
-    const uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = row < N;
     float2 g = make_float2(0.f, 0.f);
     float x = 0.5f, y = 0.5f, z = 0.5f;
     if (live) {
         g = *reinterpret_cast<const float2*>(a.dfeat + row * (2 * a.lt.n_levels) + 2 * l);
         const uint64_t ray = row % a.R; const uint32_t k = (uint32_t)(row / a.R);
-        const float step = __fdiv_rn(__fsub_rn(a.far, a.near), (float)a.S);
+        const float step = PERF_FDIV_RN(PERF_FSUB_RN(a.far, a.near), (float)a.S);
         const float jit = a.jitter ? a.jitter[ray] : 0.f;
-        const float ts = __fadd_rn(a.near, __fmul_rn(__fadd_rn((float)k, jit), step));
-        const float te = __fadd_rn(a.near, __fmul_rn(__fadd_rn((float)(k + 1), jit), step));
-        const float tsum = __fadd_rn(ts, te);
-        x = __fdiv_rn(__fsub_rn(__fadd_rn(a.rays_o[3 * ray], __fmul_rn(a.rays_d[3 * ray], tsum) * 0.5f), a.aabb_min[0]), a.aabb_ext[0]);
-        y = __fdiv_rn(__fsub_rn(__fadd_rn(a.rays_o[3 * ray + 1], __fmul_rn(a.rays_d[3 * ray + 1], tsum) * 0.5f), a.aabb_min[1]), a.aabb_ext[1]);
-        z = __fdiv_rn(__fsub_rn(__fadd_rn(a.rays_o[3 * ray + 2], __fmul_rn(a.rays_d[3 * ray + 2], tsum) * 0.5f), a.aabb_min[2]), a.aabb_ext[2]);
+        const float ts = PERF_FADD_RN(a.near, PERF_FMUL_RN(PERF_FADD_RN((float)k, jit), step));
+        const float te = PERF_FADD_RN(a.near, PERF_FMUL_RN(PERF_FADD_RN((float)(k + 1), jit), step));
+        const float tsum = PERF_FADD_RN(ts, te);
+        x = PERF_FDIV_RN(PERF_FSUB_RN(PERF_FADD_RN(a.rays_o[3 * ray], PERF_FMUL_RN(a.rays_d[3 * ray], tsum) * 0.5f), a.aabb_min[0]), a.aabb_ext[0]);
+        y = PERF_FDIV_RN(PERF_FSUB_RN(PERF_FADD_RN(a.rays_o[3 * ray + 1], PERF_FMUL_RN(a.rays_d[3 * ray + 1], tsum) * 0.5f), a.aabb_min[1]), a.aabb_ext[1]);
+        z = PERF_FDIV_RN(PERF_FSUB_RN(PERF_FADD_RN(a.rays_o[3 * ray + 2], PERF_FMUL_RN(a.rays_d[3 * ray + 2], tsum) * 0.5f), a.aabb_min[2]), a.aabb_ext[2]);
     }
     const bool active = live && (g.x != 0.f || g.y != 0.f);
     // level addressing with a dynamic level index (constant bank, uniform per block)
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(256) hashgrid_bwd_rays_kernel(const __grid_con
     float2 v[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const float w = active ? __fmul_rn(__fmul_rn((k & 1) ? wx : ox, (k & 2) ? wy : oy), (k & 4) ? wz : oz) : 0.f;
+        const float w = active ? PERF_FMUL_RN(PERF_FMUL_RN((k & 1) ? wx : ox, (k & 2) ? wy : oy), (k & 4) ? wz : oz) : 0.f;
         v[k] = make_float2(w * g.x, w * g.y);
     }
     if (active) {
@@ -172,21 +172,23 @@ __global__ void __launch_bounds__(256) hashgrid_bwd_rays_kernel(const __grid_con
     }
 }
 
+template <bool V4>
+__global__ void __launch_bounds__(256) hashgrid_bwd_rays_kernel(const __grid_constant__ GridBwdRaysArgs a)
+{
+    bwd_rays_row_level<V4>(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, (int)blockIdx.y);
+}
+
 // Coarse levels: one thread per (ray, level) walks the ray's S samples in order and keeps the 8
 // corner sums of the CURRENT cell in registers; the 8 float2 atomics are issued only when the ray
 // leaves the cell (consecutive samples of a ray stay ~17 / 12 / 8 / 5 ... samples in a level-0/1/2/3
 // cell).  This divides the atomic count of the coarse levels -- the ones whose few addresses are hit
 // by every ray near the camera -- by the run length.
-__global__ void __launch_bounds__(128) hashgrid_bwd_march_kernel(const __grid_constant__ GridBwdRaysArgs a)
+__host__ __device__ __forceinline__ void bwd_march_ray_level(const GridBwdRaysArgs& a, uint64_t ray, int l, uint32_t piece, uint32_t n_pieces)
 {
-    const int l = blockIdx.y;
-    const uint64_t ray = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (ray >= a.R) return;
-    // blockIdx.z: piece of the ray walked by this thread (more threads, shorter dependent loops;
-    // costs one extra flush per piece)
-    const uint32_t k_per = (a.S + gridDim.z - 1) / gridDim.z;
-    const uint32_t k_lo = blockIdx.z * k_per, k_hi = min(a.S, k_lo + k_per);
-    const float step = __fdiv_rn(__fsub_rn(a.far, a.near), (float)a.S);
+    // piece of the ray walked by this thread (more threads, shorter dependent loops; costs one extra flush per piece)
+    const uint32_t k_per = (a.S + n_pieces - 1) / n_pieces;
+    const uint32_t k_lo = piece * k_per, k_hi = a.S < k_lo + k_per ? a.S : k_lo + k_per;
+    const float step = PERF_FDIV_RN(PERF_FSUB_RN(a.far, a.near), (float)a.S);
     const float jit = a.jitter ? a.jitter[ray] : 0.f;
     const float ox = a.rays_o[3 * ray], oy = a.rays_o[3 * ray + 1], oz = a.rays_o[3 * ray + 2];
     const float dx = a.rays_d[3 * ray], dy = a.rays_d[3 * ray + 1], dz = a.rays_d[3 * ray + 2];
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(128) hashgrid_bwd_march_kernel(const __grid_co
         for (int k = 0; k < 8; ++k) {
             if (acc[k].x != 0.f || acc[k].y != 0.f) {
                 const uint32_t idx = off + level_index(cx + (k & 1), cy + ((k >> 1) & 1), cz + ((k >> 2) & 1), hashed, pow2, res, size);
-                atomicAdd(a.dtable + idx, acc[k]);
+                grad_add2(a.dtable + idx, acc[k]);
             }
             acc[k] = make_float2(0.f, 0.f);
         }
@@ -213,12 +215,12 @@ __global__ void __launch_bounds__(128) hashgrid_bwd_march_kernel(const __grid_co
     for (uint32_t ks = k_lo; ks < k_hi; ++ks) {
         const float2 g = *reinterpret_cast<const float2*>(a.dfeat + ((uint64_t)ks * a.R + ray) * stride + 2 * l);
         if (g.x == 0.f && g.y == 0.f) continue;
-        const float ts = __fadd_rn(a.near, __fmul_rn(__fadd_rn((float)ks, jit), step));
-        const float te = __fadd_rn(a.near, __fmul_rn(__fadd_rn((float)(ks + 1), jit), step));
-        const float tsum = __fadd_rn(ts, te);
-        const float x = __fdiv_rn(__fsub_rn(__fadd_rn(ox, __fmul_rn(dx, tsum) * 0.5f), a.aabb_min[0]), a.aabb_ext[0]);
-        const float y = __fdiv_rn(__fsub_rn(__fadd_rn(oy, __fmul_rn(dy, tsum) * 0.5f), a.aabb_min[1]), a.aabb_ext[1]);
-        const float z = __fdiv_rn(__fsub_rn(__fadd_rn(oz, __fmul_rn(dz, tsum) * 0.5f), a.aabb_min[2]), a.aabb_ext[2]);
+        const float ts = PERF_FADD_RN(a.near, PERF_FMUL_RN(PERF_FADD_RN((float)ks, jit), step));
+        const float te = PERF_FADD_RN(a.near, PERF_FMUL_RN(PERF_FADD_RN((float)(ks + 1), jit), step));
+        const float tsum = PERF_FADD_RN(ts, te);
+        const float x = PERF_FDIV_RN(PERF_FSUB_RN(PERF_FADD_RN(ox, PERF_FMUL_RN(dx, tsum) * 0.5f), a.aabb_min[0]), a.aabb_ext[0]);
+        const float y = PERF_FDIV_RN(PERF_FSUB_RN(PERF_FADD_RN(oy, PERF_FMUL_RN(dy, tsum) * 0.5f), a.aabb_min[1]), a.aabb_ext[1]);
+        const float z = PERF_FDIV_RN(PERF_FSUB_RN(PERF_FADD_RN(oz, PERF_FMUL_RN(dz, tsum) * 0.5f), a.aabb_min[2]), a.aabb_ext[2]);
         const float px = fmaf(scale, x, 0.5f), py = fmaf(scale, y, 0.5f), pz = fmaf(scale, z, 0.5f);
         const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
         const uint32_t gx = (uint32_t)(int)fx, gy = (uint32_t)(int)fy, gz = (uint32_t)(int)fz;
@@ -231,11 +233,17 @@ __global__ void __launch_bounds__(128) hashgrid_bwd_march_kernel(const __grid_co
         const float oxw = 1.f - wx, oyw = 1.f - wy, ozw = 1.f - wz;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const float w = __fmul_rn(__fmul_rn((k & 1) ? wx : oxw, (k & 2) ? wy : oyw), (k & 4) ? wz : ozw);
+            const float w = PERF_FMUL_RN(PERF_FMUL_RN((k & 1) ? wx : oxw, (k & 2) ? wy : oyw), (k & 4) ? wz : ozw);
             acc[k].x = fmaf(w, g.x, acc[k].x); acc[k].y = fmaf(w, g.y, acc[k].y);
         }
     }
     if (have) flush();
+}
+
+__global__ void __launch_bounds__(128) hashgrid_bwd_march_kernel(const __grid_constant__ GridBwdRaysArgs a)
+{
+    const uint64_t ray = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ray < a.R) bwd_march_ray_level(a, ray, (int)blockIdx.y, blockIdx.z, gridDim.z);
 }
 
 }  // namespace perf
@@ -273,21 +281,38 @@ int perf_train_backward_composite(int phase, uint32_t n_samples, uint32_t segmen
     return PERF_OK;
 }
 
+// argument blocks of the two scatter launches: `a` = all levels (the coarse launch uses levels [0, n_agg)),
+// `b` = the remaining levels shifted down to index 0 (level table window + dfeat column window)
+static int setup_bwd_rays(const perf_grid_cfg* cfg, const float* aabb6, const float* rays_o, const float* rays_d, const float* jitter,
+                          uint64_t R, uint32_t n_samples, float near, float far, const float* dfeat, float* dtable,
+                          GridBwdRaysArgs& a, GridBwdRaysArgs& b, uint32_t& n_agg)
+{
+    PERF_CHECK_ARG(aabb6 && rays_o && rays_d && dfeat && dtable, "NULL pointer");
+    PERF_CHECK_ARG((uintptr_t)dtable % 8 == 0 && (uintptr_t)dfeat % 8 == 0, "misaligned dtable/dfeat");
+    memset(&a, 0, sizeof(a));
+    int rc = build_level_table(cfg, &a.lt, nullptr); if (rc) return rc;
+    for (int i = 0; i < 3; ++i) { a.aabb_min[i] = aabb6[i]; a.aabb_ext[i] = aabb6[3 + i] - aabb6[i]; }
+    a.rays_o = rays_o; a.rays_d = rays_d; a.jitter = jitter; a.R = R; a.S = n_samples; a.near = near; a.far = far;
+    a.dfeat = dfeat; a.dtable = (float2*)dtable;
+    // coarse levels: per-ray marching with register accumulation per cell; fine levels: direct atomics
+    n_agg = a.lt.n_levels < 8 ? a.lt.n_levels : 8;
+    b = a;
+    for (uint32_t l = n_agg; l < a.lt.n_levels; ++l) {
+        b.lt.scale[l - n_agg] = a.lt.scale[l]; b.lt.res[l - n_agg] = a.lt.res[l]; b.lt.size[l - n_agg] = a.lt.size[l]; b.lt.offset[l - n_agg] = a.lt.offset[l];
+    }
+    b.lt.hashed_mask = a.lt.hashed_mask >> n_agg; b.lt.pow2_mask = a.lt.pow2_mask >> n_agg;
+    b.dfeat = a.dfeat + 2 * n_agg;                           // column window; row stride stays 2 * n_levels
+    return PERF_OK;
+}
+
 int perf_hashgrid_bwd_rays(const perf_grid_cfg* cfg, const float* aabb6, const float* d_rays_o, const float* d_rays_d,
                            const float* d_jitter, uint64_t R, uint32_t n_samples, float near, float far,
                            const float* d_dfeat, float* d_dtable, void* stream)
 {
-    PERF_CHECK_ARG(aabb6 && d_rays_o && d_rays_d && d_dfeat && d_dtable, "NULL pointer");
-    PERF_CHECK_ARG((uintptr_t)d_dtable % 8 == 0 && (uintptr_t)d_dfeat % 8 == 0, "misaligned dtable/dfeat");
-    GridBwdRaysArgs a; memset(&a, 0, sizeof(a));
-    int rc = build_level_table(cfg, &a.lt, nullptr); if (rc) return rc;
-    for (int i = 0; i < 3; ++i) { a.aabb_min[i] = aabb6[i]; a.aabb_ext[i] = aabb6[3 + i] - aabb6[i]; }
-    a.rays_o = d_rays_o; a.rays_d = d_rays_d; a.jitter = d_jitter; a.R = R; a.S = n_samples; a.near = near; a.far = far;
-    a.dfeat = d_dfeat; a.dtable = (float2*)d_dtable;
+    GridBwdRaysArgs a, b; uint32_t n_agg = 0;
+    int rc = setup_bwd_rays(cfg, aabb6, d_rays_o, d_rays_d, d_jitter, R, n_samples, near, far, d_dfeat, d_dtable, a, b, n_agg); if (rc) return rc;
     const uint64_t N = R * n_samples;
     if (N == 0) return PERF_OK;
-    // coarse levels: per-ray marching with register accumulation per cell; fine levels: direct atomics
-    const uint32_t n_agg = a.lt.n_levels < 8 ? a.lt.n_levels : 8;
     // enough (ray, level, piece) threads to fill the machine; pieces of >= 16 samples
     unsigned pieces = 1;
     while (pieces < 8 && (uint64_t)R * n_agg * pieces < (uint64_t)num_sms() * 2048 && n_samples / (pieces * 2) >= 16) pieces *= 2;
@@ -295,13 +320,6 @@ int perf_hashgrid_bwd_rays(const perf_grid_cfg* cfg, const float* aabb6, const f
     hashgrid_bwd_march_kernel<<<g_agg, 128, 0, (cudaStream_t)stream>>>(a);
     PERF_LAUNCH_CHECK();
     if (a.lt.n_levels > n_agg) {
-        // shift the level window: pass the remaining levels by offsetting blockIdx.y through a copy
-        GridBwdRaysArgs b = a;
-        for (uint32_t l = n_agg; l < a.lt.n_levels; ++l) {
-            b.lt.scale[l - n_agg] = a.lt.scale[l]; b.lt.res[l - n_agg] = a.lt.res[l]; b.lt.size[l - n_agg] = a.lt.size[l]; b.lt.offset[l - n_agg] = a.lt.offset[l];
-        }
-        b.lt.hashed_mask = a.lt.hashed_mask >> n_agg; b.lt.pow2_mask = a.lt.pow2_mask >> n_agg;
-        b.dfeat = a.dfeat + 2 * n_agg;                       // column window; row stride stays 2 * n_levels
         dim3 g_rest((unsigned)((N + 255) / 256), a.lt.n_levels - n_agg);
         // 16-byte vector atomics for x-neighbour pairs (REDG.E.ADD.F32x4): 0.659 -> 0.586 ms for the two scatter
         // launches of an 8192 x 128 step on a B200 (tools/ab_scatter_v4.py); PERF_B200_SCATTER_V4=0 restores the 8-byte path
@@ -313,6 +331,25 @@ int perf_hashgrid_bwd_rays(const perf_grid_cfg* cfg, const float* aabb6, const f
     }
     return PERF_OK;
 }
+
+#ifdef PERF_HOST_HARNESS
+/* TEST HARNESS ONLY (never compiled into libperfb200.so): both scatter bodies over HOST arrays, one thread;
+ * `pieces` plays gridDim.z of the coarse launch, `v4` selects scatter8<true> for the fine levels. */
+int perf_host_hashgrid_bwd_rays(const perf_grid_cfg* cfg, const float* aabb6, const float* h_rays_o, const float* h_rays_d,
+                                const float* h_jitter, uint64_t R, uint32_t n_samples, float near, float far,
+                                const float* h_dfeat, float* h_dtable, int v4, uint32_t pieces)
+{
+    GridBwdRaysArgs a, b; uint32_t n_agg = 0;
+    int rc = setup_bwd_rays(cfg, aabb6, h_rays_o, h_rays_d, h_jitter, R, n_samples, near, far, h_dfeat, h_dtable, a, b, n_agg); if (rc) return rc;
+    PERF_CHECK_ARG(pieces >= 1 && (!v4 || (uintptr_t)h_dtable % 16 == 0), "bad harness arguments");
+    for (uint32_t l = 0; l < n_agg; ++l)
+        for (uint32_t p = 0; p < pieces; ++p)
+            for (uint64_t ray = 0; ray < R; ++ray) bwd_march_ray_level(a, ray, (int)l, p, pieces);
+    for (uint32_t l = 0; l + n_agg < a.lt.n_levels; ++l)
+        for (uint64_t row = 0; row < R * n_samples; ++row) { if (v4) bwd_rays_row_level<true>(b, row, (int)l); else bwd_rays_row_level<false>(b, row, (int)l); }
+    return PERF_OK;
+}
+#endif
 
 int perf_mlp_bwd_out(const float* d_dz, int n_out, const void* d_wout_half, const void* d_h, void* d_dh, uint64_t N, void* stream)
 {

@@ -12,7 +12,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(HERE), "perf_b200", "csrc")
 OUT = os.path.join(HERE, "_build", "libperf_host_harness.so")
-SOURCES = [os.path.join(CSRC, "api_basic.cu"), os.path.join(CSRC, "encoding_grad.cu"), os.path.join(CSRC, "occ.cu"),
+SOURCES = [os.path.join(CSRC, "api_basic.cu"), os.path.join(CSRC, "encoding_grad.cu"), os.path.join(CSRC, "occ.cu"), os.path.join(CSRC, "train.cu"),
            os.path.join(HERE, "host_harness.cu")]
 _LIB = None
 
@@ -101,3 +101,21 @@ def occ_sample(binaries: np.ndarray, aabb, rays_o: np.ndarray, rays_d: np.ndarra
     ri, ts, te = np.zeros(max(n, 1), np.int64), np.zeros(max(n, 1), np.float32), np.zeros(max(n, 1), np.float32)
     assert f(1, *args, None, _p(offsets), _p(ri), _p(ts), _p(te)) == 0
     return ri[:n], ts[:n], te[:n]
+
+
+def hashgrid_bwd_rays(grid_cfg, aabb, rays_o, rays_d, jitter, n_samples: int, near: float, far: float, dfeat: np.ndarray,
+                      v4: bool = True, pieces: int = 1) -> np.ndarray:
+    """Both scatter bodies of csrc/train.cu (coarse: per-ray cell accumulation in `pieces` pieces; fine: per row,
+    scatter8<v4>) -> d table [n_entries, 2] f32.  dfeat [S*R, 2L] f32, rows sample-major (row = k * R + ray)."""
+    R = rays_o.shape[0]
+    raw = np.zeros(2 * grid_cfg.n_entries + 4, np.float32)
+    shift = (-raw.ctypes.data % 16) // 4
+    dtable = raw[shift:shift + 2 * grid_cfg.n_entries].reshape(-1, 2)
+    a6 = (C.c_float * 6)(*[float(v) for v in aabb])
+    o, d = np.ascontiguousarray(rays_o, np.float32), np.ascontiguousarray(rays_d, np.float32)
+    j = None if jitter is None else np.ascontiguousarray(jitter, np.float32)
+    rc = lib().perf_host_hashgrid_bwd_rays(C.byref(grid_cfg.c()), a6, _p(o), _p(d), _p(j), C.c_uint64(R), C.c_uint32(n_samples),
+                                           C.c_float(near), C.c_float(far), _p(np.ascontiguousarray(dfeat, np.float32)), _p(dtable),
+                                           int(v4), C.c_uint32(pieces))
+    assert rc == 0, rc
+    return dtable.copy()
