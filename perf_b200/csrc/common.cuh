@@ -187,7 +187,7 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b)
     __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
 }
-__device__ __forceinline__ float2 unpack_half2(uint32_t u)
+__host__ __device__ __forceinline__ float2 unpack_half2(uint32_t u)
 {
     return __half22float2(*reinterpret_cast<__half2*>(&u));
 }

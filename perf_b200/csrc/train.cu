@@ -20,12 +20,10 @@ struct CompBwdArgs {
 //   dDL/dw_i = 2/3 iv_i w_i + 2 (m_i Wx_i - WMx_i) + 2 (WMsuf_i - m_i Wsuf_i)
 // and dL/d(sigma_i dt_i) = (T_i - w_i) g_i - sum_{j>i} w_j g_j.
 template <int PHASE>
-__global__ void __launch_bounds__(128) composite_bwd_kernel(const CompBwdArgs a)
+__host__ __device__ __forceinline__ void composite_bwd_ray(const CompBwdArgs& a, uint64_t ray)
 {
-    const uint64_t ray = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (ray >= a.R) return;
     const uint32_t S = a.S;
-    const float step = __fdiv_rn(__fsub_rn(a.far, a.near), (float)S);
+    const float step = PERF_FDIV_RN(PERF_FSUB_RN(a.far, a.near), (float)S);
     const float jit = a.jitter ? a.jitter[ray] : 0.f;
     if constexpr (PHASE == PERF_PHASE_APP) {
         float gr = 0.f, gg = 0.f, gb = 0.f;
@@ -55,9 +53,9 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(const CompBwdArgs a)
             const uint64_t row = (uint64_t)kk * a.R + ray;
             const float toff = a.seg > 1 ? a.toff[(uint64_t)(kk / kps) * a.R + ray] : 1.f;     // segment-local -> global
             const float w = a.w[row] * toff, T = a.T[row] * toff, sig = a.sigma[row];
-            const float ts = __fadd_rn(a.near, __fmul_rn(__fadd_rn((float)kk, jit), step));
-            const float te = __fadd_rn(a.near, __fmul_rn(__fadd_rn((float)(kk + 1), jit), step));
-            const float m = __fadd_rn(ts, te) * 0.5f, dt = __fsub_rn(te, ts);
+            const float ts = PERF_FADD_RN(a.near, PERF_FMUL_RN(PERF_FADD_RN((float)kk, jit), step));
+            const float te = PERF_FADD_RN(a.near, PERF_FMUL_RN(PERF_FADD_RN((float)(kk + 1), jit), step));
+            const float m = PERF_FADD_RN(ts, te) * 0.5f, dt = PERF_FSUB_RN(te, ts);
             const float Wx = O - Wsuf - w, WMx = D - WMsuf - w * m;
             const float ddl = (2.f / 3.f) * dt * w + 2.f * (m * Wx - WMx) + 2.f * (WMsuf - m * Wsuf);
             const float g = gd * m + gO + gdl * ddl;
@@ -67,6 +65,13 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(const CompBwdArgs a)
             suf_wg = fmaf(w, g, suf_wg); Wsuf += w; WMsuf = fmaf(w, m, WMsuf);
         }
     }
+}
+
+template <int PHASE>
+__global__ void __launch_bounds__(128) composite_bwd_kernel(const CompBwdArgs a)
+{
+    const uint64_t ray = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ray < a.R) composite_bwd_ray<PHASE>(a, ray);
 }
 
 // dh[n][j] = (sum_o dz[n][o] * wout[o][j]) * (h[n][j] > 0)   -- output layer backward + ReLU mask,
@@ -253,33 +258,59 @@ using namespace perf;
 extern "C" {
 #pragma GCC visibility push(default)
 
+static int setup_composite_bwd(int phase, uint32_t n_samples, uint32_t segments, float near, float far, uint64_t R,
+                               const float* jitter, const float* bg_noise, const perf_train_buffers* buf,
+                               const float* g_rgb, const float* g_distance, const float* g_opacity, const float* g_distloss,
+                               const float* distance_out, const float* opacity_out, float* out, CompBwdArgs& a)
+{
+    PERF_CHECK_ARG(buf && out, "NULL pointer");
+    PERF_CHECK_ARG(phase == PERF_PHASE_GEO || phase == PERF_PHASE_APP, "bad phase");
+    PERF_CHECK_ARG(n_samples >= 1 && far > near, "bad sampling range");
+    memset(&a, 0, sizeof(a));
+    PERF_CHECK_ARG(segments >= 1 && n_samples % segments == 0 && (segments == 1 || buf->d_seg_trans), "bad segment count %u", segments);
+    a.S = n_samples; a.seg = segments; a.toff = buf->d_seg_trans; a.near = near; a.far = far; a.R = R; a.jitter = jitter; a.bg_noise = bg_noise;
+    a.sigma = buf->d_sigma; a.w = buf->d_weights; a.T = buf->d_trans; a.rgb = (const __half*)buf->d_rgb; a.dist_acc = buf->d_dist_acc;
+    a.g_rgb = g_rgb; a.g_dist = g_distance; a.g_op = g_opacity; a.g_dl = g_distloss;
+    a.dist_out = distance_out; a.op_out = opacity_out; a.out = out;
+    if (R == 0) return PERF_OK;
+    if (phase == PERF_PHASE_GEO) PERF_CHECK_ARG(a.sigma && a.w && a.T && a.dist_acc && a.dist_out && a.op_out, "density phase needs sigma/w/T/dist_acc and the forward outputs");
+    else PERF_CHECK_ARG(a.w && a.rgb, "colour phase needs w and rgb");
+    return PERF_OK;
+}
+
 int perf_train_backward_composite(int phase, uint32_t n_samples, uint32_t segments, float near, float far, uint64_t R,
                                   const float* d_jitter, const float* d_bg_noise, const perf_train_buffers* buf,
                                   const float* d_g_rgb, const float* d_g_distance, const float* d_g_opacity,
                                   const float* d_g_distloss, const float* d_distance_out, const float* d_opacity_out,
                                   float* d_out, void* stream)
 {
-    PERF_CHECK_ARG(buf && d_out, "NULL pointer");
-    PERF_CHECK_ARG(phase == PERF_PHASE_GEO || phase == PERF_PHASE_APP, "bad phase");
-    PERF_CHECK_ARG(n_samples >= 1 && far > near, "bad sampling range");
-    CompBwdArgs a; memset(&a, 0, sizeof(a));
-    PERF_CHECK_ARG(segments >= 1 && n_samples % segments == 0 && (segments == 1 || buf->d_seg_trans), "bad segment count %u", segments);
-    a.S = n_samples; a.seg = segments; a.toff = buf->d_seg_trans; a.near = near; a.far = far; a.R = R; a.jitter = d_jitter; a.bg_noise = d_bg_noise;
-    a.sigma = buf->d_sigma; a.w = buf->d_weights; a.T = buf->d_trans; a.rgb = (const __half*)buf->d_rgb; a.dist_acc = buf->d_dist_acc;
-    a.g_rgb = d_g_rgb; a.g_dist = d_g_distance; a.g_op = d_g_opacity; a.g_dl = d_g_distloss;
-    a.dist_out = d_distance_out; a.op_out = d_opacity_out; a.out = d_out;
+    CompBwdArgs a;
+    int rc = setup_composite_bwd(phase, n_samples, segments, near, far, R, d_jitter, d_bg_noise, buf, d_g_rgb, d_g_distance, d_g_opacity,
+                                 d_g_distloss, d_distance_out, d_opacity_out, d_out, a);
+    if (rc) return rc;
     if (R == 0) return PERF_OK;
     const unsigned grid = (unsigned)((R + 127) / 128);
-    if (phase == PERF_PHASE_GEO) {
-        PERF_CHECK_ARG(a.sigma && a.w && a.T && a.dist_acc && a.dist_out && a.op_out, "density phase needs sigma/w/T/dist_acc and the forward outputs");
-        composite_bwd_kernel<PERF_PHASE_GEO><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
-    } else {
-        PERF_CHECK_ARG(a.w && a.rgb, "colour phase needs w and rgb");
-        composite_bwd_kernel<PERF_PHASE_APP><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
-    }
+    if (phase == PERF_PHASE_GEO) composite_bwd_kernel<PERF_PHASE_GEO><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+    else composite_bwd_kernel<PERF_PHASE_APP><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
     PERF_LAUNCH_CHECK();
     return PERF_OK;
 }
+
+#ifdef PERF_HOST_HARNESS
+/* TEST HARNESS ONLY (never compiled into libperfb200.so): composite_bwd_ray over HOST arrays. */
+int perf_host_train_backward_composite(int phase, uint32_t n_samples, uint32_t segments, float near, float far, uint64_t R,
+                                       const float* h_jitter, const float* h_bg_noise, const perf_train_buffers* buf,
+                                       const float* h_g_rgb, const float* h_g_distance, const float* h_g_opacity,
+                                       const float* h_g_distloss, const float* h_distance_out, const float* h_opacity_out, float* h_out)
+{
+    CompBwdArgs a;
+    int rc = setup_composite_bwd(phase, n_samples, segments, near, far, R, h_jitter, h_bg_noise, buf, h_g_rgb, h_g_distance, h_g_opacity,
+                                 h_g_distloss, h_distance_out, h_opacity_out, h_out, a);
+    if (rc) return rc;
+    for (uint64_t ray = 0; ray < R; ++ray) { if (phase == PERF_PHASE_GEO) composite_bwd_ray<PERF_PHASE_GEO>(a, ray); else composite_bwd_ray<PERF_PHASE_APP>(a, ray); }
+    return PERF_OK;
+}
+#endif
 
 // argument blocks of the two scatter launches: `a` = all levels (the coarse launch uses levels [0, n_agg)),
 // `b` = the remaining levels shifted down to index 0 (level table window + dfeat column window)

@@ -119,3 +119,22 @@ def hashgrid_bwd_rays(grid_cfg, aabb, rays_o, rays_d, jitter, n_samples: int, ne
                                            int(v4), C.c_uint32(pieces))
     assert rc == 0, rc
     return dtable.copy()
+
+
+def composite_backward(phase: int, S: int, segments: int, near: float, far: float, jitter, bg_noise, sigma, w, T, rgb_half, dist_acc,
+                       seg_trans, g_rgb, g_dist, g_op, g_dl, dist_out, op_out) -> np.ndarray:
+    """composite_bwd_ray of csrc/train.cu.  Rows are sample-major (row = k * R + ray); returns d loss / d (raw output):
+    [S*R] for the density phase (phase 1), [S*R, 3] for the colour phase (phase 2).  None = NULL pointer."""
+    from perf_b200._lib import TrainBuffers
+    R = (w.shape[0]) // S
+    keep = [None if x is None else np.ascontiguousarray(x) for x in (jitter, bg_noise, sigma, w, T, rgb_half, dist_acc, seg_trans,
+                                                                      g_rgb, g_dist, g_op, g_dl, dist_out, op_out)]
+    jitter, bg_noise, sigma, w, T, rgb_half, dist_acc, seg_trans, g_rgb, g_dist, g_op, g_dl, dist_out, op_out = keep
+    ptr = lambda x: None if x is None else x.ctypes.data
+    buf = TrainBuffers(ptr(sigma), ptr(w), ptr(T), ptr(rgb_half), None, None, None, ptr(dist_acc), None, ptr(seg_trans), None)
+    out = np.zeros(S * R * (3 if phase == 2 else 1), np.float32)
+    rc = lib().perf_host_train_backward_composite(int(phase), C.c_uint32(S), C.c_uint32(segments), C.c_float(near), C.c_float(far), C.c_uint64(R),
+                                                  _p(jitter), _p(bg_noise), C.byref(buf), _p(g_rgb), _p(g_dist), _p(g_op), _p(g_dl),
+                                                  _p(dist_out), _p(op_out), _p(out))
+    assert rc == 0, rc
+    return out.reshape(S * R, 3) if phase == 2 else out
