@@ -182,7 +182,7 @@ __host__ __device__ __forceinline__ void scatter8(float2* __restrict__ dtable, c
     }
 }
 
-__device__ __forceinline__ uint32_t pack_half2(float a, float b)
+__host__ __device__ __forceinline__ uint32_t pack_half2(float a, float b)
 {
     __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);

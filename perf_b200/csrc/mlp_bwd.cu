@@ -24,6 +24,7 @@
 //     between 8-row K groups (128), SBO = byte distance between 8-element MN groups (rows * 16)
 // (cute::UMMA canonical layout ((T,1,m),(8,k)):((1,T,SBO),(1T,LBO))), with bits 15 / 16 of the instruction
 // descriptor selecting MN-major for A / B.
+#include <stdlib.h>
 #include "mlp_tc.cuh"
 
 namespace perf {
@@ -49,7 +50,7 @@ __device__ __forceinline__ uint64_t desc_mn(uint32_t img, int rows, int ks) { re
 // K-major view of an activation image (128 rows), K-step ks (16 columns)
 __device__ __forceinline__ uint64_t desc_k(uint32_t img, int ks) { return umma_desc(img + ks * 2 * A_LBO, A_LBO, X_SBO); }
 
-__device__ __forceinline__ float img_at(const uint8_t* img, int rows, int r, int c)
+__host__ __device__ __forceinline__ float img_at(const uint8_t* img, int rows, int r, int c)
 {
     return __half2float(*reinterpret_cast<const __half*>(img + ((c >> 3) * rows + r) * 16 + (c & 7) * 2));
 }
@@ -61,30 +62,34 @@ template <> struct BwdSmem<true> {
                          DZP = FEAT + A32_BYTES, W2 = DZP + 2 * TILE * 16, W1 = W2 + W64_BYTES, WOUT = W1 + W32_BYTES,
                          BAR = WOUT + 3 * HID * 4, TOTAL = BAR + 16;
     static constexpr int TM_D1 = 0, TM_D2 = 64, TM_G1 = 96, TM_G2 = 192, TM_COLS = 256, N_G1 = 96, N_G2 = 16;
+    static constexpr int GA = DH2 /* [DH2|DH1] */, GB = H1 /* [H1|FEAT] */;
 };
 template <> struct BwdSmem<false> {
     static constexpr int DH1 = 0, H1 = DH1 + A64_BYTES, FEAT = H1 + A64_BYTES, DZP = FEAT + A32_BYTES, W1 = DZP + 2 * TILE * 16,
                          WOUT = W1 + W32_BYTES, BAR = WOUT + 3 * HID * 4, TOTAL = BAR + 16;
     static constexpr int TM_D2 = 0, TM_G1 = 32, TM_COLS = 128, N_G1 = 48;
+    static constexpr int GA = DH1 /* [DH1|H1] */, GB = FEAT /* [FEAT|DZP] */;
+    static constexpr int DH2 = 0, H2 = 0, W2 = 0, TM_D1 = 0, TM_G2 = 0, N_G2 = 0;      // unused with one hidden layer
 };
+constexpr int N_GACC = 112;       // CUDA-core twin of the TMEM weight-gradient accumulators: 96 (G1) + 16 (G2) columns of row t
 
 template <int KGS>
-__device__ __forceinline__ void store_row(uint8_t* img, int row, const uint4 (&v)[KGS])
+__host__ __device__ __forceinline__ void store_row(uint8_t* img, int row, const uint4 (&v)[KGS])
 {
 #pragma unroll
     for (int kg = 0; kg < KGS; ++kg) *reinterpret_cast<uint4*>(img + (kg * TILE + row) * 16) = v[kg];
 }
+__host__ __device__ __forceinline__ uint32_t word_of(const uint4& q, int i) { return i == 0 ? q.x : i == 1 ? q.y : i == 2 ? q.z : q.w; }
 
 // dh[j] = (h[j] > 0) ? sum_o dz[o] * wout[o][j] : 0, rounded to fp16, written as this thread's row of `dst`
-__device__ __forceinline__ void out_layer_backward(uint8_t* dst, int row, const uint4 (&h)[8], const float (&dz)[3], int n_out, const float* wout)
+__host__ __device__ __forceinline__ void out_layer_backward(uint8_t* dst, int row, const uint4 (&h)[8], const float (&dz)[3], int n_out, const float* wout)
 {
 #pragma unroll
     for (int kg = 0; kg < 8; ++kg) {
-        const uint32_t hw[4] = {h[kg].x, h[kg].y, h[kg].z, h[kg].w};
         uint32_t o4[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const float2 hh = unpack_half2(hw[q]);
+            const float2 hh = unpack_half2(word_of(h[kg], q));
             const int j = kg * 8 + 2 * q;
             float a = 0.f, b = 0.f;
 #pragma unroll
@@ -96,15 +101,134 @@ __device__ __forceinline__ void out_layer_backward(uint8_t* dst, int row, const 
     }
 }
 
-// CUDA-core twins of the MMAs, reading the same images.
-// D[row][n] = sum_k A[row][k] * Wimg[k][n]   (A: activation image K-major; Wimg: forward weight image [64 rows k][ncols])
-__device__ __forceinline__ void simt_dgrad(const uint8_t* A, const uint8_t* Wimg, int row, int n0, float (&v)[32])
+// ---- the per-thread phases of one tile (thread t = row t).  Between two phases every thread of the CTA must have
+// finished the previous one (__syncthreads in the kernel, a loop over t in the host harness).
+
+// phase 1: stage the saved activations and dz as operand images, output-layer backward on CUDA cores
+template <bool TWO>
+__host__ __device__ __forceinline__ void bwd_phase_stage(uint8_t* smem, const float* s_wout, const MlpBwdArgs& a, uint64_t tile, int t)
+{
+    using L = BwdSmem<TWO>;
+    const uint64_t row = tile * TILE + t;
+    const bool valid = row < a.N;
+    const int n_out = (int)a.n_out;
+    uint4 f4[4], h1v[8], hlast[8];
+    float dz[3] = {0.f, 0.f, 0.f};
+    const uint4 z4 = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) f4[q] = valid ? a.feat[row * 4 + q] : z4;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) h1v[q] = valid ? a.h1[row * 8 + q] : z4;
+    if constexpr (TWO) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) hlast[q] = valid ? a.h2[row * 8 + q] : z4;
+    }
+#pragma unroll
+    for (int o = 0; o < 3; ++o) if (valid && o < n_out) dz[o] = a.dz[row * n_out + o];
+    store_row(smem + L::FEAT, t, f4);
+    store_row(smem + L::H1, t, h1v);
+    // dz as 16 fp16 columns (cols >= n_out are zero)
+    *reinterpret_cast<uint4*>(smem + L::DZP + (0 * TILE + t) * 16) = make_uint4(pack_half2(dz[0], dz[1]), pack_half2(dz[2], 0.f), 0u, 0u);
+    *reinterpret_cast<uint4*>(smem + L::DZP + (1 * TILE + t) * 16) = z4;
+    if constexpr (TWO) {
+        store_row(smem + L::H2, t, hlast);
+        out_layer_backward(smem + L::DH2, t, hlast, dz, n_out, s_wout);
+    } else {
+        out_layer_backward(smem + L::DH1, t, h1v, dz, n_out, s_wout);
+    }
+}
+
+// CUDA-core twin of a data-gradient MMA: D[row][n0 + j] = sum_k A[row][k] * Wimg[k][n0 + j]
+// (A: activation image, K-major; Wimg: forward weight image [64 rows k][n cols], i.e. the MN-major B operand)
+__host__ __device__ __forceinline__ void simt_dgrad(const uint8_t* A, const uint8_t* Wimg, int row, int n0, float (&v)[32])
 {
     for (int j = 0; j < 32; ++j) {
         float acc = 0.f;
         for (int k = 0; k < HID; ++k) acc = fmaf(img_at(A, TILE, row, k), img_at(Wimg, HID, k, n0 + j), acc);
         v[j] = acc;
     }
+}
+
+// phase 2 (two hidden layers): 32 columns [32c, 32c+32) of D1 = dh2 W2 -> dh1 = D1 . [h1 > 0] into the DH1 image
+__host__ __device__ __forceinline__ void bwd_phase_hidden_chunk(uint8_t* smem, int t, int c, const float (&v)[32])
+{
+    using L = BwdSmem<true>;
+    uint32_t p[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const uint4 hq = *reinterpret_cast<const uint4*>(smem + L::H1 + ((4 * c + j / 4) * TILE + t) * 16);
+        const float2 hh = unpack_half2(word_of(hq, j % 4));
+        p[j] = pack_half2(hh.x > 0.f ? v[2 * j] : 0.f, hh.y > 0.f ? v[2 * j + 1] : 0.f);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<uint4*>(smem + L::DH1 + ((4 * c + q) * TILE + t) * 16) = make_uint4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
+}
+
+// phase 3, CUDA-core twin of the weight-gradient MMAs: row m = t of G1 (+= A[n][m] B[n][c] over the tile's rows) and G2
+template <bool TWO>
+__host__ __device__ __forceinline__ void simt_wgrad(const uint8_t* smem, int t, float* gacc /* [N_GACC] of this thread */)
+{
+    using L = BwdSmem<TWO>;
+    for (int c = 0; c < L::N_G1; ++c) {
+        float acc = gacc[c];
+        for (int n = 0; n < TILE; ++n) acc = fmaf(img_at(smem + L::GA, TILE, n, t), img_at(smem + L::GB, TILE, n, c), acc);
+        gacc[c] = acc;
+    }
+    if constexpr (TWO) {
+        for (int c = 0; c < L::N_G2; ++c) {
+            float acc = gacc[96 + c];
+            for (int n = 0; n < TILE; ++n) acc = fmaf(img_at(smem + L::H2, TILE, n, t), img_at(smem + L::DZP, TILE, n, c), acc);
+            gacc[96 + c] = acc;
+        }
+    }
+}
+
+// phase 3: dfeat row from D2 = dh1 W1
+__host__ __device__ __forceinline__ void bwd_phase_dfeat(const MlpBwdArgs& a, uint64_t tile, int t, const float (&v)[32])
+{
+    const uint64_t row = tile * TILE + t;
+    if (row < a.N) {
+        float4* dst = reinterpret_cast<float4*>(a.dfeat + row * 32);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+}
+
+__host__ __device__ __forceinline__ void wgrad_add(float* p, float v)
+{
+#ifdef __CUDA_ARCH__
+    atomicAdd(p, v);
+#else
+    *p += v;
+#endif
+}
+// epilogue: 32 columns [c0, c0+32) of row m = t of G1 -> global gradient
+template <bool TWO>
+__host__ __device__ __forceinline__ void bwd_flush_g1(const MlpBwdArgs& a, int t, int c0, const float (&v)[32])
+{
+    using L = BwdSmem<TWO>;
+    float* dW1 = a.dW;
+    float* dW2 = a.dW + 64 * 32;
+    float* dWo = a.dW + 64 * 32 + (TWO ? 64 * 64 : 0);
+    for (int j = 0; j < 32; ++j) {
+        const int c = c0 + j;
+        if (c >= L::N_G1) break;
+        if constexpr (TWO) {
+            if (t < 64 && c < 64) wgrad_add(dW2 + t * 64 + c, v[j]);                               // dh2^T h1
+            else if (t >= 64 && c >= 64) wgrad_add(dW1 + (t - 64) * 32 + (c - 64), v[j]);          // dh1^T feat
+        } else {
+            if (t < 64 && c < 32) wgrad_add(dW1 + t * 32 + c, v[j]);                               // dh1^T feat
+            else if (t >= 64 && c >= 32 && c - 32 < (int)a.n_out) wgrad_add(dWo + (c - 32) * 64 + (t - 64), v[j]);   // h1^T dz
+        }
+    }
+}
+// epilogue (two hidden layers): row m = t of G2 = [h2|h1]^T [dz|0]
+__host__ __device__ __forceinline__ void bwd_flush_g2(const MlpBwdArgs& a, int t, const float (&v)[32])
+{
+    float* dWo = a.dW + 64 * 32 + 64 * 64;
+#pragma unroll
+    for (int o = 0; o < 3; ++o) if (t < 64 && o < (int)a.n_out) wgrad_add(dWo + o * 64 + t, v[o]);
 }
 
 template <bool TWO, bool SIMT>
@@ -116,13 +240,12 @@ __global__ void __launch_bounds__(128) mlp_bwd_kernel(const MlpBwdArgs a)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::BAR + 8);
     float* s_wout = reinterpret_cast<float*>(smem + L::WOUT);
     const int t = threadIdx.x, warp = t >> 5;
-    const int n_out = (int)a.n_out;
 
     // weights: forward canonical images (read MN-major by the dgrad MMAs) + fp32 output matrix
     load_weight_canonical(a.w, 32, smem + L::W1, t, TILE);
     const __half* wout_g = a.w + 64 * 32;
     if constexpr (TWO) { load_weight_canonical(a.w + 64 * 32, 64, smem + L::W2, t, TILE); wout_g += 64 * 64; }
-    load_wout(wout_g, n_out, s_wout, t, TILE);
+    load_wout(wout_g, (int)a.n_out, s_wout, t, TILE);
     uint32_t tmem_base = 0;
     if constexpr (!SIMT) {
         if (t == 0) { mbar_init(bar, 1); fence_mbar_init(); }
@@ -133,41 +256,13 @@ __global__ void __launch_bounds__(128) mlp_bwd_kernel(const MlpBwdArgs a)
     if constexpr (!SIMT) { tc_fence_after(); tmem_base = *tmem_slot; }
     const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
     uint32_t phase = 0;
-    float gacc[SIMT ? 112 : 1];                       // SIMT twin of the TMEM weight-gradient accumulators (row m = t)
-    if constexpr (SIMT) { for (int i = 0; i < 112; ++i) gacc[i] = 0.f; }
+    float gacc[SIMT ? N_GACC : 1];
+    if constexpr (SIMT) { for (int i = 0; i < N_GACC; ++i) gacc[i] = 0.f; }
 
     const uint64_t n_tiles = (a.N + TILE - 1) / TILE;
     bool first = true;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, first = false) {
-        const uint64_t row = tile * TILE + t;
-        const bool valid = row < a.N;
-        uint4 f4[4], h1v[8], hlast[8];
-        float dz[3] = {0.f, 0.f, 0.f};
-        const uint4 z4 = make_uint4(0, 0, 0, 0);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) f4[q] = valid ? a.feat[row * 4 + q] : z4;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) h1v[q] = valid ? a.h1[row * 8 + q] : z4;
-        if constexpr (TWO) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) hlast[q] = valid ? a.h2[row * 8 + q] : z4;
-        }
-#pragma unroll
-        for (int o = 0; o < 3; ++o) if (valid && o < n_out) dz[o] = a.dz[row * n_out + o];
-
-        store_row(smem + L::FEAT, t, f4);
-        store_row(smem + L::H1, t, h1v);
-        {   // dz as 16 fp16 columns (cols >= n_out are zero)
-            uint8_t* p = smem + L::DZP;
-            *reinterpret_cast<uint4*>(p + (0 * TILE + t) * 16) = make_uint4(pack_half2(dz[0], dz[1]), pack_half2(dz[2], 0.f), 0u, 0u);
-            *reinterpret_cast<uint4*>(p + (1 * TILE + t) * 16) = z4;
-        }
-        if constexpr (TWO) {
-            store_row(smem + L::H2, t, hlast);
-            out_layer_backward(smem + L::DH2, t, hlast, dz, n_out, s_wout);
-        } else {
-            out_layer_backward(smem + L::DH1, t, h1v, dz, n_out, s_wout);
-        }
+        bwd_phase_stage<TWO>(smem, s_wout, a, tile, t);
         if constexpr (!SIMT) { fence_proxy_async(); tc_fence_before(); }
         __syncthreads();
 
@@ -189,14 +284,7 @@ __global__ void __launch_bounds__(128) mlp_bwd_kernel(const MlpBwdArgs a)
                 float v[32];
                 if constexpr (SIMT) simt_dgrad(smem + L::DH2, smem + L::W2, t, 32 * c, v);
                 else tmem_ld32(tmem_row + L::TM_D1 + 32 * c, v);
-                uint32_t p[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const uint4 hq = h1v[4 * c + j / 4];
-                    const float2 hh = unpack_half2((j % 4) == 0 ? hq.x : (j % 4) == 1 ? hq.y : (j % 4) == 2 ? hq.z : hq.w);
-                    p[j] = pack_half2(hh.x > 0.f ? v[2 * j] : 0.f, hh.y > 0.f ? v[2 * j + 1] : 0.f);
-                }
-                store_chunk_canonical(smem + L::DH1, t, 4 * c, p);
+                bwd_phase_hidden_chunk(smem, t, c, v);
             }
             if constexpr (!SIMT) { fence_proxy_async(); tc_fence_before(); }
             __syncthreads();
@@ -210,46 +298,27 @@ __global__ void __launch_bounds__(128) mlp_bwd_kernel(const MlpBwdArgs a)
                 for (int ks = 0; ks < 4; ++ks)
                     umma_f16(tmem_base + L::TM_D2, desc_k(smem_u32(smem + L::DH1), ks), desc_mn(smem_u32(smem + L::W1), HID, ks), id2, ks > 0);
                 constexpr uint32_t idg = idesc_f16_major(TILE, L::N_G1, true, true);
-                const uint32_t a_img = smem_u32(smem + (TWO ? 0 /* DH2|DH1 */ : L::DH1 /* DH1|H1 */));
-                const uint32_t b_img = smem_u32(smem + (TWO ? L::H1 /* H1|FEAT */ : L::FEAT /* FEAT|DZP */));
                 for (int ks = 0; ks < 8; ++ks)
-                    umma_f16(tmem_base + L::TM_G1, desc_mn(a_img, TILE, ks), desc_mn(b_img, TILE, ks), idg, (!first || ks > 0) ? 1u : 0u);
+                    umma_f16(tmem_base + L::TM_G1, desc_mn(smem_u32(smem + L::GA), TILE, ks), desc_mn(smem_u32(smem + L::GB), TILE, ks), idg,
+                             (!first || ks > 0) ? 1u : 0u);
                 if constexpr (TWO) {
-                    constexpr uint32_t idg2 = idesc_f16_major(TILE, BwdSmem<true>::N_G2, true, true);
+                    constexpr uint32_t idg2 = idesc_f16_major(TILE, L::N_G2, true, true);
                     for (int ks = 0; ks < 8; ++ks)
-                        umma_f16(tmem_base + BwdSmem<true>::TM_G2, desc_mn(smem_u32(smem + BwdSmem<true>::H2), TILE, ks),
-                                 desc_mn(smem_u32(smem + L::DZP), TILE, ks), idg2, (!first || ks > 0) ? 1u : 0u);
+                        umma_f16(tmem_base + L::TM_G2, desc_mn(smem_u32(smem + L::H2), TILE, ks), desc_mn(smem_u32(smem + L::DZP), TILE, ks), idg2,
+                                 (!first || ks > 0) ? 1u : 0u);
                 }
                 umma_commit(bar);
             }
             mbar_wait(bar, phase); phase ^= 1u;
             tc_fence_after();
         } else {
-            // weight gradients, row m = t of G: sum over the tile's 128 rows of A[n][m] * B[n][c]
-            const uint8_t* a_img = smem + (TWO ? 0 : L::DH1);
-            const uint8_t* b_img = smem + (TWO ? L::H1 : L::FEAT);
-            for (int c = 0; c < L::N_G1; ++c) {
-                float acc = gacc[c];
-                for (int n = 0; n < TILE; ++n) acc = fmaf(img_at(a_img, TILE, n, t), img_at(b_img, TILE, n, c), acc);
-                gacc[c] = acc;
-            }
-            if constexpr (TWO) {
-                for (int c = 0; c < 16; ++c) {
-                    float acc = gacc[96 + c];
-                    for (int n = 0; n < TILE; ++n) acc = fmaf(img_at(smem + BwdSmem<true>::H2, TILE, n, t), img_at(smem + L::DZP, TILE, n, c), acc);
-                    gacc[96 + c] = acc;
-                }
-            }
+            simt_wgrad<TWO>(smem, t, gacc);
         }
         {
             float v[32];
             if constexpr (SIMT) simt_dgrad(smem + L::DH1, smem + L::W1, t, 0, v);
             else tmem_ld32(tmem_row + L::TM_D2, v);
-            if (valid) {
-                float4* dst = reinterpret_cast<float4*>(a.dfeat + row * 32);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-            }
+            bwd_phase_dfeat(a, tile, t, v);
         }
         if constexpr (!SIMT) tc_fence_before();
         __syncthreads();                                   // images and D1 / D2 are rewritten by the next tile
@@ -257,32 +326,18 @@ __global__ void __launch_bounds__(128) mlp_bwd_kernel(const MlpBwdArgs a)
 
     // ---- weight gradients of this CTA -> global (row m = t of the accumulators)
     if (!first) {
-        float* dW1 = a.dW;
-        float* dW2 = a.dW + 64 * 32;
-        float* dWo = a.dW + 64 * 32 + (TWO ? 64 * 64 : 0);
         if constexpr (!SIMT) tc_fence_after();
         for (int c0 = 0; c0 < L::N_G1; c0 += 32) {
             float v[32];
             if constexpr (SIMT) { for (int j = 0; j < 32; ++j) v[j] = (c0 + j < L::N_G1) ? gacc[c0 + j] : 0.f; }
             else tmem_ld32(tmem_row + L::TM_G1 + c0, v);
-            for (int j = 0; j < 32; ++j) {
-                const int c = c0 + j;
-                if (c >= L::N_G1) break;
-                if constexpr (TWO) {
-                    if (t < 64 && c < 64) atomicAdd(dW2 + t * 64 + c, v[j]);
-                    else if (t >= 64 && c >= 64) atomicAdd(dW1 + (t - 64) * 32 + (c - 64), v[j]);
-                } else {
-                    if (t < 64 && c < 32) atomicAdd(dW1 + t * 32 + c, v[j]);
-                    else if (t >= 64 && c >= 32 && c - 32 < n_out) atomicAdd(dWo + (c - 32) * 64 + (t - 64), v[j]);
-                }
-            }
+            bwd_flush_g1<TWO>(a, t, c0, v);
         }
         if constexpr (TWO) {
             float v[32];
             if constexpr (SIMT) { for (int j = 0; j < 32; ++j) v[j] = j < 16 ? gacc[96 + j] : 0.f; }
-            else tmem_ld32(tmem_row + BwdSmem<true>::TM_G2, v);
-#pragma unroll
-            for (int o = 0; o < 3; ++o) if (t < 64 && o < n_out) atomicAdd(dWo + o * 64 + t, v[o]);
+            else tmem_ld32(tmem_row + L::TM_G2, v);
+            bwd_flush_g2(a, t, v);
         }
     }
     if constexpr (!SIMT) {
@@ -310,6 +365,55 @@ static int launch_mlp_bwd(const MlpBwdArgs& a, cudaStream_t stream)
 
 using namespace perf;
 
+#ifdef PERF_HOST_HARNESS
+/* TEST HARNESS ONLY (never compiled into libperfb200.so): one CTA of the CUDA-core twin emulated on the host -- the
+ * per-thread phases above run for t = 0..127 where the kernel has a __syncthreads -- over HOST arrays.  It checks
+ * the operand images, the transposed reads, the block layout of the weight-gradient accumulators and the flush;
+ * only the tcgen05 descriptors themselves need a GPU. */
+template <bool TWO>
+static void host_mlp_bwd(const MlpBwdArgs& a, uint8_t* smem, float* gacc /* [128][N_GACC] */)
+{
+    using L = BwdSmem<TWO>;
+    float* s_wout = reinterpret_cast<float*>(smem + L::WOUT);
+    auto load_w = [&](const __half* gW, int K, uint8_t* dst) {      // load_weight_canonical
+        for (int c = 0; c < HID * (K / 8); ++c) { const int n = c % HID, kg = c / HID;
+            *reinterpret_cast<uint4*>(dst + (kg * HID + n) * 16) = *reinterpret_cast<const uint4*>(gW + (size_t)n * K + kg * 8); }
+    };
+    load_w(a.w, 32, smem + L::W1);
+    const __half* wout_g = a.w + 64 * 32;
+    if (TWO) { load_w(a.w + 64 * 32, 64, smem + L::W2); wout_g += 64 * 64; }
+    for (int c = 0; c < (int)a.n_out * HID; ++c) s_wout[c] = __half2float(wout_g[c]);
+    const uint64_t n_tiles = (a.N + TILE - 1) / TILE;
+    for (uint64_t tile = 0; tile < n_tiles; ++tile) {
+        for (int t = 0; t < TILE; ++t) bwd_phase_stage<TWO>(smem, s_wout, a, tile, t);
+        if (TWO) {
+            float v[TILE][2][32];
+            for (int t = 0; t < TILE; ++t) for (int c = 0; c < 2; ++c) simt_dgrad(smem + L::DH2, smem + L::W2, t, 32 * c, v[t][c]);
+            for (int t = 0; t < TILE; ++t) for (int c = 0; c < 2; ++c) bwd_phase_hidden_chunk(smem, t, c, v[t][c]);
+        }
+        for (int t = 0; t < TILE; ++t) {
+            simt_wgrad<TWO>(smem, t, gacc + t * N_GACC);
+            float v[32];
+            simt_dgrad(smem + L::DH1, smem + L::W1, t, 0, v);
+            bwd_phase_dfeat(a, tile, t, v);
+        }
+    }
+    for (int t = 0; t < TILE; ++t) {
+        for (int c0 = 0; c0 < L::N_G1; c0 += 32) {
+            float v[32];
+            for (int j = 0; j < 32; ++j) v[j] = (c0 + j < L::N_G1) ? gacc[t * N_GACC + c0 + j] : 0.f;
+            bwd_flush_g1<TWO>(a, t, c0, v);
+        }
+        if (TWO) {
+            float v[32];
+            for (int j = 0; j < 32; ++j) v[j] = j < 16 ? gacc[t * N_GACC + 96 + j] : 0.f;
+            bwd_flush_g2(a, t, v);
+        }
+    }
+}
+
+#endif
+
 extern "C" {
 #pragma GCC visibility push(default)
 
@@ -329,6 +433,26 @@ int perf_mlp_bwd(const perf_mlp_cfg* mlp, const void* d_weights_half, const void
     if (mlp->n_hidden_layers == 2) return simt ? launch_mlp_bwd<true, true>(a, (cudaStream_t)stream) : launch_mlp_bwd<true, false>(a, (cudaStream_t)stream);
     return simt ? launch_mlp_bwd<false, true>(a, (cudaStream_t)stream) : launch_mlp_bwd<false, false>(a, (cudaStream_t)stream);
 }
+
+#ifdef PERF_HOST_HARNESS
+/* TEST HARNESS ONLY: see host_mlp_bwd above. */
+int perf_host_mlp_bwd(const perf_mlp_cfg* mlp, const void* h_weights_half, const void* h_feat, const void* h_h1, const void* h_h2,
+                      const float* h_dz, uint64_t N, float* h_dweights, float* h_dfeat)
+{
+    int rc = check_mlp(mlp); if (rc) return rc;
+    PERF_CHECK_ARG(h_weights_half && h_feat && h_h1 && h_dz && h_dweights && h_dfeat && (mlp->n_hidden_layers == 1 || h_h2), "NULL pointer");
+    PERF_CHECK_SUP(mlp->n_out <= 3, "n_out=%u", mlp->n_out);
+    MlpBwdArgs a;
+    a.w = (const __half*)h_weights_half; a.feat = (const uint4*)h_feat; a.h1 = (const uint4*)h_h1; a.h2 = (const uint4*)h_h2;
+    a.dz = h_dz; a.N = N; a.dW = h_dweights; a.dfeat = h_dfeat; a.n_out = mlp->n_out;
+    uint8_t* smem = (uint8_t*)aligned_alloc(128, (size_t)(BwdSmem<true>::TOTAL + 127) / 128 * 128);
+    float* gacc = (float*)calloc((size_t)TILE * N_GACC, sizeof(float));
+    if (!smem || !gacc) { free(smem); free(gacc); return PERF_ECUDA; }
+    if (mlp->n_hidden_layers == 2) host_mlp_bwd<true>(a, smem, gacc); else host_mlp_bwd<false>(a, smem, gacc);
+    free(smem); free(gacc);
+    return PERF_OK;
+}
+#endif
 
 #pragma GCC visibility pop
 }  // extern "C"

@@ -13,13 +13,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(HERE), "perf_b200", "csrc")
 OUT = os.path.join(HERE, "_build", "libperf_host_harness.so")
 SOURCES = [os.path.join(CSRC, "api_basic.cu"), os.path.join(CSRC, "encoding_grad.cu"), os.path.join(CSRC, "occ.cu"), os.path.join(CSRC, "train.cu"),
+           os.path.join(CSRC, "mlp_bwd.cu"),
            os.path.join(HERE, "host_harness.cu")]
 _LIB = None
 
 
 def build() -> str:
     from perf_b200.build import _nvcc
-    deps = SOURCES + [os.path.join(CSRC, "common.cuh")]
+    deps = SOURCES + [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "mlp_tc.cuh")]
     if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
         os.makedirs(os.path.dirname(OUT), exist_ok=True)
         tmp = f"{OUT}.{os.getpid()}.tmp"
@@ -138,3 +139,17 @@ def composite_backward(phase: int, S: int, segments: int, near: float, far: floa
                                                   _p(dist_out), _p(op_out), _p(out))
     assert rc == 0, rc
     return out.reshape(S * R, 3) if phase == 2 else out
+
+
+def mlp_backward(mlp_cfg, weights_half: np.ndarray, feat: np.ndarray, h1: np.ndarray, h2, dz: np.ndarray):
+    """One CTA of csrc/mlp_bwd.cu's CUDA-core twin emulated on the host (perf_host_mlp_bwd).
+    weights_half [n_params] f16, feat [N,32] f16, h1 / h2 [N,64] f16 (h2 None for one hidden layer), dz [N,n_out] f32
+    -> (d weights [n_params] f32, dfeat [N,32] f32)."""
+    N = feat.shape[0]
+    c16 = lambda x: None if x is None else np.ascontiguousarray(x, np.float16)
+    w, f, a1, a2 = c16(weights_half), c16(feat), c16(h1), c16(h2)
+    dz = np.ascontiguousarray(dz, np.float32).reshape(N, -1)
+    dW, dfeat = np.zeros(w.shape[0], np.float32), np.zeros((N, 32), np.float32)
+    rc = lib().perf_host_mlp_bwd(C.byref(mlp_cfg.c()), _p(w), _p(f), _p(a1), _p(a2), _p(dz), C.c_uint64(N), _p(dW), _p(dfeat))
+    assert rc == 0, rc
+    return dW, dfeat
