@@ -10,3 +10,4 @@ for k in "simt and density" "simt and colour" "tcgen05 and density" "tcgen05 and
 done
 timeout 120 python tools/ab_mlp_bwd.py 2>&1 | tail -6 | tee -a gpurun_out/round2_first.log
 timeout 60 python tools/ab_scatter_v4.py 2>&1 | tail -2 | tee -a gpurun_out/round2_first.log
+timeout 120 python tools/encode_microbench.py 2>&1 | tail -5 | tee -a gpurun_out/round2_first.log
