@@ -188,6 +188,7 @@ __global__ void __launch_bounds__(256) hashgrid_bwd_rays_kernel(const __grid_con
 // leaves the cell (consecutive samples of a ray stay ~17 / 12 / 8 / 5 ... samples in a level-0/1/2/3
 // cell).  This divides the atomic count of the coarse levels -- the ones whose few addresses are hit
 // by every ray near the camera -- by the run length.
+template <bool V4>
 __host__ __device__ __forceinline__ void bwd_march_ray_level(const GridBwdRaysArgs& a, uint64_t ray, int l, uint32_t piece, uint32_t n_pieces)
 {
     // piece of the ray walked by this thread (more threads, shorter dependent loops; costs one extra flush per piece)
@@ -207,13 +208,22 @@ __host__ __device__ __forceinline__ void bwd_march_ray_level(const GridBwdRaysAr
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = make_float2(0.f, 0.f);
     auto flush = [&]() {
+        if constexpr (V4) {                                   // x-neighbour pairs as one 16-byte atomic (experimental, see perf_hashgrid_bwd_rays)
+            uint32_t idx[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if (acc[k].x != 0.f || acc[k].y != 0.f) {
-                const uint32_t idx = off + level_index(cx + (k & 1), cy + ((k >> 1) & 1), cz + ((k >> 2) & 1), hashed, pow2, res, size);
-                grad_add2(a.dtable + idx, acc[k]);
+            for (int k = 0; k < 8; ++k) idx[k] = off + level_index(cx + (k & 1), cy + ((k >> 1) & 1), cz + ((k >> 2) & 1), hashed, pow2, res, size);
+            scatter8<true>(a.dtable, idx, acc);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] = make_float2(0.f, 0.f);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (acc[k].x != 0.f || acc[k].y != 0.f) {
+                    const uint32_t idx = off + level_index(cx + (k & 1), cy + ((k >> 1) & 1), cz + ((k >> 2) & 1), hashed, pow2, res, size);
+                    grad_add2(a.dtable + idx, acc[k]);
+                }
+                acc[k] = make_float2(0.f, 0.f);
             }
-            acc[k] = make_float2(0.f, 0.f);
         }
     };
 #pragma unroll 2
@@ -245,10 +255,11 @@ __host__ __device__ __forceinline__ void bwd_march_ray_level(const GridBwdRaysAr
     if (have) flush();
 }
 
+template <bool V4>
 __global__ void __launch_bounds__(128) hashgrid_bwd_march_kernel(const __grid_constant__ GridBwdRaysArgs a)
 {
     const uint64_t ray = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (ray < a.R) bwd_march_ray_level(a, ray, (int)blockIdx.y, blockIdx.z, gridDim.z);
+    if (ray < a.R) bwd_march_ray_level<V4>(a, ray, (int)blockIdx.y, blockIdx.z, gridDim.z);
 }
 
 }  // namespace perf
@@ -348,7 +359,10 @@ int perf_hashgrid_bwd_rays(const perf_grid_cfg* cfg, const float* aabb6, const f
     unsigned pieces = 1;
     while (pieces < 8 && (uint64_t)R * n_agg * pieces < (uint64_t)num_sms() * 2048 && n_samples / (pieces * 2) >= 16) pieces *= 2;
     dim3 g_agg((unsigned)((R + 127) / 128), n_agg, pieces);
-    hashgrid_bwd_march_kernel<<<g_agg, 128, 0, (cudaStream_t)stream>>>(a);
+    // the coarse flush can use the same 16-byte pair atomics; not timed yet, so opt-in (PERF_B200_SCATTER_V4_COARSE=1)
+    const char* env_v4c = getenv("PERF_B200_SCATTER_V4_COARSE");
+    if (env_v4c && env_v4c[0] == '1' && (uintptr_t)a.dtable % 16 == 0) hashgrid_bwd_march_kernel<true><<<g_agg, 128, 0, (cudaStream_t)stream>>>(a);
+    else hashgrid_bwd_march_kernel<false><<<g_agg, 128, 0, (cudaStream_t)stream>>>(a);
     PERF_LAUNCH_CHECK();
     if (a.lt.n_levels > n_agg) {
         dim3 g_rest((unsigned)((N + 255) / 256), a.lt.n_levels - n_agg);
@@ -365,7 +379,7 @@ int perf_hashgrid_bwd_rays(const perf_grid_cfg* cfg, const float* aabb6, const f
 
 #ifdef PERF_HOST_HARNESS
 /* TEST HARNESS ONLY (never compiled into libperfb200.so): both scatter bodies over HOST arrays, one thread;
- * `pieces` plays gridDim.z of the coarse launch, `v4` selects scatter8<true> for the fine levels. */
+ * `pieces` plays gridDim.z of the coarse launch, `v4` bit 0 / bit 1 select scatter8<true> for the fine / coarse levels. */
 int perf_host_hashgrid_bwd_rays(const perf_grid_cfg* cfg, const float* aabb6, const float* h_rays_o, const float* h_rays_d,
                                 const float* h_jitter, uint64_t R, uint32_t n_samples, float near, float far,
                                 const float* h_dfeat, float* h_dtable, int v4, uint32_t pieces)
@@ -375,9 +389,9 @@ int perf_host_hashgrid_bwd_rays(const perf_grid_cfg* cfg, const float* aabb6, co
     PERF_CHECK_ARG(pieces >= 1 && (!v4 || (uintptr_t)h_dtable % 16 == 0), "bad harness arguments");
     for (uint32_t l = 0; l < n_agg; ++l)
         for (uint32_t p = 0; p < pieces; ++p)
-            for (uint64_t ray = 0; ray < R; ++ray) bwd_march_ray_level(a, ray, (int)l, p, pieces);
+            for (uint64_t ray = 0; ray < R; ++ray) { if (v4 & 2) bwd_march_ray_level<true>(a, ray, (int)l, p, pieces); else bwd_march_ray_level<false>(a, ray, (int)l, p, pieces); }
     for (uint32_t l = 0; l + n_agg < a.lt.n_levels; ++l)
-        for (uint64_t row = 0; row < R * n_samples; ++row) { if (v4) bwd_rays_row_level<true>(b, row, (int)l); else bwd_rays_row_level<false>(b, row, (int)l); }
+        for (uint64_t row = 0; row < R * n_samples; ++row) { if (v4 & 1) bwd_rays_row_level<true>(b, row, (int)l); else bwd_rays_row_level<false>(b, row, (int)l); }
     return PERF_OK;
 }
 #endif

@@ -105,9 +105,10 @@ def occ_sample(binaries: np.ndarray, aabb, rays_o: np.ndarray, rays_d: np.ndarra
 
 
 def hashgrid_bwd_rays(grid_cfg, aabb, rays_o, rays_d, jitter, n_samples: int, near: float, far: float, dfeat: np.ndarray,
-                      v4: bool = True, pieces: int = 1) -> np.ndarray:
-    """Both scatter bodies of csrc/train.cu (coarse: per-ray cell accumulation in `pieces` pieces; fine: per row,
-    scatter8<v4>) -> d table [n_entries, 2] f32.  dfeat [S*R, 2L] f32, rows sample-major (row = k * R + ray)."""
+                      v4: int = 1, pieces: int = 1) -> np.ndarray:
+    """Both scatter bodies of csrc/train.cu (coarse: per-ray cell accumulation in `pieces` pieces; fine: per row)
+    -> d table [n_entries, 2] f32.  `v4` bit 0 / bit 1: 16-byte pair atomics on the fine / coarse levels.
+    dfeat [S*R, 2L] f32, rows sample-major (row = k * R + ray)."""
     R = rays_o.shape[0]
     raw = np.zeros(2 * grid_cfg.n_entries + 4, np.float32)
     shift = (-raw.ctypes.data % 16) // 4

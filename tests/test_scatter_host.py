@@ -46,7 +46,7 @@ def test_host_compiled_scatter_matches_oracle(cfg, S, pieces):
     pcfg = GridConfig(cfg.n_levels, 2, cfg.log2_hashmap_size, cfg.base_resolution, cfg.per_level_scale, cfg.interpolation)
     assert pcfg.n_entries == n_table_entries(cfg)
     scale = np.abs(want).max()
-    for v4 in (False, True):
+    for v4 in (0, 1, 2, 3):                              # bit 0: pair atomics on the fine levels, bit 1: on the coarse flush
         got = hh.hashgrid_bwd_rays(pcfg, AABB, o.numpy(), d.numpy(), None if jitter is None else jitter.numpy(), S, near, far,
                                    dfeat.numpy(), v4=v4, pieces=pieces)
         assert np.abs(got - want).max() <= 2e-5 * scale, (v4, np.abs(got - want).max(), scale)

@@ -17,8 +17,9 @@ dfeat = torch.randn(R * S, 32, generator=g).cuda()
 out = torch.zeros(ops.PERF_GRID.n_entries, 2, device="cuda")
 
 
-def run(v4, iters=20):
+def run(v4, iters=20, coarse=False):
     os.environ["PERF_B200_SCATTER_V4"] = "1" if v4 else "0"
+    os.environ["PERF_B200_SCATTER_V4_COARSE"] = "1" if coarse else "0"
     for _ in range(3):
         ops.hashgrid_bwd_rays(o, d, jit, S, 1e-2, 1.0, dfeat, out=out.zero_())
     torch.cuda.synchronize()
@@ -34,4 +35,6 @@ def run(v4, iters=20):
 
 t0, r0 = run(False)
 t1, r1 = run(True)
-print(f"coarse+fine scatter: default {t0:.3f} ms, v4 {t1:.3f} ms, max|diff| {(r0 - r1).abs().max().item():.3e} of {r0.abs().max().item():.3e}")
+t2, r2 = run(True, coarse=True)
+print(f"coarse+fine scatter: 8-byte atomics {t0:.3f} ms, pair atomics on the fine levels (default) {t1:.3f} ms, also on the coarse flush {t2:.3f} ms; "
+      f"max|diff| {(r0 - r1).abs().max().item():.3e} / {(r0 - r2).abs().max().item():.3e} of {r0.abs().max().item():.3e}")
