@@ -197,3 +197,16 @@ if __name__ == "__main__":        # mint tests/golden/sup_info.npz from the refe
     sc = _scene()
     np.savez_compressed(GOLDEN, **_golden_payload(_pool(ref.SupInfoPool, *sc), sc))
     print("wrote", GOLDEN)
+
+
+def test_factor_downsampling_is_opencv_inter_area():
+    """`PanoSupInfo(factor=2)` (`sup_info.py:54-66`): the reference resizes with cv.INTER_AREA; for an integer factor
+    that is the box average torch's 'area' mode computes."""
+    rgb, dist, mask, normal, _ = _scene(32, 64)
+    info = S.PanoSupInfo(torch.eye(4), mask, rgb, dist, normal, factor=2)
+    assert (info.height, info.width) == (16, 32)
+    want = cv2.resize(rgb.numpy(), (32, 16), interpolation=cv2.INTER_AREA)
+    np.testing.assert_allclose(info.color_map.numpy(), want, atol=1e-6)
+    want_d = cv2.resize(dist.numpy(), (32, 16), interpolation=cv2.INTER_AREA)
+    np.testing.assert_allclose(info.distance_map[..., 0].numpy(), want_d, atol=1e-6)
+    assert info.mask.shape == (16, 32, 1) and len(info.sup_colors) == int(info.mask.sum())
