@@ -7,10 +7,11 @@ Mirrors `/root/reference/core_exp_runner.py:36-256` for everything that does not
   ``render_dense(n_poses, cam)``  `:223-246`  the dense tour (north-star workload), frames row-tiled over ranks
   ``save_checkpoint`` / ``load_checkpoint``   `:217-221,248-256`  same file, same keys (`scene`, `sup_pool`, `phase`)
 
-The inpainting loop of ``train`` (`:126-177`: Stable Diffusion / LaMa inpainting and the monocular depth
-predictor for every new view) is out of scope and raises; the geometry side of that loop --
-visibility masks, ``geo_check``, ``register_sup_info`` of a new panorama, re-fit -- is available through
-``NeRFScene.get_pano_visibility_mask`` and ``SupInfoPool``.
+The 2-D priors of the inpainting loop of ``train`` (`:126-177`: Stable Diffusion / LaMa inpainting, the monocular depth
+predictor) are out of scope.  The loop itself -- visibility masks, ``geo_check``, mask arithmetic,
+``register_sup_info`` of each completed panorama, re-fit, checkpoint per anchor -- is here and runs when the caller
+injects those models (``CoreRunner(conf, inpainter=..., geo_predictor=...)``); without them ``train`` raises after
+the raw phase.
 
     python -m perf_b200.runner --config-dir /path/to/PeRF/configs mode=train dataset.image_path=... [key=value ...]
 """
@@ -31,8 +32,11 @@ from .sup_info import SupInfoPool
 
 
 class CoreRunner:
-    def __init__(self, conf, device=None, scene_kwargs=None):
+    def __init__(self, conf, device=None, scene_kwargs=None, inpainter=None, geo_predictor=None):
         self.conf = conf = Conf.wrap(conf)
+        # the reference's 2-D priors, injected by the caller (PanoPersFusionInpainter / PanoJointPredictor objects or
+        # anything with the same call signatures); without them only the raw phase and render_dense are available
+        self.inpainter, self.geo_predictor = inpainter, geo_predictor
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.dataset = WildDataset(conf.dataset, device=self.device)
         self.base_exp_dir = conf.device.base_exp_dir
@@ -85,10 +89,71 @@ class CoreRunner:
             self.save_checkpoint()
             if raw_only:
                 return result
-        raise NotImplementedError(
-            "the inpainting phases of CoreRunner.train (core_exp_runner.py:126-177) need the reference's Stable Diffusion / "
-            "LaMa / Omnidata models, which are outside the per-ray path; run train(raw_only=True), or drive the loop yourself "
-            "with NeRFScene.get_pano_visibility_mask, SupInfoPool.geo_check and SupInfoPool.register_sup_info")
+        if self.inpainter is None or (self.geo_predictor is None and not self.conf.get("rgbd_inpaint", False)):
+            raise NotImplementedError(
+                "the inpainting phases of CoreRunner.train (core_exp_runner.py:126-177) call the reference's Stable Diffusion / "
+                "LaMa inpainter and its monocular depth predictor, which are outside the per-ray path: run train(raw_only=True), "
+                "or pass those objects as CoreRunner(conf, inpainter=..., geo_predictor=...)")
+        return self._train_inpainting_phases()
+
+    def _train_inpainting_phases(self, geo_check=True):
+        """`core_exp_runner.py:126-177`: for every anchor pose not done yet -- render the current scene there, find what no
+        registered panorama sees, let the injected priors invent colour and geometry for it, drop what contradicts the
+        known geometry, register the completed panorama as new supervision and re-fit."""
+        height, width = self.dataset.height, self.dataset.width
+        for anchor in range(max(self.phase, 0), self.pose_sampler.n_anchors):
+            pose = self.pose_sampler.sample_pose(anchor)
+            rays = gen_pano_rays(pose, height, width, device=self.device)
+            self.set_eval()
+            visible = self.scene.get_pano_visibility_mask(self.sup_pool, rays)             # 1 = seen by a registered panorama
+            view = self.scene.render(rays, query_keys=["rgb", "distance"])
+            colors, distances, normals = view["rgb"], view["distance"], None
+            hole = 1. - visible
+            if visible.min().item() <= .5:                                                 # something to invent (n_repeats = 1 upstream)
+                colors, distances, normals = self.inpaint_new_panorama(0, anchor, colors=colors, distances=distances, mask=hole)
+                if geo_check:
+                    hole = hole * (1. - self.sup_pool.geo_check(rays, distances))            # keep only what conflicts with nothing known
+                else:
+                    hole = hole * 0
+            # never trust invented content closer than 0.1 -- and never overwrite what was visible
+            hole = torch.minimum(torch.maximum(hole, (distances.squeeze() < 0.1).float()), 1. - visible)
+            if self.is_main:
+                vis_dir = pjoin(self.exp_dir, "inpaint_vis", "{:0>4d}".format(anchor))
+                os.makedirs(vis_dir, exist_ok=True)
+                write_image(pjoin(vis_dir, "final_mask.jpg"), hole[..., None] * 255.)
+                write_image(pjoin(vis_dir, "final_masked.jpg"), (colors * (1. - hole)[..., None]) * 255.)
+            new_sup = (1. - visible) - torch.minimum(1. - visible, hole)                   # invisible before, accepted now
+            self.sup_pool.register_sup_info(pose=pose, mask=new_sup, rgb=colors, distance=distances, normal=normals)
+            self.set_train()
+            self.scene.fit(self.sup_pool)
+            self.phase += 1
+            self.save_checkpoint()
+
+    def inpaint_new_panorama(self, phase, anchor_idx, colors, distances, mask):
+        """`core_exp_runner.py:179-215`: colours from ``inpainter.inpaint`` then geometry from ``geo_predictor`` (aligned to the
+        rendered distances outside the mask), or both at once from ``inpainter.inpaint_rgbd`` when ``rgbd_inpaint`` is set."""
+        distances, mask = distances.squeeze()[..., None], mask.squeeze()[..., None]
+        vis_dir = pjoin(self.exp_dir, "inpaint_vis", "{:0>4d}".format(anchor_idx))
+        if self.is_main:
+            os.makedirs(vis_dir, exist_ok=True)
+            for name, img in (("uninpainted", colors * 255.), ("uninpainted_disparity", colorize_single_channel_image(distances.min() / distances)),
+                              ("mask", mask * 255.), ("masked", colors * (1. - mask) * 255.)):
+                write_image(pjoin(vis_dir, "{}_{}.jpg".format(name, phase)), img)
+        normals = None
+        if self.conf.get("rgbd_inpaint", False):
+            image, new_distances = self.inpainter.inpaint_rgbd(colors, distances, mask)
+        else:
+            image = self.inpainter.inpaint(colors, mask).to(self.device)
+            new_distances, normals = self.geo_predictor(image, distances, mask=mask, reg_loss_weight=0.,
+                                                        normal_loss_weight=5e-2, normal_tv_loss_weight=5e-2)
+        new_distances = new_distances.squeeze()
+        if self.is_main:
+            write_image(pjoin(vis_dir, "inpainted_{}.jpg".format(phase)), image * 255.)
+            write_image(pjoin(vis_dir, "aligned_disparity_{}.jpg".format(phase)),
+                        colorize_single_channel_image(new_distances.min().item() / new_distances[:, :, None]))
+            if normals is not None:
+                write_image(pjoin(vis_dir, "aligned_normals_{}.jpg".format(phase)), (normals * .5 + .5).clip(0., 1.) * 255.)
+        return image, new_distances, normals
 
     @torch.no_grad()
     def render_dense(self, n_poses=180, cam_type="pano", height=512, width=1024, write=True):

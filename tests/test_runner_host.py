@@ -104,3 +104,88 @@ def test_runner_config_plumbing_without_gpu(tmp_path):
     assert conf.scene.estimator_type == "occ" and conf.scene.train_conf.raw_phase_iter_geo == 10
     assert conf.pose_sampler.n_anchors_per_ratio == [8, 8, 8] and conf.device.base_exp_dir == "."
     assert conf.dataset.image_resize == [2048, 1024]
+
+
+def test_inpainting_phase_loop_with_injected_priors(tmp_path, monkeypatch):
+    """The orchestration of `core_exp_runner.py:126-177` (visibility -> inpaint -> geometric check -> mask arithmetic ->
+    register -> re-fit -> checkpoint) with the scene and the 2-D priors replaced by CPU stand-ins."""
+    from perf_b200 import runner as R
+    from perf_b200.config import Conf
+    from perf_b200.scene import Rays
+    from perf_b200.sup_info import SupInfoPool, apply_rot, pano_dirs
+    h, w = 32, 64
+    dist0 = box_room_distance(h, w).reshape(h, w)
+    dist0 = dist0 / (dist0.max() * 1.05)
+    rgb0 = smooth_rgb(h, w, seed=3)
+
+    def cpu_rays(pose, height, width, device="cpu"):
+        pose = torch.as_tensor(pose, dtype=torch.float32)
+        return Rays(pose[None, None, :3, 3].repeat(height, width, 1), apply_rot(pano_dirs(height, width, "cpu"), pose[:3, :3]))
+    monkeypatch.setattr(R, "gen_pano_rays", cpu_rays)
+
+    class FakeScene:
+        fits = 0
+
+        def get_pano_visibility_mask(self, pool, rays):
+            m = torch.ones(h, w)
+            m[8:20, 10:30] = 0.0                              # a region no registered panorama sees
+            return m
+
+        def render(self, rays, query_keys):
+            return {"rgb": rgb0.clone(), "distance": dist0.clone()[..., None]}
+
+        def fit(self, pool):
+            FakeScene.fits += 1
+
+        def set_train(self): pass
+        def set_eval(self): pass
+        def state_dict(self): return {"render": {}, "nerf": {}, "estimator": {}}
+
+    class FakeInpainter:
+        def inpaint(self, colors, mask):
+            out = colors.clone()
+            out[mask.squeeze() > 0.5] = torch.tensor([1.0, 0.0, 0.0])
+            return out
+
+    calls = []
+
+    def fake_geo(img, distances, mask=None, reg_loss_weight=None, normal_loss_weight=None, normal_tv_loss_weight=None):
+        calls.append((reg_loss_weight, normal_loss_weight, normal_tv_loss_weight))
+        d = distances.clone()
+        d[10:14, 12:20] = 0.05                                 # invented content too close to the camera: must be rejected
+        return d, None
+
+    class Anchors:
+        n_anchors = 2
+
+        def sample_pose(self, i):
+            p = torch.eye(4)
+            p[0, 3] = 0.05 * (i + 1)
+            return p
+
+    run = R.CoreRunner.__new__(R.CoreRunner)
+    run.conf = Conf.wrap({"rgbd_inpaint": False})
+    run.device, run.is_main, run.exp_dir, run.phase = torch.device("cpu"), True, str(tmp_path), 0
+    run.dataset = type("D", (), {"height": h, "width": w})()
+    run.scene, run.pose_sampler, run.inpainter, run.geo_predictor = FakeScene(), Anchors(), FakeInpainter(), fake_geo
+    run.sup_pool = SupInfoPool(locality_sort=False)
+    run.sup_pool.register_sup_info(pose=torch.eye(4), mask=torch.ones(h, w), rgb=rgb0, distance=dist0, normal=None)
+    n0 = len(run.sup_pool.all_sup_colors)
+    run.train()
+    assert run.phase == 2 and FakeScene.fits == 2 and len(run.sup_pool.sup_infos) == 3
+    assert calls == [(0., 5e-2, 5e-2)] * 2                       # the reference's keyword arguments (core_exp_runner.py:203-208)
+    new = run.sup_pool.sup_infos[1]
+    # only pixels that were invisible can become supervision, and the too-close invented block was rejected
+    assert not new.mask_raw[:8].any() and not new.mask_raw[:, :10].any()
+    assert not new.mask_raw[10:14, 12:20].any()
+    assert len(run.sup_pool.all_sup_colors) > n0
+    red = (new.sup_colors - torch.tensor([1.0, 0.0, 0.0])).abs().max()
+    assert float(red) == 0.0                                      # the new supervision is exactly the inpainted content
+    ck = torch.load(os.path.join(str(tmp_path), "checkpoints", "ckpt.pth"), weights_only=False)
+    assert ck["phase"] == 2 and ck["sup_pool"]["n_sup_infos"] == 3
+    for f in ("final_mask.jpg", "final_masked.jpg", "uninpainted_0.jpg", "mask_0.jpg", "inpainted_0.jpg", "aligned_disparity_0.jpg"):
+        assert os.path.exists(os.path.join(str(tmp_path), "inpaint_vis", "0000", f)), f
+    # without the priors the raw phase is all there is
+    run.inpainter = None
+    with pytest.raises(NotImplementedError, match="inpainter"):
+        run.train()
