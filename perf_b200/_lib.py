@@ -102,9 +102,12 @@ def load(rebuild_if_stale: bool = True) -> C.CDLL:
     if rebuild_if_stale and (not os.path.exists(path) or _build.is_stale()):
         try:
             _build.build()
-        except Exception as e:                      # no nvcc on this box: use the shipped .so
+        except _build.NvccMissing as e:             # no compiler on this box: the shipped .so is all there is
             if not os.path.exists(path):
                 raise ImportError(f"libperfb200.so is missing and could not be built: {e}") from e
+            import warnings
+            warnings.warn("libperfb200.so is older than its sources and nvcc is not available: using the shipped binary")
+        # any other failure (an nvcc compile error after a kernel edit) propagates: never run a stale binary silently
     lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)                     # AttributeError if the symbol is not exported

@@ -20,11 +20,15 @@ NVCC_FLAGS = [
 ]
 
 
+class NvccMissing(RuntimeError):
+    """No nvcc on this machine (the only build failure a caller may answer by loading the shipped .so)."""
+
+
 def _nvcc() -> str:
     for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):
             return cand
-    raise RuntimeError("nvcc not found: libperfb200.so cannot be built on this machine")
+    raise NvccMissing("nvcc not found: libperfb200.so cannot be built on this machine")
 
 
 def sources():

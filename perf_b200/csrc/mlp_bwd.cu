@@ -1,11 +1,12 @@
 // mlp_bwd.cu -- backward of the 64-wide bias-free MLP from the saved fp16 activations, ONE kernel on the
-// 5th-gen tensor cores (replaces tcnn FullyFusedMLP::backward_impl for PeRF's two networks; today's default
-// path hands the five matrix products to cuBLAS from Python, ops.mlp_backward_half).
+// 5th-gen tensor cores (replaces tcnn FullyFusedMLP::backward_impl + its CUTLASS dW GEMMs for PeRF's two networks;
+// the default path of ops.mlp_backward_half since round 2).
 //
-// STATUS: written at the end of round 1 WITHOUT GPU time left to run it; it is NOT on any default path
-// (ops.mlp_backward_half only calls it when PERF_B200_TC_MLP_BWD=1, its GPU tests are gated by
-// PERF_B200_EXPERIMENTAL=1).  It carries a CUDA-core twin (PERF_FLAG_SIMT_MLP) that reads the same
-// shared-memory operand images, so descriptor mistakes can be told from arithmetic ones.
+// STATUS: validated on B200 (round 2): tools/diag_mlp_bwd.py against a torch fp32 reference -- every output block
+// (dfeat, dW1, dW2, dWout) within 2e-5 relative for both networks, CUDA-core twin (PERF_FLAG_SIMT_MLP, same
+// shared-memory operand images) and tcgen05; 8192 x 128 samples: 0.180 ms (density) / 0.228 ms (colour) against
+// 0.291 / 0.589 ms for the cuBLAS GEMM path it replaced (tools/ab_mlp_bwd.py).  The MN-major descriptors are as
+// documented below (the swapped LBO / SBO variant, flags bit 8, produces garbage -- kept as a negative control).
 //
 // Rows are samples (any order), thread t of a 128-thread CTA owns row t of the current 128-row tile.
 //   colour net (two hidden layers), per tile:
@@ -39,6 +40,7 @@ struct MlpBwdArgs {
     float*        dW;        // flat fp32 gradient of the MLP params, accumulated (+=)
     float*        dfeat;     // [N,32] fp32
     uint32_t      n_out;     // 1..3
+    uint32_t      dbg;       // bring-up only (flags >> 8): bit 0 swaps LBO / SBO of the MN-major descriptors
 };
 
 __host__ __device__ constexpr uint32_t idesc_f16_major(int M, int N, bool a_mn, bool b_mn)
@@ -46,7 +48,10 @@ __host__ __device__ constexpr uint32_t idesc_f16_major(int M, int N, bool a_mn, 
     return umma_idesc_f16(M, N) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16);
 }
 // MN-major view of a canonical image with `rows` rows, K-step ks (16 rows)
-__device__ __forceinline__ uint64_t desc_mn(uint32_t img, int rows, int ks) { return umma_desc(img + ks * 256, 128u, (uint32_t)rows * 16u); }
+__device__ __forceinline__ uint64_t desc_mn(uint32_t img, int rows, int ks, uint32_t dbg = 0)
+{
+    return (dbg & 1u) ? umma_desc(img + ks * 256, (uint32_t)rows * 16u, 128u) : umma_desc(img + ks * 256, 128u, (uint32_t)rows * 16u);
+}
 // K-major view of an activation image (128 rows), K-step ks (16 columns)
 __device__ __forceinline__ uint64_t desc_k(uint32_t img, int ks) { return umma_desc(img + ks * 2 * A_LBO, A_LBO, X_SBO); }
 
@@ -273,7 +278,7 @@ __global__ void __launch_bounds__(128) mlp_bwd_kernel(const MlpBwdArgs a)
                     tc_fence_after();
                     constexpr uint32_t id = idesc_f16_major(TILE, HID, false, true);
                     for (int ks = 0; ks < 4; ++ks)
-                        umma_f16(tmem_base + L::TM_D1, desc_k(smem_u32(smem + L::DH2), ks), desc_mn(smem_u32(smem + L::W2), HID, ks), id, ks > 0);
+                        umma_f16(tmem_base + L::TM_D1, desc_k(smem_u32(smem + L::DH2), ks), desc_mn(smem_u32(smem + L::W2), HID, ks, a.dbg), id, ks > 0);
                     umma_commit(bar);
                 }
                 mbar_wait(bar, phase); phase ^= 1u;
@@ -296,15 +301,15 @@ __global__ void __launch_bounds__(128) mlp_bwd_kernel(const MlpBwdArgs a)
                 tc_fence_after();
                 constexpr uint32_t id2 = idesc_f16_major(TILE, 32, false, true);
                 for (int ks = 0; ks < 4; ++ks)
-                    umma_f16(tmem_base + L::TM_D2, desc_k(smem_u32(smem + L::DH1), ks), desc_mn(smem_u32(smem + L::W1), HID, ks), id2, ks > 0);
+                    umma_f16(tmem_base + L::TM_D2, desc_k(smem_u32(smem + L::DH1), ks), desc_mn(smem_u32(smem + L::W1), HID, ks, a.dbg), id2, ks > 0);
                 constexpr uint32_t idg = idesc_f16_major(TILE, L::N_G1, true, true);
                 for (int ks = 0; ks < 8; ++ks)
-                    umma_f16(tmem_base + L::TM_G1, desc_mn(smem_u32(smem + L::GA), TILE, ks), desc_mn(smem_u32(smem + L::GB), TILE, ks), idg,
+                    umma_f16(tmem_base + L::TM_G1, desc_mn(smem_u32(smem + L::GA), TILE, ks, a.dbg), desc_mn(smem_u32(smem + L::GB), TILE, ks, a.dbg), idg,
                              (!first || ks > 0) ? 1u : 0u);
                 if constexpr (TWO) {
                     constexpr uint32_t idg2 = idesc_f16_major(TILE, L::N_G2, true, true);
                     for (int ks = 0; ks < 8; ++ks)
-                        umma_f16(tmem_base + L::TM_G2, desc_mn(smem_u32(smem + L::H2), TILE, ks), desc_mn(smem_u32(smem + L::DZP), TILE, ks), idg2,
+                        umma_f16(tmem_base + L::TM_G2, desc_mn(smem_u32(smem + L::H2), TILE, ks, a.dbg), desc_mn(smem_u32(smem + L::DZP), TILE, ks, a.dbg), idg2,
                                  (!first || ks > 0) ? 1u : 0u);
                 }
                 umma_commit(bar);
@@ -428,7 +433,7 @@ int perf_mlp_bwd(const perf_mlp_cfg* mlp, const void* d_weights_half, const void
     if (N == 0) return PERF_OK;
     MlpBwdArgs a;
     a.w = (const __half*)d_weights_half; a.feat = (const uint4*)d_feat; a.h1 = (const uint4*)d_h1; a.h2 = (const uint4*)d_h2;
-    a.dz = d_dz; a.N = N; a.dW = d_dweights; a.dfeat = d_dfeat; a.n_out = mlp->n_out;
+    a.dz = d_dz; a.N = N; a.dW = d_dweights; a.dfeat = d_dfeat; a.n_out = mlp->n_out; a.dbg = flags >> 8;
     const bool simt = (flags & PERF_FLAG_SIMT_MLP) != 0;
     if (mlp->n_hidden_layers == 2) return simt ? launch_mlp_bwd<true, true>(a, (cudaStream_t)stream) : launch_mlp_bwd<true, false>(a, (cudaStream_t)stream);
     return simt ? launch_mlp_bwd<false, true>(a, (cudaStream_t)stream) : launch_mlp_bwd<false, false>(a, (cudaStream_t)stream);
@@ -444,7 +449,7 @@ int perf_host_mlp_bwd(const perf_mlp_cfg* mlp, const void* h_weights_half, const
     PERF_CHECK_SUP(mlp->n_out <= 3, "n_out=%u", mlp->n_out);
     MlpBwdArgs a;
     a.w = (const __half*)h_weights_half; a.feat = (const uint4*)h_feat; a.h1 = (const uint4*)h_h1; a.h2 = (const uint4*)h_h2;
-    a.dz = h_dz; a.N = N; a.dW = h_dweights; a.dfeat = h_dfeat; a.n_out = mlp->n_out;
+    a.dz = h_dz; a.N = N; a.dW = h_dweights; a.dfeat = h_dfeat; a.n_out = mlp->n_out; a.dbg = 0;
     uint8_t* smem = (uint8_t*)aligned_alloc(128, (size_t)(BwdSmem<true>::TOTAL + 127) / 128 * 128);
     float* gacc = (float*)calloc((size_t)TILE * N_GACC, sizeof(float));
     if (!smem || !gacc) { free(smem); free(gacc); return PERF_ECUDA; }

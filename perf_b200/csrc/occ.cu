@@ -7,6 +7,8 @@
 
 namespace perf {
 
+constexpr uint32_t PERF_OCC_MAX_STEPS = 1u << 22;      // lattice points one ray may visit (PeRF: 1.5 / 5e-4 = 3000)
+
 struct OccArgs {
     const uint8_t* binaries; int rx, ry, rz;
     float amin[3], aext[3], amax[3];
@@ -39,7 +41,12 @@ __host__ __device__ __forceinline__ void occ_march_ray(const OccArgs& a, uint64_
         // first lattice index whose midpoint can reach tn (minus a safety margin; exact test below)
         float kf = floorf((tn - a.near) / a.step - u - 0.5f) - 2.0f;
         uint32_t k = kf > 0.f ? (uint32_t)kf : 0u;
-        for (;; ++k) {
+        // Bounded walk: at most the lattice points between tn and tf (+ margin).  A ray whose overlap with the box
+        // is not bounded by the box (|d| ~ 0 with far_plane = 1e10, or a tiny step) would otherwise spin once
+        // (float)k stops changing at 2^24; such a ray yields no samples.
+        const float span = (tf - tn) / a.step;
+        const uint32_t k_end = span < (float)PERF_OCC_MAX_STEPS ? k + (uint32_t)span + 8u : k;
+        for (; k < k_end; ++k) {
             const float ts = PERF_FADD_RN(a.near, PERF_FMUL_RN(PERF_FADD_RN((float)k, u), a.step));
             const float mid = PERF_FADD_RN(ts, half_step);
             if (mid > tf) break;

@@ -67,6 +67,35 @@ constexpr int RS_CARRY = RS_TAILS + 2 * 4 * 8 * 4;  // [2 parities][8] floats
 constexpr int RS_BAR   = RS_CARRY + 2 * 8 * 4;
 constexpr int RS_TOTAL = RS_BAR + 16;
 
+// Output-layer weights of both networks as fp32 in the CONSTANT bank: [0,64) density row, [64,256) the three colour
+// rows.  The 64 * n_out FMAs per sample of the output layers then take their weight operand straight from c[bank][imm]
+// -- no load instruction.  (Round 1 kept them in shared memory: 64 broadcast LDS.128 per thread and sample, 1.2e9
+// shared-load wavefronts per panorama on the L1 data pipe that bounds the kernel, profiles/r01_*.)  Filled from the fp16
+// parameter vectors by wout_to_const_kernel, stream-ordered in front of every render launch (graph-capturable).
+// One slot per device: renders of DIFFERENT fields on the same device must not overlap in time (different streams).
+__constant__ float c_wout[4 * HID];
+
+__global__ void wout_to_const_kernel(const __half* __restrict__ geo_wout, const __half* __restrict__ app_wout, float* __restrict__ dst)
+{
+    const int i = threadIdx.x;                       // 256 threads
+    dst[i] = __half2float(i < HID ? geo_wout[i] : app_wout[i - HID]);
+}
+
+// acc[o] += sum_j h[32c + j] * c_wout[BASE + 64 o + 32 c + j], C a compile-time constant (immediate constant offsets)
+template <int NOUT, int BASE, int C>
+__device__ __forceinline__ void out_dots_const(const uint32_t (&p)[16], float (&acc)[NOUT])
+{
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float2 f = unpack_half2(p[j]);
+#pragma unroll
+        for (int o = 0; o < NOUT; ++o) {
+            acc[o] = fmaf(f.x, c_wout[BASE + o * HID + 32 * C + 2 * j], acc[o]);
+            acc[o] = fmaf(f.y, c_wout[BASE + o * HID + 32 * C + 2 * j + 1], acc[o]);
+        }
+    }
+}
+
 __device__ __forceinline__ float linspace_val_r(int i, int n)
 {
     const float start = (float)(0.5 / (double)n), end = (float)(1.0 - 0.5 / (double)n);
@@ -227,13 +256,13 @@ __device__ __forceinline__ void eval_fields(const RenderArgs& a, const RenderSme
 
     // density: ReLU hidden -> 64-long dot -> fp16 logit -> exp     (ngp_nerf.py:141-150)
     float og[1] = {0.f};
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {                          // unrolled: the constant-bank offsets must be immediates
         float v[32]; uint32_t hp[16];
         acc_chunk<SIMT>(c, 32, tmem_row, sAg, sW1g, tid, v);
         relu_pack(v, hp);
         if constexpr (SAVE == 1) { if (srow != ~0ull) store_chunk_global(a.s_h1 + srow * 8, c, hp); }
-        out_dots<1>(hp, sWoutG, c, 1, og);
+        if (c == 0) out_dots_const<1, 0, 0>(hp, og); else out_dots_const<1, 0, 1>(hp, og);
     }
     sigma = selector ? expf(finish_output(og[0], 0)) : 0.f;
 
@@ -261,13 +290,13 @@ __device__ __forceinline__ void eval_fields(const RenderArgs& a, const RenderSme
         __syncthreads();
     }
     float oa[3] = {0.f, 0.f, 0.f};
-#pragma unroll 1
+#pragma unroll
     for (int c = 0; c < 2; ++c) {
         float v[32]; uint32_t hp[16];
         acc_chunk<SIMT>(c, 64, tmem_row + 64, sA, sW2a, tid, v);
         relu_pack(v, hp);
         if constexpr (SAVE == 2) { if (srow != ~0ull) store_chunk_global(a.s_h2 + srow * 8, c, hp); }
-        out_dots<3>(hp, sWoutA, c, 3, oa);
+        if (c == 0) out_dots_const<3, HID, 0>(hp, oa); else out_dots_const<3, HID, 1>(hp, oa);
     }
     cr = selector ? finish_output(oa[0], 1) : 0.f;      // ngp_nerf.py:156-161
     cg = selector ? finish_output(oa[1], 1) : 0.f;
@@ -295,10 +324,8 @@ __global__ void __launch_bounds__(TILE, 4) render_kernel(const __grid_constant__
     const RenderSmem sm = {sA, sAg, sAa, sW1g, sW1a, sW2a, sWoutG, sWoutA, bar};
 
     load_weight_canonical(a.geo_w, 32, sW1g, tid, TILE);
-    load_wout(a.geo_w + HID * 32, 1, sWoutG, tid, TILE);
     load_weight_canonical(a.app_w, 32, sW1a, tid, TILE);
     load_weight_canonical(a.app_w + HID * 32, 64, sW2a, tid, TILE);
-    load_wout(a.app_w + HID * 32 + HID * HID, 3, sWoutA, tid, TILE);
     uint32_t tmem_base = 0;
     if (!SIMT) {
         if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
@@ -435,10 +462,8 @@ __global__ void __launch_bounds__(TILE, 4) render_march_kernel(const __grid_cons
     const RenderSmem sm = {sA, sA, sA + A32_BYTES, sW1g, sW1a, sW2a, sWoutG, sWoutA, bar};
 
     load_weight_canonical(a.geo_w, 32, sW1g, tid, TILE);
-    load_wout(a.geo_w + HID * 32, 1, sWoutG, tid, TILE);
     load_weight_canonical(a.app_w, 32, sW1a, tid, TILE);
     load_weight_canonical(a.app_w + HID * 32, 64, sW2a, tid, TILE);
-    load_wout(a.app_w + HID * 32 + HID * HID, 3, sWoutA, tid, TILE);
     uint32_t tmem_base = 0;
     if (!SIMT) {
         if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
@@ -656,6 +681,13 @@ static int launch_render(const perf_render_args* args, RenderArgs& a, bool pano,
         n_work = (a.R + rpt - 1) / rpt;
     }
     const unsigned grid = (unsigned)(n_work < (uint64_t)num_sms() * 4 ? n_work : (uint64_t)num_sms() * 4);
+    {   // output-layer weights -> constant bank (see c_wout)
+        static thread_local int sym_dev = -1; static thread_local float* sym = nullptr;
+        int dev_ = 0; PERF_CUDA(cudaGetDevice(&dev_));
+        if (sym_dev != dev_) { PERF_CUDA(cudaGetSymbolAddress((void**)&sym, c_wout)); sym_dev = dev_; }
+        wout_to_const_kernel<<<1, 4 * HID, 0, stream>>>(a.geo_w + HID * 32, a.app_w + HID * 32 + HID * HID, sym);
+        PERF_LAUNCH_CHECK();
+    }
 #define PERF_RENDER_LAUNCH(...) do { \
         auto k = __VA_ARGS__; \
         static thread_local int attr_dev = -1; int dev_ = 0; PERF_CUDA(cudaGetDevice(&dev_)); \

@@ -74,6 +74,95 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(const CompBwdArgs a)
     if (ray < a.R) composite_bwd_ray<PHASE>(a, ray);
 }
 
+// Chunk-parallel version of composite_bwd_ray (same formulas): an 8192-ray batch is only 64 CTAs of the kernel above,
+// each thread walking 128 dependent samples (100 us of a 1.5 ms step, profiles/r02_train_launches_*).  Here a block is
+// 32 consecutive rays (lanes: coalesced rows) x C chunks of S / C samples (warps); the suffix sums the backward scan
+// needs (sum w, sum w m, sum w g over the LATER samples of the ray) are exchanged between the chunks through shared
+// memory: pass 1 chunk sums of w and w m, pass 2 the backward walk inside the chunk, pass 3 the correction by the
+// later chunks' sum w g.  Density phase only needs this; the colour phase has no dependence along the ray.
+template <int PHASE, int C>
+__global__ void __launch_bounds__(32 * C) composite_bwd_chunk_kernel(const CompBwdArgs a)
+{
+    const int rx = threadIdx.x, c = threadIdx.y;
+    const uint64_t ray = (uint64_t)blockIdx.x * 32 + rx;
+    const bool valid = ray < a.R;
+    const uint32_t S = a.S, K = S / C, k_lo = c * K, k_hi = k_lo + K;
+    const uint32_t kps = S / a.seg;
+    const float step = __fdiv_rn(__fsub_rn(a.far, a.near), (float)S);
+    const float jit = (valid && a.jitter) ? a.jitter[ray] : 0.f;
+    if constexpr (PHASE == PERF_PHASE_APP) {
+        if (!valid) return;
+        float gr = 0.f, gg = 0.f, gb = 0.f;
+        if (a.g_rgb) { gr = a.g_rgb[3 * ray]; gg = a.g_rgb[3 * ray + 1]; gb = a.g_rgb[3 * ray + 2]; }
+        for (uint32_t k = k_lo; k < k_hi; ++k) {
+            const uint64_t row = (uint64_t)k * a.R + ray;
+            const float w = a.w[row] * (a.seg > 1 ? a.toff[(uint64_t)(k / kps) * a.R + ray] : 1.f);
+            const uint2 cc = *reinterpret_cast<const uint2*>(a.rgb + row * 4);
+            const float2 c01 = unpack_half2(cc.x), c2 = unpack_half2(cc.y);
+            a.out[row * 3 + 0] = gr * w * c01.x * (1.f - c01.x);
+            a.out[row * 3 + 1] = gg * w * c01.y * (1.f - c01.y);
+            a.out[row * 3 + 2] = gb * w * c2.x * (1.f - c2.x);
+        }
+    } else {
+        __shared__ float sW[C][32], sWM[C][32], sWG[C][32];
+        auto t_mid = [&](uint32_t k, float& m, float& dt) {
+            const float ts = __fadd_rn(a.near, __fmul_rn(__fadd_rn((float)k, jit), step));
+            const float te = __fadd_rn(a.near, __fmul_rn(__fadd_rn((float)(k + 1), jit), step));
+            m = __fadd_rn(ts, te) * 0.5f; dt = __fsub_rn(te, ts);
+        };
+        // pass 1: this chunk's sum w and sum w m
+        float Wc = 0.f, WMc = 0.f;
+        if (valid) {
+            for (uint32_t k = k_lo; k < k_hi; ++k) {
+                const uint64_t row = (uint64_t)k * a.R + ray;
+                const float w = a.w[row] * (a.seg > 1 ? a.toff[(uint64_t)(k / kps) * a.R + ray] : 1.f);
+                float m, dt; t_mid(k, m, dt);
+                Wc += w; WMc = fmaf(w, m, WMc);
+            }
+        }
+        sW[c][rx] = Wc; sWM[c][rx] = WMc;
+        __syncthreads();
+        float Wsuf = 0.f, WMsuf = 0.f;
+        for (int cc = C - 1; cc > c; --cc) { Wsuf += sW[cc][rx]; WMsuf += sWM[cc][rx]; }
+        // pass 2: backward walk inside the chunk
+        float suf_wg = 0.f;
+        float O = 0.f, D = 0.f, gd = 0.f, gO = 0.f, gdl = 0.f;
+        if (valid) {
+            O = a.op_out[ray]; D = a.dist_acc[ray];
+            float cbg = 0.f;
+            if (a.bg_noise) cbg = a.bg_noise[4 * ray + 3] * 2.f - 1.f;
+            const float mask = a.dist_out[ray] > 0.f ? 1.f : 0.f;
+            gd = (a.g_dist ? a.g_dist[ray] : 0.f) * mask;
+            gO = (a.g_op ? a.g_op[ray] : 0.f) - gd * cbg;
+            gdl = a.g_dl ? a.g_dl[ray] : 0.f;
+            for (uint32_t kk = k_hi; kk-- > k_lo;) {
+                const uint64_t row = (uint64_t)kk * a.R + ray;
+                const float toff = a.seg > 1 ? a.toff[(uint64_t)(kk / kps) * a.R + ray] : 1.f;
+                const float w = a.w[row] * toff, T = a.T[row] * toff, sig = a.sigma[row];
+                float m, dt; t_mid(kk, m, dt);
+                const float Wx = O - Wsuf - w, WMx = D - WMsuf - w * m;
+                const float ddl = (2.f / 3.f) * dt * w + 2.f * (m * Wx - WMx) + 2.f * (WMsuf - m * Wsuf);
+                const float g = gd * m + gO + gdl * ddl;
+                const float dsd = (T - w) * g - suf_wg;
+                a.out[row] = dsd * dt * fminf(sig, 3269017.3724721107f);
+                suf_wg = fmaf(w, g, suf_wg); Wsuf += w; WMsuf = fmaf(w, m, WMsuf);
+            }
+        }
+        sWG[c][rx] = suf_wg;
+        __syncthreads();
+        // pass 3: sum w g of the later chunks
+        float off = 0.f;
+        for (int cc = C - 1; cc > c; --cc) off += sWG[cc][rx];
+        if (valid && off != 0.f) {
+            for (uint32_t k = k_lo; k < k_hi; ++k) {
+                const uint64_t row = (uint64_t)k * a.R + ray;
+                float m, dt; t_mid(k, m, dt);
+                a.out[row] -= off * dt * fminf(a.sigma[row], 3269017.3724721107f);
+            }
+        }
+    }
+}
+
 // dh[n][j] = (sum_o dz[n][o] * wout[o][j]) * (h[n][j] > 0)   -- output layer backward + ReLU mask,
 // one pass over the saved fp16 activations (8 columns per thread).
 __global__ void __launch_bounds__(256)
@@ -300,9 +389,18 @@ int perf_train_backward_composite(int phase, uint32_t n_samples, uint32_t segmen
                                  d_g_distloss, d_distance_out, d_opacity_out, d_out, a);
     if (rc) return rc;
     if (R == 0) return PERF_OK;
-    const unsigned grid = (unsigned)((R + 127) / 128);
-    if (phase == PERF_PHASE_GEO) composite_bwd_kernel<PERF_PHASE_GEO><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
-    else composite_bwd_kernel<PERF_PHASE_APP><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+    // chunk-parallel kernel when the ray-sequential one would leave the machine empty (PERF_B200_COMPBWD_CHUNKS=1: A/B)
+    const char* env_c = getenv("PERF_B200_COMPBWD_CHUNKS");
+    const bool chunked = !(env_c && env_c[0] == '1') && n_samples % 8 == 0 && n_samples >= 32 && (R + 127) / 128 < (uint64_t)num_sms() * 8;
+    if (chunked) {
+        const unsigned gridc = (unsigned)((R + 31) / 32);
+        if (phase == PERF_PHASE_GEO) composite_bwd_chunk_kernel<PERF_PHASE_GEO, 8><<<gridc, dim3(32, 8), 0, (cudaStream_t)stream>>>(a);
+        else composite_bwd_chunk_kernel<PERF_PHASE_APP, 8><<<gridc, dim3(32, 8), 0, (cudaStream_t)stream>>>(a);
+    } else {
+        const unsigned grid = (unsigned)((R + 127) / 128);
+        if (phase == PERF_PHASE_GEO) composite_bwd_kernel<PERF_PHASE_GEO><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+        else composite_bwd_kernel<PERF_PHASE_APP><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+    }
     PERF_LAUNCH_CHECK();
     return PERF_OK;
 }
@@ -359,9 +457,10 @@ int perf_hashgrid_bwd_rays(const perf_grid_cfg* cfg, const float* aabb6, const f
     unsigned pieces = 1;
     while (pieces < 8 && (uint64_t)R * n_agg * pieces < (uint64_t)num_sms() * 2048 && n_samples / (pieces * 2) >= 16) pieces *= 2;
     dim3 g_agg((unsigned)((R + 127) / 128), n_agg, pieces);
-    // the coarse flush can use the same 16-byte pair atomics; not timed yet, so opt-in (PERF_B200_SCATTER_V4_COARSE=1)
+    // the coarse flush uses the same 16-byte pair atomics: 0.586 -> 0.528 ms for both scatter launches of an 8192 x 128
+    // step (tools/ab_scatter_v4.py, B200, round 2); PERF_B200_SCATTER_V4_COARSE=0 restores the 8-byte flush
     const char* env_v4c = getenv("PERF_B200_SCATTER_V4_COARSE");
-    if (env_v4c && env_v4c[0] == '1' && (uintptr_t)a.dtable % 16 == 0) hashgrid_bwd_march_kernel<true><<<g_agg, 128, 0, (cudaStream_t)stream>>>(a);
+    if (!(env_v4c && env_v4c[0] == '0') && (uintptr_t)a.dtable % 16 == 0) hashgrid_bwd_march_kernel<true><<<g_agg, 128, 0, (cudaStream_t)stream>>>(a);
     else hashgrid_bwd_march_kernel<false><<<g_agg, 128, 0, (cudaStream_t)stream>>>(a);
     PERF_LAUNCH_CHECK();
     if (a.lt.n_levels > n_agg) {

@@ -500,14 +500,22 @@ class FusedTrainContext:
 
 def mlp_backward_half(mlp: MLPConfig, weights_half: torch.Tensor, feat, h1, h2, dz: torch.Tensor,
                       grad_out: Optional[torch.Tensor] = None):
-    """MLP backward from saved fp16 activations: fp16 tensor-core GEMMs (cuBLAS, fp32 out) for the
-    matrix products, libperfb200 kernels for the fused output-layer backward + ReLU masks.
+    """MLP backward from saved fp16 activations (tcnn ``FullyFusedMLP::backward_impl``, reached from
+    `ngp_nerf.py:142,158` under autograd): ONE tcgen05 kernel, :func:`mlp_backward_fused` (csrc/mlp_bwd.cu).
     ``dz`` [N, n_out] fp32: gradient w.r.t. the output layer's pre-activation.
-    Returns (d_weights_flat fp32 [mlp.n_params] -- written into ``grad_out`` when given --, dfeat fp32 [N,32])."""
+    Returns (d_weights_flat fp32 [mlp.n_params] -- written into ``grad_out`` when given --, dfeat fp32 [N,32]).
+    ``PERF_B200_GEMM_MLP_BWD=1`` selects :func:`mlp_backward_gemm` (library GEMMs; the A/B reference of round 1)."""
+    if os.environ.get("PERF_B200_GEMM_MLP_BWD") == "1":
+        return mlp_backward_gemm(mlp, weights_half, feat, h1, h2, dz, grad_out)
+    return mlp_backward_fused(mlp, weights_half, feat, h1, h2, dz, grad_out)
+
+
+def mlp_backward_gemm(mlp: MLPConfig, weights_half: torch.Tensor, feat, h1, h2, dz: torch.Tensor,
+                      grad_out: Optional[torch.Tensor] = None):
+    """Round-1 path, kept as the A/B reference of the tests and tools/ab_mlp_bwd.py only: the five matrix products as
+    fp16 cuBLAS GEMMs (fp32 out) around perf_mlp_bwd_out / perf_relu_mask.  NOT on any default path."""
     N, dev = dz.shape[0], dz.device
     W = weights_half
-    if os.environ.get("PERF_B200_TC_MLP_BWD") == "1":         # experimental single-kernel backward (csrc/mlp_bwd.cu)
-        return mlp_backward_fused(mlp, weights_half, feat, h1, h2, dz, grad_out)
     w1 = W[:64 * 32].view(64, 32)
     p = 64 * 32
     w2 = None
@@ -536,9 +544,11 @@ def mlp_backward_half(mlp: MLPConfig, weights_half: torch.Tensor, feat, h1, h2, 
 
 
 def mlp_backward_fused(mlp: MLPConfig, weights_half: torch.Tensor, feat, h1, h2, dz: torch.Tensor,
-                       grad_out: Optional[torch.Tensor] = None, simt: bool = False):
-    """Same contract as :func:`mlp_backward_half`, as ONE tcgen05 kernel (perf_mlp_bwd).  EXPERIMENTAL: written
-    at the end of round 1 without GPU time to validate it; only reached with PERF_B200_TC_MLP_BWD=1."""
+                       grad_out: Optional[torch.Tensor] = None, simt: bool = False, dbg: int = 0):
+    """The whole MLP backward as ONE tcgen05 kernel (perf_mlp_bwd, csrc/mlp_bwd.cu): output-layer backward on CUDA
+    cores, data gradients dh W as MMAs against the forward weight images read MN-major, weight gradients
+    [dh]^T [h] accumulated in TMEM over the CTA's tiles and flushed once.  Validated on B200 in round 2 against a
+    torch fp32 reference (tools/diag_mlp_bwd.py: rel. err <= 2e-5) and the GEMM path (tests/test_gpu_train.py)."""
     N, dev = dz.shape[0], dz.device
     if grad_out is None:
         grad_out = torch.zeros(mlp.n_params, dtype=torch.float32, device=dev)
@@ -549,14 +559,14 @@ def mlp_backward_fused(mlp: MLPConfig, weights_half: torch.Tensor, feat, h1, h2,
     with torch.cuda.device(dev):
         _call(_L().perf_mlp_bwd, mlp.c(), _p(_chk(weights_half, torch.float16, "weights")), _p(_chk(feat, torch.float16, "feat")),
               _p(_chk(h1, torch.float16, "h1")), _p(None if h2 is None else _chk(h2, torch.float16, "h2")), _p(dz), N,
-              _p(grad_out), _p(dfeat), _lib.PERF_FLAG_SIMT_MLP if simt else 0, _stream())
+              _p(grad_out), _p(dfeat), (_lib.PERF_FLAG_SIMT_MLP if simt else 0) | (dbg << 8), _stream())
     return grad_out, dfeat
 
 
 class _FusedTrainStep(torch.autograd.Function):
     """(rgb, distance, opacity, distloss_numerator_per_ray) of a training-mode render, differentiable
     w.r.t. the flat params of the network selected by ``phase``.  Forward = ONE kernel
-    (perf_train_forward), backward = composite-backward kernel, 5-8 cuBLAS GEMMs, grid scatter."""
+    (perf_train_forward), backward = composite-backward kernel, ONE tcgen05 MLP-backward kernel, grid scatter."""
 
     @staticmethod
     def forward(ctx, params, rays_o, rays_d, jitter, bg_noise, tc: FusedTrainContext, phase: int):

@@ -215,6 +215,10 @@ class CoreRunner:
         checkpoint = torch.load(pjoin(self.exp_dir, "checkpoints", checkpoint_name), map_location=self.device, weights_only=False)
         self.scene.load_state_dict(checkpoint["scene"])
         self.phase = checkpoint["phase"]
+        # the reference never reloads the pool (core_exp_runner.py:217-221), which silently drops the content
+        # inpainted for earlier anchors on resume (every fit calls reset_geo); the key has been saved all along
+        if "sup_pool" in checkpoint:
+            self.sup_pool.load_state_dict(checkpoint["sup_pool"])
 
 
 def main(argv=None):

@@ -121,6 +121,36 @@ def test_fused_train_step_equals_modular_step(golden_field, phase):
     assert (gf[:n_mlp] - gm[:n_mlp]).abs().max() <= 2e-2 * gm[:n_mlp].abs().max()
 
 
+def test_chunk_parallel_composite_backward_equals_ray_sequential(golden_field):
+    """The chunk-parallel composite backward (32 rays x 8 chunks per block, suffix sums exchanged through shared
+    memory) against the ray-sequential kernel (PERF_B200_COMPBWD_CHUNKS=1) inside the same fused density step, at the
+    benchmark's 128 samples/ray with ray splitting active: same loss, same gradient up to fp32 summation order."""
+    from perf_b200 import synthetic
+    from perf_b200.scene import RaySupervision, FusedAdam
+    h, w = 32, 64
+    rgb, dist = synthetic.smooth_rgb(h, w, device="cuda"), synthetic.box_room_distance(h, w, device="cuda")
+    out = {}
+    for seq in (False, True):
+        if seq:
+            os.environ["PERF_B200_COMPBWD_CHUNKS"] = "1"
+        try:
+            sc = make_scene(golden_field, 128, fused_train=True)
+            sc.train_conf["pixel_loss_batch_size"] = 1500
+            sc.set_train()
+            pool = RaySupervision.from_panorama(torch.eye(4), rgb, dist, seed=3)
+            opt = FusedAdam(sc.nerf.geo_mlp.params, lr=0.0, module=sc.nerf.geo_mlp)
+            torch.manual_seed(13)
+            loss = sc.train_one_step_geo(opt, pool, progress=0.4)
+            out[seq] = (float(loss), sc.nerf.geo_mlp.params.grad.detach().clone())
+        finally:
+            os.environ.pop("PERF_B200_COMPBWD_CHUNKS", None)
+    (lc, gc), (ls, gs) = out[False], out[True]
+    assert lc == ls
+    assert float(gs.abs().max()) > 0
+    assert (gc - gs).abs().max() <= 1e-3 * gs.abs().max(), float((gc - gs).abs().max() / gs.abs().max())
+    assert F.cosine_similarity(gc, gs, dim=0) > 0.999999
+
+
 def test_fit_reduces_losses_and_checkpoint_roundtrip(golden_field, tmp_path):
     from perf_b200 import synthetic
     from perf_b200.config import Conf
@@ -273,13 +303,11 @@ def test_vector_atomic_scatter_matches_scalar_pairs():
     assert float(want.abs().max()) > 0 and (got - want).abs().max() <= 1e-4 * want.abs().max()
 
 
-@pytest.mark.skipif(os.environ.get("PERF_B200_EXPERIMENTAL") != "1",
-                    reason="experimental kernel (csrc/mlp_bwd.cu, written without GPU time in round 1): set PERF_B200_EXPERIMENTAL=1")
 @pytest.mark.parametrize("two_hidden", [False, True], ids=["density", "colour"])
 @pytest.mark.parametrize("simt", [True, False], ids=["simt", "tcgen05"])
 def test_single_kernel_mlp_backward_matches_gemm_path(two_hidden, simt):
-    """perf_mlp_bwd (one tcgen05 kernel; CUDA-core twin on the same shared-memory images) against the default
-    path (cuBLAS fp16 GEMMs + perf_mlp_bwd_out / perf_relu_mask) on the same saved activations."""
+    """perf_mlp_bwd (one tcgen05 kernel, the default; CUDA-core twin on the same shared-memory images) against the
+    round-1 path (cuBLAS fp16 GEMMs + perf_mlp_bwd_out / perf_relu_mask) on the same saved activations."""
     from perf_b200 import ops
     from perf_b200.config import APP_MLP, GEO_MLP
     mlp = APP_MLP if two_hidden else GEO_MLP
@@ -293,8 +321,7 @@ def test_single_kernel_mlp_backward_matches_gemm_path(two_hidden, simt):
     if two_hidden:
         h2 = torch.relu(h1.float() @ W[2048:2048 + 4096].view(64, 64).float().t()).half()
     dz = (torch.randn(N, mlp.n_out, generator=g) * 0.1).cuda()
-    os.environ.pop("PERF_B200_TC_MLP_BWD", None)
-    want_w, want_f = ops.mlp_backward_half(mlp, W, feat, h1, h2, dz)
+    want_w, want_f = ops.mlp_backward_gemm(mlp, W, feat, h1, h2, dz)
     got_w, got_f = ops.mlp_backward_fused(mlp, W, feat, h1, h2, dz, simt=simt)
     torch.cuda.synchronize()
     n_real = 2048 + (4096 if two_hidden else 0)

@@ -55,3 +55,33 @@ def test_non_cubic_box_and_full_grid_counts():
     t_exit = torch.minimum(torch.maximum((aabb[:3] - o) * inv, (aabb[3:] - o) * inv).amin(-1), torch.tensor(far))
     counts = np.bincount(ri, minlength=32)
     assert np.all(np.abs(counts - (t_exit / step).numpy()) <= 2)
+
+
+def test_one_cell_grid_reproduces_the_global_lattice():
+    """The lattice decision written in oracle/occ_sampler.py: samples sit on t_k = near + (k + u) * step of ONE
+    per-ray lattice.  A single occupied cell in the middle of the box: the first emitted interval starts at a
+    lattice point, NOT at the cell entry (a per-run re-phased sampler would start there), and exactly the
+    lattice intervals whose midpoint is inside the cell are emitted."""
+    res, step, near = 5, 0.03, 0.0
+    binaries = torch.zeros(res, res, res, dtype=torch.bool)
+    binaries[2, 2, 2] = True                                   # cell [-0.2, 0.2]^3
+    aabb = torch.tensor([-1.0, -1.0, -1.0, 1.0, 1.0, 1.0])
+    o = torch.tensor([[-0.96, 0.01, -0.02], [-0.96, 0.01, -0.02]])
+    d = torch.tensor([[1.0, 0.0, 0.0], [1.0, 0.0, 0.0]])
+    jitter = torch.tensor([0.0, 0.37])
+    t_in, t_out = 0.76, 1.16                                    # the ray crosses the cell for t in [0.76, 1.16]
+    for impl in ("oracle", "host"):
+        if impl == "oracle":
+            ri, ts, te = occ_sample(binaries, aabb, o, d, near, 1.5, step, jitter)
+            ri, ts, te = ri.numpy(), ts.numpy(), te.numpy()
+        else:
+            ri, ts, te = hh.occ_sample(binaries.numpy(), aabb.tolist(), o.numpy(), d.numpy(), near, 1.5, step, jitter.numpy())
+        for r in range(2):
+            t0 = ts[ri == r]
+            k = (t0 - near) / step - float(jitter[r])
+            assert np.allclose(k, np.round(k), atol=1e-3), "samples must sit on the global lattice"
+            mids = t0 + 0.5 * step
+            assert mids.min() >= t_in and mids.max() <= t_out
+            assert mids.min() - step < t_in and mids.max() + step > t_out        # nothing inside the cell was skipped
+            assert abs(t0[0] - t_in) > 1e-3                                      # not re-phased to the cell entry
+            assert np.allclose(np.diff(t0), step, atol=1e-6)

@@ -185,6 +185,12 @@ def test_inpainting_phase_loop_with_injected_priors(tmp_path, monkeypatch):
     assert ck["phase"] == 2 and ck["sup_pool"]["n_sup_infos"] == 3
     for f in ("final_mask.jpg", "final_masked.jpg", "uninpainted_0.jpg", "mask_0.jpg", "inpainted_0.jpg", "aligned_disparity_0.jpg"):
         assert os.path.exists(os.path.join(str(tmp_path), "inpaint_vis", "0000", f)), f
+    # resume: the pool saved at phase k comes back with its k+1 panoramas (it used to be dropped)
+    FakeScene.load_state_dict = lambda self, sd: None
+    n_all = len(run.sup_pool.all_sup_colors)
+    run.sup_pool, run.phase = SupInfoPool(locality_sort=False), 0
+    run.load_checkpoint("ckpt.pth")
+    assert run.phase == 2 and len(run.sup_pool.sup_infos) == 3 and len(run.sup_pool.all_sup_colors) == n_all
     # without the priors the raw phase is all there is
     run.inpainter = None
     with pytest.raises(NotImplementedError, match="inpainter"):

@@ -13,7 +13,6 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from perf_b200 import ops  # noqa: E402
 from perf_b200.config import APP_MLP, GEO_MLP  # noqa: E402
 
-os.environ.pop("PERF_B200_TC_MLP_BWD", None)
 N = 8192 * 128
 g = torch.Generator().manual_seed(0)
 
@@ -37,7 +36,7 @@ for name, mlp in (("density", GEO_MLP), ("colour", APP_MLP)):
     h1 = torch.relu(feat.float() @ W[:2048].view(64, 32).float().t()).half()
     h2 = torch.relu(h1.float() @ W[2048:6144].view(64, 64).float().t()).half() if mlp.n_hidden_layers == 2 else None
     dz = (torch.randn(N, mlp.n_out, generator=g) * 0.1).cuda()
-    t_ref, (w_ref, f_ref) = timed(lambda: ops.mlp_backward_half(mlp, W, feat, h1, h2, dz))
+    t_ref, (w_ref, f_ref) = timed(lambda: ops.mlp_backward_gemm(mlp, W, feat, h1, h2, dz))
     for simt in ((True, False) if "--simt" in sys.argv else (False,)):
         t_new, (w_new, f_new) = timed(lambda: ops.mlp_backward_fused(mlp, W, feat, h1, h2, dz, simt=simt), iters=3 if simt else 10)
         print(f"{name:8s} {'simt' if simt else 'tcgen05':8s}: gemm path {t_ref:.3f} ms, single kernel {t_new:.3f} ms; "

@@ -1,13 +1,15 @@
 #!/bin/bash
-# First GPU call of the next round: everything written at the end of round 1 without GPU time.
-#   /usr/local/graft/bin/gpurun --timeout 400 -- 'bash tools/round2_first_call.sh'
-# Each step has its own timeout: the experimental kernel traps (bounded mbarrier wait) rather than hangs, but
-# a trap poisons the CUDA context of that process only.
+# First GPU call of round 2: validate csrc/mlp_bwd.cu (written blind in round 1), then the A/B and microbenchmarks.
 mkdir -p gpurun_out
-export PERF_B200_EXPERIMENTAL=1
-for k in "simt and density" "simt and colour" "tcgen05 and density" "tcgen05 and colour"; do
-  timeout 90 python -m pytest tests/test_gpu_train.py -q -x --timeout 60 -k "single_kernel_mlp_backward and $k" 2>&1 | tail -4 | tee -a gpurun_out/round2_first.log
-done
-timeout 120 python tools/ab_mlp_bwd.py 2>&1 | tail -6 | tee -a gpurun_out/round2_first.log
-timeout 60 python tools/ab_scatter_v4.py 2>&1 | tail -2 | tee -a gpurun_out/round2_first.log
-timeout 120 python tools/encode_microbench.py 2>&1 | tail -5 | tee -a gpurun_out/round2_first.log
+L=gpurun_out/round2_first.log; : > $L
+for net in density colour; do for mode in simt tc; do
+  timeout 60 python tools/diag_mlp_bwd.py $net $mode 0 2>&1 | tail -5 | tee -a $L
+done; done
+for net in density colour; do timeout 60 python tools/diag_mlp_bwd.py $net tc 1 2>&1 | tail -5 | tee -a $L; done
+timeout 120 python tools/ab_mlp_bwd.py 2>&1 | tail -6 | tee -a $L
+timeout 60 python tools/ab_scatter_v4.py 2>&1 | tail -2 | tee -a $L
+timeout 120 python tools/encode_microbench.py 2>&1 | tail -5 | tee -a $L
+GRAPH=1 timeout 120 python tools/train_bench.py 2>&1 | tail -3 | tee -a $L
+PHASES=geo bash tools/profile_train.sh 2>&1 | tail -20 | tee -a $L
+cp gpurun_out/train_launches.csv gpurun_out/train_launches_geo.csv
+PHASES=app bash tools/profile_train.sh 2>&1 | tail -20 | tee -a $L
