@@ -131,7 +131,7 @@ int perf_hashgrid_bwd_bwd_input(const perf_grid_cfg* cfg, const void* d_table_ha
  * else NULL): fp16 saves of perf_network_fwd / perf_train_forward; d_dz [N,n_out] fp32 = gradient w.r.t. the
  * output pre-activation (n_out <= 3).  d_dweights: fp32 gradient of the flat MLP params, ACCUMULATED (caller
  * zeroes); d_dfeat [N,32] fp32 overwritten.  flags: PERF_FLAG_SIMT_MLP selects the CUDA-core twin.
- * EXPERIMENTAL in round 1 (not yet run on a GPU): the default training path does not call it. */
+ * Validated on B200 in round 2; the training steps call it (no library GEMM is left on that path). */
 int perf_mlp_bwd(const perf_mlp_cfg* mlp, const void* d_weights_half, const void* d_feat, const void* d_h1, const void* d_h2,
                  const float* d_dz, uint64_t N, float* d_dweights, float* d_dfeat, uint32_t flags, void* stream);
 
@@ -256,6 +256,50 @@ int perf_occ_count(const uint8_t* d_binaries, const int* h_res3, const float* h_
 int perf_occ_write(const uint8_t* d_binaries, const int* h_res3, const float* h_aabb6, const float* d_rays_o, const float* d_rays_d,
                    const float* d_jitter, uint64_t R, float near, float far, float step, const int64_t* d_offsets,
                    int64_t* d_ray_indices, float* d_t_starts, float* d_t_ends, void* stream);
+
+/* ---- fused training step for PACKED samples (the occupancy sampler PeRF trains with, configs/nerf.yaml:25;
+ * nerf_renderer.py:145-183, nerf.py:186-297): perf_occ_count/write -> perf_fields_packed ->
+ * perf_composite_packed_fwd -> losses -> perf_composite_packed_bwd -> perf_mlp_bwd -> perf_hashgrid_bwd_merged.
+ * All per-sample buffers are indexed by the packed sample number n (sorted by ray). */
+
+/* Both fields at N packed samples in one launch: position o + d (ts+te)/2, aabb normalisation and selector
+ * (ngp_nerf.py:136-162), encode of both grids, both MLPs.  args: only grid / tables / weights / aabb / flags are read.
+ * d_sigma [N] fp32, d_rgb_half4 [N,4] fp16 (4th lane unused), d_x01 [N,3] fp32 (normalised position; masked-out
+ * samples get the in-box stand-in their features were taken at).  phase 0: no saves; PERF_PHASE_GEO / _APP: also
+ * d_feat [N,32], d_h1 [N,64] (and d_h2 [N,64] for _APP) fp16 of the trained network. */
+int perf_fields_packed(const perf_render_args* args, const float* d_rays_o, const float* d_rays_d, const int64_t* d_ray_indices,
+                       const float* d_t_starts, const float* d_t_ends, uint64_t N, int phase, float* d_sigma, void* d_rgb_half4,
+                       float* d_x01, void* d_feat, void* d_h1, void* d_h2, void* stream);
+
+/* Composite of packed samples, one warp per ray: w, T (nerfacc render_weight_from_density), opacity / distance /
+ * colour (accumulate_along_rays), background rule (PERF_FLAG_TRAINING in flags: nerf_renderer.py:192-194, else
+ * :195-197), distortion-loss numerator per ray (flatten_eff_distloss * n_rays).  Samples whose transmittance is below
+ * early_stop_eps get weight 0 and T = 0 -- identical to nerfacc dropping them inside OccGridEstimator.sampling.
+ * d_offsets int64 [R+1]; d_weights / d_trans [N]; d_rgb_out [R,3]; the others [R]. */
+int perf_composite_packed_fwd(const int64_t* d_offsets, const float* d_t_starts, const float* d_t_ends, const float* d_sigma,
+                              const void* d_rgb_half4, uint64_t R, float early_stop_eps, uint32_t flags, const float* d_bg_noise,
+                              float* d_weights, float* d_trans, float* d_rgb_out, float* d_distance_out, float* d_opacity_out,
+                              float* d_dist_acc, float* d_distloss, void* stream);
+/* Its backward: d_dz [N] = dL/d(raw density logit) (PERF_PHASE_GEO, trunc_exp backward included) or [N,3] =
+ * dL/d(colour pre-sigmoid) (PERF_PHASE_APP).  d_g_* [R,.] may be NULL. */
+int perf_composite_packed_bwd(int phase, const int64_t* d_offsets, const float* d_t_starts, const float* d_t_ends, const float* d_sigma,
+                              const void* d_rgb_half4, uint64_t R, const float* d_bg_noise, const float* d_weights, const float* d_trans,
+                              const float* d_distance_out, const float* d_opacity_out, const float* d_dist_acc,
+                              const float* d_g_rgb, const float* d_g_distance, const float* d_g_opacity, const float* d_g_distloss,
+                              float* d_dz, void* stream);
+/* perf_hashgrid_bwd with the number of levels whose same-cell runs of consecutive samples are merged before the
+ * atomics chosen by the caller (packed samples are 5e-4 apart: runs exist up to resolution ~1000). */
+int perf_hashgrid_bwd_merged(const perf_grid_cfg* cfg, const float* d_x01, const float* d_dfeat, uint64_t N, float* d_dtable,
+                             uint32_t n_merge_levels, void* stream);
+
+/* Occupancy-grid update (nerfacc OccGridEstimator.update_every_n_steps, levels = 1; nerf.py:159-168).
+ * perf_occ_points: a uniformly jittered point inside each listed cell (d_cell_idx int64 [n], NULL = cells 0..n-1),
+ * d_x [n,3]; the caller evaluates its occ_eval_fn there.  perf_occ_update: occs[c] = max(occs[c] * ema_decay, occ),
+ * then binaries = occs > min(mean(occs), occ_thre) (deterministic two-stage mean).  d_workspace: 2 * PERF_OCC_PARTIALS doubles. */
+#define PERF_OCC_PARTIALS 1024
+int perf_occ_points(const int64_t* d_cell_idx, uint64_t n, const int* h_res3, const float* h_aabb6, uint64_t seed, float* d_x, void* stream);
+int perf_occ_update(float* d_occs, uint64_t n_cells, const int64_t* d_cell_idx, const float* d_occ_new, uint64_t n, float ema_decay,
+                    float occ_thre, uint8_t* d_binaries, double* d_workspace, void* stream);
 
 /* MLP backward helpers on the saved fp16 activations (tcnn kernel_mlp_fused_backward pieces; the
  * matrix products themselves are plain GEMMs left to cuBLAS):

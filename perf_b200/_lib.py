@@ -79,6 +79,12 @@ SIGNATURES = {
     "perf_occ_count": (i32, [vp, P(i32), P(f32), vp, vp, vp, u64, f32, f32, f32, vp, vp]),
     "perf_occ_write": (i32, [vp, P(i32), P(f32), vp, vp, vp, u64, f32, f32, f32, vp, vp, vp, vp, vp]),
     "perf_mlp_bwd": (i32, [P(MlpCfg), vp, vp, vp, vp, vp, u64, vp, vp, u32, vp]),
+    "perf_fields_packed": (i32, [P(RenderArgs), vp, vp, vp, vp, vp, u64, i32, vp, vp, vp, vp, vp, vp, vp]),
+    "perf_composite_packed_fwd": (i32, [vp, vp, vp, vp, vp, u64, f32, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "perf_composite_packed_bwd": (i32, [i32, vp, vp, vp, vp, vp, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "perf_hashgrid_bwd_merged": (i32, [P(GridCfg), vp, vp, u64, vp, u32, vp]),
+    "perf_occ_points": (i32, [vp, u64, P(i32), P(f32), u64, vp, vp]),
+    "perf_occ_update": (i32, [vp, u64, vp, vp, u64, f32, f32, vp, vp, vp]),
     "perf_mlp_bwd_out": (i32, [vp, i32, vp, vp, vp, u64, vp]),
     "perf_relu_mask": (i32, [vp, vp, u64, vp]),
     "perf_adam_step": (i32, [vp, vp, vp, vp, vp, u64, f32, f32, f32, f32, u32, f32, vp]),

@@ -498,6 +498,25 @@ int perf_hashgrid_bwd(const perf_grid_cfg* cfg, const float* d_x01, const float*
     return PERF_OK;
 }
 
+int perf_hashgrid_bwd_merged(const perf_grid_cfg* cfg, const float* d_x01, const float* d_dfeat, uint64_t N, float* d_dtable,
+                             uint32_t n_merge_levels, void* stream)
+{
+    PERF_CHECK_ARG(cfg && d_x01 && d_dfeat && d_dtable, "NULL pointer");
+    LevelTable lt; int rc = build_level_table(cfg, &lt, nullptr); if (rc) return rc;
+    PERF_CHECK_ARG((uintptr_t)d_dtable % 8 == 0 && (uintptr_t)d_dfeat % 8 == 0, "misaligned dtable/dfeat");
+    if (N == 0) return PERF_OK;
+    const uint32_t n_merge = n_merge_levels < lt.n_levels ? n_merge_levels : lt.n_levels;
+    if (n_merge > 0) {
+        hashgrid_bwd_kernel<true><<<dim3(blocks_for(N, 256), n_merge), 256, 0, S(stream)>>>(lt, 0, d_x01, d_dfeat, N, (float2*)d_dtable);
+        PERF_LAUNCH_CHECK();
+    }
+    if (lt.n_levels > n_merge) {
+        hashgrid_bwd_kernel<false><<<dim3(blocks_for(N, 256), lt.n_levels - n_merge), 256, 0, S(stream)>>>(lt, (int)n_merge, d_x01, d_dfeat, N, (float2*)d_dtable);
+        PERF_LAUNCH_CHECK();
+    }
+    return PERF_OK;
+}
+
 int perf_weights_from_density(const float* d_t_starts, const float* d_t_ends, const float* d_sigmas,
                               const int64_t* d_ray_indices, uint64_t N, uint64_t n_rays,
                               float* d_weights, float* d_trans, float* d_alphas, void* stream)

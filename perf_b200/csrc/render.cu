@@ -650,6 +650,89 @@ __global__ void __launch_bounds__(TILE, 4) render_march_kernel(const __grid_cons
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// packed_fields_kernel: both fields at PACKED samples (the output of the occupancy sampler), thread = sample,
+// a tile = 128 CONSECUTIVE packed samples.  Consecutive samples of a ray are 5e-4 apart (nerf_renderer.py:151):
+// a warp's 32 lanes sit in one cell of every level up to resolution ~1000, the best gather locality there is.
+// Used by the fused occupancy-sampler training step (perf_train_forward_packed): writes sigma, the fp16 colour and
+// the normalised position of every sample and saves the trained network's features / hidden activations at row n.
+struct PackedFieldArgs {
+    const int64_t* ray_indices;   // [N]
+    const float*   ts;            // [N]
+    const float*   te;            // [N]
+    uint64_t       N;
+    float*         sigma;         // [N]
+    __half*        rgb;           // [N,4] fp16
+    float*         x01;           // [N,3]
+};
+
+template <int NDENSE, int SAVE>
+__global__ void __launch_bounds__(TILE, 4) packed_fields_kernel(const __grid_constant__ RenderArgs a, const PackedFieldArgs p)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sA   = smem + RS_A;
+    uint8_t* sW1g = smem + RS_W1G;
+    uint8_t* sW1a = smem + RS_W1A;
+    uint8_t* sW2a = smem + RS_W2A;
+    float*   sWoutG = reinterpret_cast<float*>(smem + RS_WOUT);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + RS_BAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + RS_BAR + 8);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const RenderSmem sm = {sA, sA, sA + A32_BYTES, sW1g, sW1a, sW2a, sWoutG, sWoutG + HID, bar};
+    load_weight_canonical(a.geo_w, 32, sW1g, tid, TILE);
+    load_weight_canonical(a.app_w, 32, sW1a, tid, TILE);
+    load_weight_canonical(a.app_w + HID * 32, 64, sW2a, tid, TILE);
+    if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    __syncwarp();
+    if (warp == 0) tmem_alloc<128>(tmem_slot);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    uint32_t parity = 0;
+    const uint64_t n_tiles = (p.N + TILE - 1) / TILE;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t n = tile * TILE + tid;
+        const bool valid = n < p.N;
+        float x = 0.5f, y = 0.5f, z = 0.5f;
+        if (valid) {
+            const int64_t ray = p.ray_indices[n];
+            const float tsum = __fadd_rn(p.ts[n], p.te[n]);
+            const float px = __fadd_rn(a.rays_o[3 * ray], __fmul_rn(a.rays_d[3 * ray], tsum) * 0.5f);
+            const float py = __fadd_rn(a.rays_o[3 * ray + 1], __fmul_rn(a.rays_d[3 * ray + 1], tsum) * 0.5f);
+            const float pz = __fadd_rn(a.rays_o[3 * ray + 2], __fmul_rn(a.rays_d[3 * ray + 2], tsum) * 0.5f);
+            x = __fdiv_rn(__fsub_rn(px, a.aabb_min[0]), a.aabb_ext[0]);
+            y = __fdiv_rn(__fsub_rn(py, a.aabb_min[1]), a.aabb_ext[1]);
+            z = __fdiv_rn(__fsub_rn(pz, a.aabb_min[2]), a.aabb_ext[2]);
+        }
+        const bool selector = valid && x > 0.f && x < 1.f && y > 0.f && y < 1.f && z > 0.f && z < 1.f;
+        float sigma, cr, cg, cb;
+        eval_fields<false, NDENSE, SAVE>(a, sm, x, y, z, selector, tmem_base, tmem_row, parity, tid, sigma, cr, cg, cb, valid ? n : ~0ull);
+        if (valid) {
+            p.sigma[n] = sigma;
+            const __half2 c01 = __floats2half2_rn(cr, cg), c2 = __floats2half2_rn(cb, 0.f);
+            *reinterpret_cast<uint2*>(p.rgb + n * 4) = make_uint2(*reinterpret_cast<const uint32_t*>(&c01), *reinterpret_cast<const uint32_t*>(&c2));
+            // masked-out samples: the in-box stand-in position the features were taken at (their gradient is zero)
+            p.x01[3 * n] = selector ? x : 0.5f; p.x01[3 * n + 1] = selector ? y : 0.5f; p.x01[3 * n + 2] = selector ? z : 0.5f;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<128>(tmem_base);
+}
+
+static int wout_to_const(const RenderArgs& a, cudaStream_t stream)
+{
+    static thread_local int sym_dev = -1; static thread_local float* sym = nullptr;
+    int dev_ = 0; PERF_CUDA(cudaGetDevice(&dev_));
+    if (sym_dev != dev_) { PERF_CUDA(cudaGetSymbolAddress((void**)&sym, c_wout)); sym_dev = dev_; }
+    wout_to_const_kernel<<<1, 4 * HID, 0, stream>>>(a.geo_w + HID * 32, a.app_w + HID * 32 + HID * HID, sym);
+    PERF_LAUNCH_CHECK();
+    return PERF_OK;
+}
+
 static uint32_t gcd_u32(uint32_t a, uint32_t b) { while (b) { uint32_t t = a % b; a = b; b = t; } return a; }
 
 static int launch_render(const perf_render_args* args, RenderArgs& a, bool pano, cudaStream_t stream, int save = 0)
@@ -681,13 +764,7 @@ static int launch_render(const perf_render_args* args, RenderArgs& a, bool pano,
         n_work = (a.R + rpt - 1) / rpt;
     }
     const unsigned grid = (unsigned)(n_work < (uint64_t)num_sms() * 4 ? n_work : (uint64_t)num_sms() * 4);
-    {   // output-layer weights -> constant bank (see c_wout)
-        static thread_local int sym_dev = -1; static thread_local float* sym = nullptr;
-        int dev_ = 0; PERF_CUDA(cudaGetDevice(&dev_));
-        if (sym_dev != dev_) { PERF_CUDA(cudaGetSymbolAddress((void**)&sym, c_wout)); sym_dev = dev_; }
-        wout_to_const_kernel<<<1, 4 * HID, 0, stream>>>(a.geo_w + HID * 32, a.app_w + HID * 32 + HID * HID, sym);
-        PERF_LAUNCH_CHECK();
-    }
+    rc = wout_to_const(a, stream); if (rc) return rc;       // output-layer weights -> constant bank (see c_wout)
 #define PERF_RENDER_LAUNCH(...) do { \
         auto k = __VA_ARGS__; \
         static thread_local int attr_dev = -1; int dev_ = 0; PERF_CUDA(cudaGetDevice(&dev_)); \
@@ -768,6 +845,49 @@ int perf_train_forward(const perf_render_args* args, const float* d_rays_o, cons
     if (buf->h_segments_out) *buf->h_segments_out = a.seg;
     perf_render_args t = *args; t.flags |= PERF_FLAG_TRAINING;
     return launch_render(&t, a, false, (cudaStream_t)stream, phase);
+}
+
+int perf_fields_packed(const perf_render_args* args, const float* d_rays_o, const float* d_rays_d, const int64_t* d_ray_indices,
+                       const float* d_t_starts, const float* d_t_ends, uint64_t N, int phase, float* d_sigma, void* d_rgb_half4,
+                       float* d_x01, void* d_feat, void* d_h1, void* d_h2, void* stream)
+{
+    PERF_CHECK_ARG(args && d_rays_o && d_rays_d && d_ray_indices && d_t_starts && d_t_ends && d_sigma && d_rgb_half4 && d_x01, "NULL pointer");
+    PERF_CHECK_ARG(phase == 0 || phase == PERF_PHASE_GEO || phase == PERF_PHASE_APP, "phase must be 0, PERF_PHASE_GEO or PERF_PHASE_APP");
+    PERF_CHECK_ARG(phase == 0 || (d_feat && d_h1 && (phase == PERF_PHASE_GEO || d_h2)), "NULL save buffer");
+    PERF_CHECK_ARG(args->d_packed_table && args->d_geo_mlp_half && args->d_app_mlp_half, "NULL table / weights");
+    PERF_CHECK_ARG(((uintptr_t)d_feat | (uintptr_t)d_h1 | (uintptr_t)d_h2) % 16 == 0 && (uintptr_t)d_rgb_half4 % 8 == 0, "misaligned buffer");
+    RenderArgs a; memset(&a, 0, sizeof(a));
+    int rc = build_level_table(&args->grid, &a.lt, nullptr); if (rc) return rc;
+    PERF_CHECK_SUP(args->grid.n_levels == 16, "fused field kernel needs n_levels == 16 (got %u)", args->grid.n_levels);
+    a.table = (const uint2*)args->d_packed_table;
+    a.geo_w = (const __half*)args->d_geo_mlp_half; a.app_w = (const __half*)args->d_app_mlp_half;
+    for (int i = 0; i < 3; ++i) { a.aabb_min[i] = args->aabb[i]; a.aabb_ext[i] = args->aabb[3 + i] - args->aabb[i]; }
+    a.rays_o = d_rays_o; a.rays_d = d_rays_d;
+    a.s_feat = (uint4*)d_feat; a.s_h1 = (uint4*)d_h1; a.s_h2 = (uint4*)d_h2;
+    if (N == 0) return PERF_OK;
+    PackedFieldArgs p = {d_ray_indices, d_t_starts, d_t_ends, N, d_sigma, (__half*)d_rgb_half4, d_x01};
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = wout_to_const(a, st); if (rc) return rc;
+    const uint64_t n_tiles = (N + TILE - 1) / TILE;
+    const unsigned grid = (unsigned)(n_tiles < (uint64_t)num_sms() * 4 ? n_tiles : (uint64_t)num_sms() * 4);
+    const bool fast = fast_addressing_ok(a.lt, 4) && (args->flags & PERF_FLAG_GENERIC_ADDR) == 0;
+#define PERF_PACKED_LAUNCH(...) do { \
+        auto k = __VA_ARGS__; \
+        static thread_local int attr_dev = -1; int dev_ = 0; PERF_CUDA(cudaGetDevice(&dev_)); \
+        if (attr_dev != dev_) { PERF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_TOTAL)); attr_dev = dev_; } \
+        k<<<grid, TILE, RS_TOTAL, st>>>(a, p); } while (0)
+    if (fast) {
+        if (phase == 0) PERF_PACKED_LAUNCH(packed_fields_kernel<4, 0>);
+        else if (phase == PERF_PHASE_GEO) PERF_PACKED_LAUNCH(packed_fields_kernel<4, 1>);
+        else PERF_PACKED_LAUNCH(packed_fields_kernel<4, 2>);
+    } else {
+        if (phase == 0) PERF_PACKED_LAUNCH(packed_fields_kernel<-1, 0>);
+        else if (phase == PERF_PHASE_GEO) PERF_PACKED_LAUNCH(packed_fields_kernel<-1, 1>);
+        else PERF_PACKED_LAUNCH(packed_fields_kernel<-1, 2>);
+    }
+#undef PERF_PACKED_LAUNCH
+    PERF_LAUNCH_CHECK();
+    return PERF_OK;
 }
 
 int perf_render_pano(const perf_render_args* args, const float* h_pose, int H, int W, int row0, int rows, void* stream)

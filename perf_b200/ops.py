@@ -374,6 +374,7 @@ def occ_sample(binaries: torch.Tensor, aabb, rays_o, rays_d, near: float, far: f
     incl = torch.cumsum(counts, 0, dtype=torch.int64)
     total = int(incl[-1].item()) if R else 0
     offsets = (incl - counts).contiguous()
+    occ_sample.last_offsets = torch.cat([offsets, incl[-1:]]) if R else torch.zeros(1, dtype=torch.int64, device=dev)   # [R+1]
     ri = torch.empty(total, dtype=torch.int64, device=dev)
     ts, te = torch.empty(total, dtype=torch.float32, device=dev), torch.empty(total, dtype=torch.float32, device=dev)
     if total:
@@ -443,6 +444,28 @@ def render_packed(packed_table, geo_mlp_half, app_mlp_half, rays_o, rays_d, ray_
     a = _render_args(packed_table, geo_mlp_half, app_mlp_half, aabb, 1, 0.0, 1.0, False, simt, None, None, rgb, dist, op, grid)
     with torch.cuda.device(dev):
         _call(_L().perf_render_packed, C.byref(a), _p(rays_o), _p(rays_d), R, _p(offsets), _p(t_starts), _p(t_ends), _stream())
+    return rgb, dist, op
+
+
+def render_occ(packed_table, geo_mlp_half, app_mlp_half, rays_o, rays_d, offsets, ray_indices, t_starts, t_ends,
+               early_stop_eps: float = 1e-4, aabb=(-1., -1., -1., 1., 1., 1.), grid: GridConfig = PERF_GRID):
+    """Eval render of packed intervals: perf_fields_packed (no saves) + perf_composite_packed_fwd (eval background)."""
+    rays_o, rays_d = _chk(rays_o, torch.float32, "rays_o"), _chk(rays_d, torch.float32, "rays_d")
+    offsets, ray_indices = _chk(offsets, torch.int64, "offsets"), _chk(ray_indices, torch.int64, "ray_indices")
+    t_starts, t_ends = _chk(t_starts, torch.float32, "t_starts"), _chk(t_ends, torch.float32, "t_ends")
+    R, N, dev = rays_o.shape[0], t_starts.shape[0], rays_o.device
+    f32 = lambda *sh: torch.empty(*sh, dtype=torch.float32, device=dev)
+    rgb, dist, op = f32(R, 3), f32(R, 1), f32(R, 1)
+    if R == 0:
+        return rgb, dist, op
+    sigma, c16, x01 = f32(N), torch.empty(N, 4, dtype=torch.float16, device=dev), f32(N, 3)
+    w, T, dacc, dl = f32(N), f32(N), f32(R), f32(R)
+    a = _render_args(packed_table, geo_mlp_half, app_mlp_half, aabb, 1, 0.0, 1.0, False, False, None, None, rgb, dist, op, grid)
+    with torch.cuda.device(dev):
+        _call(_L().perf_fields_packed, C.byref(a), _p(rays_o), _p(rays_d), _p(ray_indices), _p(t_starts), _p(t_ends), N, 0,
+              _p(sigma), _p(c16), _p(x01), None, None, None, _stream(), launches=2)
+        _call(_L().perf_composite_packed_fwd, _p(offsets), _p(t_starts), _p(t_ends), _p(sigma), _p(c16), R, float(early_stop_eps), 0, None,
+              _p(w), _p(T), _p(rgb), _p(dist), _p(op), _p(dacc), _p(dl), _stream())
     return rgb, dist, op
 
 
@@ -613,6 +636,87 @@ class _FusedTrainStep(torch.autograd.Function):
             _call(_L().perf_hashgrid_bwd_rays, tc.grid.c(), aabb, _p(rays_o), _p(rays_d), _p(jitter), R, S, tc.near, tc.far,
                   _p(dfeat), _p(d_table), _stream(), launches=2)
         return grad, None, None, None, None, None, None
+
+
+class _FusedPackedTrainStep(torch.autograd.Function):
+    """(rgb, distance, opacity, distloss_numerator_per_ray) of a training-mode render of PACKED samples (the
+    occupancy sampler's output, all of them -- the 1e-4 transmittance cut of ``OccGridEstimator.sampling`` is applied
+    inside the composite), differentiable w.r.t. the flat params of the network selected by ``phase``
+    (`nerf_renderer.py:145-209` under `nerf.py:186-297`).  Forward: perf_fields_packed + perf_composite_packed_fwd;
+    backward: perf_composite_packed_bwd + perf_mlp_bwd + perf_hashgrid_bwd_merged.  No torch glue on per-sample data."""
+
+    MERGE_LEVELS = 13          # same-cell runs of consecutive 5e-4 samples exist up to resolution ~1350 (level 12)
+
+    @staticmethod
+    def forward(ctx, params, rays_o, rays_d, offsets, ray_indices, t_starts, t_ends, bg_noise, tc: FusedTrainContext, phase: int,
+                early_stop_eps: float):
+        R, N, dev = rays_o.shape[0], t_starts.shape[0], rays_o.device
+        geo = phase == _lib.PERF_PHASE_GEO
+        f32 = lambda *sh: torch.empty(*sh, dtype=torch.float32, device=dev)
+        f16 = lambda *sh: torch.empty(*sh, dtype=torch.float16, device=dev)
+        b = {"sigma": f32(N), "rgb": f16(N, 4), "x01": f32(N, 3), "feat": f16(N, 32), "h1": f16(N, 64), "h2": None if geo else f16(N, 64),
+             "w": f32(N), "T": f32(N), "dacc": f32(R), "dl": f32(R)}
+        rgb, dist, op = f32(R, 3), f32(R, 1), f32(R, 1)
+        a = _render_args(tc.packed, tc.geo_half, tc.app_half, tc.aabb, 1, 0.0, 1.0, True, False, None, bg_noise, rgb, dist, op, tc.grid)
+        with torch.cuda.device(dev):
+            _call(_L().perf_fields_packed, C.byref(a), _p(rays_o), _p(rays_d), _p(ray_indices), _p(t_starts), _p(t_ends), N, phase,
+                  _p(b["sigma"]), _p(b["rgb"]), _p(b["x01"]), _p(b["feat"]), _p(b["h1"]), _p(b["h2"]), _stream(), launches=2)
+            _call(_L().perf_composite_packed_fwd, _p(offsets), _p(t_starts), _p(t_ends), _p(b["sigma"]), _p(b["rgb"]), R, float(early_stop_eps),
+                  _lib.PERF_FLAG_TRAINING, _p(bg_noise), _p(b["w"]), _p(b["T"]), _p(rgb), _p(dist), _p(op), _p(b["dacc"]), _p(b["dl"]), _stream())
+        ctx.tc, ctx.phase, ctx.b = tc, phase, b
+        ctx.save_for_backward(offsets, t_starts, t_ends, bg_noise, dist, op)
+        return rgb, dist, op, b["dl"].clone()
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_dist, g_op, g_dl):
+        offsets, t_starts, t_ends, bg_noise, dist, op = ctx.saved_tensors
+        tc, phase, b = ctx.tc, ctx.phase, ctx.b
+        R, N, dev = op.shape[0], t_starts.shape[0], op.device
+        geo = phase == _lib.PERF_PHASE_GEO
+        mlp = GEO_MLP if geo else APP_MLP
+        dz = torch.empty(N, mlp.n_out, dtype=torch.float32, device=dev)
+        c = lambda t: None if t is None else t.contiguous().float()
+        g_rgb, g_dist, g_op, g_dl = c(g_rgb), c(g_dist), c(g_op), c(g_dl)
+        with torch.cuda.device(dev):
+            _call(_L().perf_composite_packed_bwd, phase, _p(offsets), _p(t_starts), _p(t_ends), _p(b["sigma"]), _p(b["rgb"]), R, _p(bg_noise),
+                  _p(b["w"]), _p(b["T"]), _p(dist), _p(op), _p(b["dacc"]), _p(g_rgb), _p(g_dist), _p(g_op), _p(g_dl), _p(dz), _stream())
+        half = tc.geo_half if geo else tc.app_half
+        grad = torch.zeros(mlp.n_params + 2 * tc.grid.n_entries, dtype=torch.float32, device=dev)
+        _, dfeat = mlp_backward_half(mlp, half[:mlp.n_params], b["feat"], b["h1"], b["h2"], dz, grad_out=grad[:mlp.n_params])
+        with torch.cuda.device(dev):
+            _call(_L().perf_hashgrid_bwd_merged, tc.grid.c(), _p(b["x01"]), _p(dfeat), N, _p(grad[mlp.n_params:]),
+                  _FusedPackedTrainStep.MERGE_LEVELS, _stream(), launches=2)
+        return (grad,) + (None,) * 10
+
+
+def fused_packed_train_step(params, rays_o, rays_d, offsets, ray_indices, t_starts, t_ends, bg_noise, tc: FusedTrainContext, phase: int,
+                            early_stop_eps: float = 1e-4):
+    rays_o, rays_d = _chk(rays_o, torch.float32, "rays_o"), _chk(rays_d, torch.float32, "rays_d")
+    offsets, ray_indices = _chk(offsets, torch.int64, "offsets"), _chk(ray_indices, torch.int64, "ray_indices")
+    t_starts, t_ends = _chk(t_starts, torch.float32, "t_starts"), _chk(t_ends, torch.float32, "t_ends")
+    bg_noise = _chk(bg_noise, torch.float32, "bg_noise")
+    if offsets.numel() != rays_o.shape[0] + 1:
+        raise RuntimeError("perf_b200.fused_packed_train_step: offsets must have R + 1 entries")
+    return _FusedPackedTrainStep.apply(params, rays_o, rays_d, offsets, ray_indices, t_starts, t_ends, bg_noise, tc, phase, early_stop_eps)
+
+
+def occ_points(cell_idx: Optional[torch.Tensor], n: int, res3, aabb, seed: int, device) -> torch.Tensor:
+    """A uniformly jittered point in each listed occupancy cell (``cell_idx`` int64 [n]; None = cells 0..n-1) -> [n,3]."""
+    x = torch.empty(n, 3, dtype=torch.float32, device=device)
+    r3, a6 = (C.c_int * 3)(*[int(v) for v in res3]), (C.c_float * 6)(*[float(v) for v in aabb])
+    with torch.cuda.device(x.device):
+        _call(_L().perf_occ_points, _p(None if cell_idx is None else _chk(cell_idx, torch.int64, "cell_idx")), n, r3, a6, int(seed) & (2 ** 63 - 1),
+              _p(x), _stream())
+    return x
+
+
+def occ_update(occs: torch.Tensor, cell_idx: Optional[torch.Tensor], occ_new: torch.Tensor, ema_decay: float, occ_thre: float,
+               binaries_u8: torch.Tensor, workspace: torch.Tensor) -> None:
+    """occs[c] = max(occs[c] * ema_decay, occ_new) on the listed cells, then binaries = occs > min(mean(occs), occ_thre)."""
+    occs, occ_new = _chk(occs, torch.float32, "occs"), _chk(occ_new.reshape(-1), torch.float32, "occ_new")
+    with torch.cuda.device(occs.device):
+        _call(_L().perf_occ_update, _p(occs), occs.numel(), _p(None if cell_idx is None else _chk(cell_idx, torch.int64, "cell_idx")),
+              _p(occ_new), occ_new.numel(), float(ema_decay), float(occ_thre), _p(binaries_u8), _p(workspace), _stream(), launches=3)
 
 
 def fused_train_step(params, rays_o, rays_d, jitter, bg_noise, tc: FusedTrainContext, phase: int):

@@ -38,15 +38,9 @@ def render_frames(renderer: FusedPanoRenderer, poses, height: int, width: int, n
         pose = torch.as_tensor(pose, dtype=torch.float32).clone()
         pose[:3, :3] = torch.eye(3)                                  # core_exp_runner.py:232
         out = renderer.render_pano(pose, height, width, n_samples, row0=sl.start, rows=sl.stop - sl.start)
-        tile = torch.cat([out["rgb"], out["distance"]], -1)
-        if world > 1:
-            import torch.distributed as dist
-            rows = [parallel.shard_slice(height, r, world) for r in range(world)]
-            tiles = [torch.empty(s.stop - s.start, width, 4, device=tile.device) for s in rows] if rank == 0 else None
-            dist.gather(tile, tiles, dst=0)
-            if rank != 0:
-                continue
-            tile = torch.cat(tiles, 0)
+        tile = parallel.gather_row_tiles(torch.cat([out["rgb"], out["distance"]], -1), height)
+        if tile is None:
+            continue
         yield tile[..., :3], tile[..., 3:]
 
 

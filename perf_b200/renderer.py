@@ -79,6 +79,16 @@ class FusedPanoRenderer:
                                           ray_indices, t_starts, t_ends, self.aabb, self.grid, simt)
         return {"rgb": rgb, "distance": dist, "opacities": op, "is_valid": True}
 
+    def render_occ(self, rays_o: torch.Tensor, rays_d: torch.Tensor, offsets: torch.Tensor, ray_indices: torch.Tensor,
+                   t_starts: torch.Tensor, t_ends: torch.Tensor, early_stop_eps: float = 1e-4) -> dict:
+        """Eval render of ALL intervals an occupancy sampler emitted (no visibility pre-pass): both fields at every
+        interval in one launch (perf_fields_packed), then the per-ray composite with nerfacc's transmittance cut applied
+        inside (perf_composite_packed_fwd) -- `nerf_renderer.py:145-197` without the second density evaluation."""
+        self._ready()
+        rgb, dist, op = ops.render_occ(self.packed, self.geo_half, self.app_half, rays_o.reshape(-1, 3), rays_d.reshape(-1, 3),
+                                       offsets, ray_indices, t_starts, t_ends, early_stop_eps, self.aabb, self.grid)
+        return {"rgb": rgb, "distance": dist, "opacities": op, "is_valid": True}
+
     def render_pano(self, pose, H: int, W: int, n_samples: int, row0: int = 0, rows: Optional[int] = None,
                     near: Optional[float] = None, far: Optional[float] = None, simt: bool = False, out=None) -> dict:
         self._ready()

@@ -177,15 +177,9 @@ class CoreRunner:
                 sl = parallel.shard_slice(height, rank, world)
                 out = self.scene.render(type(rays)(rays.o[sl], rays.d[sl]), query_keys=["rgb", "distance"])
                 colors, distances = out["rgb"], out["distance"]
-            tile = torch.cat([colors, distances], -1).contiguous()
-            if world > 1:
-                import torch.distributed as dist
-                shapes = [parallel.shard_slice(height, r, world) for r in range(world)]
-                tiles = [torch.empty(s.stop - s.start, tile.shape[1], 4, device=tile.device) for s in shapes] if rank == 0 else None
-                dist.gather(tile, tiles, dst=0)
-                if rank != 0:
-                    continue
-                tile = torch.cat(tiles, 0)
+            tile = parallel.gather_row_tiles(torch.cat([colors, distances], -1).contiguous(), height)
+            if tile is None:
+                continue
             colors, distances = tile[..., :3], tile[..., 3:]
             frames.append((colors.clip(0., 1.) * 255.).cpu().numpy().astype(np.uint8))
             if write:

@@ -200,13 +200,35 @@ class RaySupervision:
 class FusedAdam:
     """``torch.optim.Adam(params, lr)`` semantics (defaults betas=(.9,.999), eps=1e-8) on one flat
     fp32 parameter through perf_adam_step; exposes ``param_groups`` so ``update_lr`` reads as in
-    `nerf.py:300-311`.  Gradients are averaged over ranks first when distributed."""
+    `nerf.py:300-311`.
+
+    Distributed (world > 1), default ``parallel.dp_mode() == 'sharded'``: the local gradients are reduce-scattered
+    (sum; the 1/world of the mean is the Adam kernel's ``grad_scale``), this rank updates ITS contiguous 1/world shard
+    of the parameters -- the moments exist only for that shard -- and the fp16 shadow every kernel reads is
+    all-gathered.  The fp32 master vector is therefore current only inside the rank's shard until
+    :meth:`sync_master` all-gathers it (called at the end of a phase and by ``NeRFScene.state_dict``)."""
 
     def __init__(self, param: torch.nn.Parameter, lr: float = 0.0, betas=(0.9, 0.999), eps: float = 1e-8, module=None):
         self.param, self.betas, self.eps = param, betas, eps
         self.module = module        # tinycudann shim module owning `param`: its fp16 shadow is refreshed by the Adam kernel
         self.param_groups = [{"lr": lr}]
-        self.exp_avg, self.exp_avg_sq = torch.zeros_like(param.data), torch.zeros_like(param.data)
+        self.world, self.rank = parallel.world_size(), parallel.rank()
+        self.sharded = self.world > 1 and parallel.dp_mode() == "sharded" and module is not None
+        n = param.numel()
+        if self.sharded:
+            self.shard = parallel.shard_len(n, self.world)
+            self.lo = min(n, self.rank * self.shard)
+            self.hi = min(n, self.lo + self.shard)
+            self.padded = self.world * self.shard
+            z = lambda: torch.zeros(self.hi - self.lo, dtype=torch.float32, device=param.device)
+            self.exp_avg, self.exp_avg_sq = z(), z()
+            # scratch with room for the padding tail when numel is not a multiple of world * 8 (never for PeRF's nets at 2/4/8)
+            self._grad_pad = torch.zeros(self.padded, dtype=torch.float32, device=param.device) if self.padded != n else None
+            self._half_pad = torch.zeros(self.padded, dtype=torch.float16, device=param.device) if self.padded != n else None
+            self._master_pad = None
+        else:
+            self.exp_avg, self.exp_avg_sq = torch.zeros_like(param.data), torch.zeros_like(param.data)
+        self.master_stale = False
         self.step_count = 0
         # graph mode: lr / bias corrections live in a device tensor refreshed from pinned memory before each replay
         self.hyper = None
@@ -223,23 +245,80 @@ class FusedAdam:
     def zero_grad(self):
         self.param.grad = None
 
-    def step(self):
-        if self.param.grad is None:
-            return
-        g = parallel.allreduce_mean_(self.param.grad.contiguous())
-        half = None
-        if self.module is not None:
-            half = self.module._half()                       # allocate / reuse the module's fp16 shadow buffer
+    def _adam(self, p, g, m, v, half, grad_scale):
         if self.hyper is not None:                           # graph mode: schedule comes from device memory
-            ops.adam_step_dev(self.param.data, g, self.exp_avg, self.exp_avg_sq, self.hyper, params_half=half,
-                              beta1=self.betas[0], beta2=self.betas[1], eps=self.eps)
+            ops.adam_step_dev(p, g, m, v, self.hyper, params_half=half, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps,
+                              grad_scale=grad_scale)
         else:
             self.step_count += 1
-            ops.adam_step(self.param.data, g, self.exp_avg, self.exp_avg_sq, self.step_count, self.param_groups[0]["lr"],
-                          params_half=half, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps)
+            ops.adam_step(p, g, m, v, self.step_count, self.param_groups[0]["lr"], params_half=half,
+                          beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, grad_scale=grad_scale)
+
+    def step(self, valid: bool = True):
+        """One optimiser step = exchange -> Adam -> gather (see the three stage methods; `GraphedTrainStep(split=True)`
+        captures them separately to time them).  ``valid=False`` (this rank produced no samples, `nerf.py:204-206`):
+        the rank still takes part in the exchange with a zero gradient so that the other ranks do not block."""
+        if getattr(self, "deferred", False):                 # split capture: the stages are replayed on their own
+            self._valid = valid
+            return
+        if not self.stage_exchange(valid):
+            return
+        self.stage_adam()
+        self.stage_gather()
+
+    def stage_exchange(self, valid: bool = True) -> bool:
+        """Gradient exchange: reduce-scatter (sharded) or all-reduce + mean.  False = nothing to do."""
+        g = self.param.grad
+        if g is None:
+            if self.world == 1 or valid:
+                return False
+            g = torch.zeros_like(self.param.data)
+        g = g.contiguous()
+        n = self.param.numel()
+        if self.sharded:
+            if self._grad_pad is not None:
+                self._grad_pad[:n].copy_(g); g = self._grad_pad
+            self._g = parallel.reduce_scatter_sum_(g, self.shard)[: self.hi - self.lo]
+        else:
+            self._g = parallel.allreduce_mean_(g)
+        return True
+
+    def stage_adam(self):
+        half = self.module._half() if self.module is not None else None     # allocate / reuse the module's fp16 shadow buffer
+        if self.sharded:
+            self._hbuf = half if self._half_pad is None else self._half_pad
+            self._adam(self.param.data[self.lo:self.hi], self._g, self.exp_avg, self.exp_avg_sq, self._hbuf[self.lo:self.hi], 1.0 / self.world)
+        else:
+            self._adam(self.param.data, self._g, self.exp_avg, self.exp_avg_sq, half, 1.0)
+        self._g = None
+
+    def stage_gather(self):
+        if self.sharded:
+            parallel.all_gather_(self._hbuf, self.shard)
+            if self._half_pad is not None:
+                self.module._half().copy_(self._hbuf[:self.param.numel()])
+            self.master_stale = True
         # the kernel wrote through .data: bump autograd's version counter so version-keyed caches notice
         torch._C._increment_version([self.param])   # takes an ITERABLE of tensors
         if self.module is not None:                          # the shadow is already current for the new version
+            self.module._half_key = (self.param._version, self.param.data_ptr())
+
+    def sync_master(self):
+        """(sharded mode) all-gather the fp32 master parameters so that every rank holds the full current vector."""
+        if not (self.sharded and self.master_stale):
+            return
+        n = self.param.numel()
+        if self.padded != n:
+            if self._master_pad is None:
+                self._master_pad = torch.zeros(self.padded, dtype=torch.float32, device=self.param.device)
+            self._master_pad[self.lo:self.hi].copy_(self.param.data[self.lo:self.hi])
+            parallel.all_gather_(self._master_pad, self.shard)
+            self.param.data.copy_(self._master_pad[:n])
+        else:
+            parallel.all_gather_(self.param.data, self.shard)
+        self.master_stale = False
+        torch._C._increment_version([self.param])
+        if self.module is not None:
             self.module._half_key = (self.param._version, self.param.data_ptr())
 
 
@@ -255,6 +334,7 @@ class NeRFScene:
     """`nerf.py:28-396` for ``sampler: fixed``.  ``train_conf`` takes the reference's YAML node."""
 
     LOSS_SCALE = 2 ** 7                                               # GradScaler(2**7), never unscaled (nerf.py:139,249-253)
+    OCC_STEP = 5e-4                                                   # render_step_size (nerf_renderer.py:151)
 
     def __init__(self, base_exp_dir=".", train_conf=None, estimator_type="fixed", renderer_conf=None,
                  n_samples: int = 128, near: float = 1e-2, far: float = 1.0, device="cuda", writer=None, fused_train: bool = True,
@@ -271,7 +351,7 @@ class NeRFScene:
         if estimator_type == "occ":                                    # nerf.py:68
             from .shims.nerfacc.estimators.occ_grid import OccGridEstimator
             self.estimator = OccGridEstimator(roi_aabb=self.aabb, resolution=occ_resolution, levels=1).to(self.device)
-            fused_train = False                                        # the fused step is the fixed-S one
+            graph_train = False                                        # the packed step has a host read (sample count) per step
         else:
             self.estimator = FixedSampleEstimator(n_samples, near, far)
         self.renderer = NeRFOCCRenderer(**(renderer_conf or {"max_radius": 2, "bg_color": "rand_noise"}))
@@ -303,19 +383,12 @@ class NeRFScene:
         rays_o_img, rays_d_img = rays_o.float(), rays_d.float()
         rays_o, rays_d = rays_o.reshape(-1, 3).float(), rays_d.reshape(-1, 3).float()
         if self.estimator_type == "occ":
-            # nerf_renderer.py:145-197: occupancy sampling (+ visibility culling through the density
-            # kernels), then ONE fused launch for sigma / rgb / composite of the packed samples
-            was_training = self.nerf.training
-            self.set_eval()
-
-            def sigma_fn(t_starts, t_ends, ray_indices):
-                pos = rays_o[ray_indices] + rays_d[ray_indices] * (t_starts + t_ends)[:, None] / 2.0
-                return self.nerf.query_density(pos).squeeze(-1)
-            ri, ts, te = self.estimator.sampling(rays_o, rays_d, sigma_fn=sigma_fn, near_plane=0., far_plane=1.5,
-                                                 render_step_size=5e-4, stratified=False, cone_angle=0., alpha_thre=0.)
-            out = self.fused.render_packed(rays_o, rays_d, ri, ts, te)
-            if was_training:
-                self.set_train()
+            # nerf_renderer.py:145-197: occupancy sampling, both fields at every interval (one launch), composite with
+            # nerfacc's 1e-4 transmittance cut applied inside (identical to culling first; see csrc/packed.cu)
+            est = self.estimator
+            ri, ts, te = ops.occ_sample(est.binaries[0], est._aabb_list(), rays_o.contiguous(), rays_d.contiguous(), 0.0, 1.5,
+                                        self.OCC_STEP, None)
+            out = self.fused.render_occ(rays_o, rays_d, ops.occ_sample.last_offsets, ri, ts, te, early_stop_eps=1e-4)
         else:
             out = self.fused.render_rays(rays_o_img if image else rays_o, rays_d_img if image else rays_d, self.estimator.n_samples)
         return {k: out[k].reshape(pre_shape + [-1]) for k in query_keys}
@@ -356,6 +429,19 @@ class NeRFScene:
         noise = torch.cat([bg, torch.rand(R, 1, device=dev)], 1)
         phase = _lib.PERF_PHASE_APP if geo_inference else _lib.PERF_PHASE_GEO
         param = self.nerf.app_mlp.params if geo_inference else self.nerf.geo_mlp.params
+        if self.estimator_type == "occ":
+            # the sampler PeRF trains with (nerf_renderer.py:145-155): packed intervals, one offset per ray when training
+            est = self.estimator
+            ri, ts, te = ops.occ_sample(est.binaries[0], est._aabb_list(), rays_o.float().contiguous(), rays_d.float().contiguous(),
+                                        0.0, 1.5, self.OCC_STEP, jitter if self.nerf.training else None)
+            if ri.numel() <= 0:                                              # nerf_renderer.py:156-162
+                z = lambda c: torch.zeros(R, c, device=dev)
+                return {"is_valid": False, "rgb": z(3), "distance": z(1), "opacities": z(1), "dist_loss": torch.zeros((), device=dev)}
+            rgb, dist, op, dl = ops.fused_packed_train_step(param, rays_o.float(), rays_d.float(), ops.occ_sample.last_offsets, ri, ts, te,
+                                                            noise, tc, phase, 1e-4)
+            n_rays = (ri[-1] + 1).float()                                    # flatten_eff_distloss: ray_id.max() + 1
+            return {"is_valid": True, "rgb": rgb, "distance": dist, "opacities": op, "dist_loss": dl.sum() / n_rays,
+                    "n_samples": int(ri.numel())}
         rgb, dist, op, dl = ops.fused_train_step(param, rays_o, rays_d, jitter, noise, tc, phase)
         return {"is_valid": True, "rgb": rgb, "distance": dist, "opacities": op, "dist_loss": dl.sum() / R}
 
@@ -365,7 +451,7 @@ class NeRFScene:
         assert len(rays_o.shape) == 2
         if self.fused_train and self.nerf.training and (geo_inference != app_inference) and "weights" not in query_keys:
             res = self._render_once_fused(rays, geo_inference, app_inference)
-            return {k: res[k] for k in list(query_keys) + ["is_valid"]}
+            return {k: res[k] for k in list(query_keys) + ["is_valid"] if k in res}
         res = self.renderer.render(self.nerf, self.estimator, rays_o, rays_d, geo_inference=geo_inference, app_inference=app_inference)
         if (res is None) or (not res["is_valid"]):
             return res
@@ -401,6 +487,7 @@ class NeRFScene:
                 geo_step(progress)
             else:
                 self.train_one_step_geo(geo_optimizer, sup_pool, pixel_sup_rand_mode, progress=progress)
+        geo_optimizer.sync_master()
         app_optimizer = FusedAdam(self.nerf.app_mlp.params, lr=self.train_conf.app_optimizer.init_lr, module=self.nerf.app_mlp)
         app_step = GraphedTrainStep(self, "app", sup_pool, app_optimizer) if self.graph_train and app_res_iters > 0 else None
         for iter_i in range(app_res_iters):
@@ -409,6 +496,7 @@ class NeRFScene:
                 app_step(iter_i / app_res_iters)
             else:
                 self.train_one_step_app(app_optimizer, sup_pool, pixel_sup_rand_mode, progress=iter_i / app_res_iters)
+        app_optimizer.sync_master()
 
     def _local_batch(self):
         return max(1, int(self.train_conf.pixel_loss_batch_size) // parallel.world_size())
@@ -425,6 +513,7 @@ class NeRFScene:
         keys = ["rgb", "distance", "dist_loss"] if self.fused_train else ["rgb", "distance", "weights", "t_starts", "t_ends", "trans", "ray_indices"]
         res = self.render_once(rays, keys, app_inference=True)
         if (res is None) or (not res["is_valid"]):
+            optimizer.step(valid=False)            # no samples on this rank (nerf.py:204-206): still join the exchange
             self.global_iter_step_geo += 1
             return None
         if conf.depth_loss_weight > eps:
@@ -457,6 +546,7 @@ class NeRFScene:
         keys = ["rgb", "distance"] if self.fused_train else ["rgb", "distance", "weights", "t_starts", "t_ends", "trans", "ray_indices"]
         res = self.render_once(rays, keys, geo_inference=True)
         if (res is None) or (not res["is_valid"]):
+            optimizer.step(valid=False)            # no samples on this rank (nerf.py:204-206): still join the exchange
             self.global_iter_step_app += 1
             return None
         if conf.color_loss_weight > eps:
@@ -521,9 +611,12 @@ class GraphedTrainStep:
             loss = step(progress=i / app_iters)
     """
 
-    def __init__(self, scene: NeRFScene, phase: str, sup_pool: RaySupervision, optimizer: FusedAdam, warmup: int = 3):
+    def __init__(self, scene: NeRFScene, phase: str, sup_pool: RaySupervision, optimizer: FusedAdam, warmup: int = 3, split: bool = False):
+        """``split=True``: four graphs instead of one -- [batch draw + forward + losses + backward], [gradient exchange],
+        [Adam], [shadow all-gather] -- replayed back to back with CUDA events in between (``self.stage_ms`` after each
+        call): the timeline of a step (VERDICT r1 next #2).  Slightly slower than the single graph (three more launches)."""
         assert phase in ("geo", "app") and scene.fused_train
-        self.scene, self.phase, self.pool, self.opt = scene, phase, sup_pool, optimizer
+        self.scene, self.phase, self.pool, self.opt, self.split = scene, phase, sup_pool, optimizer, split
         dev = scene.device
         self.ratio = torch.zeros(1, device=dev)
         self.net = scene.nerf.geo_mlp if phase == "geo" else scene.nerf.app_mlp
@@ -531,20 +624,46 @@ class GraphedTrainStep:
         torch.cuda.manual_seed(int(sup_pool.generator.initial_seed()) + 7919 * parallel.rank())
         optimizer.enable_graph_mode()
         scene.set_train()
+        # warm-up and capture run REAL optimiser steps: snapshot the parameters and put them back afterwards, so the
+        # graphed fit starts from the same weights as the eager one for any init_lr
+        p0 = self.net.params.data.clone()
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):                         # eager warm-up on a side stream (cuBLAS workspaces, NCCL, allocator)
+        with torch.cuda.stream(side):                         # eager warm-up on a side stream (NCCL, allocator)
             for _ in range(warmup):
                 self._prepare(0.5)
                 self._body()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
-        self.graph = torch.cuda.CUDAGraph()
         self._prepare(0.5)
-        with torch.cuda.graph(self.graph):
-            self.loss = self._body()
+        if not split:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.loss = self._body()
+            self.graphs = [self.graph]
+        else:
+            pool = torch.cuda.graph_pool_handle()
+            self.graphs = [torch.cuda.CUDAGraph() for _ in range(4)]
+            optimizer.deferred = True
+            with torch.cuda.graph(self.graphs[0], pool=pool):
+                self.loss = self._body()
+            optimizer.deferred = False
+            with torch.cuda.graph(self.graphs[1], pool=pool):
+                optimizer.stage_exchange(getattr(optimizer, "_valid", True))
+            with torch.cuda.graph(self.graphs[2], pool=pool):
+                optimizer.stage_adam()
+            with torch.cuda.graph(self.graphs[3], pool=pool):
+                optimizer.stage_gather()
+            self.events = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+            self.stage_ms = None
         optimizer.step_count = 0                               # warm-up / capture steps do not count
         optimizer.exp_avg.zero_(); optimizer.exp_avg_sq.zero_()
+        self.net.params.data.copy_(p0)
+        optimizer.master_stale = False
+        ops.params_to_half(self.net.params.detach(), out=self.net._half())     # same buffer the captured kernels read
+        torch._C._increment_version([self.net.params])
+        self.net._half_key = (self.net.params._version, self.net.params.data_ptr())
+        scene._fused_key = None
 
     def _prepare(self, progress: float):
         ops.set_scalars(self.ratio, [min(progress * 2.0, 1.0)])
@@ -557,12 +676,25 @@ class GraphedTrainStep:
             return sc.train_one_step_geo(self.opt, self.pool, progress=self.ratio[0])
         return sc.train_one_step_app(self.opt, self.pool, progress=self.ratio[0])
 
+    STAGES = ("draw+forward+loss+backward", "gradient exchange", "adam", "shadow all-gather")
+
     def __call__(self, progress: float = 0.0):
         self._prepare(progress)
-        self.graph.replay()
+        if not self.split:
+            self.graph.replay()
+        else:
+            self.events[0].record()
+            for g, e in zip(self.graphs, self.events[1:]):
+                g.replay(); e.record()
+            self.opt.master_stale = self.opt.sharded
         # the replayed Adam kernel wrote params + fp16 shadow: tell the version-keyed caches
         p = self.net.params
         torch._C._increment_version([p])
         self.net._half_key = (p._version, p.data_ptr())
         self.scene._fused_key = None
+        self.opt.master_stale = self.opt.sharded
         return self.loss
+
+    def last_stage_ms(self):
+        """(split mode) device time of the four stages of the last call, after a synchronize."""
+        return [a.elapsed_time(b) for a, b in zip(self.events[:-1], self.events[1:])]

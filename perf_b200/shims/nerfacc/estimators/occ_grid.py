@@ -5,8 +5,9 @@ SURVEY.md section 8(f) row 1.  Keeps the reference's estimator interface (buffer
 ``resolution/aabbs/occs/binaries`` for checkpoints, ``update_every_n_steps``, ``sampling``); the
 marching is two libperfb200 kernels (perf_occ_count / perf_occ_write) around one cumsum, the
 per-sample work it feeds (sigma_fn -> field kernels, transmittance culling) runs on libperfb200
-too; the grid update is torch elementwise code.  Sampling rule (nerfacc's DDA for ``cone_angle=0``, restated; upstream source is not
-vendored so the exact phase of the lattice is unpinned): fixed lattice
+too; the grid update is three libperfb200 kernels (perf_occ_points, perf_occ_update) around the caller's
+``occ_eval_fn``.  Sampling rule (nerfacc's DDA for ``cone_angle=0``, restated; upstream source is not
+vendored: parity unpinned, the lattice decision is written in oracle/occ_sampler.py): fixed lattice
 ``t_k = near + (k + u_r) * step`` (one uniform offset ``u_r`` per ray when ``stratified``), a
 sample ``[t_k, t_k + step)`` is kept when its midpoint lies inside the aabb in an occupied cell,
 then samples whose transmittance fell below ``early_stop_eps`` are dropped.
@@ -40,6 +41,7 @@ class OccGridEstimator(torch.nn.Module):
         self.register_buffer("aabbs", roi[None, :].clone())
         self.register_buffer("occs", torch.zeros(self.cells_per_lvl * levels))
         self.register_buffer("binaries", torch.zeros([levels] + res.tolist(), dtype=torch.bool))
+        self._res_host = [int(v) for v in res.tolist()]
 
     # -- helpers -------------------------------------------------------------------------------
     def _cell_index(self, x: torch.Tensor) -> torch.Tensor:
@@ -63,16 +65,25 @@ class OccGridEstimator(torch.nn.Module):
         if t_min is not None or t_max is not None:
             raise NotImplementedError("perf_b200 nerfacc: per-ray t_min / t_max are not implemented (PeRF does not pass them)")
         jitter = torch.rand(R, device=dev) if stratified else None
-        ray_indices, t_starts, t_ends = ops.occ_sample(self.binaries[0], self.aabbs[0].tolist(), rays_o.float(), rays_d.float(),
+        ray_indices, t_starts, t_ends = ops.occ_sample(self.binaries[0], self._aabb_list(), rays_o.float(), rays_d.float(),
                                                        float(near_plane), float(min(far_plane, 3.0e38)), float(render_step_size), jitter)
         # visibility culling (nerfacc render_visibility_from_density): keep T >= early_stop_eps
         if sigma_fn is not None and early_stop_eps > 0 and ray_indices.numel() > 0:
             sigmas = sigma_fn(t_starts, t_ends, ray_indices).float().reshape(-1)
             _, trans, alphas = ops.weights_from_density(t_starts, t_ends, sigmas.contiguous(), ray_indices, R)
-            thre = min(alpha_thre, float(self.occs.mean().item()))
+            # min(alpha_thre, mean(occs)): occs >= 0, so for alpha_thre <= 0 (PeRF passes 0) it is alpha_thre itself --
+            # no 16.7 M-cell reduction and no device sync per call
+            thre = alpha_thre if alpha_thre <= 0 else min(alpha_thre, float(self.occs.mean().item()))
             keep = (trans >= early_stop_eps) & (alphas >= thre)
             ray_indices, t_starts, t_ends = ray_indices[keep], t_starts[keep], t_ends[keep]
         return ray_indices, t_starts, t_ends
+
+    def _aabb_list(self):
+        """The roi as Python floats, cached (a .tolist() per call is a device sync per frame)."""
+        key = (self.aabbs.data_ptr(), self.aabbs._version)
+        if getattr(self, "_aabb_key", None) != key:
+            self._aabb_host, self._aabb_key = self.aabbs[0].tolist(), key
+        return self._aabb_host
 
     @torch.no_grad()
     def update_every_n_steps(self, step: int, occ_eval_fn: Callable, occ_thre: float = 1e-2, ema_decay: float = 0.95,
@@ -85,22 +96,24 @@ class OccGridEstimator(torch.nn.Module):
     @torch.no_grad()
     def _update(self, step, occ_eval_fn, occ_thre, ema_decay, warmup_steps):
         dev = self.occs.device
-        res = self.resolution.to(dev)
         if step < warmup_steps:
-            idx = torch.arange(self.cells_per_lvl, device=dev)
+            idx, n = None, self.cells_per_lvl                    # every cell
         else:
-            n = self.cells_per_lvl // 4
-            uni = torch.randint(self.cells_per_lvl, (n,), device=dev)
+            n4 = self.cells_per_lvl // 4
+            uni = torch.randint(self.cells_per_lvl, (n4,), device=dev)
             occ_idx = torch.nonzero(self.binaries.reshape(-1))[:, 0]
-            if occ_idx.numel() > n:
-                occ_idx = occ_idx[torch.randint(occ_idx.numel(), (n,), device=dev)]
-            idx = torch.cat([uni, occ_idx])
-        ry, rz = int(res[1]), int(res[2])
-        coords = torch.stack([idx // (ry * rz), (idx // rz) % ry, idx % rz], -1).float()
-        x = (coords + torch.rand_like(coords)) / res.float()
-        amin, amax = self.aabbs[0, :3], self.aabbs[0, 3:]
-        x = amin + x * (amax - amin)
+            if occ_idx.numel() > n4:
+                occ_idx = occ_idx[torch.randint(occ_idx.numel(), (n4,), device=dev)]
+            idx = torch.cat([uni, occ_idx]).contiguous()
+            n = idx.numel()
+        if not self.occs.is_cuda:
+            raise RuntimeError("perf_b200 nerfacc: OccGridEstimator.update_every_n_steps needs the estimator on a CUDA device (there is no CPU path)")
+        self._n_updates = getattr(self, "_n_updates", 0) + 1
+        seed = (torch.initial_seed() * 0x9E3779B1 + self._n_updates * 0x85EBCA77C2B2AE63) & (2 ** 62 - 1)
+        x = ops.occ_points(idx, n, self._res_host, self._aabb_list(), seed, dev)
         occ = occ_eval_fn(x).reshape(-1).float()
-        self.occs[idx] = torch.maximum(self.occs[idx] * ema_decay, occ)
-        thre = torch.clamp(self.occs[self.occs >= 0].mean(), max=occ_thre)
-        self.binaries = (self.occs > thre).view(self.binaries.shape)
+        if getattr(self, "_ws", None) is None or self._ws.device != dev:
+            self._ws = torch.empty(2 * 1024, dtype=torch.float64, device=dev)          # PERF_OCC_PARTIALS
+        if not self.binaries.is_contiguous():
+            self.binaries = self.binaries.contiguous()
+        ops.occ_update(self.occs, idx, occ, ema_decay, occ_thre, self.binaries.view(torch.uint8), self._ws)

@@ -1,15 +1,26 @@
 #!/bin/bash
-# Generic development call: GPU tests, bench line, graphed training-step timing.  Outputs under gpurun_out/.
+# Generic development call: GPU tests (all, no -x), bench line, training launch lists, one ncu --set full of the render kernel.
+# Outputs under gpurun_out/.  Env: PYTEST_K (subset), SKIP_NCU=1, SKIP_TESTS=1.
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -q -m gpu --no-header -p no:cacheprovider --timeout=300 -x ${PYTEST_K:+-k "$PYTEST_K"} > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit=$?"
-tail -15 gpurun_out/pytest_gpu.log
-timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench exit=$?"
+if [ -z "$SKIP_TESTS" ]; then
+  timeout 1200 python -m pytest tests -q -m gpu --no-header -p no:cacheprovider --timeout=300 ${PYTEST_K:+-k "$PYTEST_K"} > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit=$?"
+  grep -E "^(FAILED|ERROR)|passed|failed" gpurun_out/pytest_gpu.log | tail -25
+fi
+timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench exit=$?"
 python - <<'PY'
 import json
 try:
     d = json.load(open('gpurun_out/bench_n1.json'))
     print('value', round(d['value'], 1), 'ms', round(d['ms_per_step'], 3), 'e2e', round(d['e2e']['value'], 1), 'frac', round(d['roofline']['frac'], 3), 'parity', d.get('parity', {}).get('max_abs_rgb'))
-    print('train', {k: round(v, 3) for k, v in (d.get('train') or {}).items() if isinstance(v, float)})
+    print('train', {k: (round(v, 3) if isinstance(v, float) else v) for k, v in (d.get('train') or {}).items() if k != 'note'})
+    for k in ('render_c4', 'render_c5'):
+        print(k, d.get(k))
+    print('cpu', d.get('cpu_baseline', {}).get('value'), d.get('cpu_baseline', {}).get('cores'))
 except Exception as e:
     print('bench unreadable', e); print(open('gpurun_out/bench_n1.err').read()[-3000:])
 PY
+if [ -z "$SKIP_NCU" ]; then
+  PHASES=geo bash tools/profile_train.sh 2>&1 | tail -14; cp gpurun_out/train_launches.csv gpurun_out/train_launches_geo.csv
+  PHASES=app bash tools/profile_train.sh 2>&1 | tail -14; cp gpurun_out/train_launches.csv gpurun_out/train_launches_app.csv
+  ROWS=256 timeout 600 ncu --set full --clock-control none --import-source on -k regex:render_march -s 1 -c 1 -f -o gpurun_out/prof_render_r02 python tools/prof_render.py > gpurun_out/prof_render_r02.log 2>&1; echo "ncu-full exit=$?"
+fi
