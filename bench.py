@@ -328,7 +328,9 @@ def bench_extra_configs(renderer, dev, rank, world, steps=2):
         sl = parallel.shard_slice(h, rank, world)
         bufs = tuple(torch.empty(sl.stop - sl.start, w, c, dtype=torch.float32, device=dev) for c in (3, 1, 1))
         run = lambda: renderer.render_pano(pose, h, w, s, row0=sl.start, rows=sl.stop - sl.start, out=bufs)
-        run()
+        r = run()
+        if gather:                                          # untimed: NCCL sets up its point-to-point channels on first use
+            parallel.gather_row_tiles(torch.cat([r["rgb"], r["distance"]], -1), h)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()

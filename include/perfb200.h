@@ -67,6 +67,8 @@ typedef struct perf_mlp_cfg {
 #define PERF_FLAG_TRAINING   1u   /* stratified jitter + training background rule        */
 #define PERF_FLAG_SIMT_MLP   2u   /* debug only: MLP on CUDA cores instead of tcgen05     */
 #define PERF_FLAG_GENERIC_ADDR 8u  /* render: disable the specialised (4 dense + hashed pow2) addressing path */
+#define PERF_FLAG_L0_SMEM 16u      /* render_pano (measured variant, profiles/r02_render_variants.md): level 0 of the table staged into
+                                      shared memory by one cp.async.bulk per CTA, 3 CTAs/SM instead of 4 */
 #define PERF_FLAG_SCAN_KERNEL 4u   /* render: samples-along-lanes kernel (warp-shuffle scan composite) instead of ray marching */
 
 int         perf_abi_version(void);
@@ -241,6 +243,16 @@ int perf_train_backward_composite(int phase, uint32_t n_samples, uint32_t segmen
                                   const float* d_g_distloss, const float* d_distance_out, const float* d_opacity_out,
                                   float* d_out, void* stream);
 
+/* The scalar losses of one training step and their gradients w.r.t. the renderer outputs in ONE launch
+ * (nerf.py:208-238: smooth-L1 depth, beta 1e-2, + w_distloss * ratio * flatten_eff_distloss; nerf.py:281-287: smooth-L1
+ * colour, beta 5e-2; torch `reduction='mean'`).  d_pred / d_gt [n] (n = R distances or 3 R colours); d_distloss [R] =
+ * per-ray numerators from the forward or NULL; d_ratio: device scalar (the ramp min(2 progress, 1)) or NULL = 1;
+ * d_inv_n_rays: device scalar 1 / (ray_id.max() + 1) or NULL = 1 / R.  d_loss3 = {total, mean smooth-L1, distortion
+ * term}; d_g_pred [n], d_g_distloss [R] = d total / d input (NOT multiplied by the 2^7 loss scale). */
+int perf_train_loss(const float* d_pred, const float* d_gt, uint64_t n, uint64_t R, float beta, float w_main,
+                    const float* d_distloss, const float* d_ratio, const float* d_inv_n_rays, float w_distloss,
+                    float* d_loss3, float* d_g_pred, float* d_g_distloss, void* stream);
+
 /* Grid gradient for sample-major rows whose positions are recomputed from the rays:
  * d_dfeat [S*R, 32] fp32.  Same-cell neighbours inside a warp are merged before the atomics. */
 int perf_hashgrid_bwd_rays(const perf_grid_cfg* cfg, const float* aabb6, const float* d_rays_o, const float* d_rays_d,
@@ -291,6 +303,10 @@ int perf_composite_packed_bwd(int phase, const int64_t* d_offsets, const float* 
  * atomics chosen by the caller (packed samples are 5e-4 apart: runs exist up to resolution ~1000). */
 int perf_hashgrid_bwd_merged(const perf_grid_cfg* cfg, const float* d_x01, const float* d_dfeat, uint64_t N, float* d_dtable,
                              uint32_t n_merge_levels, void* stream);
+
+/* Diagnostic (bench.py's train_roofline denominator): n_atomics reductions of `vec` (1, 2 or 4) floats at pseudo-random
+ * vec-aligned slots of d_table [n_floats] -- the L2 atomic rate that bounds the grid-gradient scatter. */
+int perf_debug_atomic_rate(float* d_table, uint64_t n_floats, uint64_t n_atomics, int vec, void* stream);
 
 /* Occupancy-grid update (nerfacc OccGridEstimator.update_every_n_steps, levels = 1; nerf.py:159-168).
  * perf_occ_points: a uniformly jittered point inside each listed cell (d_cell_idx int64 [n], NULL = cells 0..n-1),

@@ -16,6 +16,7 @@ PERF_FLAG_TRAINING = 1
 PERF_FLAG_SIMT_MLP = 2
 PERF_FLAG_SCAN_KERNEL = 4
 PERF_FLAG_GENERIC_ADDR = 8
+PERF_FLAG_L0_SMEM = 16
 
 
 class GridCfg(C.Structure):
@@ -83,6 +84,8 @@ SIGNATURES = {
     "perf_composite_packed_fwd": (i32, [vp, vp, vp, vp, vp, u64, f32, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "perf_composite_packed_bwd": (i32, [i32, vp, vp, vp, vp, vp, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "perf_hashgrid_bwd_merged": (i32, [P(GridCfg), vp, vp, u64, vp, u32, vp]),
+    "perf_train_loss": (i32, [vp, vp, u64, u64, f32, f32, vp, vp, vp, f32, vp, vp, vp, vp]),
+    "perf_debug_atomic_rate": (i32, [vp, u64, u64, i32, vp]),
     "perf_occ_points": (i32, [vp, u64, P(i32), P(f32), u64, vp, vp]),
     "perf_occ_update": (i32, [vp, u64, vp, vp, u64, f32, f32, vp, vp, vp]),
     "perf_mlp_bwd_out": (i32, [vp, i32, vp, vp, vp, u64, vp]),

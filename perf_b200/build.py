@@ -35,11 +35,33 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
+STAMP = os.path.join(HERE, ".libperfb200.srchash")
+
+
+def _deps():
+    return sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join(os.path.dirname(HERE), "include", "perfb200.h")]
+
+
+def source_hash() -> str:
+    """Content hash of everything the library is built from (mtimes do not survive the copy to the GPU box)."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for d in _deps():
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def is_stale() -> bool:
-    if not os.path.exists(LIB):
+    """True when libperfb200.so is missing or was built from other sources than the ones on disk: compared by content
+    (the stamp file written by build() travels with the .so), never by modification time."""
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(os.path.dirname(HERE), "include", "perfb200.h")]
-    return any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps)
+    try:
+        return open(STAMP).read().strip() != source_hash()
+    except OSError:
+        return True
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -57,6 +79,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if proc.returncode != 0:
             raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
         os.replace(tmp, LIB)
+        with open(STAMP + ".tmp", "w") as f:
+            f.write(source_hash() + "\n")
+        os.replace(STAMP + ".tmp", STAMP)
         if verbose:
             print(proc.stderr)
     return LIB

@@ -257,6 +257,21 @@ hashgrid_bwd_kernel(LevelTable lt, int level0, const float* __restrict__ x01, co
     }
 }
 
+// ---- diagnostics: the L2 atomic rate the grid-gradient scatter is bounded by (bench.py train_roofline denominator).
+// Every thread issues `per_thread` reductions of `VEC` floats at pseudo-random VEC-aligned slots of a table (no other work).
+template <int VEC>
+__global__ void __launch_bounds__(256) atomic_rate_kernel(float* __restrict__ table, uint32_t n_slots, int per_thread)
+{
+    uint32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+    for (int i = 0; i < per_thread; ++i) {
+        x ^= x << 13; x ^= x >> 17; x ^= x << 5;                       // xorshift32
+        const uint32_t slot = x % n_slots;
+        if constexpr (VEC == 4) atomicAdd(reinterpret_cast<float4*>(table) + slot, make_float4(1.f, 1.f, 1.f, 1.f));
+        else if constexpr (VEC == 2) atomicAdd(reinterpret_cast<float2*>(table) + slot, make_float2(1.f, 1.f));
+        else atomicAdd(table + slot, 1.f);
+    }
+}
+
 // ---- packed composite kernels (nerfacc semantics): one warp per ray, lanes over its samples.
 __device__ __forceinline__ uint64_t lower_bound_i64(const int64_t* a, uint64_t n, int64_t key)
 {
@@ -495,6 +510,20 @@ int perf_hashgrid_bwd(const perf_grid_cfg* cfg, const float* d_x01, const float*
         hashgrid_bwd_kernel<false><<<dim3(blocks_for(N, 256), lt.n_levels - n_merge), 256, 0, S(stream)>>>(lt, (int)n_merge, d_x01, d_dfeat, N, (float2*)d_dtable);
         PERF_LAUNCH_CHECK();
     }
+    return PERF_OK;
+}
+
+int perf_debug_atomic_rate(float* d_table, uint64_t n_floats, uint64_t n_atomics, int vec, void* stream)
+{
+    PERF_CHECK_ARG(d_table && (vec == 1 || vec == 2 || vec == 4) && n_floats >= 4 && (uintptr_t)d_table % 16 == 0, "bad arguments");
+    const int per_thread = 16;
+    const uint64_t threads = (n_atomics + per_thread - 1) / per_thread;
+    const uint32_t n_slots = (uint32_t)(n_floats / vec);
+    const unsigned grid = blocks_for(threads, 256);
+    if (vec == 4) atomic_rate_kernel<4><<<grid, 256, 0, S(stream)>>>(d_table, n_slots, per_thread);
+    else if (vec == 2) atomic_rate_kernel<2><<<grid, 256, 0, S(stream)>>>(d_table, n_slots, per_thread);
+    else atomic_rate_kernel<1><<<grid, 256, 0, S(stream)>>>(d_table, n_slots, per_thread);
+    PERF_LAUNCH_CHECK();
     return PERF_OK;
 }
 

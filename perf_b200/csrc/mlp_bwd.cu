@@ -360,7 +360,8 @@ static int launch_mlp_bwd(const MlpBwdArgs& a, cudaStream_t stream)
     int dev = 0; PERF_CUDA(cudaGetDevice(&dev));
     if (attr_dev != dev) { PERF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem<TWO>::TOTAL)); attr_dev = dev; }
     const uint64_t n_tiles = (a.N + TILE - 1) / TILE;
-    const uint64_t slots = (uint64_t)num_sms() * 2;
+    // resident CTAs per SM: TMEM columns (128 / 256 of 512) and shared memory (45 / 89 KB) allow 4 / 2
+    const uint64_t slots = (uint64_t)num_sms() * (TWO ? 2 : 4);
     k<<<(unsigned)(n_tiles < slots ? n_tiles : slots), TILE, BwdSmem<TWO>::TOTAL, stream>>>(a);
     PERF_LAUNCH_CHECK();
     return PERF_OK;

@@ -66,6 +66,12 @@ constexpr int RS_TAILS = RS_WOUT + 4 * HID * 4;     // [2 scans][4 warps][8] flo
 constexpr int RS_CARRY = RS_TAILS + 2 * 4 * 8 * 4;  // [2 parities][8] floats
 constexpr int RS_BAR   = RS_CARRY + 2 * 8 * 4;
 constexpr int RS_TOTAL = RS_BAR + 16;
+// experiment (PERF_FLAG_L0_SMEM): level 0 of the packed table (16^3 entries x 8 B = 32 KB) resident in shared memory,
+// staged once per persistent CTA by ONE bulk copy (cp.async.bulk -> UBLKCP, completion on an mbarrier)
+constexpr int RS_BAR2  = (RS_TOTAL + 127) / 128 * 128;
+constexpr int RS_L0    = RS_BAR2 + 128;
+constexpr int L0_BYTES = 4096 * 8;
+constexpr int RS_TOTAL_L0 = RS_L0 + L0_BYTES;
 
 // Output-layer weights of both networks as fp32 in the CONSTANT bank: [0,64) density row, [64,256) the three colour
 // rows.  The 64 * n_out FMAs per sample of the output layers then take their weight operand straight from c[bank][imm]
@@ -181,11 +187,12 @@ struct RenderSmem {
     uint8_t *sA, *sAg, *sAa, *sW1g, *sW1a, *sW2a;
     float *sWoutG, *sWoutA;
     uint64_t* bar;
+    const uint2* l0;        // level 0 of the packed table in shared memory, or null
 };
 
 // Levels [4q, 4q+4) of both fields -> one 16-byte k-group of each feature tile.
 // KIND 0: generic addressing, 1: dense (fast), 2: hashed power-of-two (fast).
-template <int KIND, int SAVE>
+template <int KIND, int SAVE, bool L0SMEM = false>
 __device__ __forceinline__ void encode_group(const RenderArgs& a, const RenderSmem& sm, int q, float x, float y, float z, int tid, uint64_t srow)
 {
     uint32_t pg[4], pa[4];
@@ -197,8 +204,13 @@ __device__ __forceinline__ void encode_group(const RenderArgs& a, const RenderSm
         else if constexpr (KIND == 1) level_corners_fast<false>(a.lt, l, x, y, z, c);
         else level_corners_fast<true>(a.lt, l, x, y, z, c);
         uint2 v[8];
+        if (KIND == 1 && L0SMEM && l == 0) {
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) v[kk] = __ldg(a.table + c.idx[kk]);
+            for (int kk = 0; kk < 8; ++kk) v[kk] = sm.l0[c.idx[kk]];           // offset of level 0 is 0
+        } else {
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) v[kk] = __ldg(a.table + c.idx[kk]);
+        }
         uint32_t vg[8], va[8];
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) { vg[kk] = v[kk].x; va[kk] = v[kk].y; }
@@ -216,7 +228,7 @@ __device__ __forceinline__ void encode_group(const RenderArgs& a, const RenderSm
 // power-of-two) -- branch-free and ~1/3 smaller code; NDENSE < 0: generic addressing.
 // SAVE 1 / 2: also write the fp16 features and hidden activations of the density / colour network
 // to row `srow` of the training buffers (srow == ~0: masked-out thread).
-template <bool SIMT, int NDENSE, int SAVE = 0>
+template <bool SIMT, int NDENSE, int SAVE = 0, bool L0SMEM = false>
 __device__ __forceinline__ void eval_fields(const RenderArgs& a, const RenderSmem& sm, float x, float y, float z, bool selector,
                                             uint32_t tmem_base, uint32_t tmem_row, uint32_t& parity, int tid,
                                             float& sigma, float& cr, float& cg, float& cb, uint64_t srow = ~0ull)
@@ -229,7 +241,7 @@ __device__ __forceinline__ void eval_fields(const RenderArgs& a, const RenderSme
     if constexpr (NDENSE == 4) {
         // dense group unrolled; the three hashed groups share ONE copy of the code (the fully
         // unrolled body was ~70 KB of SASS and stalled on instruction fetch)
-        encode_group<1, SAVE>(a, sm, 0, x, y, z, tid, srow);
+        encode_group<1, SAVE, L0SMEM>(a, sm, 0, x, y, z, tid, srow);
 #pragma unroll 1
         for (int q = 1; q < 4; ++q) encode_group<2, SAVE>(a, sm, q, x, y, z, tid, srow);
     } else {
@@ -321,7 +333,7 @@ __global__ void __launch_bounds__(TILE, 4) render_kernel(const __grid_constant__
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + RS_BAR + 8);
 
     const int tid = threadIdx.x, warp = tid >> 5;
-    const RenderSmem sm = {sA, sAg, sAa, sW1g, sW1a, sW2a, sWoutG, sWoutA, bar};
+    const RenderSmem sm = {sA, sAg, sAa, sW1g, sW1a, sW2a, sWoutG, sWoutA, bar, nullptr};
 
     load_weight_canonical(a.geo_w, 32, sW1g, tid, TILE);
     load_weight_canonical(a.app_w, 32, sW1a, tid, TILE);
@@ -445,8 +457,8 @@ __global__ void __launch_bounds__(TILE, 4) render_kernel(const __grid_constant__
 // per request at the coarse and middle levels) and a thread revisits the same cells from k to k+1
 // (temporal L1 reuse).  The composite is a per-thread running sum: no shuffles, no carries.
 // Transmittance uses the sequential exclusive sum, the order of the oracle's cumsum.
-template <bool PANO, bool SIMT, int NDENSE, int SAVE = 0>
-__global__ void __launch_bounds__(TILE, 4) render_march_kernel(const __grid_constant__ RenderArgs a)
+template <bool PANO, bool SIMT, int NDENSE, int SAVE = 0, bool L0SMEM = false>
+__global__ void __launch_bounds__(TILE, L0SMEM ? 3 : 4) render_march_kernel(const __grid_constant__ RenderArgs a)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sA   = smem + RS_A;
@@ -459,7 +471,8 @@ __global__ void __launch_bounds__(TILE, 4) render_march_kernel(const __grid_cons
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + RS_BAR + 8);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const RenderSmem sm = {sA, sA, sA + A32_BYTES, sW1g, sW1a, sW2a, sWoutG, sWoutA, bar};
+    const RenderSmem sm = {sA, sA, sA + A32_BYTES, sW1g, sW1a, sW2a, sWoutG, sWoutA, bar,
+                           L0SMEM ? reinterpret_cast<const uint2*>(smem + RS_L0) : nullptr};
 
     load_weight_canonical(a.geo_w, 32, sW1g, tid, TILE);
     load_weight_canonical(a.app_w, 32, sW1a, tid, TILE);
@@ -479,6 +492,17 @@ __global__ void __launch_bounds__(TILE, 4) render_march_kernel(const __grid_cons
     }
     const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
     uint32_t parity = 0;
+    if constexpr (L0SMEM) {
+        uint64_t* bar2 = reinterpret_cast<uint64_t*>(smem + RS_BAR2);
+        if (tid == 0) {
+            mbar_init(bar2, 1); fence_mbar_init();
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar2)), "r"(L0_BYTES) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(smem_u32(smem + RS_L0)), "l"(a.table), "r"(L0_BYTES), "r"(smem_u32(bar2)) : "memory");
+        }
+        __syncthreads();                                   // the barrier is initialised before anyone polls it
+        mbar_wait(bar2, 0);
+    }
 
     const uint32_t S = a.S;
     const float step = __fdiv_rn(__fsub_rn(a.far, a.near), (float)S);
@@ -571,7 +595,7 @@ __global__ void __launch_bounds__(TILE, 4) render_march_kernel(const __grid_cons
 
             float sigma, cr, cg, cb;
             const uint64_t srow = (SAVE != 0 && valid) ? (uint64_t)k * a.R + ray : ~0ull;
-            eval_fields<SIMT, NDENSE, SAVE>(a, sm, x, y, z, selector, tmem_base, tmem_row, parity, tid, sigma, cr, cg, cb, srow);
+            eval_fields<SIMT, NDENSE, SAVE, L0SMEM>(a, sm, x, y, z, selector, tmem_base, tmem_row, parity, tid, sigma, cr, cg, cb, srow);
 
             const float dt = __fsub_rn(te, ts);
             const float sd = sigma * dt;
@@ -678,7 +702,7 @@ __global__ void __launch_bounds__(TILE, 4) packed_fields_kernel(const __grid_con
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + RS_BAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + RS_BAR + 8);
     const int tid = threadIdx.x, warp = tid >> 5;
-    const RenderSmem sm = {sA, sA, sA + A32_BYTES, sW1g, sW1a, sW2a, sWoutG, sWoutG + HID, bar};
+    const RenderSmem sm = {sA, sA, sA + A32_BYTES, sW1g, sW1a, sW2a, sWoutG, sWoutG + HID, bar, nullptr};
     load_weight_canonical(a.geo_w, 32, sW1g, tid, TILE);
     load_weight_canonical(a.app_w, 32, sW1a, tid, TILE);
     load_weight_canonical(a.app_w + HID * 32, 64, sW2a, tid, TILE);
@@ -781,6 +805,12 @@ static int launch_render(const perf_render_args* args, RenderArgs& a, bool pano,
         else      { if (simt) PERF_RENDER_LAUNCH(render_kernel<false, true>); else PERF_RENDER_LAUNCH(render_kernel<false, false>); }
     } else if (simt) {
         if (pano) PERF_RENDER_LAUNCH(render_march_kernel<true, true, -1>); else PERF_RENDER_LAUNCH(render_march_kernel<false, true, -1>);
+    } else if (fast && pano && (args->flags & PERF_FLAG_L0_SMEM)) {
+        auto k = render_march_kernel<true, false, 4, 0, true>;           // experiment: level 0 in shared memory, 3 CTAs/SM
+        static thread_local int attr_dev0 = -1; int dev_ = 0; PERF_CUDA(cudaGetDevice(&dev_));
+        if (attr_dev0 != dev_) { PERF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_TOTAL_L0)); attr_dev0 = dev_; }
+        const unsigned grid3 = (unsigned)(n_work < (uint64_t)num_sms() * 3 ? n_work : (uint64_t)num_sms() * 3);
+        k<<<grid3, TILE, RS_TOTAL_L0, stream>>>(a);
     } else if (fast) {
         if (pano) PERF_RENDER_LAUNCH(render_march_kernel<true, false, 4>); else PERF_RENDER_LAUNCH(render_march_kernel<false, false, 4>);
     } else {

@@ -351,6 +351,54 @@ __global__ void __launch_bounds__(128) hashgrid_bwd_march_kernel(const __grid_co
     if (ray < a.R) bwd_march_ray_level<V4>(a, ray, (int)blockIdx.y, blockIdx.z, gridDim.z);
 }
 
+// ---- the scalar losses of a training step and their gradients w.r.t. the renderer outputs, ONE launch
+// (nerf.py:208-238 density phase: smooth-L1 depth (beta 1e-2) + ramped distortion loss; nerf.py:281-287 colour phase:
+// smooth-L1 colour (beta 5e-2)).  Replaces ~25 elementwise / reduction launches of the autograd graph per step.
+struct LossArgs {
+    uint64_t n;                  // elements of pred / gt (R or 3 R)
+    uint64_t R;
+    const float *pred, *gt; float beta, w_main;
+    const float* dl; const float* ratio; const float* inv_n_rays; float w_dl;      // distortion loss (all null / 0 = off)
+    float* loss;                 // [3]: total, main term (unweighted mean), distortion term (unweighted mean)
+    float *g_pred, *g_dl;        // d total / d pred [n], d total / d dl [R]
+};
+
+__global__ void __launch_bounds__(1024) train_loss_kernel(const LossArgs a)
+{
+    __shared__ float red[2][32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float inv_n = 1.0f / (float)a.n;
+    float s_main = 0.f, s_dl = 0.f;
+    for (uint64_t i = tid; i < a.n; i += blockDim.x) {
+        const float e = a.pred[i] - a.gt[i], ae = fabsf(e);
+        float l, g;
+        if (ae < a.beta) { l = 0.5f * e * e / a.beta; g = e / a.beta; }        // torch smooth_l1_loss
+        else { l = ae - 0.5f * a.beta; g = e > 0.f ? 1.f : -1.f; }
+        s_main += l;
+        a.g_pred[i] = g * inv_n * a.w_main;
+    }
+    float k_dl = 0.f;
+    if (a.dl) {
+        k_dl = a.w_dl * (a.ratio ? a.ratio[0] : 1.f) * (a.inv_n_rays ? a.inv_n_rays[0] : 1.0f / (float)a.R);
+        for (uint64_t r = tid; r < a.R; r += blockDim.x) { s_dl += a.dl[r]; a.g_dl[r] = k_dl; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) { s_main += __shfl_xor_sync(0xffffffffu, s_main, off); s_dl += __shfl_xor_sync(0xffffffffu, s_dl, off); }
+    if (lane == 0) { red[0][warp] = s_main; red[1][warp] = s_dl; }
+    __syncthreads();
+    if (warp == 0) {
+        float m = lane < (int)(blockDim.x >> 5) ? red[0][lane] : 0.f, d = lane < (int)(blockDim.x >> 5) ? red[1][lane] : 0.f;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) { m += __shfl_xor_sync(0xffffffffu, m, off); d += __shfl_xor_sync(0xffffffffu, d, off); }
+        if (lane == 0) {
+            const float main_mean = m * inv_n;
+            const float dl_term = a.dl ? d * (a.inv_n_rays ? a.inv_n_rays[0] : 1.0f / (float)a.R) : 0.f;       // flatten_eff_distloss
+            a.loss[1] = main_mean; a.loss[2] = dl_term;
+            a.loss[0] = a.w_main * main_mean + (a.dl ? a.w_dl * (a.ratio ? a.ratio[0] : 1.f) * dl_term : 0.f);
+        }
+    }
+}
+
 }  // namespace perf
 
 using namespace perf;
@@ -494,6 +542,22 @@ int perf_host_hashgrid_bwd_rays(const perf_grid_cfg* cfg, const float* aabb6, co
     return PERF_OK;
 }
 #endif
+
+int perf_train_loss(const float* d_pred, const float* d_gt, uint64_t n, uint64_t R, float beta, float w_main,
+                    const float* d_distloss, const float* d_ratio, const float* d_inv_n_rays, float w_distloss,
+                    float* d_loss3, float* d_g_pred, float* d_g_distloss, void* stream)
+{
+    PERF_CHECK_ARG(d_pred && d_gt && d_loss3 && d_g_pred, "NULL pointer");
+    PERF_CHECK_ARG(n >= 1 && R >= 1 && beta > 0.f, "bad sizes / beta");
+    PERF_CHECK_ARG(!d_distloss || d_g_distloss, "distortion loss needs d_g_distloss");
+    LossArgs a; memset(&a, 0, sizeof(a));
+    a.n = n; a.R = R; a.pred = d_pred; a.gt = d_gt; a.beta = beta; a.w_main = w_main;
+    a.dl = d_distloss; a.ratio = d_ratio; a.inv_n_rays = d_inv_n_rays; a.w_dl = w_distloss;
+    a.loss = d_loss3; a.g_pred = d_g_pred; a.g_dl = d_g_distloss;
+    train_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(a);
+    PERF_LAUNCH_CHECK();
+    return PERF_OK;
+}
 
 int perf_mlp_bwd_out(const float* d_dz, int n_out, const void* d_wout_half, const void* d_h, void* d_dh, uint64_t N, void* stream)
 {

@@ -42,8 +42,18 @@ def launch_count() -> int:
 _LAUNCHES = [0]
 
 
+_NVTX = os.environ.get("PERF_B200_NVTX") == "1"     # NVTX range per C-ABI call (ranges around K1-K7), for nsys / ncu --nvtx
+
+
 def _call(fn, *args, launches: int = 1):
-    _lib.check(fn(*args))
+    if _NVTX:
+        torch.cuda.nvtx.range_push(getattr(fn, "__name__", None) or getattr(fn, "_name", "perf"))
+        try:
+            _lib.check(fn(*args))
+        finally:
+            torch.cuda.nvtx.range_pop()
+    else:
+        _lib.check(fn(*args))
     _LAUNCHES[0] += launches
 
 
@@ -392,11 +402,12 @@ def _render_args(packed_table, geo_mlp_half, app_mlp_half, aabb, n_samples, near
     a.d_packed_table, a.d_geo_mlp_half, a.d_app_mlp_half = packed_table.data_ptr(), geo_mlp_half.data_ptr(), app_mlp_half.data_ptr()
     a.aabb = (C.c_float * 6)(*[float(v) for v in aabb])
     a.n_samples, a.near, a.far = int(n_samples), float(near), float(far)
-    if kernel not in ("march", "march_generic", "scan"):
+    if kernel not in ("march", "march_generic", "march_l0smem", "scan"):
         raise ValueError(f"unknown render kernel {kernel!r}")
     a.flags = ((_lib.PERF_FLAG_TRAINING if training else 0) | (_lib.PERF_FLAG_SIMT_MLP if simt else 0)
                | (_lib.PERF_FLAG_SCAN_KERNEL if kernel == "scan" else 0)
-               | (_lib.PERF_FLAG_GENERIC_ADDR if kernel == "march_generic" else 0))
+               | (_lib.PERF_FLAG_GENERIC_ADDR if kernel == "march_generic" else 0)
+               | (_lib.PERF_FLAG_L0_SMEM if kernel == "march_l0smem" else 0))
     a.d_jitter = None if jitter is None else jitter.data_ptr()
     a.d_bg_noise = None if bg_noise is None else bg_noise.data_ptr()
     a.d_rgb, a.d_distance = rgb.data_ptr(), distance.data_ptr()
@@ -698,6 +709,53 @@ def fused_packed_train_step(params, rays_o, rays_d, offsets, ray_indices, t_star
     if offsets.numel() != rays_o.shape[0] + 1:
         raise RuntimeError("perf_b200.fused_packed_train_step: offsets must have R + 1 entries")
     return _FusedPackedTrainStep.apply(params, rays_o, rays_d, offsets, ray_indices, t_starts, t_ends, bg_noise, tc, phase, early_stop_eps)
+
+
+class _FusedLoss(torch.autograd.Function):
+    """total = w_main * smooth_l1(pred, gt, beta).mean() + w_dl * ratio * dl.sum() * inv_n  as ONE kernel that also
+    produces the gradients (`nerf.py:208-238,281-287`); backward only scales them by the incoming gradient."""
+
+    @staticmethod
+    def forward(ctx, pred, gt, dl, ratio, inv_n, beta, w_main, w_dl):
+        dev, n, R = pred.device, pred.numel(), pred.shape[0]
+        loss3 = torch.empty(3, dtype=torch.float32, device=dev)
+        g_pred = torch.empty_like(pred, dtype=torch.float32)
+        g_dl = None if dl is None else torch.empty(R, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _call(_L().perf_train_loss, _p(_chk(pred.detach(), torch.float32, "pred")), _p(_chk(gt, torch.float32, "gt")), n, R, float(beta), float(w_main),
+                  _p(None if dl is None else _chk(dl.detach(), torch.float32, "dl")), _p(ratio), _p(inv_n), float(w_dl), _p(loss3), _p(g_pred), _p(g_dl), _stream())
+        ctx.save_for_backward(g_pred, g_dl)
+        ctx.terms = loss3
+        return loss3[0], loss3[1].detach(), loss3[2].detach()
+
+    @staticmethod
+    def backward(ctx, go, _g1, _g2):
+        g_pred, g_dl = ctx.saved_tensors
+        return g_pred * go, None, (None if g_dl is None else g_dl * go), None, None, None, None, None
+
+
+def fused_loss(pred, gt, beta: float, w_main: float, dl=None, ratio=None, inv_n=None, w_dl: float = 0.0):
+    """(total, main term, distortion term); see :class:`_FusedLoss`.  ``ratio`` / ``inv_n``: device scalars or None."""
+    for t in (ratio, inv_n):
+        if t is not None and not (torch.is_tensor(t) and t.is_cuda and t.dtype == torch.float32):
+            raise RuntimeError("perf_b200.fused_loss: ratio / inv_n must be fp32 CUDA tensors")
+    return _FusedLoss.apply(pred, gt.reshape(pred.shape), dl, None if ratio is None else ratio.reshape(-1).contiguous(),
+                            None if inv_n is None else inv_n.reshape(-1).contiguous(), beta, w_main, w_dl)
+
+
+def atomic_rate(n_floats: int = 2 * 8 * 262144, n_atomics: int = 1 << 26, vec: int = 4, device="cuda", iters: int = 5) -> float:
+    """Measured L2 reduction rate (atomics / s) for random vec-wide fp32 atomics into a table the size of the eight fine
+    levels' gradient (default): the physical bound of the grid-gradient scatter (bench.py `train_roofline`)."""
+    table = torch.zeros(n_floats, dtype=torch.float32, device=device)
+    fn = lambda: _call(_L().perf_debug_atomic_rate, _p(table), n_floats, n_atomics, vec, _stream())
+    with torch.cuda.device(table.device):
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+    return n_atomics * iters / (e0.elapsed_time(e1) * 1e-3)
 
 
 def occ_points(cell_idx: Optional[torch.Tensor], n: int, res3, aabb, seed: int, device) -> torch.Tensor:

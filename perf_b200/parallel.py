@@ -21,13 +21,19 @@ def init(backend: Optional[str] = None) -> tuple:
     (NCCL on GPUs, gloo on CPU) when WORLD_SIZE > 1."""
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     if world > 1 and not dist.is_initialized():
+        import datetime
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
+        # failure detection (SURVEY 5): a rank that dies or stalls must not leave the others spinning in the step's
+        # exchange for ever -- NCCL's watchdog aborts the communicator when a collective exceeds the timeout and the
+        # error surfaces as an exception on every rank (async error handling); PERF_B200_COMM_TIMEOUT_S overrides 120 s
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "1")
+        timeout = datetime.timedelta(seconds=float(os.environ.get("PERF_B200_COMM_TIMEOUT_S", "120")))
         if backend == "nccl":
             torch.cuda.set_device(local)
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=timeout)
         else:
-            dist.init_process_group(backend)
+            dist.init_process_group(backend, timeout=timeout)
     return rank, world, local
 
 

@@ -197,6 +197,16 @@ class RaySupervision:
         return self.all_sup_rays[idx], self.all_sup_colors[idx], self.all_sup_distances[idx], self.all_sup_normals[idx]
 
 
+class _Lazy:
+    """A renderer output that costs launches to form (the scalar distortion loss): evaluated only when a caller asks for it."""
+
+    def __init__(self, fn):
+        self.fn = fn
+
+    def __call__(self):
+        return self.fn()
+
+
 class FusedAdam:
     """``torch.optim.Adam(params, lr)`` semantics (defaults betas=(.9,.999), eps=1e-8) on one flat
     fp32 parameter through perf_adam_step; exposes ``param_groups`` so ``update_lr`` reads as in
@@ -440,10 +450,11 @@ class NeRFScene:
             rgb, dist, op, dl = ops.fused_packed_train_step(param, rays_o.float(), rays_d.float(), ops.occ_sample.last_offsets, ri, ts, te,
                                                             noise, tc, phase, 1e-4)
             n_rays = (ri[-1] + 1).float()                                    # flatten_eff_distloss: ray_id.max() + 1
-            return {"is_valid": True, "rgb": rgb, "distance": dist, "opacities": op, "dist_loss": dl.sum() / n_rays,
-                    "n_samples": int(ri.numel())}
+            return {"is_valid": True, "rgb": rgb, "distance": dist, "opacities": op, "dist_loss": _Lazy(lambda: dl.sum() / n_rays),
+                    "dist_loss_rays": dl, "dist_loss_inv_n": 1.0 / n_rays, "n_samples": int(ri.numel())}
         rgb, dist, op, dl = ops.fused_train_step(param, rays_o, rays_d, jitter, noise, tc, phase)
-        return {"is_valid": True, "rgb": rgb, "distance": dist, "opacities": op, "dist_loss": dl.sum() / R}
+        return {"is_valid": True, "rgb": rgb, "distance": dist, "opacities": op, "dist_loss": _Lazy(lambda: dl.sum() / R),
+                "dist_loss_rays": dl, "dist_loss_inv_n": None}
 
     def render_once(self, rays: Rays, query_keys=("rgb",), sampling_requires_grad=False, geo_inference=False, app_inference=False):
         """`nerf.py:101-123` (differentiable path used by the train steps)."""
@@ -451,7 +462,7 @@ class NeRFScene:
         assert len(rays_o.shape) == 2
         if self.fused_train and self.nerf.training and (geo_inference != app_inference) and "weights" not in query_keys:
             res = self._render_once_fused(rays, geo_inference, app_inference)
-            return {k: res[k] for k in list(query_keys) + ["is_valid"] if k in res}
+            return {k: (res[k]() if isinstance(res[k], _Lazy) else res[k]) for k in list(query_keys) + ["is_valid"] if k in res}
         res = self.renderer.render(self.nerf, self.estimator, rays_o, rays_d, geo_inference=geo_inference, app_inference=app_inference)
         if (res is None) or (not res["is_valid"]):
             return res
@@ -510,12 +521,29 @@ class NeRFScene:
         conf, eps, loss = self.train_conf, 1e-7, 0.
         optimizer.zero_grad()
         rays, gt_colors, gt_depths, _ = sup_pool.rand_ray_color_data(self._local_batch(), rand_mode=pixel_sup_rand_mode)
-        keys = ["rgb", "distance", "dist_loss"] if self.fused_train else ["rgb", "distance", "weights", "t_starts", "t_ends", "trans", "ray_indices"]
+        one_kernel_loss = self.fused_train and conf.density_loss_weight <= eps
+        keys = (["rgb", "distance", "dist_loss_rays", "dist_loss_inv_n"] if one_kernel_loss else ["rgb", "distance", "dist_loss"]) if self.fused_train \
+            else ["rgb", "distance", "weights", "t_starts", "t_ends", "trans", "ray_indices"]
         res = self.render_once(rays, keys, app_inference=True)
         if (res is None) or (not res["is_valid"]):
             optimizer.step(valid=False)            # no samples on this rank (nerf.py:204-206): still join the exchange
             self.global_iter_step_geo += 1
             return None
+        if one_kernel_loss:
+            # nerf.py:208-238 as one launch (+ its gradients): depth smooth-L1 and the ramped distortion loss
+            use_dl = conf.distortion_loss_weight > eps
+            ratio = progress if torch.is_tensor(progress) else torch.tensor([float(np.min([progress * 2., 1]))], device=self.device)
+            loss, depth_loss, dist_loss = ops.fused_loss(res["distance"], gt_depths, 1e-2,
+                                                         conf.depth_loss_weight if conf.depth_loss_weight > eps else 0.0,
+                                                         dl=res["dist_loss_rays"] if use_dl else None, ratio=ratio if use_dl else None,
+                                                         inv_n=res["dist_loss_inv_n"] if use_dl else None,
+                                                         w_dl=conf.distortion_loss_weight if use_dl else 0.0)
+            self._log("nerf_loss/depth_loss", depth_loss, self.global_iter_step_geo)
+            self._log("nerf_loss/dist_loss", dist_loss, self.global_iter_step_geo)
+            (loss * self.LOSS_SCALE).backward()
+            optimizer.step()
+            self.global_iter_step_geo += 1
+            return loss.detach()
         if conf.depth_loss_weight > eps:
             depth_loss = F.smooth_l1_loss(res["distance"], gt_depths, beta=1e-2, reduction="mean")
             loss = loss + depth_loss * conf.depth_loss_weight
@@ -549,7 +577,10 @@ class NeRFScene:
             optimizer.step(valid=False)            # no samples on this rank (nerf.py:204-206): still join the exchange
             self.global_iter_step_app += 1
             return None
-        if conf.color_loss_weight > eps:
+        if self.fused_train and conf.color_loss_weight > eps:          # nerf.py:281-287 as one launch (+ its gradient)
+            loss, color_loss, _ = ops.fused_loss(res["rgb"], gt_colors, 5e-2, conf.color_loss_weight)
+            self._log("nerf_loss/color_loss", color_loss, self.global_iter_step_app)
+        elif conf.color_loss_weight > eps:
             color_loss = F.smooth_l1_loss(res["rgb"], gt_colors, beta=5e-2, reduction="mean")
             loss = loss + color_loss * conf.color_loss_weight
             self._log("nerf_loss/color_loss", color_loss, self.global_iter_step_app)

@@ -19,6 +19,14 @@ try:
 except Exception as e:
     print('bench unreadable', e); print(open('gpurun_out/bench_n1.err').read()[-3000:])
 PY
+timeout 300 python tools/render_variants.py 5 2>&1 | tail -5 | tee gpurun_out/render_variants.log
+timeout 120 python -c "
+import sys; sys.path.insert(0, '.')
+from perf_b200 import ops
+for vec in (4, 2, 1):
+    print('L2 atomic rate, random %d-float reductions into the 16.8 MB fine-level gradient: %.1f G atomics/s' % (vec, ops.atomic_rate(vec=vec) / 1e9))
+" 2>&1 | tail -3 | tee gpurun_out/atomic_rate.log
+timeout 120 python tools/ab_mlp_bwd.py 2>&1 | tail -2 | tee gpurun_out/ab_mlp_bwd.log
 if [ -z "$SKIP_NCU" ]; then
   PHASES=geo bash tools/profile_train.sh 2>&1 | tail -14; cp gpurun_out/train_launches.csv gpurun_out/train_launches_geo.csv
   PHASES=app bash tools/profile_train.sh 2>&1 | tail -14; cp gpurun_out/train_launches.csv gpurun_out/train_launches_app.csv
