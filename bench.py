@@ -289,6 +289,7 @@ def bench_train(dev, rank, world, steps=20, warmup=5):
             opt = FusedAdam(net.params, lr=1e-3, module=net)
             graphed = GraphedTrainStep(sc, phase, pool, opt)       # the whole step = one CUDA-graph launch
             ms = timed(lambda: graphed(0.5), steps)
+            graphed.finish()                                       # last step's shadow shard + fp32 master on every rank
             dst[f"{phase}_ms_per_step"] = ms
             dst[f"{phase}_msamples_per_s"] = batch * S / ms / 1e3
             if rule == "fixed_global":
@@ -311,7 +312,55 @@ def bench_train(dev, rank, world, steps=20, warmup=5):
     sc.train_conf["pixel_loss_batch_size"] = 8192
     if world > 1:
         out["dp_check"] = _dp_check(sc, dev, rank, world)
+    else:
+        out["roofline"] = bench_train_roofline(dev)
     return out
+
+
+def bench_train_roofline(dev):
+    """Physical rooflines of the two training kernels that are NOT gather-bound (N = 1 only):
+    the grid-gradient scatter against the measured L2 reduction rate, the Adam pass against the measured HBM bandwidth."""
+    import torch
+    from perf_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    R = 8192
+    o = ((torch.rand(R, 3, generator=g) - 0.5) * 0.2).to(dev)
+    d = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1).to(dev)
+    jit = torch.rand(R, generator=g).to(dev)
+    dfeat = torch.randn(R * S, 32, generator=g).to(dev)
+    table = torch.zeros(ops.PERF_GRID.n_entries, 2, device=dev)
+
+    def timed(fn, iters=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+    ms_scatter = timed(lambda: ops.hashgrid_bwd_rays(o, d, jit, S, 1e-2, 1.0, dfeat, out=table))
+    rate4 = ops.atomic_rate(vec=4, device=dev)
+    # fine levels (8..15): per sample and level 4 x-neighbour pairs, one 16-byte reduction when the pair shares a slot
+    # (cell x even: half of the time), else two 8-byte ones -> 6 on average; coarse levels flush once per cell run
+    fine_atomics = R * S * 8 * 6
+    n = 6644288
+    p, gr, m, v = (torch.randn(n, generator=g).to(dev) for _ in range(4))
+    v.abs_()
+    half = torch.empty(n, dtype=torch.float16, device=dev)
+    ms_adam = timed(lambda: ops.adam_step(p, gr, m, v, 3, 1e-3, params_half=half))
+    peak, peak_src = measured_peak_hbm()
+    adam_gbs = n * 30 / (ms_adam * 1e-3) / 1e9
+    return {"scatter": {"kernels": "hashgrid_bwd_march_kernel + hashgrid_bwd_rays_kernel (8192 x 128 samples, both launches)",
+                        "ms": ms_scatter, "fine_level_reductions_per_step": fine_atomics,
+                        "achieved_g_reductions_per_s": fine_atomics / (ms_scatter * 1e-3) / 1e9,
+                        "peak_g_reductions_per_s": rate4 / 1e9, "frac": fine_atomics / (ms_scatter * 1e-3) / rate4,
+                        "peak_source": "measured in this run: perf_debug_atomic_rate, random 16-byte fp32 reductions into a 16.8 MB table",
+                        "note": "achieved counts only the fine levels' reductions over the time of BOTH launches (they overlap on two streams), so frac is a lower bound"},
+            "adam": {"kernel": "adam_kernel", "ms": ms_adam, "bytes_per_param": 30, "achieved": adam_gbs, "peak": peak, "unit": "GB/s",
+                     "frac": adam_gbs / peak, "peak_source": peak_src}}
 
 
 def bench_extra_configs(renderer, dev, rank, world, steps=2):
@@ -335,28 +384,31 @@ def bench_extra_configs(renderer, dev, rank, world, steps=2):
             dist.barrier()
         torch.cuda.synchronize()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-        t_render = t_gather = 0.0
+        t_render = t_total = 0.0
         for _ in range(steps):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
             ev[0].record()
             r = run()
             ev[1].record()
             if gather:
                 parallel.gather_row_tiles(torch.cat([r["rgb"], r["distance"]], -1), h)
             ev[2].record()
-            if world > 1:
-                dist.barrier()
             torch.cuda.synchronize()
-            t_render += ev[0].elapsed_time(ev[1]); t_gather += ev[1].elapsed_time(ev[2])
-        t = torch.tensor([t_render / steps, t_gather / steps], dtype=torch.float64, device=dev)
+            t_render += ev[0].elapsed_time(ev[1]); t_total += ev[0].elapsed_time(ev[2])
+        t = torch.tensor([t_render / steps, t_total / steps], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_r, ms_g = (float(v) for v in t.tolist())
+        ms_r, ms_t = (float(v) for v in t.tolist())
         n = h * w * s
         out[key] = {"H": h, "W": w, "samples_per_ray": s, "render_ms": ms_r, "msamples_per_s": n / ms_r / 1e3,
                     "rays_per_s": h * w / (ms_r / 1e3)}
         if gather:
-            out[key].update({"tile_gather_ms": ms_g, "tile_bytes_per_gpu": (sl.stop - sl.start) * w * 16,
-                             "msamples_per_s_incl_gather": n / (ms_r + ms_g) / 1e3,
+            # both maxima over ranks from a common barrier: the frame is done when rank 0 holds every tile; the exposed
+            # gather time is what that adds to the slowest rank's render (rank 0 renders the cheap pole rows and waits)
+            out[key].update({"frame_ms_incl_gather": ms_t, "tile_gather_exposed_ms": ms_t - ms_r, "tile_bytes_per_gpu": (sl.stop - sl.start) * w * 16,
+                             "msamples_per_s_incl_gather": n / ms_t / 1e3,
                              "note": "gather = torch.cat of rgb+distance into [rows,W,4] fp32 + NCCL gather to rank 0" if world > 1 else "single GPU: no gather"})
         del bufs
     return out

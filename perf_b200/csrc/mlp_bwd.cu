@@ -109,38 +109,59 @@ __host__ __device__ __forceinline__ void out_layer_backward(uint8_t* dst, int ro
 // ---- the per-thread phases of one tile (thread t = row t).  Between two phases every thread of the CTA must have
 // finished the previous one (__syncthreads in the kernel, a loop over t in the host harness).
 
-// phase 1: stage the saved activations and dz as operand images, output-layer backward on CUDA cores
+// phase 1: stage the saved activations and dz as operand images, output-layer backward on CUDA cores.
+// Split in two so that the kernel can issue the global loads of tile i+1 (into registers) right after tile i has been
+// staged: they are in flight during tile i's MMAs and epilogues instead of at the head of tile i+1.
 template <bool TWO>
-__host__ __device__ __forceinline__ void bwd_phase_stage(uint8_t* smem, const float* s_wout, const MlpBwdArgs& a, uint64_t tile, int t)
+struct TileRegs { uint4 f4[4], h1v[8], hlast[TWO ? 8 : 1]; float dz[3]; };
+
+template <bool TWO>
+__host__ __device__ __forceinline__ void bwd_phase_load(const MlpBwdArgs& a, uint64_t tile, int t, TileRegs<TWO>& r)
 {
-    using L = BwdSmem<TWO>;
     const uint64_t row = tile * TILE + t;
     const bool valid = row < a.N;
     const int n_out = (int)a.n_out;
-    uint4 f4[4], h1v[8], hlast[8];
-    float dz[3] = {0.f, 0.f, 0.f};
     const uint4 z4 = make_uint4(0, 0, 0, 0);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) f4[q] = valid ? a.feat[row * 4 + q] : z4;
+    for (int q = 0; q < 4; ++q) r.f4[q] = valid ? a.feat[row * 4 + q] : z4;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) h1v[q] = valid ? a.h1[row * 8 + q] : z4;
+    for (int q = 0; q < 8; ++q) r.h1v[q] = valid ? a.h1[row * 8 + q] : z4;
     if constexpr (TWO) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) hlast[q] = valid ? a.h2[row * 8 + q] : z4;
+        for (int q = 0; q < 8; ++q) r.hlast[q] = valid ? a.h2[row * 8 + q] : z4;
     }
 #pragma unroll
-    for (int o = 0; o < 3; ++o) if (valid && o < n_out) dz[o] = a.dz[row * n_out + o];
-    store_row(smem + L::FEAT, t, f4);
-    store_row(smem + L::H1, t, h1v);
+    for (int o = 0; o < 3; ++o) r.dz[o] = (valid && o < n_out) ? a.dz[row * n_out + o] : 0.f;
+}
+
+template <bool TWO>
+__host__ __device__ __forceinline__ void bwd_phase_store(uint8_t* smem, const float* s_wout, const MlpBwdArgs& a, int t, const TileRegs<TWO>& r)
+{
+    using L = BwdSmem<TWO>;
+    const int n_out = (int)a.n_out;
+    const uint4 z4 = make_uint4(0, 0, 0, 0);
+    store_row(smem + L::FEAT, t, r.f4);
+    store_row(smem + L::H1, t, r.h1v);
     // dz as 16 fp16 columns (cols >= n_out are zero)
-    *reinterpret_cast<uint4*>(smem + L::DZP + (0 * TILE + t) * 16) = make_uint4(pack_half2(dz[0], dz[1]), pack_half2(dz[2], 0.f), 0u, 0u);
+    *reinterpret_cast<uint4*>(smem + L::DZP + (0 * TILE + t) * 16) = make_uint4(pack_half2(r.dz[0], r.dz[1]), pack_half2(r.dz[2], 0.f), 0u, 0u);
     *reinterpret_cast<uint4*>(smem + L::DZP + (1 * TILE + t) * 16) = z4;
     if constexpr (TWO) {
-        store_row(smem + L::H2, t, hlast);
-        out_layer_backward(smem + L::DH2, t, hlast, dz, n_out, s_wout);
+        uint4 hl[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) hl[q] = r.hlast[q];
+        store_row(smem + L::H2, t, hl);
+        out_layer_backward(smem + L::DH2, t, hl, r.dz, n_out, s_wout);
     } else {
-        out_layer_backward(smem + L::DH1, t, h1v, dz, n_out, s_wout);
+        out_layer_backward(smem + L::DH1, t, r.h1v, r.dz, n_out, s_wout);
     }
+}
+
+template <bool TWO>
+__host__ __device__ __forceinline__ void bwd_phase_stage(uint8_t* smem, const float* s_wout, const MlpBwdArgs& a, uint64_t tile, int t)
+{
+    TileRegs<TWO> r;
+    bwd_phase_load<TWO>(a, tile, t, r);
+    bwd_phase_store<TWO>(smem, s_wout, a, t, r);
 }
 
 // CUDA-core twin of a data-gradient MMA: D[row][n0 + j] = sum_k A[row][k] * Wimg[k][n0 + j]
@@ -266,8 +287,11 @@ __global__ void __launch_bounds__(128) mlp_bwd_kernel(const MlpBwdArgs a)
 
     const uint64_t n_tiles = (a.N + TILE - 1) / TILE;
     bool first = true;
+    TileRegs<TWO> regs;
+    if (blockIdx.x < n_tiles) bwd_phase_load<TWO>(a, blockIdx.x, t, regs);
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, first = false) {
-        bwd_phase_stage<TWO>(smem, s_wout, a, tile, t);
+        bwd_phase_store<TWO>(smem, s_wout, a, t, regs);
+        if (tile + gridDim.x < n_tiles) bwd_phase_load<TWO>(a, tile + gridDim.x, t, regs);     // in flight during this tile's MMAs
         if constexpr (!SIMT) { fence_proxy_async(); tc_fence_before(); }
         __syncthreads();
 

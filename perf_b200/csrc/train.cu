@@ -505,11 +505,35 @@ int perf_hashgrid_bwd_rays(const perf_grid_cfg* cfg, const float* aabb6, const f
     unsigned pieces = 1;
     while (pieces < 8 && (uint64_t)R * n_agg * pieces < (uint64_t)num_sms() * 2048 && n_samples / (pieces * 2) >= 16) pieces *= 2;
     dim3 g_agg((unsigned)((R + 127) / 128), n_agg, pieces);
+    // The two launches touch disjoint halves of the gradient table and both sit on atomic latency, not bandwidth: run the
+    // coarse one on a side stream (fork / join through events; capturable into a CUDA graph).  PERF_B200_SCATTER_OVERLAP=0
+    // serialises them on the caller's stream as in round 1.
+    cudaStream_t user = (cudaStream_t)stream, side = user;
+    struct SideStream { cudaStream_t s; cudaEvent_t fork, join; };
+    static thread_local SideStream s_sides[64] = {};                  // one per device, created on first use, never freed
+    const char* env_ov = getenv("PERF_B200_SCATTER_OVERLAP");
+    bool overlap = !(env_ov && env_ov[0] == '0') && a.lt.n_levels > n_agg;
+    cudaEvent_t ev_join = nullptr;
+    if (overlap) {
+        int dev = 0; PERF_CUDA(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 64) overlap = false;
+        else {
+            SideStream& ss = s_sides[dev];
+            if (!ss.s) {
+                PERF_CUDA(cudaStreamCreateWithFlags(&ss.s, cudaStreamNonBlocking));
+                PERF_CUDA(cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming));
+                PERF_CUDA(cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming));
+            }
+            side = ss.s; ev_join = ss.join;
+            PERF_CUDA(cudaEventRecord(ss.fork, user));
+            PERF_CUDA(cudaStreamWaitEvent(side, ss.fork, 0));
+        }
+    }
     // the coarse flush uses the same 16-byte pair atomics: 0.586 -> 0.528 ms for both scatter launches of an 8192 x 128
     // step (tools/ab_scatter_v4.py, B200, round 2); PERF_B200_SCATTER_V4_COARSE=0 restores the 8-byte flush
     const char* env_v4c = getenv("PERF_B200_SCATTER_V4_COARSE");
-    if (!(env_v4c && env_v4c[0] == '0') && (uintptr_t)a.dtable % 16 == 0) hashgrid_bwd_march_kernel<true><<<g_agg, 128, 0, (cudaStream_t)stream>>>(a);
-    else hashgrid_bwd_march_kernel<false><<<g_agg, 128, 0, (cudaStream_t)stream>>>(a);
+    if (!(env_v4c && env_v4c[0] == '0') && (uintptr_t)a.dtable % 16 == 0) hashgrid_bwd_march_kernel<true><<<g_agg, 128, 0, side>>>(a);
+    else hashgrid_bwd_march_kernel<false><<<g_agg, 128, 0, side>>>(a);
     PERF_LAUNCH_CHECK();
     if (a.lt.n_levels > n_agg) {
         dim3 g_rest((unsigned)((N + 255) / 256), a.lt.n_levels - n_agg);
@@ -517,9 +541,13 @@ int perf_hashgrid_bwd_rays(const perf_grid_cfg* cfg, const float* aabb6, const f
         // launches of an 8192 x 128 step on a B200 (tools/ab_scatter_v4.py); PERF_B200_SCATTER_V4=0 restores the 8-byte path
         const char* env_v4 = getenv("PERF_B200_SCATTER_V4");
         const bool want_v4 = !(env_v4 && env_v4[0] == '0');
-        if (want_v4 && (uintptr_t)b.dtable % 16 == 0) hashgrid_bwd_rays_kernel<true><<<g_rest, 256, 0, (cudaStream_t)stream>>>(b);
-        else hashgrid_bwd_rays_kernel<false><<<g_rest, 256, 0, (cudaStream_t)stream>>>(b);
+        if (want_v4 && (uintptr_t)b.dtable % 16 == 0) hashgrid_bwd_rays_kernel<true><<<g_rest, 256, 0, user>>>(b);
+        else hashgrid_bwd_rays_kernel<false><<<g_rest, 256, 0, user>>>(b);
         PERF_LAUNCH_CHECK();
+    }
+    if (overlap) {
+        PERF_CUDA(cudaEventRecord(ev_join, side));
+        PERF_CUDA(cudaStreamWaitEvent(user, ev_join, 0));
     }
     return PERF_OK;
 }

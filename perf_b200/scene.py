@@ -274,7 +274,10 @@ class FusedAdam:
         if not self.stage_exchange(valid):
             return
         self.stage_adam()
-        self.stage_gather()
+        if getattr(self, "skip_gather", False):              # the gather is captured at the start of the NEXT step
+            self._mark_updated()
+        else:
+            self.stage_gather()
 
     def stage_exchange(self, valid: bool = True) -> bool:
         """Gradient exchange: reduce-scatter (sharded) or all-reduce + mean.  False = nothing to do."""
@@ -308,6 +311,9 @@ class FusedAdam:
             if self._half_pad is not None:
                 self.module._half().copy_(self._hbuf[:self.param.numel()])
             self.master_stale = True
+        self._mark_updated()
+
+    def _mark_updated(self):
         # the kernel wrote through .data: bump autograd's version counter so version-keyed caches notice
         torch._C._increment_version([self.param])   # takes an ITERABLE of tensors
         if self.module is not None:                          # the shadow is already current for the new version
@@ -376,6 +382,13 @@ class NeRFScene:
 
     # ---- inference ---------------------------------------------------------------------------
     def _sync_fused(self):
+        # (sharded data parallelism with the shadow all-gather moved to the START of the next step, GraphedTrainStep)
+        join, pend = getattr(self, "_join_gather", None), getattr(self, "_pending_gather", None)
+        if join is not None:                                # capture of a step: the side-stream all-gather joins here, before the pack
+            join(); self._join_gather = None
+        elif pend is not None and not torch.cuda.is_current_stream_capturing():
+            pend.stage_gather(); self._pending_gather = None            # eager use between replays: complete the shadow first
+            self._fused_key = None
         g, a = self.nerf.geo_mlp.params, self.nerf.app_mlp.params
         key = (g._version, a._version, g.data_ptr(), a.data_ptr())
         if key != self._fused_key:
@@ -498,6 +511,8 @@ class NeRFScene:
                 geo_step(progress)
             else:
                 self.train_one_step_geo(geo_optimizer, sup_pool, pixel_sup_rand_mode, progress=progress)
+        if geo_step is not None:
+            geo_step.finish()
         geo_optimizer.sync_master()
         app_optimizer = FusedAdam(self.nerf.app_mlp.params, lr=self.train_conf.app_optimizer.init_lr, module=self.nerf.app_mlp)
         app_step = GraphedTrainStep(self, "app", sup_pool, app_optimizer) if self.graph_train and app_res_iters > 0 else None
@@ -507,6 +522,8 @@ class NeRFScene:
                 app_step(iter_i / app_res_iters)
             else:
                 self.train_one_step_app(app_optimizer, sup_pool, pixel_sup_rand_mode, progress=iter_i / app_res_iters)
+        if app_step is not None:
+            app_step.finish()
         app_optimizer.sync_master()
 
     def _local_batch(self):
@@ -667,10 +684,29 @@ class GraphedTrainStep:
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self._prepare(0.5)
+        # Sharded DP: the all-gather of the fp16 shadow depends only on the PREVIOUS step's Adam, the batch draw on nothing:
+        # capture the gather at the START of the step on a side stream, concurrent with the draw, joined before the table
+        # pack (hides ~60 us of NCCL at 8 GPUs behind ~50 us of small kernels).  The shard a step's Adam writes is then
+        # gathered by the next replay -- or by finish() / the next eager _sync_fused().  PERF_B200_AG_OVERLAP=0: off.
+        import os as _os
+        self.overlap_gather = (not split) and optimizer.sharded and _os.environ.get("PERF_B200_AG_OVERLAP", "1") != "0"
         if not split:
             self.graph = torch.cuda.CUDAGraph()
+            side_ag = torch.cuda.Stream(device=dev) if self.overlap_gather else None
             with torch.cuda.graph(self.graph):
+                if self.overlap_gather:
+                    main = torch.cuda.current_stream(dev)
+                    side_ag.wait_stream(main)
+                    with torch.cuda.stream(side_ag):
+                        optimizer._hbuf = self.net._half() if optimizer._half_pad is None else optimizer._half_pad
+                        optimizer.stage_gather()
+                    scene._join_gather = lambda: main.wait_stream(side_ag)
+                    scene._pending_gather = None
+                    optimizer.skip_gather = True
                 self.loss = self._body()
+                if self.overlap_gather and scene._join_gather is not None:       # body never reached _sync_fused: join here
+                    scene._join_gather(); scene._join_gather = None
+            optimizer.skip_gather = False                      # (capture records, it does not execute: nothing to complete here)
             self.graphs = [self.graph]
         else:
             pool = torch.cuda.graph_pool_handle()
@@ -724,7 +760,16 @@ class GraphedTrainStep:
         self.net._half_key = (p._version, p.data_ptr())
         self.scene._fused_key = None
         self.opt.master_stale = self.opt.sharded
+        if self.overlap_gather:
+            self.scene._pending_gather = self.opt             # this step's shard is gathered by the next replay / eager use
         return self.loss
+
+    def finish(self):
+        """Complete the state after the last replay: gather the last step's shadow shard (overlap mode) and the fp32 master."""
+        if self.overlap_gather and getattr(self.scene, "_pending_gather", None) is self.opt:
+            self.opt.stage_gather(); self.scene._pending_gather = None
+            self.scene._fused_key = None
+        self.opt.sync_master()
 
     def last_stage_ms(self):
         """(split mode) device time of the four stages of the last call, after a synchronize."""

@@ -151,6 +151,72 @@ def test_chunk_parallel_composite_backward_equals_ray_sequential(golden_field):
     assert F.cosine_similarity(gc, gs, dim=0) > 0.999999
 
 
+@pytest.mark.parametrize("case", ["depth+dist", "depth+dist+inv_n", "colour"])
+def test_one_kernel_loss_matches_torch(case):
+    """perf_train_loss (loss terms + gradients in one launch) against the reference's torch expressions
+    (nerf.py:208-238 / :281-287) through autograd, incl. the smooth-L1 switch point on both sides of beta."""
+    from perf_b200 import ops
+    g = torch.Generator().manual_seed(17)
+    R = 777
+    if case == "colour":
+        pred = (torch.rand(R, 3, generator=g)).cuda().requires_grad_(True)
+        gt = (pred.detach().cpu() + (torch.rand(R, 3, generator=g) - .5) * 0.2).cuda()       # errors around beta = 5e-2
+        total, main, _ = ops.fused_loss(pred, gt, 5e-2, 0.7)
+        want = F.smooth_l1_loss(pred.detach().clone().requires_grad_(True), gt, beta=5e-2) * 0.7
+        p2 = pred.detach().clone().requires_grad_(True)
+        want = F.smooth_l1_loss(p2, gt, beta=5e-2) * 0.7
+        (total * 128).backward(); (want * 128).backward()
+        assert abs(float(total) - float(want)) <= 1e-6 * max(1, abs(float(want)))
+        assert torch.allclose(pred.grad, p2.grad, rtol=1e-5, atol=1e-9)
+        return
+    pred = (torch.rand(R, 1, generator=g)).cuda().requires_grad_(True)
+    gt = (pred.detach().cpu() + (torch.rand(R, 1, generator=g) - .5) * 0.04).cuda()             # errors around beta = 1e-2
+    dl = torch.rand(R, generator=g).cuda().requires_grad_(True)
+    ratio = torch.tensor([0.8], device="cuda")
+    inv_n = torch.tensor([1.0 / 700.0], device="cuda") if case.endswith("inv_n") else None
+    total, main, dterm = ops.fused_loss(pred, gt, 1e-2, 1.0, dl=dl, ratio=ratio, inv_n=inv_n, w_dl=0.1)
+    p2, d2 = pred.detach().clone().requires_grad_(True), dl.detach().clone().requires_grad_(True)
+    n = 700.0 if inv_n is not None else float(R)
+    want = F.smooth_l1_loss(p2, gt, beta=1e-2) + (d2.sum() / n) * 0.1 * ratio[0]
+    (total * 128).backward(); (want * 128).backward()
+    assert abs(float(total) - float(want)) <= 2e-6 * max(1, abs(float(want)))
+    assert abs(float(dterm) - float(d2.sum() / n)) <= 1e-5 * float(d2.sum() / n)
+    assert torch.allclose(pred.grad, p2.grad, rtol=1e-5, atol=1e-9) and torch.allclose(dl.grad, d2.grad, rtol=1e-5)
+
+
+def test_scatter_streams_overlap_equals_serial_and_captures_into_a_graph():
+    """perf_hashgrid_bwd_rays forks its coarse-level launch onto a side stream: same gradient as the serial order, and the
+    fork / join survives CUDA-graph capture (the whole training step is captured)."""
+    from perf_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    R, S = 1000, 64
+    o = ((torch.rand(R, 3, generator=g) - 0.5) * 0.2).cuda()
+    d = F.normalize(torch.randn(R, 3, generator=g), dim=-1).cuda()
+    dfeat = torch.randn(R * S, 32, generator=g).cuda()
+    os.environ["PERF_B200_SCATTER_OVERLAP"] = "0"
+    try:
+        want = ops.hashgrid_bwd_rays(o, d, None, S, 1e-2, 1.0, dfeat).clone()
+    finally:
+        os.environ.pop("PERF_B200_SCATTER_OVERLAP", None)
+    got = ops.hashgrid_bwd_rays(o, d, None, S, 1e-2, 1.0, dfeat).clone()
+    assert float(want.abs().max()) > 0 and (got - want).abs().max() <= 1e-4 * want.abs().max()
+    out = torch.zeros_like(want)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        ops.hashgrid_bwd_rays(o, d, None, S, 1e-2, 1.0, dfeat, out=out)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out.zero_()
+        ops.hashgrid_bwd_rays(o, d, None, S, 1e-2, 1.0, dfeat, out=out)
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    assert (out - want).abs().max() <= 1e-4 * want.abs().max()
+
+
 def test_fit_reduces_losses_and_checkpoint_roundtrip(golden_field, tmp_path):
     from perf_b200 import synthetic
     from perf_b200.config import Conf

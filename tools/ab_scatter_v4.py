@@ -33,8 +33,12 @@ def run(v4, iters=20, coarse=False):
     return e0.elapsed_time(e1) / iters, res
 
 
+os.environ["PERF_B200_SCATTER_OVERLAP"] = "0"
 t0, r0 = run(False)
 t1, r1 = run(True)
 t2, r2 = run(True, coarse=True)
+os.environ["PERF_B200_SCATTER_OVERLAP"] = "1"
+t3, r3 = run(True, coarse=True)
+print(f"coarse launch on a side stream (default): {t3:.3f} ms; max|diff| {(r0 - r3).abs().max().item():.3e}")
 print(f"coarse+fine scatter: 8-byte atomics {t0:.3f} ms, pair atomics on the fine levels (default) {t1:.3f} ms, also on the coarse flush {t2:.3f} ms; "
       f"max|diff| {(r0 - r1).abs().max().item():.3e} / {(r0 - r2).abs().max().item():.3e} of {r0.abs().max().item():.3e}")

@@ -10,7 +10,7 @@ KEEP = re.compile(r"gpu__time_duration.sum|dram__bytes_(read|write).sum$|lts__t_
                   r"sm__warps_active.avg.pct_of_peak_sustained_active|launch__(registers_per_thread|occupancy_limit|grid_size|block_size|shared_mem_per_block_dynamic|waves)|"
                   r"sm__inst_executed.sum$|sm__inst_executed_pipe_(lsu|alu|fma|fmaheavy|xu|tensor|uniform).*sum$|smsp__inst_executed.avg.per_cycle_active|"
                   r"pipe_tensor.*pct|smsp__issue_active.avg.pct|l1tex__data_pipe_lsu_wavefronts(_mem_shared|_mem_lg)?.sum$|"
-                  r"smsp__average_warp.*issue_stalled.*_per_warp_active.pct|sm__cycles_elapsed.max|l1tex__data_bank_conflicts_pipe_lsu.sum|achieved_occupancy|"
+                  r"smsp__average_warp.*issue_stalled.*_per_warp_active.pct|smsp__pcsamp_warps_issue_stalled_[a-z_]+$|smsp__pcsamp_sample_buffer_full|sm__cycles_elapsed.max|l1tex__data_bank_conflicts_pipe_lsu.sum|achieved_occupancy|"
                   r"smsp__thread_inst_executed_per_inst_executed.ratio|lts__t_sectors_srcunit_tex_op_read.sum$|l1tex__m_xbar2l1tex_read_sectors.sum$")
 for r in rows[2:]:
     name = r[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "?"

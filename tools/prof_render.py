@@ -5,7 +5,7 @@ import torch
 import bench
 from perf_b200.renderer import FusedPanoRenderer
 geo, app = bench.make_field("cuda")
-r = FusedPanoRenderer.from_params(geo, app)
+r = FusedPanoRenderer.from_params(geo, app, kernel=os.environ.get('KERNEL', 'march'))
 pose = bench.bench_pose()
 rows = int(os.environ.get("ROWS", 256))
 for _ in range(2):
