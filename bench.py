@@ -314,6 +314,11 @@ def bench_train(dev, rank, world, steps=20, warmup=5):
         out["dp_check"] = _dp_check(sc, dev, rank, world)
     else:
         out["roofline"] = bench_train_roofline(dev)
+        occ = bench_train_occ(dev)
+        for phase in ("geo", "app"):                          # per-sample cost against the fixed-S step
+            occ[f"{phase}_ns_per_sample_vs_fixed_s"] = (1e3 * occ[f"{phase}_ms_per_step"] / occ[f"{phase}_samples_per_step"] * 1e3) / \
+                (1e3 * out[f"{phase}_ms_per_step"] / (8192 * S) * 1e3)
+        out["occ"] = occ
     return out
 
 
@@ -361,6 +366,49 @@ def bench_train_roofline(dev):
                         "note": "achieved counts only the fine levels' reductions over the time of BOTH launches (they overlap on two streams), so frac is a lower bound"},
             "adam": {"kernel": "adam_kernel", "ms": ms_adam, "bytes_per_param": 30, "achieved": adam_gbs, "peak": peak, "unit": "GB/s",
                      "frac": adam_gbs / peak, "peak_source": peak_src}}
+
+
+def bench_train_occ(dev, steps=20, warmup=5):
+    """The optimisation step on the sampler PeRF really trains with (`estimator_type: occ`, configs/nerf.yaml:25): occupancy
+    grid = surface shell of the synthetic box room at 256^3, intervals of 5e-4, 8192 rays per step, fused packed path
+    (perf_occ_count/write, perf_fields_packed, perf_composite_packed_fwd/bwd, perf_mlp_bwd, perf_hashgrid_bwd_merged).
+    Eager (one host read of the sample count per step, as nerfacc has).  N = 1 only."""
+    import torch
+    from perf_b200 import ops, synthetic
+    from perf_b200.scene import FusedAdam, NeRFScene, RaySupervision
+    h, w = 512, 1024
+    rgb, distance = synthetic.smooth_rgb(h, w, device=dev), synthetic.box_room_distance(h, w, device=dev)
+    sc = NeRFScene(estimator_type="occ", occ_resolution=256, device=dev)
+    pool = RaySupervision.from_panorama(torch.eye(4), rgb, distance)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    sc.build_occupancy(pool)
+    e1.record()
+    torch.cuda.synchronize()
+    out = {"rays_per_step": 8192, "render_step_size": sc.OCC_STEP, "occ_resolution": 256,
+           "occupancy_build_ms_256_updates": e0.elapsed_time(e1), "occupied_cell_fraction": float(sc.estimator.binaries.float().mean())}
+    sc.set_train()
+    for phase in ("geo", "app"):
+        net = sc.nerf.geo_mlp if phase == "geo" else sc.nerf.app_mlp
+        opt = FusedAdam(net.params, lr=1e-3, module=net)
+        step = sc.train_one_step_geo if phase == "geo" else sc.train_one_step_app
+        for _ in range(warmup):
+            step(opt, pool, progress=0.5)
+        torch.cuda.synchronize()
+        n_samples = 0
+        e0.record()
+        for _ in range(steps):
+            step(opt, pool, progress=0.5)
+            n_samples += int(ops.occ_sample.last_offsets[-1])          # already on the host path of the step (sample count)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out[f"{phase}_ms_per_step"] = ms
+        out[f"{phase}_samples_per_step"] = n_samples / steps
+        out[f"{phase}_samples_per_ray"] = n_samples / steps / 8192
+        out[f"{phase}_msamples_per_s"] = n_samples / steps / ms / 1e3
+    return out
 
 
 def bench_extra_configs(renderer, dev, rank, world, steps=2):
@@ -491,10 +539,16 @@ def run_ours(args, rank, world, local_rank):
     e2e_value = samples / (e2e_ms / args.steps / 1e3) / 1e6
     peak, peak_src = measured_peak_hbm()
     achieved = ALG_BYTES_PER_SAMPLE * samples / world / (ms_per_step / 1e3) / 1e9     # per-GPU kernel
-    traffic = None
-    try:                                              # dram__bytes of this very launch from the committed ncu capture
-        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+    traffic, physical = None, {}
+    try:                                              # counters of this very launch from the committed ncu capture (profiles/)
+        t = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
         traffic = (t["dram_bytes_read"] + t["dram_bytes_write"]) if world == 1 else None
+        # the PHYSICAL limiter: the tables are L2-resident, so `frac` (algorithmic bytes / HBM peak) is not a utilisation;
+        # the unit that is busiest is the L1TEX pipe of the gathers, then instruction issue
+        physical = {"frac_physical": t["l1tex_throughput_pct"] / 100.0, "physical_unit": "L1TEX throughput (ncu l1tex__throughput.avg.pct_of_peak_sustained_elapsed)",
+                    "issue_active_frac": t["issue_active_pct"] / 100.0, "l2_throughput_frac": t["lts_throughput_pct"] / 100.0,
+                    "tensor_pipe_frac": t["tensor_pipe_pct"] / 100.0,
+                    "physical_source": "profiles/r02_traffic.json: one ncu --set full capture of the same launch, not measured in this run"}
     except Exception:
         pass
     cpu_v, cpu_s, cores = cpu_oracle_sample(4096) if world == 1 else (None, None, None)     # PyTorch port (+ parity reference)
@@ -513,7 +567,7 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "perf::render_march_kernel<PANO=true,SIMT=false,NDENSE=4>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_sample": ALG_BYTES_PER_SAMPLE,
+                         "algorithmic_bytes_per_sample": ALG_BYTES_PER_SAMPLE, **physical,
                          "note": "tables (26.6 MB fp16) are L2-resident: DRAM traffic is far below algorithmic bytes, see profiles/"}}
     if cpu_v is not None:
         # parity of THIS run's kernel against the CPU restatement on the very rays the baseline timed

@@ -304,6 +304,10 @@ int perf_composite_packed_bwd(int phase, const int64_t* d_offsets, const float* 
 int perf_hashgrid_bwd_merged(const perf_grid_cfg* cfg, const float* d_x01, const float* d_dfeat, uint64_t N, float* d_dtable,
                              uint32_t n_merge_levels, void* stream);
 
+/* Batch draw (sup_info.py:253-259): dst_k[b, :] = src_k[idx[b], :] for up to 6 row-major fp32 arrays of row widths
+ * h_width[k] in one launch.  h_src / h_dst: HOST arrays of device pointers. */
+int perf_gather_rows(const int64_t* d_idx, uint64_t B, int n_arrays, const float* const* h_src, float* const* h_dst, const int* h_width, void* stream);
+
 /* Diagnostic (bench.py's train_roofline denominator): n_atomics reductions of `vec` (1, 2 or 4) floats at pseudo-random
  * vec-aligned slots of d_table [n_floats] -- the L2 atomic rate that bounds the grid-gradient scatter. */
 int perf_debug_atomic_rate(float* d_table, uint64_t n_floats, uint64_t n_atomics, int vec, void* stream);

@@ -101,7 +101,11 @@ def network_param_count(grid: GridConfig, mlp: MLPConfig) -> int:
 # ------------------------------------------------------------------ experiment configuration
 class Conf(dict):
     """Attribute-style dict (stands in for the OmegaConf node the reference receives from Hydra)."""
-    __getattr__ = dict.__getitem__
+    def __getattr__(self, name):
+        try:
+            return self[name]
+        except KeyError:
+            raise AttributeError(name) from None         # hasattr / copy.deepcopy / pickle rely on AttributeError
 
     @staticmethod
     def wrap(v):
@@ -123,16 +127,20 @@ def _coerce(text: str):
     return v
 
 
+import re as _re
+
+_YAML11_MISSED_FLOAT = _re.compile(r"^[+-]?(\d+\.?\d*|\.\d+)[eE][+-]?\d+$")
+
+
 def _fix_floats(node):
     if isinstance(node, dict):
         return {k: _fix_floats(v) for k, v in node.items()}
     if isinstance(node, list):
         return [_fix_floats(v) for v in node]
-    if isinstance(node, str):
-        try:
-            return float(node)
-        except ValueError:
-            return node
+    if isinstance(node, str) and _YAML11_MISSED_FLOAT.match(node):
+        # PyYAML (YAML 1.1) reads "1e-2" as a string because it has no dot; OmegaConf / YAML 1.2 read a float.  Only that
+        # shape is converted: "007", "1_000", "nan", dates or names stay what the file said
+        return float(node)
     return node
 
 

@@ -257,6 +257,21 @@ hashgrid_bwd_kernel(LevelTable lt, int level0, const float* __restrict__ x01, co
     }
 }
 
+// ---- batch draw: rows idx[b] of up to 6 row-major fp32 arrays in ONE launch (sup_info.py:253-259 gathers rays_o, rays_d,
+// colours, distances, normals with the same index vector: 5-6 index kernels per training step otherwise)
+struct GatherArgs { const float* src[6]; float* dst[6]; int width[6]; int n_arrays; const int64_t* idx; uint64_t B; };
+__global__ void __launch_bounds__(256) gather_rows_kernel(const GatherArgs a)
+{
+    const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    const int64_t r = a.idx[b];
+    for (int k = 0; k < a.n_arrays; ++k) {
+        const int w = a.width[k];
+        const float* s = a.src[k] + (uint64_t)r * w; float* d = a.dst[k] + b * w;
+        for (int j = 0; j < w; ++j) d[j] = s[j];
+    }
+}
+
 // ---- diagnostics: the L2 atomic rate the grid-gradient scatter is bounded by (bench.py train_roofline denominator).
 // Every thread issues `per_thread` reductions of `VEC` floats at pseudo-random VEC-aligned slots of a table (no other work).
 template <int VEC>
@@ -370,22 +385,54 @@ __global__ void set_scalars_kernel(float* dst, Scalars8 s, int n) { if ((int)thr
 // ---- fused Adam (torch.optim.Adam semantics, amsgrad=False, weight_decay=0) + fp16 shadow.
 // `hyper` (device, optional): {lr, 1 - beta1^t, sqrt(1 - beta2^t)} read at run time, so a CUDA graph
 // holding this launch can be replayed with a new learning rate / step count.
+__device__ __forceinline__ float adam_one(float& p, float g, float& m, float& v, float lr_bc1, float b1, float b2, float eps, float bc2_sqrt, float gscale)
+{
+    const float gi = g * gscale;
+    const float mi = b1 * m + (1.f - b1) * gi;          // exp_avg.lerp_(grad, 1-beta1)
+    const float vi = b2 * v + (1.f - b2) * gi * gi;     // exp_avg_sq.mul_(b2).addcmul_(g, g, 1-b2)
+    m = mi; v = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p = p - lr_bc1 * (mi / denom);
+    return p;
+}
+
+// Four parameters per thread (16-byte loads / stores, 8-byte shadow store): the pass is pure streaming, 30 B per
+// parameter; one element per thread left the HBM pipe at 42 % (profiles/r02).  `n4` float4 groups + a scalar tail.
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
             __half* __restrict__ ph, uint64_t n, float lr, float b1, float b2, float eps,
-            float bc1, float bc2_sqrt, float gscale, const float* __restrict__ hyper)
+            float bc1, float bc2_sqrt, float gscale, const float* __restrict__ hyper, int vec)
 {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (hyper) { lr = hyper[0]; bc1 = hyper[1]; bc2_sqrt = hyper[2]; }
-    const float gi = g[i] * gscale;
-    const float mi = b1 * m[i] + (1.f - b1) * gi;          // exp_avg.lerp_(grad, 1-beta1)
-    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;     // exp_avg_sq.mul_(b2).addcmul_(g, g, 1-b2)
-    m[i] = mi; v[i] = vi;
-    const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    const float pi = p[i] - (lr / bc1) * (mi / denom);
-    p[i] = pi;
-    if (ph) ph[i] = __float2half_rn(pi);
+    const float lr_bc1 = lr / bc1;
+    const uint64_t n4 = vec ? n / 4 : 0;
+    if (t < n4) {
+        float4 pp = reinterpret_cast<float4*>(p)[t], mm = reinterpret_cast<float4*>(m)[t], vv = reinterpret_cast<float4*>(v)[t];
+        const float4 gg = reinterpret_cast<const float4*>(g)[t];
+        adam_one(pp.x, gg.x, mm.x, vv.x, lr_bc1, b1, b2, eps, bc2_sqrt, gscale);
+        adam_one(pp.y, gg.y, mm.y, vv.y, lr_bc1, b1, b2, eps, bc2_sqrt, gscale);
+        adam_one(pp.z, gg.z, mm.z, vv.z, lr_bc1, b1, b2, eps, bc2_sqrt, gscale);
+        adam_one(pp.w, gg.w, mm.w, vv.w, lr_bc1, b1, b2, eps, bc2_sqrt, gscale);
+        reinterpret_cast<float4*>(p)[t] = pp; reinterpret_cast<float4*>(m)[t] = mm; reinterpret_cast<float4*>(v)[t] = vv;
+        if (ph) {
+            const __half2 h01 = __floats2half2_rn(pp.x, pp.y), h23 = __floats2half2_rn(pp.z, pp.w);
+            reinterpret_cast<uint2*>(ph)[t] = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+        }
+    }
+    const uint64_t i = n4 * 4 + t;                       // scalar tail (or everything when the buffers are not 16-byte aligned)
+    if (i < n && t < n - n4 * 4) {
+        float pi = p[i], mi = m[i], vi = v[i];
+        adam_one(pi, g[i], mi, vi, lr_bc1, b1, b2, eps, bc2_sqrt, gscale);
+        p[i] = pi; m[i] = mi; v[i] = vi;
+        if (ph) ph[i] = __float2half_rn(pi);
+    }
+}
+
+// grid for adam_kernel: covers max(n/4 groups, tail elements)
+static inline bool adam_vec_ok(const void* p, const void* g, const void* m, const void* v, const void* ph)
+{
+    return (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) % 16 == 0) && ((uintptr_t)ph % 8 == 0);
 }
 
 }  // namespace perf
@@ -513,6 +560,21 @@ int perf_hashgrid_bwd(const perf_grid_cfg* cfg, const float* d_x01, const float*
     return PERF_OK;
 }
 
+int perf_gather_rows(const int64_t* d_idx, uint64_t B, int n_arrays, const float* const* h_src, float* const* h_dst, const int* h_width, void* stream)
+{
+    PERF_CHECK_ARG(d_idx && h_src && h_dst && h_width && n_arrays >= 1 && n_arrays <= 6, "bad arguments");
+    GatherArgs a; memset(&a, 0, sizeof(a));
+    for (int k = 0; k < n_arrays; ++k) {
+        PERF_CHECK_ARG(h_src[k] && h_dst[k] && h_width[k] >= 1 && h_width[k] <= 64, "bad array %d", k);
+        a.src[k] = h_src[k]; a.dst[k] = h_dst[k]; a.width[k] = h_width[k];
+    }
+    a.n_arrays = n_arrays; a.idx = d_idx; a.B = B;
+    if (B == 0) return PERF_OK;
+    gather_rows_kernel<<<blocks_for(B, 256), 256, 0, S(stream)>>>(a);
+    PERF_LAUNCH_CHECK();
+    return PERF_OK;
+}
+
 int perf_debug_atomic_rate(float* d_table, uint64_t n_floats, uint64_t n_atomics, int vec, void* stream)
 {
     PERF_CHECK_ARG(d_table && (vec == 1 || vec == 2 || vec == 4) && n_floats >= 4 && (uintptr_t)d_table % 16 == 0, "bad arguments");
@@ -592,8 +654,10 @@ int perf_adam_step(float* d_params, const float* d_grads, float* d_exp_avg, floa
     if (n == 0) return PERF_OK;
     const float bc1 = 1.0f - powf(beta1, (float)step);
     const float bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
-    adam_kernel<<<blocks_for(n, 256), 256, 0, S(stream)>>>(d_params, d_grads, d_exp_avg, d_exp_avg_sq, (__half*)d_params_half,
-                                                           n, lr, beta1, beta2, eps, bc1, bc2_sqrt, grad_scale, nullptr);
+    const int vec = adam_vec_ok(d_params, d_grads, d_exp_avg, d_exp_avg_sq, d_params_half) ? 1 : 0;
+    const uint64_t threads = vec ? (n / 4 > n % 4 ? n / 4 : n % 4) : n;
+    adam_kernel<<<blocks_for(threads ? threads : 1, 256), 256, 0, S(stream)>>>(d_params, d_grads, d_exp_avg, d_exp_avg_sq, (__half*)d_params_half,
+                                                           n, lr, beta1, beta2, eps, bc1, bc2_sqrt, grad_scale, nullptr, vec);
     PERF_LAUNCH_CHECK();
     return PERF_OK;
 }
@@ -612,8 +676,10 @@ int perf_adam_step_dev(float* d_params, const float* d_grads, float* d_exp_avg, 
 {
     PERF_CHECK_ARG(d_params && d_grads && d_exp_avg && d_exp_avg_sq && d_hyper, "NULL pointer");
     if (n == 0) return PERF_OK;
-    adam_kernel<<<blocks_for(n, 256), 256, 0, S(stream)>>>(d_params, d_grads, d_exp_avg, d_exp_avg_sq, (__half*)d_params_half,
-                                                           n, 0.f, beta1, beta2, eps, 1.f, 1.f, grad_scale, d_hyper);
+    const int vec = adam_vec_ok(d_params, d_grads, d_exp_avg, d_exp_avg_sq, d_params_half) ? 1 : 0;
+    const uint64_t threads = vec ? (n / 4 > n % 4 ? n / 4 : n % 4) : n;
+    adam_kernel<<<blocks_for(threads ? threads : 1, 256), 256, 0, S(stream)>>>(d_params, d_grads, d_exp_avg, d_exp_avg_sq, (__half*)d_params_half,
+                                                           n, 0.f, beta1, beta2, eps, 1.f, 1.f, grad_scale, d_hyper, vec);
     PERF_LAUNCH_CHECK();
     return PERF_OK;
 }

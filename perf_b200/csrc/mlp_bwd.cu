@@ -86,7 +86,19 @@ __host__ __device__ __forceinline__ void store_row(uint8_t* img, int row, const 
 }
 __host__ __device__ __forceinline__ uint32_t word_of(const uint4& q, int i) { return i == 0 ? q.x : i == 1 ? q.y : i == 2 ? q.z : q.w; }
 
+// Output matrix as fp32 in the constant bank for the tensor-core kernel (same reason as c_wout in render.cu: the
+// 64 * n_out multiplies per row then read their weight as c[bank][imm] instead of a broadcast shared-memory load;
+// mio_throttle was the top stall of this kernel, profiles/r02).  Filled stream-ordered in front of every launch; one slot
+// per device (launches for different networks on one device must not overlap in time).
+__constant__ float c_wout_bwd[3 * HID];
+__global__ void wout_bwd_to_const_kernel(const __half* __restrict__ wout, int n, float* __restrict__ dst)
+{
+    const int i = threadIdx.x;
+    dst[i] = i < n ? __half2float(wout[i]) : 0.f;
+}
+
 // dh[j] = (h[j] > 0) ? sum_o dz[o] * wout[o][j] : 0, rounded to fp16, written as this thread's row of `dst`
+template <bool CONSTW = false>
 __host__ __device__ __forceinline__ void out_layer_backward(uint8_t* dst, int row, const uint4 (&h)[8], const float (&dz)[3], int n_out, const float* wout)
 {
 #pragma unroll
@@ -99,7 +111,13 @@ __host__ __device__ __forceinline__ void out_layer_backward(uint8_t* dst, int ro
             float a = 0.f, b = 0.f;
 #pragma unroll
             for (int o = 0; o < 3; ++o)
-                if (o < n_out) { a = fmaf(dz[o], wout[o * HID + j], a); b = fmaf(dz[o], wout[o * HID + j + 1], b); }
+                if (o < n_out) {
+#ifdef __CUDA_ARCH__
+                    if constexpr (CONSTW) { a = fmaf(dz[o], c_wout_bwd[o * HID + j], a); b = fmaf(dz[o], c_wout_bwd[o * HID + j + 1], b); }
+                    else
+#endif
+                    { a = fmaf(dz[o], wout[o * HID + j], a); b = fmaf(dz[o], wout[o * HID + j + 1], b); }
+                }
             o4[q] = pack_half2(hh.x > 0.f ? a : 0.f, hh.y > 0.f ? b : 0.f);
         }
         *reinterpret_cast<uint4*>(dst + (kg * TILE + row) * 16) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
@@ -134,7 +152,7 @@ __host__ __device__ __forceinline__ void bwd_phase_load(const MlpBwdArgs& a, uin
     for (int o = 0; o < 3; ++o) r.dz[o] = (valid && o < n_out) ? a.dz[row * n_out + o] : 0.f;
 }
 
-template <bool TWO>
+template <bool TWO, bool CONSTW = false>
 __host__ __device__ __forceinline__ void bwd_phase_store(uint8_t* smem, const float* s_wout, const MlpBwdArgs& a, int t, const TileRegs<TWO>& r)
 {
     using L = BwdSmem<TWO>;
@@ -150,9 +168,9 @@ __host__ __device__ __forceinline__ void bwd_phase_store(uint8_t* smem, const fl
 #pragma unroll
         for (int q = 0; q < 8; ++q) hl[q] = r.hlast[q];
         store_row(smem + L::H2, t, hl);
-        out_layer_backward(smem + L::DH2, t, hl, r.dz, n_out, s_wout);
+        out_layer_backward<CONSTW>(smem + L::DH2, t, hl, r.dz, n_out, s_wout);
     } else {
-        out_layer_backward(smem + L::DH1, t, r.h1v, r.dz, n_out, s_wout);
+        out_layer_backward<CONSTW>(smem + L::DH1, t, r.h1v, r.dz, n_out, s_wout);
     }
 }
 
@@ -290,7 +308,7 @@ __global__ void __launch_bounds__(128) mlp_bwd_kernel(const MlpBwdArgs a)
     TileRegs<TWO> regs;
     if (blockIdx.x < n_tiles) bwd_phase_load<TWO>(a, blockIdx.x, t, regs);
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, first = false) {
-        bwd_phase_store<TWO>(smem, s_wout, a, t, regs);
+        bwd_phase_store<TWO, !SIMT>(smem, s_wout, a, t, regs);          // tensor-core kernel: output matrix from the constant bank
         if (tile + gridDim.x < n_tiles) bwd_phase_load<TWO>(a, tile + gridDim.x, t, regs);     // in flight during this tile's MMAs
         if constexpr (!SIMT) { fence_proxy_async(); tc_fence_before(); }
         __syncthreads();
@@ -383,6 +401,12 @@ static int launch_mlp_bwd(const MlpBwdArgs& a, cudaStream_t stream)
     static thread_local int attr_dev = -1;
     int dev = 0; PERF_CUDA(cudaGetDevice(&dev));
     if (attr_dev != dev) { PERF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem<TWO>::TOTAL)); attr_dev = dev; }
+    if (!SIMT) {
+        static thread_local int sym_dev = -1; static thread_local float* sym = nullptr;
+        if (sym_dev != dev) { PERF_CUDA(cudaGetSymbolAddress((void**)&sym, c_wout_bwd)); sym_dev = dev; }
+        wout_bwd_to_const_kernel<<<1, 3 * HID, 0, stream>>>(a.w + 64 * 32 + (TWO ? 64 * 64 : 0), (int)a.n_out * HID, sym);
+        PERF_LAUNCH_CHECK();
+    }
     const uint64_t n_tiles = (a.N + TILE - 1) / TILE;
     // resident CTAs per SM: TMEM columns (128 / 256 of 512) and shared memory (45 / 89 KB) allow 4 / 2
     const uint64_t slots = (uint64_t)num_sms() * (TWO ? 2 : 4);

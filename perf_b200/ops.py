@@ -80,10 +80,27 @@ def pack_tables(geo_half: torch.Tensor, app_half: torch.Tensor, grid: GridConfig
 
 
 # ------------------------------------------------------------------ ray generation
+_POSE_CACHE = {}
+
+
 def _pose_array(pose) -> "C.Array":
+    """The 4x4 pose by value (a kernel parameter).  A pose that lives on the GPU -- the reference makes CUDA the default
+    tensor type, `core_exp_runner.py:266` -- costs a device-to-host read: cached per (storage, version), so a pose rendered
+    again (row tiles, repeated frames) is read once."""
+    key = None
+    if torch.is_tensor(pose) and pose.is_cuda:
+        key = (pose.data_ptr(), pose._version, tuple(pose.shape))
+        hit = _POSE_CACHE.get(key)
+        if hit is not None:
+            return hit
     flat = [float(v) for v in torch.as_tensor(pose, dtype=torch.float32).cpu().reshape(-1).tolist()]
     assert len(flat) == 16, "pose must be 4x4"
-    return (C.c_float * 16)(*flat)
+    arr = (C.c_float * 16)(*flat)
+    if key is not None:
+        if len(_POSE_CACHE) > 64:
+            _POSE_CACHE.clear()
+        _POSE_CACHE[key] = arr
+    return arr
 
 
 def raygen_pano(pose, H: int, W: int, row0: int = 0, rows: Optional[int] = None, device="cuda"):
@@ -438,7 +455,7 @@ def render_rays(packed_table, geo_mlp_half, app_mlp_half, rays_o, rays_d, n_samp
 
 
 def render_packed(packed_table, geo_mlp_half, app_mlp_half, rays_o, rays_d, ray_indices, t_starts, t_ends,
-                  aabb=(-1., -1., -1., 1., 1., 1.), grid: GridConfig = PERF_GRID, simt=False):
+                  aabb=(-1., -1., -1., 1., 1., 1.), grid: GridConfig = PERF_GRID, simt=False, offsets: Optional[torch.Tensor] = None):
     """Fused eval render of packed variable-length samples (sorted by ray, as an occupancy estimator
     returns them) -> (rgb [R,3], distance [R,1], opacity [R,1])."""
     rays_o, rays_d = _chk(rays_o, torch.float32, "rays_o"), _chk(rays_d, torch.float32, "rays_d")
@@ -450,8 +467,11 @@ def render_packed(packed_table, geo_mlp_half, app_mlp_half, rays_o, rays_d, ray_
     op = torch.empty(R, 1, dtype=torch.float32, device=dev)
     if R == 0:
         return rgb, dist, op
-    offsets = torch.zeros(R + 1, dtype=torch.int64, device=dev)
-    offsets[1:] = torch.cumsum(torch.bincount(ray_indices, minlength=R), 0)
+    if offsets is None:                                   # callers that sampled with occ_sample pass occ_sample.last_offsets
+        offsets = torch.zeros(R + 1, dtype=torch.int64, device=dev)
+        offsets[1:] = torch.cumsum(torch.bincount(ray_indices, minlength=R), 0)
+    else:
+        offsets = _chk(offsets, torch.int64, "offsets")
     a = _render_args(packed_table, geo_mlp_half, app_mlp_half, aabb, 1, 0.0, 1.0, False, simt, None, None, rgb, dist, op, grid)
     with torch.cuda.device(dev):
         _call(_L().perf_render_packed, C.byref(a), _p(rays_o), _p(rays_d), R, _p(offsets), _p(t_starts), _p(t_ends), _stream())
@@ -522,7 +542,11 @@ class FusedTrainContext:
                  "toff": f32(_lib.PERF_MAX_SEGMENTS * R), "segments": C.c_uint32(1)}
             if phase == _lib.PERF_PHASE_APP:
                 b["rgb"], b["h2"] = f16(N, 4), f16(N, 64)
-            self._bufs = {key: b}                                  # keep only the latest shape
+            # keep the latest TWO shapes: dropping the previous shape's buffers while a not-yet-run backward still
+            # references them would leave that graph pointing at freed (re-usable) memory; the generation check in
+            # _FusedTrainStep.backward turns any remaining misuse into an error
+            last = list(self._bufs.items())[-1:]
+            self._bufs = dict(last + [(key, b)])
         return self._bufs[key]
 
     @staticmethod
@@ -709,6 +733,21 @@ def fused_packed_train_step(params, rays_o, rays_d, offsets, ray_indices, t_star
     if offsets.numel() != rays_o.shape[0] + 1:
         raise RuntimeError("perf_b200.fused_packed_train_step: offsets must have R + 1 entries")
     return _FusedPackedTrainStep.apply(params, rays_o, rays_d, offsets, ray_indices, t_starts, t_ends, bg_noise, tc, phase, early_stop_eps)
+
+
+def gather_rows(idx: torch.Tensor, *arrays: torch.Tensor):
+    """``tuple(a[idx] for a in arrays)`` for row-major fp32 CUDA arrays [M, w_k] in ONE launch (the batch draw of a step)."""
+    idx = _chk(idx, torch.int64, "idx")
+    B, dev = idx.shape[0], idx.device
+    srcs = [_chk(a.reshape(a.shape[0], -1), torch.float32, "array") for a in arrays]
+    outs = [torch.empty((B,) + tuple(a.shape[1:]), dtype=torch.float32, device=dev) for a in arrays]
+    n = len(srcs)
+    sp = (C.c_void_p * n)(*[s.data_ptr() for s in srcs])
+    dp = (C.c_void_p * n)(*[o.data_ptr() for o in outs])
+    wd = (C.c_int * n)(*[int(s.shape[1]) for s in srcs])
+    with torch.cuda.device(dev):
+        _call(_L().perf_gather_rows, _p(idx), B, n, sp, dp, wd, _stream())
+    return tuple(outs)
 
 
 class _FusedLoss(torch.autograd.Function):

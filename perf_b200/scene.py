@@ -194,6 +194,11 @@ class RaySupervision:
         idx = torch.randint(0, len(self.all_sup_colors), (batch_size,), device=self.all_sup_colors.device, generator=gen)
         if self.locality_key is not None:
             idx = idx[torch.argsort(self.locality_key[idx])]
+        if self.all_sup_colors.is_cuda and self.all_sup_colors.dtype == torch.float32:
+            # one gather launch for the five arrays (sup_info.py:253-259 indexes each of them separately)
+            o, d, c, dist, nrm = ops.gather_rows(idx, self.all_sup_rays.o, self.all_sup_rays.d, self.all_sup_colors,
+                                                 self.all_sup_distances, self.all_sup_normals)
+            return Rays(o, d), c, dist, nrm
         return self.all_sup_rays[idx], self.all_sup_colors[idx], self.all_sup_distances[idx], self.all_sup_normals[idx]
 
 
@@ -488,18 +493,8 @@ class NeRFScene:
     def train_one_episode(self, sup_pool, geo_res_iters, app_res_iters, pixel_sup_rand_mode="by_all_pixels"):
         """`nerf.py:137-184`: (occupancy grid from the supervision,) fresh density net, geo phase then app phase."""
         self.set_train()
-        if self.estimator_type == "occ":                                       # nerf.py:143-168
-            from .shims.nerfacc.estimators.occ_grid import OccGridEstimator
-            occ_res = self.occ_resolution
-            self.estimator = OccGridEstimator(roi_aabb=self.aabb, resolution=occ_res, levels=1).to(self.device)
-            self.estimator.train()
-            pre_grid, _ = sup_pool.gen_occ_grid(res=occ_res)
-
-            def occ_eval_fn(x):
-                x = ((x.clip(-0.999, 0.999) * .5 + .5) * occ_res).to(torch.int64)
-                return pre_grid[x[..., 0] * occ_res * occ_res + x[..., 1] * occ_res + x[..., 2]].float()
-            for i in range(256):
-                self.estimator.update_every_n_steps(step=i, occ_eval_fn=occ_eval_fn, occ_thre=1e-2, ema_decay=0.1, warmup_steps=256, n=1)
+        if self.estimator_type == "occ":
+            self.build_occupancy(sup_pool)
         self.nerf.reset_geo()
         geo_optimizer = FusedAdam(self.nerf.geo_mlp.params, lr=self.train_conf.geo_optimizer.init_lr, module=self.nerf.geo_mlp)
         geo_step = GraphedTrainStep(self, "geo", sup_pool, geo_optimizer) if self.graph_train and geo_res_iters > 0 else None
@@ -525,6 +520,22 @@ class NeRFScene:
         if app_step is not None:
             app_step.finish()
         app_optimizer.sync_master()
+
+    def build_occupancy(self, sup_pool, n_updates: int = 256):
+        """`nerf.py:143-168`: a fresh estimator whose grid is the surface shell of the supervision (voxels within one cell of
+        an un-projected RGB-D point, ``sup_pool.gen_occ_grid``), entered through 256 warm-up updates exactly as the reference
+        does (each one: perf_occ_points -> the lookup below -> perf_occ_update)."""
+        from .shims.nerfacc.estimators.occ_grid import OccGridEstimator
+        occ_res = self.occ_resolution
+        self.estimator = OccGridEstimator(roi_aabb=self.aabb, resolution=occ_res, levels=1).to(self.device)
+        self.estimator.train()
+        pre_grid, _ = sup_pool.gen_occ_grid(res=occ_res)
+
+        def occ_eval_fn(x):
+            x = ((x.clip(-0.999, 0.999) * .5 + .5) * occ_res).to(torch.int64)
+            return pre_grid[x[..., 0] * occ_res * occ_res + x[..., 1] * occ_res + x[..., 2]].float()
+        for i in range(n_updates):
+            self.estimator.update_every_n_steps(step=i, occ_eval_fn=occ_eval_fn, occ_thre=1e-2, ema_decay=0.1, warmup_steps=256, n=1)
 
     def _local_batch(self):
         return max(1, int(self.train_conf.pixel_loss_batch_size) // parallel.world_size())

@@ -144,6 +144,29 @@ def test_adam_matches_torch(ops):
     assert torch.equal(ph.cpu(), p.cpu().half())
 
 
+def test_adam_unaligned_views_and_batch_gather(ops):
+    """The vectorised Adam kernel falls back to one element per thread on views that are not 16-byte aligned (a shard of
+    an odd-length parameter); perf_gather_rows == indexing each array."""
+    g = torch.Generator().manual_seed(151)
+    n = 4099
+    base = [torch.randn(n + 1, generator=g).cuda() for _ in range(4)]
+    base[3].abs_()
+    p, gr, m, v = (t[1:] for t in base)                            # +4 bytes: misaligned for float4
+    ref = [t.clone() for t in (p, gr, m, v)]
+    ph = torch.empty(n + 1, dtype=torch.float16, device="cuda")[1:]
+    ops.adam_step(p, gr, m, v, 3, 1e-2, params_half=ph)
+    pa, ga, ma, va = (t.clone().contiguous() for t in ref)         # aligned copies through the vector path
+    pha = torch.empty(n, dtype=torch.float16, device="cuda")
+    ops.adam_step(pa, ga, ma, va, 3, 1e-2, params_half=pha)
+    assert torch.equal(p, pa) and torch.equal(m, ma) and torch.equal(v, va) and torch.equal(ph, pha)
+    M, B = 5000, 777
+    arrays = [torch.randn(M, w, generator=g).cuda() for w in (3, 3, 3, 1, 3)]
+    idx = torch.randint(0, M, (B,), generator=g).cuda()
+    got = ops.gather_rows(idx, *arrays)
+    for a, o in zip(arrays, got):
+        assert torch.equal(o, a[idx])
+
+
 def test_params_to_half_and_pack(ops):
     from perf_b200.config import APP_MLP, GEO_MLP, PERF_GRID
     g = torch.Generator().manual_seed(16)

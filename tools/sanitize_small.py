@@ -47,5 +47,26 @@ for fused in (True, False):
         opt = FusedAdam(net.params, lr=1e-3, module=net)
         (sc.train_one_step_geo if phase == "geo" else sc.train_one_step_app)(opt, pool, progress=0.3)
 sc.render_pano(torch.eye(4), h, wd)
+# round 2: occupancy-sampler scene (native grid update, fused packed train step both phases, fused eval render), the
+# L0-in-shared-memory render variant, one-kernel loss, batch gather, vector / scalar Adam, mlp_bwd CUDA-core twin
+sc = NeRFScene(estimator_type="occ", occ_resolution=32); sc.train_conf["pixel_loss_batch_size"] = 100
+pool = RaySupervision.from_panorama(torch.eye(4), rgb, dist)
+sc.build_occupancy(pool, n_updates=3)
+sc.OCC_STEP = 5e-3
+sc.set_train()
+for phase in ("geo", "app"):
+    net = sc.nerf.geo_mlp if phase == "geo" else sc.nerf.app_mlp
+    opt = FusedAdam(net.params, lr=1e-3, module=net)
+    (sc.train_one_step_geo if phase == "geo" else sc.train_one_step_app)(opt, pool, progress=0.3)
+sc.set_eval()
+sc.render_pano(torch.eye(4), h, wd)
+r.kernel = "march_l0smem"; r.render_pano(pose, 20, 40, 24); r.kernel = "march"
+W = ((torch.rand(APP_MLP.n_params, device="cuda") - .5) * .6).half()
+f16 = (torch.rand(300, 32, device="cuda") - .5).half(); h1 = torch.rand(300, 64, device="cuda").half(); h2 = torch.rand(300, 64, device="cuda").half()
+for simt in (True, False):
+    ops.mlp_backward_fused(APP_MLP, W, f16, h1, h2, torch.randn(300, 3, device="cuda"), simt=simt)
+    ops.mlp_backward_fused(GEO_MLP, W[:GEO_MLP.n_params].clone(), f16, h1, None, torch.randn(300, 1, device="cuda"), simt=simt)
+pp = torch.randn(1003, device="cuda"); ops.adam_step(pp, torch.randn(1003, device="cuda"), torch.zeros(1003, device="cuda"), torch.zeros(1003, device="cuda"), 1, 1e-3,
+                                                   params_half=torch.empty(1003, dtype=torch.float16, device="cuda"))
 torch.cuda.synchronize()
 print("sanitize_small: done")

@@ -9,9 +9,12 @@ rank, world, local = parallel.init()
 torch.cuda.set_device(local)
 h, w, S, B = 512, 1024, 128, 8192
 rgb = synthetic.smooth_rgb(h, w, device="cuda"); dist = synthetic.box_room_distance(h, w, device="cuda")
-sc = NeRFScene(n_samples=S, fused_train=os.environ.get('FUSED', '1') == '1')
-sc.set_train()
+occ = os.environ.get('OCC', '0') == '1'
+sc = NeRFScene(n_samples=S, fused_train=os.environ.get('FUSED', '1') == '1', **({"estimator_type": "occ", "occ_resolution": 256} if occ else {}))
 pool = RaySupervision.from_panorama(torch.eye(4), rgb, dist)
+if occ:
+    sc.build_occupancy(pool)
+sc.set_train()
 for phase in os.environ.get("PHASES", "geo,app").split(","):
     net = sc.nerf.geo_mlp if phase == "geo" else sc.nerf.app_mlp
     opt = FusedAdam(net.params, lr=1e-3, module=net)
