@@ -65,7 +65,10 @@ constexpr int RS_WOUT  = RS_W2A + W64_BYTES;        // fp32: geo [64] then app [
 constexpr int RS_TAILS = RS_WOUT + 4 * HID * 4;     // [2 scans][4 warps][8] floats
 constexpr int RS_CARRY = RS_TAILS + 2 * 4 * 8 * 4;  // [2 parities][8] floats
 constexpr int RS_BAR   = RS_CARRY + 2 * 8 * 4;
-constexpr int RS_TOTAL = RS_BAR + 16;
+constexpr int RS_BARW  = RS_BAR + 16;               // mbarrier of the weight bulk copy
+constexpr int RS_TOTAL = RS_BARW + 16;
+constexpr int W_IMG_BYTES = W32_BYTES + W32_BYTES + W64_BYTES;       // 16 KB: W1 density | W1 colour | W2 colour
+static_assert(RS_W1A == RS_W1G + W32_BYTES && RS_W2A == RS_W1A + W32_BYTES, "the three weight images are one contiguous block");
 // experiment (PERF_FLAG_L0_SMEM): level 0 of the packed table (16^3 entries x 8 B = 32 KB) resident in shared memory,
 // staged once per persistent CTA by ONE bulk copy (cp.async.bulk -> UBLKCP, completion on an mbarrier)
 constexpr int RS_BAR2  = (RS_TOTAL + 127) / 128 * 128;
@@ -77,14 +80,38 @@ constexpr int RS_TOTAL_L0 = RS_L0 + L0_BYTES;
 // rows.  The 64 * n_out FMAs per sample of the output layers then take their weight operand straight from c[bank][imm]
 // -- no load instruction.  (Round 1 kept them in shared memory: 64 broadcast LDS.128 per thread and sample, 1.2e9
 // shared-load wavefronts per panorama on the L1 data pipe that bounds the kernel, profiles/r01_*.)  Filled from the fp16
-// parameter vectors by wout_to_const_kernel, stream-ordered in front of every render launch (graph-capturable).
+// parameter vectors by weights_prepare_kernel, stream-ordered in front of every render launch (graph-capturable).
 // One slot per device: renders of DIFFERENT fields on the same device must not overlap in time (different streams).
 __constant__ float c_wout[4 * HID];
+// The three hidden-layer matrices as ready-made UMMA operand images (no-swizzle K-major canonical layout, mlp_tc.cuh), 16 KB:
+// every persistent CTA stages them with ONE bulk copy (cp.async.bulk -> UBLKCP, completion on an mbarrier) instead of 1024
+// 16-byte LDG + STS per CTA.  Written by the same preparation kernel, same single-slot rule as c_wout.
+__device__ uint4 g_wimg[W_IMG_BYTES / 16];
 
-__global__ void wout_to_const_kernel(const __half* __restrict__ geo_wout, const __half* __restrict__ app_wout, float* __restrict__ dst)
+__global__ void __launch_bounds__(1024) weights_prepare_kernel(const __half* __restrict__ geo_w, const __half* __restrict__ app_w, float* __restrict__ c_dst)
 {
-    const int i = threadIdx.x;                       // 256 threads
-    dst[i] = __half2float(i < HID ? geo_wout[i] : app_wout[i - HID]);
+    const int c = threadIdx.x;                       // 1024 threads = 1024 16-byte chunks of the images
+    if (c < 4 * HID) c_dst[c] = __half2float(c < HID ? geo_w[HID * 32 + c] : app_w[HID * 32 + HID * HID + (c - HID)]);
+    const __half* src; int K, cc;
+    if (c < 256)      { src = geo_w;            K = 32; cc = c; }
+    else if (c < 512) { src = app_w;            K = 32; cc = c - 256; }
+    else              { src = app_w + HID * 32; K = 64; cc = c - 512; }
+    const int n = cc % HID, kg = cc / HID;           // image chunk (kg * 64 + n) <- row n, columns [8 kg, 8 kg + 8)
+    g_wimg[c] = *reinterpret_cast<const uint4*>(src + (size_t)n * K + kg * 8);
+}
+
+// all threads of the CTA: weight images global -> shared memory by one bulk copy; returns when they have landed
+__device__ __forceinline__ void stage_weights_bulk(uint8_t* smem, int tid)
+{
+    uint64_t* barw = reinterpret_cast<uint64_t*>(smem + RS_BARW);
+    if (tid == 0) {
+        mbar_init(barw, 1); fence_mbar_init();
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(barw)), "r"(W_IMG_BYTES) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(smem_u32(smem + RS_W1G)), "l"(reinterpret_cast<const void*>(g_wimg)), "r"(W_IMG_BYTES), "r"(smem_u32(barw)) : "memory");
+    }
+    __syncthreads();                                 // the barrier is initialised before anyone polls it
+    mbar_wait(barw, 0);
 }
 
 // acc[o] += sum_j h[32c + j] * c_wout[BASE + 64 o + 32 c + j], C a compile-time constant (immediate constant offsets)
@@ -335,9 +362,7 @@ __global__ void __launch_bounds__(TILE, 4) render_kernel(const __grid_constant__
     const int tid = threadIdx.x, warp = tid >> 5;
     const RenderSmem sm = {sA, sAg, sAa, sW1g, sW1a, sW2a, sWoutG, sWoutA, bar, nullptr};
 
-    load_weight_canonical(a.geo_w, 32, sW1g, tid, TILE);
-    load_weight_canonical(a.app_w, 32, sW1a, tid, TILE);
-    load_weight_canonical(a.app_w + HID * 32, 64, sW2a, tid, TILE);
+    stage_weights_bulk(smem, tid);                   // W1 density | W1 colour | W2 colour operand images, one UBLKCP
     uint32_t tmem_base = 0;
     if (!SIMT) {
         if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
@@ -474,9 +499,7 @@ __global__ void __launch_bounds__(TILE, L0SMEM ? 3 : 4) render_march_kernel(cons
     const RenderSmem sm = {sA, sA, sA + A32_BYTES, sW1g, sW1a, sW2a, sWoutG, sWoutA, bar,
                            L0SMEM ? reinterpret_cast<const uint2*>(smem + RS_L0) : nullptr};
 
-    load_weight_canonical(a.geo_w, 32, sW1g, tid, TILE);
-    load_weight_canonical(a.app_w, 32, sW1a, tid, TILE);
-    load_weight_canonical(a.app_w + HID * 32, 64, sW2a, tid, TILE);
+    stage_weights_bulk(smem, tid);                   // W1 density | W1 colour | W2 colour operand images, one UBLKCP
     uint32_t tmem_base = 0;
     if (!SIMT) {
         if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
@@ -703,9 +726,7 @@ __global__ void __launch_bounds__(TILE, 4) packed_fields_kernel(const __grid_con
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + RS_BAR + 8);
     const int tid = threadIdx.x, warp = tid >> 5;
     const RenderSmem sm = {sA, sA, sA + A32_BYTES, sW1g, sW1a, sW2a, sWoutG, sWoutG + HID, bar, nullptr};
-    load_weight_canonical(a.geo_w, 32, sW1g, tid, TILE);
-    load_weight_canonical(a.app_w, 32, sW1a, tid, TILE);
-    load_weight_canonical(a.app_w + HID * 32, 64, sW2a, tid, TILE);
+    stage_weights_bulk(smem, tid);                   // W1 density | W1 colour | W2 colour operand images, one UBLKCP
     if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
     __syncwarp();
     if (warp == 0) tmem_alloc<128>(tmem_slot);
@@ -747,12 +768,12 @@ __global__ void __launch_bounds__(TILE, 4) packed_fields_kernel(const __grid_con
     if (warp == 0) tmem_dealloc<128>(tmem_base);
 }
 
-static int wout_to_const(const RenderArgs& a, cudaStream_t stream)
+static int prepare_weights(const RenderArgs& a, cudaStream_t stream)
 {
     static thread_local int sym_dev = -1; static thread_local float* sym = nullptr;
     int dev_ = 0; PERF_CUDA(cudaGetDevice(&dev_));
     if (sym_dev != dev_) { PERF_CUDA(cudaGetSymbolAddress((void**)&sym, c_wout)); sym_dev = dev_; }
-    wout_to_const_kernel<<<1, 4 * HID, 0, stream>>>(a.geo_w + HID * 32, a.app_w + HID * 32 + HID * HID, sym);
+    weights_prepare_kernel<<<1, 1024, 0, stream>>>(a.geo_w, a.app_w, sym);
     PERF_LAUNCH_CHECK();
     return PERF_OK;
 }
@@ -788,7 +809,7 @@ static int launch_render(const perf_render_args* args, RenderArgs& a, bool pano,
         n_work = (a.R + rpt - 1) / rpt;
     }
     const unsigned grid = (unsigned)(n_work < (uint64_t)num_sms() * 4 ? n_work : (uint64_t)num_sms() * 4);
-    rc = wout_to_const(a, stream); if (rc) return rc;       // output-layer weights -> constant bank (see c_wout)
+    rc = prepare_weights(a, stream); if (rc) return rc;     // constant-bank output weights + operand images (c_wout, g_wimg)
 #define PERF_RENDER_LAUNCH(...) do { \
         auto k = __VA_ARGS__; \
         static thread_local int attr_dev = -1; int dev_ = 0; PERF_CUDA(cudaGetDevice(&dev_)); \
@@ -897,7 +918,7 @@ int perf_fields_packed(const perf_render_args* args, const float* d_rays_o, cons
     if (N == 0) return PERF_OK;
     PackedFieldArgs p = {d_ray_indices, d_t_starts, d_t_ends, N, d_sigma, (__half*)d_rgb_half4, d_x01};
     cudaStream_t st = (cudaStream_t)stream;
-    rc = wout_to_const(a, st); if (rc) return rc;
+    rc = prepare_weights(a, st); if (rc) return rc;
     const uint64_t n_tiles = (N + TILE - 1) / TILE;
     const unsigned grid = (unsigned)(n_tiles < (uint64_t)num_sms() * 4 ? n_tiles : (uint64_t)num_sms() * 4);
     const bool fast = fast_addressing_ok(a.lt, 4) && (args->flags & PERF_FLAG_GENERIC_ADDR) == 0;
