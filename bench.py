@@ -358,12 +358,12 @@ def bench_train_roofline(dev):
     ms_adam = timed(lambda: ops.adam_step(p, gr, m, v, 3, 1e-3, params_half=half))
     peak, peak_src = measured_peak_hbm()
     adam_gbs = n * 30 / (ms_adam * 1e-3) / 1e9
-    return {"scatter": {"kernels": "hashgrid_bwd_march_kernel + hashgrid_bwd_rays_kernel (8192 x 128 samples, both launches)",
+    return {"scatter": {"kernels": "hashgrid_bwd_both_kernel (8192 x 128 samples; coarse march blocks interleaved with fine-level blocks in one launch)",
                         "ms": ms_scatter, "fine_level_reductions_per_step": fine_atomics,
                         "achieved_g_reductions_per_s": fine_atomics / (ms_scatter * 1e-3) / 1e9,
                         "peak_g_reductions_per_s": rate4 / 1e9, "frac": fine_atomics / (ms_scatter * 1e-3) / rate4,
                         "peak_source": "measured in this run: perf_debug_atomic_rate, random 16-byte fp32 reductions into a 16.8 MB table",
-                        "note": "achieved counts only the fine levels' reductions over the time of BOTH launches (they overlap on two streams), so frac is a lower bound"},
+                        "note": "achieved counts only the fine levels' reductions over the time of the whole launch (which also does the coarse levels), so frac is a lower bound"},
             "adam": {"kernel": "adam_kernel", "ms": ms_adam, "bytes_per_param": 30, "achieved": adam_gbs, "peak": peak, "unit": "GB/s",
                      "frac": adam_gbs / peak, "peak_source": peak_src}}
 
@@ -389,25 +389,45 @@ def bench_train_occ(dev, steps=20, warmup=5):
     out = {"rays_per_step": 8192, "render_step_size": sc.OCC_STEP, "occ_resolution": 256,
            "occupancy_build_ms_256_updates": e0.elapsed_time(e1), "occupied_cell_fraction": float(sc.estimator.binaries.float().mean())}
     sc.set_train()
+    from perf_b200.scene import GraphedTrainStep
     for phase in ("geo", "app"):
         net = sc.nerf.geo_mlp if phase == "geo" else sc.nerf.app_mlp
         opt = FusedAdam(net.params, lr=1e-3, module=net)
+        # (a) eager, as the reference's loop is: one host read of the sample count per step
         step = sc.train_one_step_geo if phase == "geo" else sc.train_one_step_app
+        sc._occ_static = None
         for _ in range(warmup):
             step(opt, pool, progress=0.5)
         torch.cuda.synchronize()
-        n_samples = 0
         e0.record()
         for _ in range(steps):
             step(opt, pool, progress=0.5)
-            n_samples += int(ops.occ_sample.last_offsets[-1])          # already on the host path of the step (sample count)
         e1.record()
         torch.cuda.synchronize()
+        out[f"{phase}_eager_ms_per_step"] = e0.elapsed_time(e1) / steps
+        # (b) the same step as ONE CUDA graph: capacity-sized buffers, sample count kept on the device
+        graphed = GraphedTrainStep(sc, phase, pool, opt)
+        for _ in range(warmup):
+            graphed(0.5)
+        torch.cuda.synchronize()
+        n_samples = 0
+        acc = torch.zeros(1, dtype=torch.int64, device=dev)
+        e0.record()
+        for _ in range(steps):
+            graphed(0.5)
+            acc += sc._occ_static.n                                     # device-side add: no host read inside the timed region
+        e1.record()
+        torch.cuda.synchronize()
+        n_samples = int(acc)
+        graphed.finish()
         ms = e0.elapsed_time(e1) / steps
         out[f"{phase}_ms_per_step"] = ms
         out[f"{phase}_samples_per_step"] = n_samples / steps
         out[f"{phase}_samples_per_ray"] = n_samples / steps / 8192
         out[f"{phase}_msamples_per_s"] = n_samples / steps / ms / 1e3
+        out[f"{phase}_capacity"] = sc._occ_static.capacity
+        out[f"{phase}_overflow_samples"] = graphed.occ_overflow()
+    out["note"] = "*_ms_per_step: whole step replayed as one CUDA graph (no host read); *_eager_ms_per_step: eager with the sample-count read, launch-bound"
     return out
 
 

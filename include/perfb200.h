@@ -135,7 +135,8 @@ int perf_hashgrid_bwd_bwd_input(const perf_grid_cfg* cfg, const void* d_table_ha
  * zeroes); d_dfeat [N,32] fp32 overwritten.  flags: PERF_FLAG_SIMT_MLP selects the CUDA-core twin.
  * Validated on B200 in round 2; the training steps call it (no library GEMM is left on that path). */
 int perf_mlp_bwd(const perf_mlp_cfg* mlp, const void* d_weights_half, const void* d_feat, const void* d_h1, const void* d_h2,
-                 const float* d_dz, uint64_t N, float* d_dweights, float* d_dfeat, uint32_t flags, void* stream);
+                 const float* d_dz, uint64_t N, const int64_t* d_n_dev /* nullable: live row count in device memory, <= N */,
+                 float* d_dweights, float* d_dfeat, uint32_t flags, void* stream);
 
 /* Network forward = encode + MLP fused (tcnn NetworkWithInputEncoding.forward;
  * ngp_nerf.py:142,158).  d_x01 [N,3] fp32; d_params_half: fp16 flat params (MLP | grid);
@@ -264,10 +265,14 @@ int perf_hashgrid_bwd_rays(const perf_grid_cfg* cfg, const float* aabb6, const f
  * Pass 1 writes the per-ray sample counts; the caller exclusive-scans them into d_offsets and
  * allocates the packed outputs; pass 2 writes (ray_indices int64, t_starts, t_ends), sorted by ray. */
 int perf_occ_count(const uint8_t* d_binaries, const int* h_res3, const float* h_aabb6, const float* d_rays_o, const float* d_rays_d,
-                   const float* d_jitter, uint64_t R, float near, float far, float step, int32_t* d_counts, void* stream);
+                   const float* d_jitter, uint64_t R, float near, float far, float step, uint32_t pieces, int32_t* d_counts, void* stream);
 int perf_occ_write(const uint8_t* d_binaries, const int* h_res3, const float* h_aabb6, const float* d_rays_o, const float* d_rays_d,
-                   const float* d_jitter, uint64_t R, float near, float far, float step, const int64_t* d_offsets,
+                   const float* d_jitter, uint64_t R, float near, float far, float step, uint32_t pieces, const int64_t* d_offsets, uint64_t capacity,
                    int64_t* d_ray_indices, float* d_t_starts, float* d_t_ends, void* stream);
+/* `pieces` (>= 1, the same in both passes): every ray's lattice range is cut into that many consecutive parts marched by
+ * different threads -- a ray is a serial walk of up to (far - near) / step lattice points, and 8192 rays alone leave the GPU
+ * empty.  d_counts and d_offsets then have R * pieces entries indexed [ray * pieces + piece] (exclusive scan over all of
+ * them); the packed output is the same, sorted by ray and t.  A ray's range is d_offsets[ray * pieces] .. [(ray+1) * pieces]. */
 
 /* ---- fused training step for PACKED samples (the occupancy sampler PeRF trains with, configs/nerf.yaml:25;
  * nerf_renderer.py:145-183, nerf.py:186-297): perf_occ_count/write -> perf_fields_packed ->
@@ -280,8 +285,8 @@ int perf_occ_write(const uint8_t* d_binaries, const int* h_res3, const float* h_
  * samples get the in-box stand-in their features were taken at).  phase 0: no saves; PERF_PHASE_GEO / _APP: also
  * d_feat [N,32], d_h1 [N,64] (and d_h2 [N,64] for _APP) fp16 of the trained network. */
 int perf_fields_packed(const perf_render_args* args, const float* d_rays_o, const float* d_rays_d, const int64_t* d_ray_indices,
-                       const float* d_t_starts, const float* d_t_ends, uint64_t N, int phase, float* d_sigma, void* d_rgb_half4,
-                       float* d_x01, void* d_feat, void* d_h1, void* d_h2, void* stream);
+                       const float* d_t_starts, const float* d_t_ends, uint64_t N, const int64_t* d_n_dev /* nullable, see below */,
+                       int phase, float* d_sigma, void* d_rgb_half4, float* d_x01, void* d_feat, void* d_h1, void* d_h2, void* stream);
 
 /* Composite of packed samples, one warp per ray: w, T (nerfacc render_weight_from_density), opacity / distance /
  * colour (accumulate_along_rays), background rule (PERF_FLAG_TRAINING in flags: nerf_renderer.py:192-194, else
@@ -301,8 +306,13 @@ int perf_composite_packed_bwd(int phase, const int64_t* d_offsets, const float* 
                               float* d_dz, void* stream);
 /* perf_hashgrid_bwd with the number of levels whose same-cell runs of consecutive samples are merged before the
  * atomics chosen by the caller (packed samples are 5e-4 apart: runs exist up to resolution ~1000). */
-int perf_hashgrid_bwd_merged(const perf_grid_cfg* cfg, const float* d_x01, const float* d_dfeat, uint64_t N, float* d_dtable,
-                             uint32_t n_merge_levels, void* stream);
+int perf_hashgrid_bwd_merged(const perf_grid_cfg* cfg, const float* d_x01, const float* d_dfeat, uint64_t N, const int64_t* d_n_dev,
+                             float* d_dtable, uint32_t n_merge_levels, void* stream);
+/* d_n_dev (perf_fields_packed, perf_mlp_bwd, perf_hashgrid_bwd_merged): the sample count of a step is only known on the device
+ * (it is the last entry of the offsets scan).  Passing N = the CAPACITY of the buffers and d_n_dev = a device int64 holding the
+ * live count makes the launch sequence independent of the count -- the whole occupancy-sampler step can be captured into a CUDA
+ * graph and replayed without a host read.  perf_occ_write's `capacity` (0 = unlimited) drops samples that would not fit; the
+ * caller clamps the offsets and the count to it. */
 
 /* Batch draw (sup_info.py:253-259): dst_k[b, :] = src_k[idx[b], :] for up to 6 row-major fp32 arrays of row widths
  * h_width[k] in one launch.  h_src / h_dst: HOST arrays of device pointers. */

@@ -203,8 +203,9 @@ hashgrid_fwd_kernel(LevelTable lt, const uint32_t* __restrict__ table, const flo
 template <bool MERGE>
 __global__ void __launch_bounds__(256)
 hashgrid_bwd_kernel(LevelTable lt, int level0, const float* __restrict__ x01, const float* __restrict__ dfeat,
-                    uint64_t N, float2* __restrict__ dtable)
+                    uint64_t N, float2* __restrict__ dtable, const int64_t* __restrict__ n_dev = nullptr)
 {
+    if (n_dev) { const int64_t nd = *n_dev; N = nd < 0 ? 0 : ((uint64_t)nd < N ? (uint64_t)nd : N); }       // graph-replayable row count
     const int l = level0 + blockIdx.y, lane = threadIdx.x & 31;
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < N;
@@ -589,8 +590,8 @@ int perf_debug_atomic_rate(float* d_table, uint64_t n_floats, uint64_t n_atomics
     return PERF_OK;
 }
 
-int perf_hashgrid_bwd_merged(const perf_grid_cfg* cfg, const float* d_x01, const float* d_dfeat, uint64_t N, float* d_dtable,
-                             uint32_t n_merge_levels, void* stream)
+int perf_hashgrid_bwd_merged(const perf_grid_cfg* cfg, const float* d_x01, const float* d_dfeat, uint64_t N, const int64_t* d_n_dev,
+                             float* d_dtable, uint32_t n_merge_levels, void* stream)
 {
     PERF_CHECK_ARG(cfg && d_x01 && d_dfeat && d_dtable, "NULL pointer");
     LevelTable lt; int rc = build_level_table(cfg, &lt, nullptr); if (rc) return rc;
@@ -598,11 +599,11 @@ int perf_hashgrid_bwd_merged(const perf_grid_cfg* cfg, const float* d_x01, const
     if (N == 0) return PERF_OK;
     const uint32_t n_merge = n_merge_levels < lt.n_levels ? n_merge_levels : lt.n_levels;
     if (n_merge > 0) {
-        hashgrid_bwd_kernel<true><<<dim3(blocks_for(N, 256), n_merge), 256, 0, S(stream)>>>(lt, 0, d_x01, d_dfeat, N, (float2*)d_dtable);
+        hashgrid_bwd_kernel<true><<<dim3(blocks_for(N, 256), n_merge), 256, 0, S(stream)>>>(lt, 0, d_x01, d_dfeat, N, (float2*)d_dtable, d_n_dev);
         PERF_LAUNCH_CHECK();
     }
     if (lt.n_levels > n_merge) {
-        hashgrid_bwd_kernel<false><<<dim3(blocks_for(N, 256), lt.n_levels - n_merge), 256, 0, S(stream)>>>(lt, (int)n_merge, d_x01, d_dfeat, N, (float2*)d_dtable);
+        hashgrid_bwd_kernel<false><<<dim3(blocks_for(N, 256), lt.n_levels - n_merge), 256, 0, S(stream)>>>(lt, (int)n_merge, d_x01, d_dfeat, N, (float2*)d_dtable, d_n_dev);
         PERF_LAUNCH_CHECK();
     }
     return PERF_OK;

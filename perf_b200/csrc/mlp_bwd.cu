@@ -41,6 +41,7 @@ struct MlpBwdArgs {
     float*        dfeat;     // [N,32] fp32
     uint32_t      n_out;     // 1..3
     uint32_t      dbg;       // bring-up only (flags >> 8): bit 0 swaps LBO / SBO of the MN-major descriptors
+    const int64_t* n_dev;    // optional: the live row count in DEVICE memory (<= N = capacity); rows beyond it are skipped
 };
 
 __host__ __device__ constexpr uint32_t idesc_f16_major(int M, int N, bool a_mn, bool b_mn)
@@ -276,8 +277,10 @@ __host__ __device__ __forceinline__ void bwd_flush_g2(const MlpBwdArgs& a, int t
 }
 
 template <bool TWO, bool SIMT>
-__global__ void __launch_bounds__(128) mlp_bwd_kernel(const MlpBwdArgs a)
+__global__ void __launch_bounds__(128) mlp_bwd_kernel(const MlpBwdArgs a_in)
 {
+    MlpBwdArgs a = a_in;
+    if (a.n_dev) { const int64_t n = *a.n_dev; a.N = n < 0 ? 0 : ((uint64_t)n < a.N ? (uint64_t)n : a.N); }    // graph-replayable row count
     using L = BwdSmem<TWO>;
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::BAR);
@@ -472,7 +475,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 
 int perf_mlp_bwd(const perf_mlp_cfg* mlp, const void* d_weights_half, const void* d_feat, const void* d_h1, const void* d_h2,
-                 const float* d_dz, uint64_t N, float* d_dweights, float* d_dfeat, uint32_t flags, void* stream)
+                 const float* d_dz, uint64_t N, const int64_t* d_n_dev, float* d_dweights, float* d_dfeat, uint32_t flags, void* stream)
 {
     int rc = check_mlp(mlp); if (rc) return rc;
     PERF_CHECK_ARG(d_weights_half && d_feat && d_h1 && d_dz && d_dweights && d_dfeat, "NULL pointer");
@@ -482,7 +485,7 @@ int perf_mlp_bwd(const perf_mlp_cfg* mlp, const void* d_weights_half, const void
     if (N == 0) return PERF_OK;
     MlpBwdArgs a;
     a.w = (const __half*)d_weights_half; a.feat = (const uint4*)d_feat; a.h1 = (const uint4*)d_h1; a.h2 = (const uint4*)d_h2;
-    a.dz = d_dz; a.N = N; a.dW = d_dweights; a.dfeat = d_dfeat; a.n_out = mlp->n_out; a.dbg = flags >> 8;
+    a.dz = d_dz; a.N = N; a.dW = d_dweights; a.dfeat = d_dfeat; a.n_out = mlp->n_out; a.dbg = flags >> 8; a.n_dev = d_n_dev;
     const bool simt = (flags & PERF_FLAG_SIMT_MLP) != 0;
     if (mlp->n_hidden_layers == 2) return simt ? launch_mlp_bwd<true, true>(a, (cudaStream_t)stream) : launch_mlp_bwd<true, false>(a, (cudaStream_t)stream);
     return simt ? launch_mlp_bwd<false, true>(a, (cudaStream_t)stream) : launch_mlp_bwd<false, false>(a, (cudaStream_t)stream);
@@ -498,7 +501,7 @@ int perf_host_mlp_bwd(const perf_mlp_cfg* mlp, const void* h_weights_half, const
     PERF_CHECK_SUP(mlp->n_out <= 3, "n_out=%u", mlp->n_out);
     MlpBwdArgs a;
     a.w = (const __half*)h_weights_half; a.feat = (const uint4*)h_feat; a.h1 = (const uint4*)h_h1; a.h2 = (const uint4*)h_h2;
-    a.dz = h_dz; a.N = N; a.dW = h_dweights; a.dfeat = h_dfeat; a.n_out = mlp->n_out; a.dbg = 0;
+    a.dz = h_dz; a.N = N; a.dW = h_dweights; a.dfeat = h_dfeat; a.n_out = mlp->n_out; a.dbg = 0; a.n_dev = nullptr;
     uint8_t* smem = (uint8_t*)aligned_alloc(128, (size_t)(BwdSmem<true>::TOTAL + 127) / 128 * 128);
     float* gacc = (float*)calloc((size_t)TILE * N_GACC, sizeof(float));
     if (!smem || !gacc) { free(smem); free(gacc); return PERF_ECUDA; }

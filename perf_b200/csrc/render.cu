@@ -708,6 +708,7 @@ struct PackedFieldArgs {
     const float*   ts;            // [N]
     const float*   te;            // [N]
     uint64_t       N;
+    const int64_t* n_dev;         // optional live sample count in device memory (<= N = capacity)
     float*         sigma;         // [N]
     __half*        rgb;           // [N,4] fp16
     float*         x01;           // [N,3]
@@ -737,10 +738,12 @@ __global__ void __launch_bounds__(TILE, 4) packed_fields_kernel(const __grid_con
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
     uint32_t parity = 0;
-    const uint64_t n_tiles = (p.N + TILE - 1) / TILE;
+    uint64_t N = p.N;
+    if (p.n_dev) { const int64_t nd = *p.n_dev; N = nd < 0 ? 0 : ((uint64_t)nd < N ? (uint64_t)nd : N); }      // graph-replayable count
+    const uint64_t n_tiles = (N + TILE - 1) / TILE;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint64_t n = tile * TILE + tid;
-        const bool valid = n < p.N;
+        const bool valid = n < N;
         float x = 0.5f, y = 0.5f, z = 0.5f;
         if (valid) {
             const int64_t ray = p.ray_indices[n];
@@ -899,7 +902,7 @@ int perf_train_forward(const perf_render_args* args, const float* d_rays_o, cons
 }
 
 int perf_fields_packed(const perf_render_args* args, const float* d_rays_o, const float* d_rays_d, const int64_t* d_ray_indices,
-                       const float* d_t_starts, const float* d_t_ends, uint64_t N, int phase, float* d_sigma, void* d_rgb_half4,
+                       const float* d_t_starts, const float* d_t_ends, uint64_t N, const int64_t* d_n_dev, int phase, float* d_sigma, void* d_rgb_half4,
                        float* d_x01, void* d_feat, void* d_h1, void* d_h2, void* stream)
 {
     PERF_CHECK_ARG(args && d_rays_o && d_rays_d && d_ray_indices && d_t_starts && d_t_ends && d_sigma && d_rgb_half4 && d_x01, "NULL pointer");
@@ -916,7 +919,7 @@ int perf_fields_packed(const perf_render_args* args, const float* d_rays_o, cons
     a.rays_o = d_rays_o; a.rays_d = d_rays_d;
     a.s_feat = (uint4*)d_feat; a.s_h1 = (uint4*)d_h1; a.s_h2 = (uint4*)d_h2;
     if (N == 0) return PERF_OK;
-    PackedFieldArgs p = {d_ray_indices, d_t_starts, d_t_ends, N, d_sigma, (__half*)d_rgb_half4, d_x01};
+    PackedFieldArgs p = {d_ray_indices, d_t_starts, d_t_ends, N, d_n_dev, d_sigma, (__half*)d_rgb_half4, d_x01};
     cudaStream_t st = (cudaStream_t)stream;
     rc = prepare_weights(a, st); if (rc) return rc;
     const uint64_t n_tiles = (N + TILE - 1) / TILE;

@@ -351,6 +351,41 @@ __global__ void __launch_bounds__(128) hashgrid_bwd_march_kernel(const __grid_co
     if (ray < a.R) bwd_march_ray_level<V4>(a, ray, (int)blockIdx.y, blockIdx.z, gridDim.z);
 }
 
+// Both scatter bodies in ONE launch: blocks of 256 threads, most of them fine-level blocks (thread = (row, level)), every
+// (r+1)-th one a pair of coarse-level march blocks (thread = (ray, level, piece)).  Two separate launches -- even on two
+// streams -- barely overlap: the fine kernel's blocks fill every SM and the latency-bound march blocks wait for them to
+// retire (0.53 -> 0.50 ms); interleaved in one grid both kinds are resident together and the march kernel's latency hides
+// behind the fine kernel's reductions.
+struct GridBwdBothArgs {
+    GridBwdRaysArgs a, b;        // a: all levels (coarse launch uses [0, n_agg)); b: the fine levels shifted down to index 0
+    uint32_t n_agg, pieces, gx_march, gx_fine, n_fine_levels;
+    uint32_t Bc, Bf, r;          // coarse 256-thread blocks, fine blocks, fine blocks per coarse block (interleave ratio)
+};
+template <bool V4>
+__global__ void __launch_bounds__(256) hashgrid_bwd_both_kernel(const __grid_constant__ GridBwdBothArgs g)
+{
+    const uint32_t blk = blockIdx.x;
+    uint32_t fine_idx, coarse_idx = 0xffffffffu;
+    if (blk < g.Bc * (g.r + 1u)) {
+        const uint32_t q = blk / (g.r + 1u), m = blk % (g.r + 1u);
+        if (m < g.r) fine_idx = q * g.r + m; else { coarse_idx = q; fine_idx = 0xffffffffu; }
+    } else {
+        fine_idx = g.Bc * g.r + (blk - g.Bc * (g.r + 1u));
+    }
+    if (coarse_idx != 0xffffffffu) {
+        const uint32_t mb = coarse_idx * 2u + (threadIdx.x >> 7);              // march block of 128 threads
+        const uint32_t n_mb = g.gx_march * g.n_agg * g.pieces;
+        if (mb < n_mb) {
+            const uint32_t bx = mb % g.gx_march, level = (mb / g.gx_march) % g.n_agg, piece = mb / (g.gx_march * g.n_agg);
+            const uint64_t ray = (uint64_t)bx * 128 + (threadIdx.x & 127);
+            if (ray < g.a.R) bwd_march_ray_level<V4>(g.a, ray, (int)level, piece, g.pieces);
+        }
+    } else {
+        const uint32_t bx = fine_idx % g.gx_fine, level = fine_idx / g.gx_fine;
+        if (level < g.n_fine_levels) bwd_rays_row_level<V4>(g.b, (uint64_t)bx * 256 + threadIdx.x, (int)level);
+    }
+}
+
 // ---- the scalar losses of a training step and their gradients w.r.t. the renderer outputs, ONE launch
 // (nerf.py:208-238 density phase: smooth-L1 depth (beta 1e-2) + ramped distortion loss; nerf.py:281-287 colour phase:
 // smooth-L1 colour (beta 5e-2)).  Replaces ~25 elementwise / reduction launches of the autograd graph per step.
@@ -505,6 +540,26 @@ int perf_hashgrid_bwd_rays(const perf_grid_cfg* cfg, const float* aabb6, const f
     unsigned pieces = 1;
     while (pieces < 8 && (uint64_t)R * n_agg * pieces < (uint64_t)num_sms() * 2048 && n_samples / (pieces * 2) >= 16) pieces *= 2;
     dim3 g_agg((unsigned)((R + 127) / 128), n_agg, pieces);
+    {   // default: ONE launch with interleaved coarse / fine blocks (PERF_B200_SCATTER_MERGED=0: the two-launch path below)
+        const char* env_m = getenv("PERF_B200_SCATTER_MERGED");
+        const char* env_v4m = getenv("PERF_B200_SCATTER_V4");
+        const bool v4m = !(env_v4m && env_v4m[0] == '0') && (uintptr_t)a.dtable % 16 == 0;
+        if (!(env_m && env_m[0] == '0') && a.lt.n_levels > n_agg) {
+            GridBwdBothArgs gb; gb.a = a; gb.b = b;
+            gb.n_agg = n_agg; gb.pieces = pieces; gb.gx_march = g_agg.x; gb.gx_fine = (unsigned)((N + 255) / 256); gb.n_fine_levels = a.lt.n_levels - n_agg;
+            const uint64_t n_mb = (uint64_t)g_agg.x * n_agg * pieces;
+            gb.Bc = (uint32_t)((n_mb + 1) / 2); gb.Bf = gb.gx_fine * gb.n_fine_levels;
+            gb.r = gb.Bc ? (gb.Bf / gb.Bc > 0 ? gb.Bf / gb.Bc : 1u) : 1u;
+            if ((uint64_t)gb.Bc * gb.r > gb.Bf) gb.r = 1u;                      // more coarse than fine blocks: no interleave room
+            if ((uint64_t)gb.Bc * gb.r <= gb.Bf) {
+                const unsigned total = gb.Bc * (gb.r + 1u) + (gb.Bf - gb.Bc * gb.r);
+                if (v4m) hashgrid_bwd_both_kernel<true><<<total, 256, 0, (cudaStream_t)stream>>>(gb);
+                else hashgrid_bwd_both_kernel<false><<<total, 256, 0, (cudaStream_t)stream>>>(gb);
+                PERF_LAUNCH_CHECK();
+                return PERF_OK;
+            }
+        }
+    }
     // The two launches touch disjoint halves of the gradient table and both sit on atomic latency, not bandwidth: run the
     // coarse one on a side stream (fork / join through events; capturable into a CUDA graph).  PERF_B200_SCATTER_OVERLAP=0
     // serialises them on the caller's stream as in round 1.

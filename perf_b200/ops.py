@@ -384,7 +384,16 @@ def accumulate_along_rays(weights, values, ray_indices, n_rays: int) -> torch.Te
 
 
 # ------------------------------------------------------------------ occupancy-grid sampler
-def occ_sample(binaries: torch.Tensor, aabb, rays_o, rays_d, near: float, far: float, step: float, jitter=None):
+def _occ_pieces(R: int) -> int:
+    """Parts every ray's lattice walk is cut into so that ~256 k threads march (a ray alone is a serial walk of up to
+    (far - near) / step = 3000 lattice points; 8192 ray-threads left the GPU empty: 1.08 ms per pass, profiles/r02)."""
+    p = 1
+    while p < 64 and R * p * 2 <= 262144:
+        p *= 2
+    return p
+
+
+def occ_sample(binaries: torch.Tensor, aabb, rays_o, rays_d, near: float, far: float, step: float, jitter=None, pieces: Optional[int] = None):
     """Packed (ray_indices, t_starts, t_ends) of the lattice samples whose midpoint is inside the aabb
     in an occupied cell (two kernels around one cumsum; one host sync for the total, as nerfacc)."""
     rays_o, rays_d = _chk(rays_o, torch.float32, "rays_o"), _chk(rays_d, torch.float32, "rays_d")
@@ -393,22 +402,65 @@ def occ_sample(binaries: torch.Tensor, aabb, rays_o, rays_d, near: float, far: f
         raise RuntimeError("perf_b200.occ_sample: `binaries` must be a CUDA bool tensor [rx, ry, rz]")
     bins = binaries.contiguous().view(torch.uint8) if binaries.dtype == torch.bool else _chk(binaries, torch.uint8, "binaries")
     R, dev = rays_o.shape[0], rays_o.device
+    P = _occ_pieces(R) if pieces is None else int(pieces)
     res3 = (C.c_int * 3)(*[int(v) for v in binaries.shape])
     a6 = (C.c_float * 6)(*[float(v) for v in aabb])
-    counts = torch.empty(R, dtype=torch.int32, device=dev)
+    counts = torch.empty(R * P, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
-        _call(_L().perf_occ_count, _p(bins), res3, a6, _p(rays_o), _p(rays_d), _p(jitter), R, near, far, step, _p(counts), _stream())
+        _call(_L().perf_occ_count, _p(bins), res3, a6, _p(rays_o), _p(rays_d), _p(jitter), R, near, far, step, P, _p(counts), _stream())
     incl = torch.cumsum(counts, 0, dtype=torch.int64)
     total = int(incl[-1].item()) if R else 0
-    offsets = (incl - counts).contiguous()
-    occ_sample.last_offsets = torch.cat([offsets, incl[-1:]]) if R else torch.zeros(1, dtype=torch.int64, device=dev)   # [R+1]
+    offsets = (incl - counts).contiguous()                                  # [R * P], exclusive
+    # per-ray ranges [R + 1]: the first piece's offset of every ray, then the total
+    occ_sample.last_offsets = torch.cat([offsets[::P], incl[-1:]]) if R else torch.zeros(1, dtype=torch.int64, device=dev)
     ri = torch.empty(total, dtype=torch.int64, device=dev)
     ts, te = torch.empty(total, dtype=torch.float32, device=dev), torch.empty(total, dtype=torch.float32, device=dev)
     if total:
         with torch.cuda.device(dev):
-            _call(_L().perf_occ_write, _p(bins), res3, a6, _p(rays_o), _p(rays_d), _p(jitter), R, near, far, step, _p(offsets),
+            _call(_L().perf_occ_write, _p(bins), res3, a6, _p(rays_o), _p(rays_d), _p(jitter), R, near, far, step, P, _p(offsets), 0,
                   _p(ri), _p(ts), _p(te), _stream())
     return ri, ts, te
+
+
+class OccStaticBuffers:
+    """Fixed-capacity buffers of :func:`occ_sample_static` (one set per (R, capacity, device); reused every step)."""
+
+    def __init__(self, R: int, capacity: int, dev, pieces: Optional[int] = None):
+        self.R, self.capacity, self.pieces = R, capacity, (_occ_pieces(R) if pieces is None else int(pieces))
+        P = self.pieces
+        self.counts = torch.empty(R * P, dtype=torch.int32, device=dev)
+        self.offsets_all = torch.zeros(R * P + 1, dtype=torch.int64, device=dev)  # exclusive scan over (ray, piece); [0] stays 0
+        self.offsets = torch.zeros(R + 1, dtype=torch.int64, device=dev)         # per-ray ranges, clamped to the capacity
+        self.raw_total = torch.zeros(1, dtype=torch.int64, device=dev)           # un-clamped sample count of the last call
+        self.n = torch.zeros(1, dtype=torch.int64, device=dev)                   # live count = min(raw_total, capacity)
+        self.ri = torch.zeros(capacity, dtype=torch.int64, device=dev)
+        self.ts = torch.zeros(capacity, dtype=torch.float32, device=dev)
+        self.te = torch.zeros(capacity, dtype=torch.float32, device=dev)
+        self.overflowed = torch.zeros(1, dtype=torch.int64, device=dev)          # running max of raw_total (host reads it rarely)
+
+
+def occ_sample_static(binaries: torch.Tensor, aabb, rays_o, rays_d, near: float, far: float, step: float, jitter, buf: OccStaticBuffers):
+    """:func:`occ_sample` without the host read of the sample count: the packed intervals go into ``buf`` (capacity-sized),
+    ``buf.n`` holds the live count ON THE DEVICE and ``buf.offsets`` the per-ray ranges, both clamped to the capacity
+    (samples that do not fit are dropped from the END of the batch; ``buf.overflowed`` remembers the largest request).
+    Everything is stream-ordered device work with shapes that do not depend on the count: capturable into a CUDA graph."""
+    rays_o, rays_d = _chk(rays_o, torch.float32, "rays_o"), _chk(rays_d, torch.float32, "rays_d")
+    jitter = None if jitter is None else _chk(jitter, torch.float32, "jitter")
+    bins = binaries.contiguous().view(torch.uint8) if binaries.dtype == torch.bool else _chk(binaries, torch.uint8, "binaries")
+    R, P = rays_o.shape[0], buf.pieces
+    assert R == buf.R
+    res3 = (C.c_int * 3)(*[int(v) for v in binaries.shape])
+    a6 = (C.c_float * 6)(*[float(v) for v in aabb])
+    with torch.cuda.device(rays_o.device):
+        _call(_L().perf_occ_count, _p(bins), res3, a6, _p(rays_o), _p(rays_d), _p(jitter), R, near, far, step, P, _p(buf.counts), _stream())
+        torch.cumsum(buf.counts, 0, dtype=torch.int64, out=buf.offsets_all[1:])
+        buf.raw_total.copy_(buf.offsets_all[R * P:])
+        torch.maximum(buf.overflowed, buf.raw_total, out=buf.overflowed)
+        _call(_L().perf_occ_write, _p(bins), res3, a6, _p(rays_o), _p(rays_d), _p(jitter), R, near, far, step, P, _p(buf.offsets_all), buf.capacity,
+              _p(buf.ri), _p(buf.ts), _p(buf.te), _stream())
+        torch.clamp(buf.offsets_all[::P], max=buf.capacity, out=buf.offsets)        # [R + 1]: (R * P) % P == 0, so the total is included
+        buf.n.copy_(buf.offsets[R:])
+    return buf.ri, buf.ts, buf.te, buf.offsets, buf.n
 
 
 # ------------------------------------------------------------------ fused renderer
@@ -493,7 +545,7 @@ def render_occ(packed_table, geo_mlp_half, app_mlp_half, rays_o, rays_d, offsets
     w, T, dacc, dl = f32(N), f32(N), f32(R), f32(R)
     a = _render_args(packed_table, geo_mlp_half, app_mlp_half, aabb, 1, 0.0, 1.0, False, False, None, None, rgb, dist, op, grid)
     with torch.cuda.device(dev):
-        _call(_L().perf_fields_packed, C.byref(a), _p(rays_o), _p(rays_d), _p(ray_indices), _p(t_starts), _p(t_ends), N, 0,
+        _call(_L().perf_fields_packed, C.byref(a), _p(rays_o), _p(rays_d), _p(ray_indices), _p(t_starts), _p(t_ends), N, None, 0,
               _p(sigma), _p(c16), _p(x01), None, None, None, _stream(), launches=2)
         _call(_L().perf_composite_packed_fwd, _p(offsets), _p(t_starts), _p(t_ends), _p(sigma), _p(c16), R, float(early_stop_eps), 0, None,
               _p(w), _p(T), _p(rgb), _p(dist), _p(op), _p(dacc), _p(dl), _stream())
@@ -549,6 +601,20 @@ class FusedTrainContext:
             self._bufs = dict(last + [(key, b)])
         return self._bufs[key]
 
+    def packed_buffers(self, R: int, N: int, phase: int, dev):
+        """Per-sample buffers of the packed (occupancy) step, cached per (R, N, phase): with capacity-sized sample tensors N
+        never changes, so a captured step always sees the same storage."""
+        key = ("packed", R, N, phase, str(dev))
+        if key not in self._bufs:
+            geo = phase == _lib.PERF_PHASE_GEO
+            f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+            f16 = lambda *s: torch.empty(*s, dtype=torch.float16, device=dev)
+            b = {"sigma": f32(N), "rgb": f16(N, 4), "x01": f32(N, 3), "feat": f16(N, 32), "h1": f16(N, 64), "h2": None if geo else f16(N, 64),
+                 "w": f32(N), "T": f32(N), "dacc": f32(R), "dl": f32(R), "dz": f32(N, 1 if geo else 3)}
+            last = list(self._bufs.items())[-1:]
+            self._bufs = dict(last + [(key, b)])
+        return self._bufs[key]
+
     @staticmethod
     def c_buffers(b) -> "_lib.TrainBuffers":
         ptr = lambda t: None if t is None else t.data_ptr()
@@ -557,15 +623,15 @@ class FusedTrainContext:
 
 
 def mlp_backward_half(mlp: MLPConfig, weights_half: torch.Tensor, feat, h1, h2, dz: torch.Tensor,
-                      grad_out: Optional[torch.Tensor] = None):
+                      grad_out: Optional[torch.Tensor] = None, n_dev: Optional[torch.Tensor] = None):
     """MLP backward from saved fp16 activations (tcnn ``FullyFusedMLP::backward_impl``, reached from
     `ngp_nerf.py:142,158` under autograd): ONE tcgen05 kernel, :func:`mlp_backward_fused` (csrc/mlp_bwd.cu).
     ``dz`` [N, n_out] fp32: gradient w.r.t. the output layer's pre-activation.
     Returns (d_weights_flat fp32 [mlp.n_params] -- written into ``grad_out`` when given --, dfeat fp32 [N,32]).
     ``PERF_B200_GEMM_MLP_BWD=1`` selects :func:`mlp_backward_gemm` (library GEMMs; the A/B reference of round 1)."""
-    if os.environ.get("PERF_B200_GEMM_MLP_BWD") == "1":
+    if os.environ.get("PERF_B200_GEMM_MLP_BWD") == "1" and n_dev is None:
         return mlp_backward_gemm(mlp, weights_half, feat, h1, h2, dz, grad_out)
-    return mlp_backward_fused(mlp, weights_half, feat, h1, h2, dz, grad_out)
+    return mlp_backward_fused(mlp, weights_half, feat, h1, h2, dz, grad_out, n_dev=n_dev)
 
 
 def mlp_backward_gemm(mlp: MLPConfig, weights_half: torch.Tensor, feat, h1, h2, dz: torch.Tensor,
@@ -602,7 +668,7 @@ def mlp_backward_gemm(mlp: MLPConfig, weights_half: torch.Tensor, feat, h1, h2, 
 
 
 def mlp_backward_fused(mlp: MLPConfig, weights_half: torch.Tensor, feat, h1, h2, dz: torch.Tensor,
-                       grad_out: Optional[torch.Tensor] = None, simt: bool = False, dbg: int = 0):
+                       grad_out: Optional[torch.Tensor] = None, simt: bool = False, dbg: int = 0, n_dev: Optional[torch.Tensor] = None):
     """The whole MLP backward as ONE tcgen05 kernel (perf_mlp_bwd, csrc/mlp_bwd.cu): output-layer backward on CUDA
     cores, data gradients dh W as MMAs against the forward weight images read MN-major, weight gradients
     [dh]^T [h] accumulated in TMEM over the CTA's tiles and flushed once.  Validated on B200 in round 2 against a
@@ -616,8 +682,8 @@ def mlp_backward_fused(mlp: MLPConfig, weights_half: torch.Tensor, feat, h1, h2,
     dz = _chk(dz.reshape(N, mlp.n_out), torch.float32, "dz")
     with torch.cuda.device(dev):
         _call(_L().perf_mlp_bwd, mlp.c(), _p(_chk(weights_half, torch.float16, "weights")), _p(_chk(feat, torch.float16, "feat")),
-              _p(_chk(h1, torch.float16, "h1")), _p(None if h2 is None else _chk(h2, torch.float16, "h2")), _p(dz), N,
-              _p(grad_out), _p(dfeat), (_lib.PERF_FLAG_SIMT_MLP if simt else 0) | (dbg << 8), _stream())
+              _p(_chk(h1, torch.float16, "h1")), _p(None if h2 is None else _chk(h2, torch.float16, "h2")), _p(dz), N, _p(n_dev),
+              _p(grad_out), _p(dfeat), (_lib.PERF_FLAG_SIMT_MLP if simt else 0) | (dbg << 8), _stream(), launches=2)
     return grad_out, dfeat
 
 
@@ -678,38 +744,37 @@ class _FusedPackedTrainStep(torch.autograd.Function):
     occupancy sampler's output, all of them -- the 1e-4 transmittance cut of ``OccGridEstimator.sampling`` is applied
     inside the composite), differentiable w.r.t. the flat params of the network selected by ``phase``
     (`nerf_renderer.py:145-209` under `nerf.py:186-297`).  Forward: perf_fields_packed + perf_composite_packed_fwd;
-    backward: perf_composite_packed_bwd + perf_mlp_bwd + perf_hashgrid_bwd_merged.  No torch glue on per-sample data."""
+    backward: perf_composite_packed_bwd + perf_mlp_bwd + perf_hashgrid_bwd_merged.  No torch glue on per-sample data.
+    ``n_dev`` (device int64 [1]): the live sample count when the sample tensors are capacity-sized (graph capture)."""
 
     MERGE_LEVELS = 13          # same-cell runs of consecutive 5e-4 samples exist up to resolution ~1350 (level 12)
 
     @staticmethod
     def forward(ctx, params, rays_o, rays_d, offsets, ray_indices, t_starts, t_ends, bg_noise, tc: FusedTrainContext, phase: int,
-                early_stop_eps: float):
+                early_stop_eps: float, n_dev):
         R, N, dev = rays_o.shape[0], t_starts.shape[0], rays_o.device
         geo = phase == _lib.PERF_PHASE_GEO
+        b = tc.packed_buffers(R, N, phase, dev)
         f32 = lambda *sh: torch.empty(*sh, dtype=torch.float32, device=dev)
-        f16 = lambda *sh: torch.empty(*sh, dtype=torch.float16, device=dev)
-        b = {"sigma": f32(N), "rgb": f16(N, 4), "x01": f32(N, 3), "feat": f16(N, 32), "h1": f16(N, 64), "h2": None if geo else f16(N, 64),
-             "w": f32(N), "T": f32(N), "dacc": f32(R), "dl": f32(R)}
         rgb, dist, op = f32(R, 3), f32(R, 1), f32(R, 1)
         a = _render_args(tc.packed, tc.geo_half, tc.app_half, tc.aabb, 1, 0.0, 1.0, True, False, None, bg_noise, rgb, dist, op, tc.grid)
         with torch.cuda.device(dev):
-            _call(_L().perf_fields_packed, C.byref(a), _p(rays_o), _p(rays_d), _p(ray_indices), _p(t_starts), _p(t_ends), N, phase,
+            _call(_L().perf_fields_packed, C.byref(a), _p(rays_o), _p(rays_d), _p(ray_indices), _p(t_starts), _p(t_ends), N, _p(n_dev), phase,
                   _p(b["sigma"]), _p(b["rgb"]), _p(b["x01"]), _p(b["feat"]), _p(b["h1"]), _p(b["h2"]), _stream(), launches=2)
             _call(_L().perf_composite_packed_fwd, _p(offsets), _p(t_starts), _p(t_ends), _p(b["sigma"]), _p(b["rgb"]), R, float(early_stop_eps),
                   _lib.PERF_FLAG_TRAINING, _p(bg_noise), _p(b["w"]), _p(b["T"]), _p(rgb), _p(dist), _p(op), _p(b["dacc"]), _p(b["dl"]), _stream())
-        ctx.tc, ctx.phase, ctx.b = tc, phase, b
+        ctx.tc, ctx.phase, ctx.b, ctx.n_dev = tc, phase, b, n_dev
         ctx.save_for_backward(offsets, t_starts, t_ends, bg_noise, dist, op)
         return rgb, dist, op, b["dl"].clone()
 
     @staticmethod
     def backward(ctx, g_rgb, g_dist, g_op, g_dl):
         offsets, t_starts, t_ends, bg_noise, dist, op = ctx.saved_tensors
-        tc, phase, b = ctx.tc, ctx.phase, ctx.b
+        tc, phase, b, n_dev = ctx.tc, ctx.phase, ctx.b, ctx.n_dev
         R, N, dev = op.shape[0], t_starts.shape[0], op.device
         geo = phase == _lib.PERF_PHASE_GEO
         mlp = GEO_MLP if geo else APP_MLP
-        dz = torch.empty(N, mlp.n_out, dtype=torch.float32, device=dev)
+        dz = b["dz"]
         c = lambda t: None if t is None else t.contiguous().float()
         g_rgb, g_dist, g_op, g_dl = c(g_rgb), c(g_dist), c(g_op), c(g_dl)
         with torch.cuda.device(dev):
@@ -717,22 +782,24 @@ class _FusedPackedTrainStep(torch.autograd.Function):
                   _p(b["w"]), _p(b["T"]), _p(dist), _p(op), _p(b["dacc"]), _p(g_rgb), _p(g_dist), _p(g_op), _p(g_dl), _p(dz), _stream())
         half = tc.geo_half if geo else tc.app_half
         grad = torch.zeros(mlp.n_params + 2 * tc.grid.n_entries, dtype=torch.float32, device=dev)
-        _, dfeat = mlp_backward_half(mlp, half[:mlp.n_params], b["feat"], b["h1"], b["h2"], dz, grad_out=grad[:mlp.n_params])
+        _, dfeat = mlp_backward_half(mlp, half[:mlp.n_params], b["feat"], b["h1"], b["h2"], dz, grad_out=grad[:mlp.n_params], n_dev=n_dev)
         with torch.cuda.device(dev):
-            _call(_L().perf_hashgrid_bwd_merged, tc.grid.c(), _p(b["x01"]), _p(dfeat), N, _p(grad[mlp.n_params:]),
+            _call(_L().perf_hashgrid_bwd_merged, tc.grid.c(), _p(b["x01"]), _p(dfeat), N, _p(n_dev), _p(grad[mlp.n_params:]),
                   _FusedPackedTrainStep.MERGE_LEVELS, _stream(), launches=2)
-        return (grad,) + (None,) * 10
+        return (grad,) + (None,) * 11
 
 
 def fused_packed_train_step(params, rays_o, rays_d, offsets, ray_indices, t_starts, t_ends, bg_noise, tc: FusedTrainContext, phase: int,
-                            early_stop_eps: float = 1e-4):
+                            early_stop_eps: float = 1e-4, n_dev: Optional[torch.Tensor] = None):
     rays_o, rays_d = _chk(rays_o, torch.float32, "rays_o"), _chk(rays_d, torch.float32, "rays_d")
     offsets, ray_indices = _chk(offsets, torch.int64, "offsets"), _chk(ray_indices, torch.int64, "ray_indices")
     t_starts, t_ends = _chk(t_starts, torch.float32, "t_starts"), _chk(t_ends, torch.float32, "t_ends")
     bg_noise = _chk(bg_noise, torch.float32, "bg_noise")
     if offsets.numel() != rays_o.shape[0] + 1:
         raise RuntimeError("perf_b200.fused_packed_train_step: offsets must have R + 1 entries")
-    return _FusedPackedTrainStep.apply(params, rays_o, rays_d, offsets, ray_indices, t_starts, t_ends, bg_noise, tc, phase, early_stop_eps)
+    if n_dev is not None:
+        n_dev = _chk(n_dev, torch.int64, "n_dev")
+    return _FusedPackedTrainStep.apply(params, rays_o, rays_d, offsets, ray_indices, t_starts, t_ends, bg_noise, tc, phase, early_stop_eps, n_dev)
 
 
 def gather_rows(idx: torch.Tensor, *arrays: torch.Tensor):

@@ -372,7 +372,6 @@ class NeRFScene:
         if estimator_type == "occ":                                    # nerf.py:68
             from .shims.nerfacc.estimators.occ_grid import OccGridEstimator
             self.estimator = OccGridEstimator(roi_aabb=self.aabb, resolution=occ_resolution, levels=1).to(self.device)
-            graph_train = False                                        # the packed step has a host read (sample count) per step
         else:
             self.estimator = FixedSampleEstimator(n_samples, near, far)
         self.renderer = NeRFOCCRenderer(**(renderer_conf or {"max_radius": 2, "bg_color": "rand_noise"}))
@@ -460,6 +459,17 @@ class NeRFScene:
         if self.estimator_type == "occ":
             # the sampler PeRF trains with (nerf_renderer.py:145-155): packed intervals, one offset per ray when training
             est = self.estimator
+            static = getattr(self, "_occ_static", None)
+            if static is not None and static.R == R:
+                # capacity-sized buffers, sample count stays on the device: no host read, graph-capturable (GraphedTrainStep);
+                # a batch without samples is a no-op step here instead of the reference's early return (nerf_renderer.py:156-162)
+                ri, ts, te, offsets, n_dev = ops.occ_sample_static(est.binaries[0], est._aabb_list(), rays_o.float().contiguous(),
+                                                                   rays_d.float().contiguous(), 0.0, 1.5, self.OCC_STEP,
+                                                                   jitter if self.nerf.training else None, static)
+                rgb, dist, op, dl = ops.fused_packed_train_step(param, rays_o.float(), rays_d.float(), offsets, ri, ts, te, noise, tc, phase, 1e-4, n_dev=n_dev)
+                n_rays = (ri[(n_dev - 1).clamp(min=0)] + 1).float().reshape(())       # flatten_eff_distloss: ray_id.max() + 1
+                return {"is_valid": True, "rgb": rgb, "distance": dist, "opacities": op, "dist_loss": _Lazy(lambda: dl.sum() / n_rays),
+                        "dist_loss_rays": dl, "dist_loss_inv_n": 1.0 / n_rays}
             ri, ts, te = ops.occ_sample(est.binaries[0], est._aabb_list(), rays_o.float().contiguous(), rays_d.float().contiguous(),
                                         0.0, 1.5, self.OCC_STEP, jitter if self.nerf.training else None)
             if ri.numel() <= 0:                                              # nerf_renderer.py:156-162
@@ -670,13 +680,27 @@ class GraphedTrainStep:
             loss = step(progress=i / app_iters)
     """
 
-    def __init__(self, scene: NeRFScene, phase: str, sup_pool: RaySupervision, optimizer: FusedAdam, warmup: int = 3, split: bool = False):
+    def __init__(self, scene: NeRFScene, phase: str, sup_pool: RaySupervision, optimizer: FusedAdam, warmup: int = 3, split: bool = False,
+                 occ_capacity: int = 0):
         """``split=True``: four graphs instead of one -- [batch draw + forward + losses + backward], [gradient exchange],
         [Adam], [shadow all-gather] -- replayed back to back with CUDA events in between (``self.stage_ms`` after each
         call): the timeline of a step (VERDICT r1 next #2).  Slightly slower than the single graph (three more launches)."""
         assert phase in ("geo", "app") and scene.fused_train
         self.scene, self.phase, self.pool, self.opt, self.split = scene, phase, sup_pool, optimizer, split
         dev = scene.device
+        if scene.estimator_type == "occ":
+            # Occupancy sampler: the sample count of a batch is data dependent.  Probe it once (eager, one host read), give the
+            # step capacity-sized buffers with head-room and keep the live count on the device from then on
+            # (ops.occ_sample_static): the replayed launch sequence does not depend on the count.  `occ_overflow()` reports
+            # whether any replayed batch asked for more than the capacity (its last samples were then dropped).
+            R = scene._local_batch()
+            rays, _, _, _ = sup_pool.rand_ray_color_data(R)
+            ro, rd = rays.collapse()
+            est = scene.estimator
+            probe = ops.occ_sample(est.binaries[0], est._aabb_list(), ro.float().contiguous(), rd.float().contiguous(), 0.0, 1.5,
+                                   scene.OCC_STEP, torch.rand(R, device=dev))[0].numel()
+            cap = occ_capacity or int(max(probe * 1.5, R * 16)) // 128 * 128 + 128
+            scene._occ_static = ops.OccStaticBuffers(R, cap, dev)
         self.ratio = torch.zeros(1, device=dev)
         self.net = scene.nerf.geo_mlp if phase == "geo" else scene.nerf.app_mlp
         sup_pool.use_default_generator = True                 # graph-safe RNG; decorrelate the ranks' batches
@@ -774,6 +798,11 @@ class GraphedTrainStep:
         if self.overlap_gather:
             self.scene._pending_gather = self.opt             # this step's shard is gathered by the next replay / eager use
         return self.loss
+
+    def occ_overflow(self) -> int:
+        """(occupancy scenes) samples the largest replayed batch asked for beyond the capacity (0 = every batch fitted)."""
+        st = getattr(self.scene, "_occ_static", None)
+        return 0 if st is None else max(0, int(st.overflowed) - st.capacity)
 
     def finish(self):
         """Complete the state after the last replay: gather the last step's shadow shard (overlap mode) and the fp32 master."""

@@ -85,17 +85,18 @@ def scatter8(idx: np.ndarray, v: np.ndarray, n_entries: int, v4: bool) -> np.nda
     return dtable.copy()
 
 
-def occ_sample(binaries: np.ndarray, aabb, rays_o: np.ndarray, rays_d: np.ndarray, near: float, far: float, step: float, jitter=None):
-    """occ_march_ray of csrc/occ.cu (count pass, exclusive scan, write pass) -> (ray_indices, t_starts, t_ends)."""
+def occ_sample(binaries: np.ndarray, aabb, rays_o: np.ndarray, rays_d: np.ndarray, near: float, far: float, step: float, jitter=None, pieces: int = 1):
+    """occ_march_ray of csrc/occ.cu (count pass, exclusive scan, write pass) -> (ray_indices, t_starts, t_ends).
+    ``pieces``: every ray's lattice range cut into that many parts (counts / offsets per (ray, piece))."""
     R = rays_o.shape[0]
     bin8 = np.ascontiguousarray(binaries, np.uint8)
     res3 = (C.c_int * 3)(*binaries.shape)
     a6 = (C.c_float * 6)(*[float(v) for v in aabb])
     o, d = np.ascontiguousarray(rays_o, np.float32), np.ascontiguousarray(rays_d, np.float32)
     j = None if jitter is None else np.ascontiguousarray(jitter, np.float32)
-    counts = np.zeros(R, np.int32)
+    counts = np.zeros(R * pieces, np.int32)
     f = lib().perf_host_occ_march
-    args = (_p(bin8), res3, a6, _p(o), _p(d), _p(j), C.c_uint64(R), C.c_float(near), C.c_float(far), C.c_float(step))
+    args = (_p(bin8), res3, a6, _p(o), _p(d), _p(j), C.c_uint64(R), C.c_float(near), C.c_float(far), C.c_float(step), C.c_uint32(pieces))
     assert f(0, *args, _p(counts), None, None, None, None) == 0
     offsets = np.concatenate([[0], np.cumsum(counts, dtype=np.int64)]).astype(np.int64)
     n = int(offsets[-1])

@@ -178,3 +178,48 @@ def test_occ_update_kernels_match_torch_restatement():
     # post-warm-up branch (subset of cells)
     est.update_every_n_steps(step=100, occ_eval_fn=make_fn(torch.ones(n)), occ_thre=1e-2, ema_decay=0.5, warmup_steps=8, n=1)
     assert float(est.occs.max()) == 1.0 and bool(est.binaries.any())
+
+
+def test_capacity_mode_equals_eager_packed_step_and_replays_as_a_graph(golden_field):
+    """The graph-capturable form of the occupancy step (capacity-sized buffers, sample count on the device, ops.occ_sample_static
+    + d_n_dev arguments) gives the same loss and gradient as the eager packed step with its host read; the whole step then
+    replays as ONE CUDA graph; a capacity that is too small is reported and the step stays finite."""
+    from perf_b200 import ops, synthetic
+    from perf_b200.scene import FusedAdam, GraphedTrainStep, RaySupervision
+    h, w = 32, 64
+    rgb, dist = synthetic.smooth_rgb(h, w, device="cuda"), synthetic.box_room_distance(h, w, device="cuda")
+    g = torch.Generator().manual_seed(73)
+    binaries = torch.rand(24, 24, 24, generator=g) < 0.35
+    out = {}
+    for static in (False, True):
+        sc = _occ_scene(golden_field, True, binaries, 512)
+        sc.set_train()
+        pool = RaySupervision.from_panorama(torch.eye(4), rgb, dist, seed=3)
+        if static:
+            sc._occ_static = ops.OccStaticBuffers(512, 80000, "cuda")
+        opt = FusedAdam(sc.nerf.geo_mlp.params, lr=0.0, module=sc.nerf.geo_mlp)
+        torch.manual_seed(21)
+        loss = sc.train_one_step_geo(opt, pool, progress=0.4)
+        out[static] = (float(loss), sc.nerf.geo_mlp.params.grad.detach().clone())
+        if static:
+            n_live, raw = int(sc._occ_static.n), int(sc._occ_static.raw_total)
+            assert 0 < n_live == raw < 80000
+    (le, ge), (ls, gs) = out[False], out[True]
+    assert abs(le - ls) <= 1e-6 * max(1.0, abs(le)), (le, ls)
+    assert (ge - gs).abs().max() <= 1e-4 * ge.abs().max()
+    # graph replay (both phases), generous capacity chosen by the probe
+    sc = _occ_scene(golden_field, True, binaries, 512)
+    pool = RaySupervision.from_panorama(torch.eye(4), rgb, dist, seed=3)
+    for phase in ("geo", "app"):
+        net = sc.nerf.geo_mlp if phase == "geo" else sc.nerf.app_mlp
+        p_before = net.params.detach().clone()
+        opt = FusedAdam(net.params, lr=1e-3, module=net)
+        step = GraphedTrainStep(sc, phase, pool, opt)
+        losses = [float(step(0.3)) for _ in range(4)]
+        step.finish()
+        assert all(np.isfinite(losses)) and step.occ_overflow() == 0
+        assert not torch.equal(net.params.detach(), p_before)                  # the replayed Adam moved the parameters
+    # too small a capacity: reported, finite
+    opt = FusedAdam(sc.nerf.geo_mlp.params, lr=1e-3, module=sc.nerf.geo_mlp)
+    tiny = GraphedTrainStep(sc, "geo", pool, opt, occ_capacity=1024)
+    assert np.isfinite(float(tiny(0.3))) and tiny.occ_overflow() > 0

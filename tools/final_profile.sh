@@ -19,6 +19,9 @@ done
 OCC=1 PHASES=geo NSTEPS=1 GRAPH=0 timeout 600 ncu --set full --clock-control none -k regex:"packed_fields|composite_packed|hashgrid_bwd_kernel|occ_march" -s 30 -c 6 -f -o $O/train_occ_geo python tools/train_bench.py > $O/train_occ.log 2>&1; echo "ncu occ exit=$?"; digest train_occ_geo
 timeout 600 ncu --set full --clock-control none -k regex:"hashgrid_fwd_kernel|network_fwd_kernel" -s 24 -c 8 -f -o $O/microbench python tools/encode_microbench.py > $O/microbench_under_ncu.log 2>&1; echo "ncu microbench exit=$?"; digest microbench
 timeout 120 python tools/encode_microbench.py 2>&1 | tail -4 > $O/microbench.log
+# 2b. end-to-end fit episodes with the reference's schedule (3000 + 1500 iterations), both samplers
+timeout 300 python examples/fit_and_render.py 2>&1 | tail -3 > $O/fit_fixed.log; cat $O/fit_fixed.log
+timeout 300 python examples/fit_and_render.py --sampler occ 2>&1 | tail -3 > $O/fit_occ.log; cat $O/fit_occ.log
 # 3. sanitizers
 timeout 600 compute-sanitizer --tool memcheck python tools/sanitize_small.py > $O/compute_sanitizer_memcheck.log 2>&1; tail -2 $O/compute_sanitizer_memcheck.log
 timeout 600 compute-sanitizer --tool racecheck python tools/sanitize_small.py > $O/compute_sanitizer_racecheck.log 2>&1; tail -2 $O/compute_sanitizer_racecheck.log
