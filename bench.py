@@ -316,8 +316,10 @@ def bench_train(dev, rank, world, steps=20, warmup=5):
         out["roofline"] = bench_train_roofline(dev)
         occ = bench_train_occ(dev)
         for phase in ("geo", "app"):                          # per-sample cost against the fixed-S step
-            occ[f"{phase}_ns_per_sample_vs_fixed_s"] = (1e3 * occ[f"{phase}_ms_per_step"] / occ[f"{phase}_samples_per_step"] * 1e3) / \
-                (1e3 * out[f"{phase}_ms_per_step"] / (8192 * S) * 1e3)
+            fixed_ns = 1e6 * out[f"{phase}_ms_per_step"] / (8192 * S)
+            occ[f"{phase}_ns_per_sample_vs_fixed_s"] = (1e6 * occ[f"{phase}_ms_per_step"] / occ[f"{phase}_samples_per_step"]) / fixed_ns
+            eqs = occ["equal_samples"]
+            eqs[f"{phase}_ns_per_sample_vs_fixed_s"] = (1e6 * eqs[f"{phase}_ms_per_step"] / eqs[f"{phase}_samples_per_step"]) / fixed_ns
         out["occ"] = occ
     return out
 
@@ -428,6 +430,32 @@ def bench_train_occ(dev, steps=20, warmup=5):
         out[f"{phase}_capacity"] = sc._occ_static.capacity
         out[f"{phase}_overflow_samples"] = graphed.occ_overflow()
     out["note"] = "*_ms_per_step: whole step replayed as one CUDA graph (no host read); *_eager_ms_per_step: eager with the sample-count read, launch-bound"
+    # The same step at the SAMPLE count of the fixed-S step (8192 x 128): 38.5 samples per ray make the reference's 8192-ray batch
+    # 3.3x smaller than the fixed-S one, so its fixed costs (batch draw, Adam over 6.6 M parameters, table pack, the marcher's
+    # empty space) weigh 3.3x more per sample; with as many rays as give 1.05 M samples the two steps do the same amount of field work.
+    r2 = int(8192 * (8192 * S) / max(out["geo_samples_per_step"], 1.0)) // 128 * 128
+    sc.train_conf["pixel_loss_batch_size"] = r2
+    eq = {"rays_per_step": r2}
+    for phase in ("geo", "app"):
+        net = sc.nerf.geo_mlp if phase == "geo" else sc.nerf.app_mlp
+        opt = FusedAdam(net.params, lr=1e-3, module=net)
+        graphed = GraphedTrainStep(sc, phase, pool, opt)
+        for _ in range(warmup):
+            graphed(0.5)
+        torch.cuda.synchronize()
+        acc = torch.zeros(1, dtype=torch.int64, device=dev)
+        e0.record()
+        for _ in range(steps):
+            graphed(0.5)
+            acc += sc._occ_static.n
+        e1.record()
+        torch.cuda.synchronize()
+        graphed.finish()
+        ms, n = e0.elapsed_time(e1) / steps, int(acc) / steps
+        eq[f"{phase}_ms_per_step"], eq[f"{phase}_samples_per_step"], eq[f"{phase}_msamples_per_s"] = ms, n, n / ms / 1e3
+        eq[f"{phase}_overflow_samples"] = graphed.occ_overflow()
+    out["equal_samples"] = eq
+    sc.train_conf["pixel_loss_batch_size"] = 8192
     return out
 
 
