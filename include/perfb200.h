@@ -318,6 +318,13 @@ int perf_hashgrid_bwd_merged(const perf_grid_cfg* cfg, const float* d_x01, const
  * h_width[k] in one launch.  h_src / h_dst: HOST arrays of device pointers. */
 int perf_gather_rows(const int64_t* d_idx, uint64_t B, int n_arrays, const float* const* h_src, float* const* h_dst, const int* h_width, void* stream);
 
+/* The whole batch draw in one launch: B SORTED uniform row indices in [0, M) from the running sums d_csum [B+1] (fp64) of i.i.d.
+ * Exp(1) variates -- S_k / S_{B+1} are the order statistics of B uniforms, i.e. torch.randint followed by a sort, without the
+ * sort -- and the gather of perf_gather_rows with them.  d_idx_out [B] int64 or NULL.  With the pool stored in Morton order
+ * of its pixels a sorted batch is a spatially coherent one. */
+int perf_draw_gather_rows(const double* d_csum, uint64_t B, uint64_t M, int64_t* d_idx_out, int n_arrays, const float* const* h_src,
+                          float* const* h_dst, const int* h_width, void* stream);
+
 /* Diagnostic (bench.py's train_roofline denominator): n_atomics reductions of `vec` (1, 2 or 4) floats at pseudo-random
  * vec-aligned slots of d_table [n_floats] -- the L2 atomic rate that bounds the grid-gradient scatter. */
 int perf_debug_atomic_rate(float* d_table, uint64_t n_floats, uint64_t n_atomics, int vec, void* stream);

@@ -85,6 +85,7 @@ SIGNATURES = {
     "perf_composite_packed_bwd": (i32, [i32, vp, vp, vp, vp, vp, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "perf_hashgrid_bwd_merged": (i32, [P(GridCfg), vp, vp, u64, vp, vp, u32, vp]),
     "perf_gather_rows": (i32, [vp, u64, i32, vp, vp, vp, vp]),
+    "perf_draw_gather_rows": (i32, [vp, u64, u64, vp, i32, vp, vp, vp, vp]),
     "perf_train_loss": (i32, [vp, vp, u64, u64, f32, f32, vp, vp, vp, f32, vp, vp, vp, vp]),
     "perf_debug_atomic_rate": (i32, [vp, u64, u64, i32, vp]),
     "perf_occ_points": (i32, [vp, u64, P(i32), P(f32), u64, vp, vp]),

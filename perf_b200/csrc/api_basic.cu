@@ -260,12 +260,22 @@ hashgrid_bwd_kernel(LevelTable lt, int level0, const float* __restrict__ x01, co
 
 // ---- batch draw: rows idx[b] of up to 6 row-major fp32 arrays in ONE launch (sup_info.py:253-259 gathers rays_o, rays_d,
 // colours, distances, normals with the same index vector: 5-6 index kernels per training step otherwise)
-struct GatherArgs { const float* src[6]; float* dst[6]; int width[6]; int n_arrays; const int64_t* idx; uint64_t B; };
+struct GatherArgs { const float* src[6]; float* dst[6]; int width[6]; int n_arrays; const int64_t* idx; uint64_t B;
+                    const double* csum; uint64_t M; int64_t* idx_out; };
 __global__ void __launch_bounds__(256) gather_rows_kernel(const GatherArgs a)
 {
     const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= a.B) return;
-    const int64_t r = a.idx[b];
+    int64_t r;
+    if (a.csum) {
+        // sorted uniform draw: csum = running sums S_1 .. S_{B+1} of i.i.d. Exp(1); S_k / S_{B+1}, k = 1..B, are distributed as the
+        // ORDER STATISTICS of B i.i.d. U(0,1) -- the batch torch.randint + sort would give, without the sort
+        r = (int64_t)(a.csum[b] / a.csum[a.B] * (double)a.M);
+        r = r < 0 ? 0 : (r > (int64_t)a.M - 1 ? (int64_t)a.M - 1 : r);
+        if (a.idx_out) a.idx_out[b] = r;
+    } else {
+        r = a.idx[b];
+    }
     for (int k = 0; k < a.n_arrays; ++k) {
         const int w = a.width[k];
         const float* s = a.src[k] + (uint64_t)r * w; float* d = a.dst[k] + b * w;
@@ -570,6 +580,22 @@ int perf_gather_rows(const int64_t* d_idx, uint64_t B, int n_arrays, const float
         a.src[k] = h_src[k]; a.dst[k] = h_dst[k]; a.width[k] = h_width[k];
     }
     a.n_arrays = n_arrays; a.idx = d_idx; a.B = B;
+    if (B == 0) return PERF_OK;
+    gather_rows_kernel<<<blocks_for(B, 256), 256, 0, S(stream)>>>(a);
+    PERF_LAUNCH_CHECK();
+    return PERF_OK;
+}
+
+int perf_draw_gather_rows(const double* d_csum, uint64_t B, uint64_t M, int64_t* d_idx_out, int n_arrays, const float* const* h_src,
+                          float* const* h_dst, const int* h_width, void* stream)
+{
+    PERF_CHECK_ARG(d_csum && h_src && h_dst && h_width && n_arrays >= 1 && n_arrays <= 6 && M >= 1, "bad arguments");
+    GatherArgs a; memset(&a, 0, sizeof(a));
+    for (int k = 0; k < n_arrays; ++k) {
+        PERF_CHECK_ARG(h_src[k] && h_dst[k] && h_width[k] >= 1 && h_width[k] <= 64, "bad array %d", k);
+        a.src[k] = h_src[k]; a.dst[k] = h_dst[k]; a.width[k] = h_width[k];
+    }
+    a.n_arrays = n_arrays; a.B = B; a.csum = d_csum; a.M = M; a.idx_out = d_idx_out;
     if (B == 0) return PERF_OK;
     gather_rows_kernel<<<blocks_for(B, 256), 256, 0, S(stream)>>>(a);
     PERF_LAUNCH_CHECK();

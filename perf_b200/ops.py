@@ -817,6 +817,23 @@ def gather_rows(idx: torch.Tensor, *arrays: torch.Tensor):
     return tuple(outs)
 
 
+def draw_gather_rows(csum: torch.Tensor, M: int, *arrays: torch.Tensor, want_idx: bool = False):
+    """Sorted uniform batch draw + gather in ONE launch: ``csum`` [B+1] fp64 = cumsum of i.i.d. Exp(1); row index of draw b =
+    floor(csum[b] / csum[B] * M).  Returns the gathered arrays (and the indices when ``want_idx``)."""
+    csum = _chk(csum, torch.float64, "csum")
+    B, dev = csum.shape[0] - 1, csum.device
+    srcs = [_chk(a.reshape(a.shape[0], -1), torch.float32, "array") for a in arrays]
+    outs = [torch.empty((B,) + tuple(a.shape[1:]), dtype=torch.float32, device=dev) for a in arrays]
+    idx = torch.empty(B, dtype=torch.int64, device=dev) if want_idx else None
+    n = len(srcs)
+    sp = (C.c_void_p * n)(*[s_.data_ptr() for s_ in srcs])
+    dp = (C.c_void_p * n)(*[o.data_ptr() for o in outs])
+    wd = (C.c_int * n)(*[int(s_.shape[1]) for s_ in srcs])
+    with torch.cuda.device(dev):
+        _call(_L().perf_draw_gather_rows, _p(csum), B, int(M), _p(idx), n, sp, dp, wd, _stream())
+    return tuple(outs) + ((idx,) if want_idx else ())
+
+
 class _FusedLoss(torch.autograd.Function):
     """total = w_main * smooth_l1(pred, gt, beta).mean() + w_dl * ratio * dl.sum() * inv_n  as ONE kernel that also
     produces the gradients (`nerf.py:208-238,281-287`); backward only scales them by the incoming gradient."""

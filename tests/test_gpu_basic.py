@@ -167,6 +167,19 @@ def test_adam_unaligned_views_and_batch_gather(ops):
         assert torch.equal(o, a[idx])
 
 
+def test_draw_gather_rows_matches_the_host_formula(ops):
+    """perf_draw_gather_rows: index b = floor(csum[b] / csum[B] * M) (sorted uniform draw, tests/test_batch_draw.py) + gather."""
+    g = torch.Generator().manual_seed(152)
+    M, B = 524288, 8192
+    csum = torch.cumsum(torch.empty(B + 1, dtype=torch.float64).exponential_(generator=g), 0).cuda()
+    arrays = [torch.randn(M, w, generator=g).cuda() for w in (3, 3, 1)]
+    *got, idx = ops.draw_gather_rows(csum, M, *arrays, want_idx=True)
+    want = (csum[:-1] / csum[-1] * M).to(torch.int64).clamp_(0, M - 1)
+    assert torch.equal(idx, want) and bool((idx[1:] >= idx[:-1]).all())
+    for a, o in zip(arrays, got):
+        assert torch.equal(o, a[idx])
+
+
 def test_params_to_half_and_pack(ops):
     from perf_b200.config import APP_MLP, GEO_MLP, PERF_GRID
     g = torch.Generator().manual_seed(16)
