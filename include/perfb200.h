@@ -265,10 +265,14 @@ int perf_hashgrid_bwd_rays(const perf_grid_cfg* cfg, const float* aabb6, const f
  * Pass 1 writes the per-ray sample counts; the caller exclusive-scans them into d_offsets and
  * allocates the packed outputs; pass 2 writes (ray_indices int64, t_starts, t_ends), sorted by ray. */
 int perf_occ_count(const uint8_t* d_binaries, const int* h_res3, const float* h_aabb6, const float* d_rays_o, const float* d_rays_d,
-                   const float* d_jitter, uint64_t R, float near, float far, float step, uint32_t pieces, int32_t* d_counts, void* stream);
+                   const float* d_jitter, uint64_t R, float near, float far, float step, uint32_t pieces, int32_t* d_counts,
+                   uint32_t* d_masks /* nullable, see below */, void* stream);
 int perf_occ_write(const uint8_t* d_binaries, const int* h_res3, const float* h_aabb6, const float* d_rays_o, const float* d_rays_d,
                    const float* d_jitter, uint64_t R, float near, float far, float step, uint32_t pieces, const int64_t* d_offsets, uint64_t capacity,
-                   int64_t* d_ray_indices, float* d_t_starts, float* d_t_ends, void* stream);
+                   const uint32_t* d_masks /* nullable */, int64_t* d_ray_indices, float* d_t_starts, float* d_t_ends, void* stream);
+/* d_masks [R * pieces * 4] uint32 (optional, the same buffer in both passes): the count pass records WHICH lattice points of
+ * every piece are samples (one bit each) and the write pass only expands those bits -- the grid is marched once, not twice.
+ * Usable when a piece holds at most 128 lattice points, i.e. (far - near) / step / pieces + 1 <= 128 (else PERF_EINVAL). */
 /* `pieces` (>= 1, the same in both passes): every ray's lattice range is cut into that many consecutive parts marched by
  * different threads -- a ray is a serial walk of up to (far - near) / step lattice points, and 8192 rays alone leave the GPU
  * empty.  d_counts and d_offsets then have R * pieces entries indexed [ray * pieces + piece] (exclusive scan over all of

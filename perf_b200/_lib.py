@@ -77,8 +77,8 @@ SIGNATURES = {
     "perf_train_forward": (i32, [P(RenderArgs), vp, vp, u64, i32, P(TrainBuffers), vp]),
     "perf_train_backward_composite": (i32, [i32, u32, u32, f32, f32, u64, vp, vp, P(TrainBuffers), vp, vp, vp, vp, vp, vp, vp, vp]),
     "perf_hashgrid_bwd_rays": (i32, [P(GridCfg), P(f32), vp, vp, vp, u64, u32, f32, f32, vp, vp, vp]),
-    "perf_occ_count": (i32, [vp, P(i32), P(f32), vp, vp, vp, u64, f32, f32, f32, u32, vp, vp]),
-    "perf_occ_write": (i32, [vp, P(i32), P(f32), vp, vp, vp, u64, f32, f32, f32, u32, vp, u64, vp, vp, vp, vp]),
+    "perf_occ_count": (i32, [vp, P(i32), P(f32), vp, vp, vp, u64, f32, f32, f32, u32, vp, vp, vp]),
+    "perf_occ_write": (i32, [vp, P(i32), P(f32), vp, vp, vp, u64, f32, f32, f32, u32, vp, u64, vp, vp, vp, vp, vp]),
     "perf_mlp_bwd": (i32, [P(MlpCfg), vp, vp, vp, vp, vp, u64, vp, vp, vp, u32, vp]),
     "perf_fields_packed": (i32, [P(RenderArgs), vp, vp, vp, vp, vp, u64, vp, i32, vp, vp, vp, vp, vp, vp, vp]),
     "perf_composite_packed_fwd": (i32, [vp, vp, vp, vp, vp, u64, f32, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),

@@ -8,6 +8,7 @@
 namespace perf {
 
 constexpr uint32_t PERF_OCC_MAX_STEPS = 1u << 22;      // lattice points one ray may visit (PeRF: 1.5 / 5e-4 = 3000)
+constexpr int PERF_OCC_MASK_WORDS = 4;
 
 struct OccArgs {
     const uint8_t* binaries; int rx, ry, rz;
@@ -19,6 +20,9 @@ struct OccArgs {
     int64_t capacity;            // write pass: samples at positions >= capacity are dropped (0 = no limit)
     uint32_t pieces;             // every ray's lattice range is cut into `pieces` consecutive parts marched by different threads:
                                  // counts / offsets are indexed [ray * pieces + piece] (the packed output order is unchanged)
+    uint32_t* masks;             // optional [R * pieces][PERF_OCC_MASK_WORDS]: bit j of a slot = lattice point (first index of the
+                                 // piece + j) is a sample.  Written by the count pass; the write pass then only expands the bits
+                                 // (no second march, no second read of the grid).  Needs <= 32 * PERF_OCC_MASK_WORDS points per piece.
 };
 
 // One ray.  __host__ __device__: tests/host_harness.py compiles this file with -DPERF_HOST_HARNESS into a separate
@@ -28,6 +32,8 @@ __host__ __device__ __forceinline__ void occ_march_ray(const OccArgs& a, uint64_
 {
     const uint32_t P = a.pieces ? a.pieces : 1u;
     const uint64_t slot = ray * P + piece;
+    uint32_t bits[PERF_OCC_MASK_WORDS] = {0u, 0u, 0u, 0u};
+    const bool expand = WRITE && a.masks != nullptr;          // write pass with masks: expand the count pass's bits, do not march
     const float o[3] = {a.rays_o[3 * ray], a.rays_o[3 * ray + 1], a.rays_o[3 * ray + 2]};
     const float d[3] = {a.rays_d[3 * ray], a.rays_d[3 * ray + 1], a.rays_d[3 * ray + 2]};
     float tn = -INFINITY, tf = INFINITY;
@@ -57,6 +63,18 @@ __host__ __device__ __forceinline__ void occ_march_ray(const OccArgs& a, uint64_
             k_end = (lo + per < k_end) ? lo + per : k_end;
             k = lo < k_end ? lo : k_end;
         }
+        const uint32_t k_first = k;
+        if (expand) {
+            for (int j = 0; j < 32 * PERF_OCC_MASK_WORDS; ++j) {
+                if ((a.masks[slot * PERF_OCC_MASK_WORDS + (j >> 5)] >> (j & 31)) & 1u) {
+                    const uint32_t kk = k_first + (uint32_t)j;
+                    const float ts = PERF_FADD_RN(a.near, PERF_FMUL_RN(PERF_FADD_RN((float)kk, u), a.step));
+                    if (a.capacity == 0 || pos < a.capacity) { a.ray_indices[pos] = (int64_t)ray; a.t_starts[pos] = ts; a.t_ends[pos] = PERF_FADD_RN(ts, a.step); }
+                    ++pos;
+                }
+            }
+            k = k_end;                                         // skip the march below
+        }
         for (; k < k_end; ++k) {
             const float ts = PERF_FADD_RN(a.near, PERF_FMUL_RN(PERF_FADD_RN((float)k, u), a.step));
             const float mid = PERF_FADD_RN(ts, half_step);
@@ -75,6 +93,9 @@ __host__ __device__ __forceinline__ void occ_march_ray(const OccArgs& a, uint64_
                 if (WRITE) {
                     if (a.capacity == 0 || pos < a.capacity) { a.ray_indices[pos] = (int64_t)ray; a.t_starts[pos] = ts; a.t_ends[pos] = PERF_FADD_RN(ts, a.step); }
                     ++pos;
+                } else if (a.masks) {
+                    const uint32_t j = k - k_first;            // < 32 * PERF_OCC_MASK_WORDS (checked on the host)
+                    bits[j >> 5] |= 1u << (j & 31);
                 }
                 ++n;
             } else {
@@ -98,7 +119,10 @@ __host__ __device__ __forceinline__ void occ_march_ray(const OccArgs& a, uint64_
             }
         }
     }
-    if (!WRITE) a.counts[slot] = n;
+    if (!WRITE) {
+        a.counts[slot] = n;
+        if (a.masks) { for (int w = 0; w < PERF_OCC_MASK_WORDS; ++w) a.masks[slot * PERF_OCC_MASK_WORDS + w] = bits[w]; }
+    }
 }
 
 template <bool WRITE>
@@ -125,16 +149,28 @@ static int fill(OccArgs& a, const uint8_t* bin, const int* res3, const float* aa
     a.pieces = pieces;
     return PERF_OK;
 }
+// masks are usable when no piece can hold more lattice points than the mask has bits
+static int check_masks(const OccArgs& a, const void* masks)
+{
+    if (!masks) return PERF_OK;
+    PERF_CHECK_ARG((uintptr_t)masks % 4 == 0, "misaligned masks");
+    const double max_points = ((double)a.far - (double)a.near) / (double)a.step + 16.0;
+    PERF_CHECK_ARG(max_points / (double)a.pieces + 1.0 <= 32.0 * PERF_OCC_MASK_WORDS,
+                   "sample masks need <= %d lattice points per piece: (far - near) / step / pieces = %.0f", 32 * PERF_OCC_MASK_WORDS, max_points / a.pieces);
+    return PERF_OK;
+}
 
 extern "C" {
 #pragma GCC visibility push(default)
 
 int perf_occ_count(const uint8_t* d_binaries, const int* h_res3, const float* h_aabb6, const float* d_rays_o, const float* d_rays_d,
-                   const float* d_jitter, uint64_t R, float near, float far, float step, uint32_t pieces, int32_t* d_counts, void* stream)
+                   const float* d_jitter, uint64_t R, float near, float far, float step, uint32_t pieces, int32_t* d_counts, uint32_t* d_masks,
+                   void* stream)
 {
     OccArgs a; int rc = fill(a, d_binaries, h_res3, h_aabb6, d_rays_o, d_rays_d, d_jitter, R, near, far, step, pieces); if (rc) return rc;
     PERF_CHECK_ARG(d_counts, "NULL counts");
-    a.counts = d_counts;
+    rc = check_masks(a, d_masks); if (rc) return rc;
+    a.counts = d_counts; a.masks = d_masks;
     if (R == 0) return PERF_OK;
     occ_march_kernel<false><<<dim3((unsigned)((R + 127) / 128), pieces), 128, 0, (cudaStream_t)stream>>>(a);
     PERF_LAUNCH_CHECK();
@@ -143,9 +179,11 @@ int perf_occ_count(const uint8_t* d_binaries, const int* h_res3, const float* h_
 
 int perf_occ_write(const uint8_t* d_binaries, const int* h_res3, const float* h_aabb6, const float* d_rays_o, const float* d_rays_d,
                    const float* d_jitter, uint64_t R, float near, float far, float step, uint32_t pieces, const int64_t* d_offsets, uint64_t capacity,
-                   int64_t* d_ray_indices, float* d_t_starts, float* d_t_ends, void* stream)
+                   const uint32_t* d_masks, int64_t* d_ray_indices, float* d_t_starts, float* d_t_ends, void* stream)
 {
     OccArgs a; int rc = fill(a, d_binaries, h_res3, h_aabb6, d_rays_o, d_rays_d, d_jitter, R, near, far, step, pieces); if (rc) return rc;
+    rc = check_masks(a, d_masks); if (rc) return rc;
+    a.masks = const_cast<uint32_t*>(d_masks);
     PERF_CHECK_ARG(d_offsets && d_ray_indices && d_t_starts && d_t_ends, "NULL output");
     a.offsets = d_offsets; a.ray_indices = d_ray_indices; a.t_starts = d_t_starts; a.t_ends = d_t_ends; a.capacity = (int64_t)capacity;
     if (R == 0) return PERF_OK;
@@ -158,9 +196,11 @@ int perf_occ_write(const uint8_t* d_binaries, const int* h_res3, const float* h_
 /* TEST HARNESS ONLY (never compiled into libperfb200.so): the per-ray body over HOST arrays.  pass 0 = count, 1 = write. */
 int perf_host_occ_march(int pass, const uint8_t* h_binaries, const int* h_res3, const float* h_aabb6, const float* h_rays_o,
                         const float* h_rays_d, const float* h_jitter, uint64_t R, float near, float far, float step, uint32_t pieces,
-                        int32_t* h_counts, const int64_t* h_offsets, int64_t* h_ray_indices, float* h_t_starts, float* h_t_ends)
+                        int32_t* h_counts, const int64_t* h_offsets, int64_t* h_ray_indices, float* h_t_starts, float* h_t_ends, uint32_t* h_masks)
 {
     OccArgs a; int rc = fill(a, h_binaries, h_res3, h_aabb6, h_rays_o, h_rays_d, h_jitter, R, near, far, step, pieces); if (rc) return rc;
+    rc = check_masks(a, h_masks); if (rc) return rc;
+    a.masks = h_masks;
     a.counts = h_counts; a.offsets = h_offsets; a.ray_indices = h_ray_indices; a.t_starts = h_t_starts; a.t_ends = h_t_ends;
     for (uint32_t pc = 0; pc < pieces; ++pc)
         for (uint64_t r = 0; r < R; ++r) { if (pass == 0) occ_march_ray<false>(a, r, pc); else occ_march_ray<true>(a, r, pc); }

@@ -393,6 +393,11 @@ def _occ_pieces(R: int) -> int:
     return p
 
 
+def _occ_masks_ok(near: float, far: float, step: float, pieces: int) -> bool:
+    """The single-march form (sample bits recorded by the count pass, expanded by the write pass) needs <= 128 lattice points per piece."""
+    return ((far - near) / step + 16.0) / pieces + 1.0 <= 126.0
+
+
 def occ_sample(binaries: torch.Tensor, aabb, rays_o, rays_d, near: float, far: float, step: float, jitter=None, pieces: Optional[int] = None):
     """Packed (ray_indices, t_starts, t_ends) of the lattice samples whose midpoint is inside the aabb
     in an occupied cell (two kernels around one cumsum; one host sync for the total, as nerfacc)."""
@@ -406,8 +411,9 @@ def occ_sample(binaries: torch.Tensor, aabb, rays_o, rays_d, near: float, far: f
     res3 = (C.c_int * 3)(*[int(v) for v in binaries.shape])
     a6 = (C.c_float * 6)(*[float(v) for v in aabb])
     counts = torch.empty(R * P, dtype=torch.int32, device=dev)
+    masks = torch.empty(R * P * 4, dtype=torch.int32, device=dev) if _occ_masks_ok(near, far, step, P) else None
     with torch.cuda.device(dev):
-        _call(_L().perf_occ_count, _p(bins), res3, a6, _p(rays_o), _p(rays_d), _p(jitter), R, near, far, step, P, _p(counts), _stream())
+        _call(_L().perf_occ_count, _p(bins), res3, a6, _p(rays_o), _p(rays_d), _p(jitter), R, near, far, step, P, _p(counts), _p(masks), _stream())
     incl = torch.cumsum(counts, 0, dtype=torch.int64)
     total = int(incl[-1].item()) if R else 0
     offsets = (incl - counts).contiguous()                                  # [R * P], exclusive
@@ -418,7 +424,7 @@ def occ_sample(binaries: torch.Tensor, aabb, rays_o, rays_d, near: float, far: f
     if total:
         with torch.cuda.device(dev):
             _call(_L().perf_occ_write, _p(bins), res3, a6, _p(rays_o), _p(rays_d), _p(jitter), R, near, far, step, P, _p(offsets), 0,
-                  _p(ri), _p(ts), _p(te), _stream())
+                  _p(masks), _p(ri), _p(ts), _p(te), _stream())
     return ri, ts, te
 
 
@@ -437,6 +443,7 @@ class OccStaticBuffers:
         self.ts = torch.zeros(capacity, dtype=torch.float32, device=dev)
         self.te = torch.zeros(capacity, dtype=torch.float32, device=dev)
         self.overflowed = torch.zeros(1, dtype=torch.int64, device=dev)          # running max of raw_total (host reads it rarely)
+        self.masks = torch.zeros(R * P * 4, dtype=torch.int32, device=dev)        # sample bits per (ray, piece), when usable
 
 
 def occ_sample_static(binaries: torch.Tensor, aabb, rays_o, rays_d, near: float, far: float, step: float, jitter, buf: OccStaticBuffers):
@@ -451,13 +458,14 @@ def occ_sample_static(binaries: torch.Tensor, aabb, rays_o, rays_d, near: float,
     assert R == buf.R
     res3 = (C.c_int * 3)(*[int(v) for v in binaries.shape])
     a6 = (C.c_float * 6)(*[float(v) for v in aabb])
+    masks = buf.masks if _occ_masks_ok(near, far, step, P) else None
     with torch.cuda.device(rays_o.device):
-        _call(_L().perf_occ_count, _p(bins), res3, a6, _p(rays_o), _p(rays_d), _p(jitter), R, near, far, step, P, _p(buf.counts), _stream())
+        _call(_L().perf_occ_count, _p(bins), res3, a6, _p(rays_o), _p(rays_d), _p(jitter), R, near, far, step, P, _p(buf.counts), _p(masks), _stream())
         torch.cumsum(buf.counts, 0, dtype=torch.int64, out=buf.offsets_all[1:])
         buf.raw_total.copy_(buf.offsets_all[R * P:])
         torch.maximum(buf.overflowed, buf.raw_total, out=buf.overflowed)
         _call(_L().perf_occ_write, _p(bins), res3, a6, _p(rays_o), _p(rays_d), _p(jitter), R, near, far, step, P, _p(buf.offsets_all), buf.capacity,
-              _p(buf.ri), _p(buf.ts), _p(buf.te), _stream())
+              _p(masks), _p(buf.ri), _p(buf.ts), _p(buf.te), _stream())
         torch.clamp(buf.offsets_all[::P], max=buf.capacity, out=buf.offsets)        # [R + 1]: (R * P) % P == 0, so the total is included
         buf.n.copy_(buf.offsets[R:])
     return buf.ri, buf.ts, buf.te, buf.offsets, buf.n

@@ -85,7 +85,8 @@ def scatter8(idx: np.ndarray, v: np.ndarray, n_entries: int, v4: bool) -> np.nda
     return dtable.copy()
 
 
-def occ_sample(binaries: np.ndarray, aabb, rays_o: np.ndarray, rays_d: np.ndarray, near: float, far: float, step: float, jitter=None, pieces: int = 1):
+def occ_sample(binaries: np.ndarray, aabb, rays_o: np.ndarray, rays_d: np.ndarray, near: float, far: float, step: float, jitter=None, pieces: int = 1,
+               masks: bool = False):
     """occ_march_ray of csrc/occ.cu (count pass, exclusive scan, write pass) -> (ray_indices, t_starts, t_ends).
     ``pieces``: every ray's lattice range cut into that many parts (counts / offsets per (ray, piece))."""
     R = rays_o.shape[0]
@@ -97,11 +98,12 @@ def occ_sample(binaries: np.ndarray, aabb, rays_o: np.ndarray, rays_d: np.ndarra
     counts = np.zeros(R * pieces, np.int32)
     f = lib().perf_host_occ_march
     args = (_p(bin8), res3, a6, _p(o), _p(d), _p(j), C.c_uint64(R), C.c_float(near), C.c_float(far), C.c_float(step), C.c_uint32(pieces))
-    assert f(0, *args, _p(counts), None, None, None, None) == 0
+    mk = np.zeros(R * pieces * 4, np.uint32) if masks else None      # count pass records the sample bits, write pass expands them
+    assert f(0, *args, _p(counts), None, None, None, None, _p(mk)) == 0
     offsets = np.concatenate([[0], np.cumsum(counts, dtype=np.int64)]).astype(np.int64)
     n = int(offsets[-1])
     ri, ts, te = np.zeros(max(n, 1), np.int64), np.zeros(max(n, 1), np.float32), np.zeros(max(n, 1), np.float32)
-    assert f(1, *args, None, _p(offsets), _p(ri), _p(ts), _p(te)) == 0
+    assert f(1, *args, None, _p(offsets), _p(ri), _p(ts), _p(te), _p(mk)) == 0
     return ri[:n], ts[:n], te[:n]
 
 

@@ -105,3 +105,8 @@ def test_piece_parallel_marching_is_bit_identical():
         for pieces in (1, 2, 7, 32):
             got = hh.occ_sample(binaries.numpy(), aabb.tolist(), o.numpy(), d.numpy(), near, far, step, None if jit is None else jit.numpy(), pieces=pieces)
             assert np.array_equal(got[0], want[0].numpy()) and np.array_equal(got[1], want[1].numpy()) and np.array_equal(got[2], want[2].numpy()), (seed, pieces)
+        # single march: the count pass records sample bits, the write pass expands them (needs <= 128 lattice points per piece)
+        pieces = int(np.ceil(((far - near) / step + 17) / 127))
+        if pieces <= 1024:
+            got = hh.occ_sample(binaries.numpy(), aabb.tolist(), o.numpy(), d.numpy(), near, far, step, None if jit is None else jit.numpy(), pieces=pieces, masks=True)
+            assert np.array_equal(got[0], want[0].numpy()) and np.array_equal(got[1], want[1].numpy()) and np.array_equal(got[2], want[2].numpy()), (seed, "masks")
