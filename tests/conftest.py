@@ -12,6 +12,12 @@ if os.path.dirname(os.path.abspath(__file__)) not in sys.path:      # tests/host
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+try:                                       # OpenCV must be fully imported before any test rearranges sys.path / sys.modules for the
+    import cv2  # noqa: F401               # reference checkout: a first import in that state fails inside cv2.typing (order dependent)
+except Exception:
+    pass
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
     try:                                   # the oracle is many small torch ops: 64 threads thrash

@@ -195,3 +195,17 @@ def test_inpainting_phase_loop_with_injected_priors(tmp_path, monkeypatch):
     run.inpainter = None
     with pytest.raises(NotImplementedError, match="inpainter"):
         run.train()
+
+
+def test_config_scalar_coercion_and_attribute_protocol(tmp_path):
+    """only strings shaped like a float with an exponent (what PyYAML's YAML 1.1 misses: `1e-2`) become floats --
+    `007`, names, dates stay strings -- and a missing key raises AttributeError (hasattr / deepcopy / pickle rely on it)."""
+    import copy
+    from perf_b200.config import Conf, load_config
+    (tmp_path / "nerf.yaml").write_text("exp_name: '007'\nlr: 1e-2\nstep: 5e-4\nname: run_1e3x\nnested:\n  peak_lr: 1.5E-3\n  tag: '1_000'\n")
+    conf = load_config(str(tmp_path), "nerf", ["nested.extra=3e-1"])
+    assert conf.exp_name == "007" and conf.lr == 1e-2 and conf.step == 5e-4 and conf.name == "run_1e3x"
+    assert conf.nested.peak_lr == 1.5e-3 and conf.nested.tag == "1_000" and conf.nested.extra == 0.3
+    assert not hasattr(conf, "missing") and copy.deepcopy(conf).nested.peak_lr == 1.5e-3
+    with pytest.raises(AttributeError):
+        Conf.wrap({"a": 1}).b
