@@ -227,7 +227,7 @@ typedef struct perf_train_buffers {
     float*    d_seg_trans;
     uint32_t* h_segments_out;
 } perf_train_buffers;
-#define PERF_MAX_SEGMENTS 16
+#define PERF_MAX_SEGMENTS 64
 
 /* Forward of a training step: like perf_render_rays (PERF_FLAG_TRAINING semantics: jitter, training
  * background rule) and additionally fills `buf`. */
@@ -259,6 +259,20 @@ int perf_train_loss(const float* d_pred, const float* d_gt, uint64_t n, uint64_t
 int perf_hashgrid_bwd_rays(const perf_grid_cfg* cfg, const float* aabb6, const float* d_rays_o, const float* d_rays_d,
                            const float* d_jitter, uint64_t R, uint32_t n_samples, float near, float far,
                            const float* d_dfeat, float* d_dtable, void* stream);
+
+/* The fixed-S training step's MLP backward WITH the fine-level grid scatter in its epilogue: perf_mlp_bwd on the R x S
+ * sample-major rows (row = k * R + ray) of perf_train_forward; the thread that owns a row issues the reductions of levels
+ * [8, 16) into d_dtable itself (positions recomputed from the rays as in perf_hashgrid_bwd_rays) and writes only the coarse
+ * half (columns [0, 16)) of d_dfeat [N, 32].  Follow with perf_hashgrid_bwd_rays_coarse for levels [0, 8).  Together they
+ * replace perf_mlp_bwd + perf_hashgrid_bwd_rays; the fine half of dfeat never reaches HBM and the L2-reduction-bound
+ * scatter overlaps the latency-bound MMA phases. */
+int perf_mlp_bwd_scatter(const perf_mlp_cfg* mlp, const void* d_weights_half, const void* d_feat, const void* d_h1, const void* d_h2,
+                         const float* d_dz, uint64_t N, float* d_dweights, float* d_dfeat,
+                         const perf_grid_cfg* grid, const float* aabb6, const float* d_rays_o, const float* d_rays_d, const float* d_jitter,
+                         uint64_t R, uint32_t n_samples, float near, float far, float* d_dtable, void* stream);
+int perf_hashgrid_bwd_rays_coarse(const perf_grid_cfg* cfg, const float* aabb6, const float* d_rays_o, const float* d_rays_d,
+                                  const float* d_jitter, uint64_t R, uint32_t n_samples, float near, float far,
+                                  const float* d_dfeat, float* d_dtable, void* stream);
 
 /* Occupancy-grid interval sampler (nerfacc OccGridEstimator.sampling, levels=1, cone_angle=0;
  * nerf_renderer.py:145-155).  d_binaries: bool/uint8 [rx*ry*rz] (x slowest).

@@ -40,7 +40,7 @@ class RenderArgs(C.Structure):
 
 
 P_u32 = C.POINTER(u32)
-PERF_MAX_SEGMENTS = 16
+PERF_MAX_SEGMENTS = 64
 
 
 class TrainBuffers(C.Structure):
@@ -80,6 +80,8 @@ SIGNATURES = {
     "perf_occ_count": (i32, [vp, P(i32), P(f32), vp, vp, vp, u64, f32, f32, f32, u32, vp, vp, vp]),
     "perf_occ_write": (i32, [vp, P(i32), P(f32), vp, vp, vp, u64, f32, f32, f32, u32, vp, u64, vp, vp, vp, vp, vp]),
     "perf_mlp_bwd": (i32, [P(MlpCfg), vp, vp, vp, vp, vp, u64, vp, vp, vp, u32, vp]),
+    "perf_mlp_bwd_scatter": (i32, [P(MlpCfg), vp, vp, vp, vp, vp, u64, vp, vp, P(GridCfg), P(f32), vp, vp, vp, u64, u32, f32, f32, vp, vp]),
+    "perf_hashgrid_bwd_rays_coarse": (i32, [P(GridCfg), P(f32), vp, vp, vp, u64, u32, f32, f32, vp, vp, vp]),
     "perf_fields_packed": (i32, [P(RenderArgs), vp, vp, vp, vp, vp, u64, vp, i32, vp, vp, vp, vp, vp, vp, vp]),
     "perf_composite_packed_fwd": (i32, [vp, vp, vp, vp, vp, u64, f32, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "perf_composite_packed_bwd": (i32, [i32, vp, vp, vp, vp, vp, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),

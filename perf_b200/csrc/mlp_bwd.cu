@@ -44,6 +44,18 @@ struct MlpBwdArgs {
     const int64_t* n_dev;    // optional: the live row count in DEVICE memory (<= N = capacity); rows beyond it are skipped
 };
 
+// Fine-level grid scatter fused into the epilogue (perf_mlp_bwd_scatter): rows are the fixed-S training step's sample-major
+// rows (row = k * R + ray); the thread that owns a row has its 32 feature gradients in registers and issues the reductions
+// of levels [n_coarse, n_levels) itself, so that half of dfeat never goes to HBM and the L2-reduction-bound scatter overlaps
+// the latency-bound MMA phases of the other resident CTAs.  The coarse levels keep their run-merging march kernel.
+struct ScatterCtx {
+    LevelTable lt;
+    float aabb_min[3], aabb_ext[3];
+    const float *rays_o, *rays_d, *jitter;
+    uint64_t R; uint32_t S; float near, far;
+    float2* dtable; uint32_t n_coarse;
+};
+
 __host__ __device__ constexpr uint32_t idesc_f16_major(int M, int N, bool a_mn, bool b_mn)
 {
     return umma_idesc_f16(M, N) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16);
@@ -240,6 +252,31 @@ __host__ __device__ __forceinline__ void bwd_phase_dfeat(const MlpBwdArgs& a, ui
     }
 }
 
+// reductions of the fine levels for one row; same position / weight / index arithmetic as bwd_rays_row_level (train.cu)
+__device__ __forceinline__ void scatter_fine_levels(const ScatterCtx& c, uint64_t row, const float (&v)[32])
+{
+    const uint64_t ray = row % c.R; const uint32_t k = (uint32_t)(row / c.R);
+    const float step = __fdiv_rn(__fsub_rn(c.far, c.near), (float)c.S);
+    const float jit = c.jitter ? c.jitter[ray] : 0.f;
+    const float ts = __fadd_rn(c.near, __fmul_rn(__fadd_rn((float)k, jit), step));
+    const float te = __fadd_rn(c.near, __fmul_rn(__fadd_rn((float)(k + 1), jit), step));
+    const float tsum = __fadd_rn(ts, te);
+    const float x = __fdiv_rn(__fsub_rn(__fadd_rn(c.rays_o[3 * ray], __fmul_rn(c.rays_d[3 * ray], tsum) * 0.5f), c.aabb_min[0]), c.aabb_ext[0]);
+    const float y = __fdiv_rn(__fsub_rn(__fadd_rn(c.rays_o[3 * ray + 1], __fmul_rn(c.rays_d[3 * ray + 1], tsum) * 0.5f), c.aabb_min[1]), c.aabb_ext[1]);
+    const float z = __fdiv_rn(__fsub_rn(__fadd_rn(c.rays_o[3 * ray + 2], __fmul_rn(c.rays_d[3 * ray + 2], tsum) * 0.5f), c.aabb_min[2]), c.aabb_ext[2]);
+#pragma unroll
+    for (int l = 8; l < 16; ++l) {                             // register indices of v must be compile-time: n_coarse == 8, 16 levels
+        const float gx = v[2 * l], gy = v[2 * l + 1];
+        if (gx == 0.f && gy == 0.f) continue;
+        Corner8 cn;
+        level_corners(c.lt, l, x, y, z, cn);
+        float2 g8[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) g8[q] = make_float2(cn.w[q] * gx, cn.w[q] * gy);
+        scatter8<true>(c.dtable, cn.idx, g8);
+    }
+}
+
 __host__ __device__ __forceinline__ void wgrad_add(float* p, float v)
 {
 #ifdef __CUDA_ARCH__
@@ -276,8 +313,8 @@ __host__ __device__ __forceinline__ void bwd_flush_g2(const MlpBwdArgs& a, int t
     for (int o = 0; o < 3; ++o) if (t < 64 && o < (int)a.n_out) wgrad_add(dWo + o * 64 + t, v[o]);
 }
 
-template <bool TWO, bool SIMT>
-__global__ void __launch_bounds__(128) mlp_bwd_kernel(const MlpBwdArgs a_in)
+template <bool TWO, bool SIMT, bool FUSE = false>
+__global__ void __launch_bounds__(128) mlp_bwd_kernel(const MlpBwdArgs a_in, const __grid_constant__ ScatterCtx sc)
 {
     MlpBwdArgs a = a_in;
     if (a.n_dev) { const int64_t n = *a.n_dev; a.N = n < 0 ? 0 : ((uint64_t)n < a.N ? (uint64_t)n : a.N); }    // graph-replayable row count
@@ -368,7 +405,17 @@ __global__ void __launch_bounds__(128) mlp_bwd_kernel(const MlpBwdArgs a_in)
             float v[32];
             if constexpr (SIMT) simt_dgrad(smem + L::DH1, smem + L::W1, t, 0, v);
             else tmem_ld32(tmem_row + L::TM_D2, v);
-            bwd_phase_dfeat(a, tile, t, v);
+            if constexpr (FUSE) {
+                const uint64_t row = tile * TILE + t;
+                if (row < a.N) {
+                    float4* dst = reinterpret_cast<float4*>(a.dfeat + row * 32);          // coarse half only: levels 0-7 for the march kernel
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    scatter_fine_levels(sc, row, v);
+                }
+            } else {
+                bwd_phase_dfeat(a, tile, t, v);
+            }
         }
         if constexpr (!SIMT) tc_fence_before();
         __syncthreads();                                   // images and D1 / D2 are rewritten by the next tile
@@ -397,10 +444,12 @@ __global__ void __launch_bounds__(128) mlp_bwd_kernel(const MlpBwdArgs a_in)
     }
 }
 
-template <bool TWO, bool SIMT>
-static int launch_mlp_bwd(const MlpBwdArgs& a, cudaStream_t stream)
+template <bool TWO, bool SIMT, bool FUSE = false>
+static int launch_mlp_bwd(const MlpBwdArgs& a, cudaStream_t stream, const ScatterCtx* scp = nullptr)
 {
-    auto k = mlp_bwd_kernel<TWO, SIMT>;
+    auto k = mlp_bwd_kernel<TWO, SIMT, FUSE>;
+    static ScatterCtx sc_none;                                  // zero-initialised: unused when !FUSE
+    const ScatterCtx& sc = scp ? *scp : sc_none;
     static thread_local int attr_dev = -1;
     int dev = 0; PERF_CUDA(cudaGetDevice(&dev));
     if (attr_dev != dev) { PERF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem<TWO>::TOTAL)); attr_dev = dev; }
@@ -413,7 +462,7 @@ static int launch_mlp_bwd(const MlpBwdArgs& a, cudaStream_t stream)
     const uint64_t n_tiles = (a.N + TILE - 1) / TILE;
     // resident CTAs per SM: TMEM columns (128 / 256 of 512) and shared memory (45 / 89 KB) allow 4 / 2
     const uint64_t slots = (uint64_t)num_sms() * (TWO ? 2 : 4);
-    k<<<(unsigned)(n_tiles < slots ? n_tiles : slots), TILE, BwdSmem<TWO>::TOTAL, stream>>>(a);
+    k<<<(unsigned)(n_tiles < slots ? n_tiles : slots), TILE, BwdSmem<TWO>::TOTAL, stream>>>(a, sc);
     PERF_LAUNCH_CHECK();
     return PERF_OK;
 }
@@ -489,6 +538,31 @@ int perf_mlp_bwd(const perf_mlp_cfg* mlp, const void* d_weights_half, const void
     const bool simt = (flags & PERF_FLAG_SIMT_MLP) != 0;
     if (mlp->n_hidden_layers == 2) return simt ? launch_mlp_bwd<true, true>(a, (cudaStream_t)stream) : launch_mlp_bwd<true, false>(a, (cudaStream_t)stream);
     return simt ? launch_mlp_bwd<false, true>(a, (cudaStream_t)stream) : launch_mlp_bwd<false, false>(a, (cudaStream_t)stream);
+}
+
+int perf_mlp_bwd_scatter(const perf_mlp_cfg* mlp, const void* d_weights_half, const void* d_feat, const void* d_h1, const void* d_h2,
+                         const float* d_dz, uint64_t N, float* d_dweights, float* d_dfeat,
+                         const perf_grid_cfg* grid, const float* aabb6, const float* d_rays_o, const float* d_rays_d, const float* d_jitter,
+                         uint64_t R, uint32_t n_samples, float near, float far, float* d_dtable, void* stream)
+{
+    int rc = check_mlp(mlp); if (rc) return rc;
+    PERF_CHECK_ARG(d_weights_half && d_feat && d_h1 && d_dz && d_dweights && d_dfeat && grid && aabb6 && d_rays_o && d_rays_d && d_dtable, "NULL pointer");
+    PERF_CHECK_ARG(mlp->n_hidden_layers == 1 || d_h2, "two hidden layers need d_h2");
+    PERF_CHECK_SUP(mlp->n_out <= 3, "n_out=%u (the backward kernel implements 1..3 outputs)", mlp->n_out);
+    PERF_CHECK_ARG(((uintptr_t)d_weights_half | (uintptr_t)d_feat | (uintptr_t)d_h1 | (uintptr_t)d_h2 | (uintptr_t)d_dfeat | (uintptr_t)d_dtable) % 16 == 0, "misaligned buffer");
+    PERF_CHECK_ARG(N == R * (uint64_t)n_samples && n_samples >= 1 && far > near, "rows must be the R x S sample-major rows of a fixed-S step");
+    if (N == 0) return PERF_OK;
+    ScatterCtx sc; memset(&sc, 0, sizeof(sc));
+    rc = build_level_table(grid, &sc.lt, nullptr); if (rc) return rc;
+    PERF_CHECK_SUP(sc.lt.n_levels == 16, "fused scatter needs n_levels == 16 (got %u)", sc.lt.n_levels);
+    for (int i = 0; i < 3; ++i) { sc.aabb_min[i] = aabb6[i]; sc.aabb_ext[i] = aabb6[3 + i] - aabb6[i]; }
+    sc.rays_o = d_rays_o; sc.rays_d = d_rays_d; sc.jitter = d_jitter; sc.R = R; sc.S = n_samples; sc.near = near; sc.far = far;
+    sc.dtable = (float2*)d_dtable; sc.n_coarse = 8;
+    MlpBwdArgs a;
+    a.w = (const __half*)d_weights_half; a.feat = (const uint4*)d_feat; a.h1 = (const uint4*)d_h1; a.h2 = (const uint4*)d_h2;
+    a.dz = d_dz; a.N = N; a.dW = d_dweights; a.dfeat = d_dfeat; a.n_out = mlp->n_out; a.dbg = 0; a.n_dev = nullptr;
+    if (mlp->n_hidden_layers == 2) return launch_mlp_bwd<true, false, true>(a, (cudaStream_t)stream, &sc);
+    return launch_mlp_bwd<false, false, true>(a, (cudaStream_t)stream, &sc);
 }
 
 #ifdef PERF_HOST_HARNESS

@@ -607,6 +607,24 @@ int perf_hashgrid_bwd_rays(const perf_grid_cfg* cfg, const float* aabb6, const f
     return PERF_OK;
 }
 
+/* The coarse levels [0, 8) only (run-merging march kernel): the companion of perf_mlp_bwd_scatter, whose epilogue has already
+ * issued the fine levels' reductions.  d_dfeat rows keep the [N, 32] stride; only columns [0, 16) are read. */
+int perf_hashgrid_bwd_rays_coarse(const perf_grid_cfg* cfg, const float* aabb6, const float* d_rays_o, const float* d_rays_d,
+                                  const float* d_jitter, uint64_t R, uint32_t n_samples, float near, float far,
+                                  const float* d_dfeat, float* d_dtable, void* stream)
+{
+    GridBwdRaysArgs a, b; uint32_t n_agg = 0;
+    int rc = setup_bwd_rays(cfg, aabb6, d_rays_o, d_rays_d, d_jitter, R, n_samples, near, far, d_dfeat, d_dtable, a, b, n_agg); if (rc) return rc;
+    if (R * (uint64_t)n_samples == 0) return PERF_OK;
+    unsigned pieces = 1;
+    while (pieces < 8 && (uint64_t)R * n_agg * pieces < (uint64_t)num_sms() * 2048 && n_samples / (pieces * 2) >= 16) pieces *= 2;
+    dim3 g_agg((unsigned)((R + 127) / 128), n_agg, pieces);
+    if ((uintptr_t)a.dtable % 16 == 0) hashgrid_bwd_march_kernel<true><<<g_agg, 128, 0, (cudaStream_t)stream>>>(a);
+    else hashgrid_bwd_march_kernel<false><<<g_agg, 128, 0, (cudaStream_t)stream>>>(a);
+    PERF_LAUNCH_CHECK();
+    return PERF_OK;
+}
+
 #ifdef PERF_HOST_HARNESS
 /* TEST HARNESS ONLY (never compiled into libperfb200.so): both scatter bodies over HOST arrays, one thread;
  * `pieces` plays gridDim.z of the coarse launch, `v4` bit 0 / bit 1 select scatter8<true> for the fine / coarse levels. */

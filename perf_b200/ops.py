@@ -736,11 +736,23 @@ class _FusedTrainStep(torch.autograd.Function):
             _call(_L().perf_train_backward_composite, phase, S, int(b["segments"].value), tc.near, tc.far, R, _p(jitter), _p(bg_noise), C.byref(cb),
                   _p(g_rgb), _p(g_dist), _p(g_op), _p(g_dl), _p(dist), _p(op), _p(dz), _stream())
         half = tc.geo_half if geo else tc.app_half
-        # ONE flat gradient in the parameter layout [MLP | grid]: the GEMMs and the scatter write into it
+        # ONE flat gradient in the parameter layout [MLP | grid]: the MLP backward and the scatter write into it
         grad = torch.zeros(mlp.n_params + 2 * tc.grid.n_entries, dtype=torch.float32, device=dev)
-        _, dfeat = mlp_backward_half(mlp, half[:mlp.n_params], b["feat"], b["h1"], b["h2"], dz, grad_out=grad[:mlp.n_params])
         d_table = grad[mlp.n_params:]
         aabb = (C.c_float * 6)(*tc.aabb)
+        fuse = (os.environ.get("PERF_B200_FUSE_SCATTER", "1") != "0" and os.environ.get("PERF_B200_GEMM_MLP_BWD") != "1"
+                and tc.grid.n_levels == 16 and d_table.data_ptr() % 16 == 0)
+        if fuse:
+            # MLP backward with the fine levels' reductions issued from its epilogue, then the coarse levels' march kernel
+            dfeat = torch.empty(N, 32, dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                _call(_L().perf_mlp_bwd_scatter, mlp.c(), _p(half[:mlp.n_params]), _p(b["feat"]), _p(b["h1"]), _p(b["h2"]), _p(dz.reshape(N, mlp.n_out)), N,
+                      _p(grad[:mlp.n_params]), _p(dfeat), tc.grid.c(), aabb, _p(rays_o), _p(rays_d), _p(jitter), R, S, tc.near, tc.far, _p(d_table),
+                      _stream(), launches=2)
+                _call(_L().perf_hashgrid_bwd_rays_coarse, tc.grid.c(), aabb, _p(rays_o), _p(rays_d), _p(jitter), R, S, tc.near, tc.far,
+                      _p(dfeat), _p(d_table), _stream())
+            return grad, None, None, None, None, None, None
+        _, dfeat = mlp_backward_half(mlp, half[:mlp.n_params], b["feat"], b["h1"], b["h2"], dz, grad_out=grad[:mlp.n_params])
         with torch.cuda.device(dev):
             _call(_L().perf_hashgrid_bwd_rays, tc.grid.c(), aabb, _p(rays_o), _p(rays_d), _p(jitter), R, S, tc.near, tc.far,
                   _p(dfeat), _p(d_table), _stream(), launches=2)

@@ -217,6 +217,40 @@ def test_scatter_streams_overlap_equals_serial_and_captures_into_a_graph():
     assert (out - want).abs().max() <= 1e-4 * want.abs().max()
 
 
+@pytest.mark.parametrize("phase", ["geo", "app"])
+def test_scatter_fused_into_mlp_backward_equals_separate_kernels(golden_field, phase):
+    """perf_mlp_bwd_scatter (fine levels' reductions issued from the MLP-backward epilogue) + perf_hashgrid_bwd_rays_coarse
+    against perf_mlp_bwd + perf_hashgrid_bwd_rays (PERF_B200_FUSE_SCATTER=0) inside the same fused step, at the benchmark's
+    128 samples per ray with ray splitting and a ragged last tile: same loss, same gradient up to the order of the atomics."""
+    from perf_b200 import synthetic
+    from perf_b200.scene import RaySupervision, FusedAdam
+    h, w = 32, 64
+    rgb, dist = synthetic.smooth_rgb(h, w, device="cuda"), synthetic.box_room_distance(h, w, device="cuda")
+    out = {}
+    for fused in (True, False):
+        if not fused:
+            os.environ["PERF_B200_FUSE_SCATTER"] = "0"
+        try:
+            sc = make_scene(golden_field, 128, fused_train=True)
+            sc.train_conf["pixel_loss_batch_size"] = 1501
+            sc.set_train()
+            pool = RaySupervision.from_panorama(torch.eye(4), rgb, dist, seed=3)
+            net = sc.nerf.geo_mlp if phase == "geo" else sc.nerf.app_mlp
+            opt = FusedAdam(net.params, lr=0.0, module=net)
+            torch.manual_seed(14)
+            step = sc.train_one_step_geo if phase == "geo" else sc.train_one_step_app
+            loss = step(opt, pool, progress=0.4)
+            out[fused] = (float(loss), net.params.grad.detach().clone())
+        finally:
+            os.environ.pop("PERF_B200_FUSE_SCATTER", None)
+    (lf, gf), (ls, gs) = out[True], out[False]
+    assert lf == ls and float(gs.abs().max()) > 0
+    n_mlp = 3072 if phase == "geo" else 7168
+    assert torch.equal(gf[:n_mlp], gs[:n_mlp]) or (gf[:n_mlp] - gs[:n_mlp]).abs().max() <= 1e-5 * gs[:n_mlp].abs().max()
+    assert (gf - gs).abs().max() <= 1e-4 * gs.abs().max(), float((gf - gs).abs().max() / gs.abs().max())
+    assert ((gf != 0) == (gs != 0)).float().mean() > 0.9999
+
+
 def test_fit_reduces_losses_and_checkpoint_roundtrip(golden_field, tmp_path):
     from perf_b200 import synthetic
     from perf_b200.config import Conf
