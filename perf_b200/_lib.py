@@ -112,6 +112,9 @@ def load(rebuild_if_stale: bool = True) -> C.CDLL:
     if _LIB is not None:
         return _LIB
     path = lib_path()
+    override = os.environ.get("PERF_B200_LIB")           # A/B of kernel variants (tools/ab_lib.py): load this build as it is
+    if override:
+        path, rebuild_if_stale = override, False
     if rebuild_if_stale and (not os.path.exists(path) or _build.is_stale()):
         try:
             _build.build()

@@ -132,6 +132,63 @@ __host__ __device__ __forceinline__ void level_corners_fast(const LevelTable& lt
         }
     }
 }
+// Opaque bit operations (device: inline PTX the optimiser cannot re-associate; host harness: plain C).
+// (a ^ b ^ c) & m is what the compiler makes of the hashed index -- per corner one 3-input XOR, one AND and one ADD of
+// the level offset.  Masking the x term and the four (y ^ z) terms ONCE per level leaves a single 2-input XOR per corner.
+__host__ __device__ __forceinline__ uint32_t xor_and_u32(uint32_t a, uint32_t b, uint32_t m)
+{
+#ifdef __CUDA_ARCH__
+    uint32_t r; asm("lop3.b32 %0, %1, %2, %3, 0x28;" : "=r"(r) : "r"(a), "r"(b), "r"(m)); return r;     // (a ^ b) & m
+#else
+    return (a ^ b) & m;
+#endif
+}
+__host__ __device__ __forceinline__ uint32_t and_u32(uint32_t a, uint32_t m)
+{
+#ifdef __CUDA_ARCH__
+    uint32_t r; asm("and.b32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(m)); return r;
+#else
+    return a & m;
+#endif
+}
+
+// level_corners_fast() with indices RELATIVE to the level's first entry: the caller adds lt.offset[l] to the table
+// pointer once per level (idx_fast[k] == lt.offset[l] + idx[k], weights identical; tests/test_addressing_host.py).
+// Hashed levels: 4 + 2 masked terms and one XOR per corner (see xor_and_u32).  Dense levels: the `% size` wrap can
+// only trigger in cells on the far faces of the box, so ONE comparison per level guards the eight per-corner wraps.
+template <bool HASHED>
+__host__ __device__ __forceinline__ void level_corners_rel(const LevelTable& lt, int l, float x, float y, float z, uint32_t (&idx)[8], float (&w)[8])
+{
+    const float scale = lt.scale[l];
+    const uint32_t res = lt.res[l], size = lt.size[l];
+    const float px = fmaf(scale, x, 0.5f), py = fmaf(scale, y, 0.5f), pz = fmaf(scale, z, 0.5f);
+    const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+    const uint32_t gx = (uint32_t)(int)fx, gy = (uint32_t)(int)fy, gz = (uint32_t)(int)fz;
+    const float wx = px - fx, wy = py - fy, wz = pz - fz;
+    const float ox = 1.0f - wx, oy = 1.0f - wy, oz = 1.0f - wz;
+    const float wxy[4] = {PERF_FMUL_RN(ox, oy), PERF_FMUL_RN(wx, oy), PERF_FMUL_RN(ox, wy), PERF_FMUL_RN(wx, wy)};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[k] = PERF_FMUL_RN(wxy[k & 3], (k & 4) ? wz : oz);
+    if constexpr (HASHED) {
+        const uint32_t mask = size - 1u;
+        const uint32_t hy0 = gy * 2654435761u, hy1 = hy0 + 2654435761u;
+        const uint32_t hz0 = gz * 805459861u,  hz1 = hz0 + 805459861u;
+        const uint32_t hyz[4] = {xor_and_u32(hy0, hz0, mask), xor_and_u32(hy1, hz0, mask), xor_and_u32(hy0, hz1, mask), xor_and_u32(hy1, hz1, mask)};
+        const uint32_t hx[2] = {and_u32(gx, mask), and_u32(gx + 1u, mask)};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) idx[k] = hx[k & 1] ^ hyz[k >> 1];
+    } else {
+        const uint32_t r2 = res * res;
+        const uint32_t b00 = gx + gy * res + gz * r2;
+        const uint32_t base[4] = {b00, b00 + res, b00 + r2, b00 + res + r2};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) idx[k] = base[k >> 1] + (uint32_t)(k & 1);
+        if (base[3] + 1u >= size) {                             // the largest of the eight; every index is < 2*size
+#pragma unroll
+            for (int k = 0; k < 8; ++k) idx[k] = (idx[k] >= size) ? idx[k] - size : idx[k];
+        }
+    }
+}
 // host-side precondition of the fast path: `n_dense` leading dense levels, every other level
 // hashed with a power-of-two size, Linear interpolation
 inline bool fast_addressing_ok(const LevelTable& lt, uint32_t n_dense)

@@ -85,15 +85,20 @@ __device__ __forceinline__ void acc_chunk(int c, int K, uint32_t tmem_row, const
 }
 
 // ReLU + round to fp16 (tcnn keeps hidden activations in __half), two values per instruction:
-// cvt.rn.f16x2.f32 packs a pair, HMNMX2 clamps at zero (max(round(x),0) == round(max(x,0))).
+// cvt.rn.relu.f16x2.f32 rounds a pair and clamps it at zero in ONE instruction (round(max(x,0)) == max(round(x),0);
+// until round 2 this was F2FP + HMNMX2, 96 more instructions per sample in the render kernel).
 __device__ __forceinline__ void relu_pack(const float (&v)[32], uint32_t (&p)[16])
 {
-    const __half2 zero = __float2half2_rn(0.f);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        __half2 h = __hmax2(__floats2half2_rn(v[2 * j], v[2 * j + 1]), zero);
-        p[j] = *reinterpret_cast<uint32_t*>(&h);
-    }
+    for (int j = 0; j < 16; ++j)
+        asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(p[j]) : "f"(v[2 * j + 1]), "f"(v[2 * j]));     // d = {hi: a, lo: b}
+}
+
+// Packed fp32 FMA of Blackwell (FFMA2): acc.x += a.x * b.x, acc.y += a.y * b.y in one issue slot.
+__device__ __forceinline__ void ffma2(float2& acc, float2 a, float2 b)
+{
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(reinterpret_cast<unsigned long long&>(acc))
+        : "l"(reinterpret_cast<const unsigned long long&>(a)), "l"(reinterpret_cast<const unsigned long long&>(b)));
 }
 
 // write 32 packed fp16 values as k-groups [kg0, kg0+4) of this thread's row of an activation tile
@@ -111,29 +116,33 @@ __device__ __forceinline__ void store_chunk_global(uint4* row_ptr /* 8 uint4 per
         row_ptr[4 * c + q] = make_uint4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
 }
 
-// out[o] += sum_j h[j] * wout[o][32c + j]   (output layer on CUDA cores: n_out is 1 or 3, a
-// padded N=16 MMA + another smem round trip would cost more than 64*n_out FMAs per row)
+// Output layer on CUDA cores (n_out is 1 or 3: a padded N=16 MMA + another smem round trip would cost more than the
+// 64*n_out FMAs per row).  Every output keeps TWO partial sums -- acc[o].x over the even hidden units, acc[o].y over
+// the odd ones, in increasing order -- so that one FFMA2 serves a packed pair of activations; the pre-activation is
+// acc[o].x + acc[o].y (out_sum).  All forward kernels share this order.
+//   acc[o] += h[32c + 2j, 32c + 2j + 1] * wout[o][32c + 2j, 32c + 2j + 1]      (wout: fp32 in shared memory)
 template <int NOUT_MAX>
-__device__ __forceinline__ void out_dots(const uint32_t (&p)[16], const float* wout, int c, int n_out, float (&acc)[NOUT_MAX])
+__device__ __forceinline__ void out_dots(const uint32_t (&p)[16], const float* wout, int c, int n_out, float2 (&acc)[NOUT_MAX])
 {
-    float v[32];
+    float2 v[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) { const float2 f = unpack_half2(p[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
+    for (int j = 0; j < 16; ++j) v[j] = unpack_half2(p[j]);
 #pragma unroll
     for (int o = 0; o < NOUT_MAX; ++o) {
         if (o < n_out) {
             const float4* w4 = reinterpret_cast<const float4*>(wout + o * HID + 32 * c);
-            float a = acc[o];
+            float2 a = acc[o];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const float4 w = w4[q];
-                a = fmaf(v[4 * q + 0], w.x, a); a = fmaf(v[4 * q + 1], w.y, a);
-                a = fmaf(v[4 * q + 2], w.z, a); a = fmaf(v[4 * q + 3], w.w, a);
+                ffma2(a, v[2 * q], make_float2(w.x, w.y));
+                ffma2(a, v[2 * q + 1], make_float2(w.z, w.w));
             }
             acc[o] = a;
         }
     }
 }
+__device__ __forceinline__ float out_sum(float2 acc) { return __fadd_rn(acc.x, acc.y); }
 
 // tcnn output: pre-activation rounded to fp16, activation in fp32, result rounded to fp16
 __device__ __forceinline__ float finish_output(float acc, uint32_t out_act)

@@ -115,9 +115,9 @@ __global__ void __launch_bounds__(TILE, 4) network_fwd_kernel(const __grid_const
             __syncthreads();
         }
 
-        float out_acc[16];
+        float2 out_acc[16];                     // even / odd partial sums of every output (mlp_tc.cuh::out_dots)
 #pragma unroll
-        for (int o = 0; o < 16; ++o) out_acc[o] = 0.f;
+        for (int o = 0; o < 16; ++o) out_acc[o] = make_float2(0.f, 0.f);
 
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(TILE, 4) network_fwd_kernel(const __grid_const
         if (valid) {
 #pragma unroll
             for (int o = 0; o < 16; ++o)
-                if (o < (int)a.n_out) a.out[i * a.n_out + o] = __float2half_rn(finish_output(out_acc[o], a.out_act));
+                if (o < (int)a.n_out) a.out[i * a.n_out + o] = __float2half_rn(finish_output(out_sum(out_acc[o]), a.out_act));
         }
         if constexpr (SIMT) __syncthreads();   // rows of sA/sH are rewritten next tile
     }

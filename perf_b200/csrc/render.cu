@@ -114,18 +114,18 @@ __device__ __forceinline__ void stage_weights_bulk(uint8_t* smem, int tid)
     mbar_wait(barw, 0);
 }
 
-// acc[o] += sum_j h[32c + j] * c_wout[BASE + 64 o + 32 c + j], C a compile-time constant (immediate constant offsets)
+// acc[o] += h[32C + 2j, 32C + 2j + 1] * c_wout[BASE + 64 o + 32 C + 2j, ... + 1]: even / odd partial sums, one FFMA2 per
+// packed pair of activations (mlp_tc.cuh::out_dots has the same order); C is a compile-time constant so that the
+// weights come straight from the constant bank (LDCU.128 of four weights into uniform registers).
 template <int NOUT, int BASE, int C>
-__device__ __forceinline__ void out_dots_const(const uint32_t (&p)[16], float (&acc)[NOUT])
+__device__ __forceinline__ void out_dots_const(const uint32_t (&p)[16], float2 (&acc)[NOUT])
 {
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
         const float2 f = unpack_half2(p[j]);
 #pragma unroll
-        for (int o = 0; o < NOUT; ++o) {
-            acc[o] = fmaf(f.x, c_wout[BASE + o * HID + 32 * C + 2 * j], acc[o]);
-            acc[o] = fmaf(f.y, c_wout[BASE + o * HID + 32 * C + 2 * j + 1], acc[o]);
-        }
+        for (int o = 0; o < NOUT; ++o)
+            ffma2(acc[o], f, make_float2(c_wout[BASE + o * HID + 32 * C + 2 * j], c_wout[BASE + o * HID + 32 * C + 2 * j + 1]));
     }
 }
 
@@ -217,6 +217,14 @@ struct RenderSmem {
     const uint2* l0;        // level 0 of the packed table in shared memory, or null
 };
 
+// base + 8 * idx as ONE IMAD.WIDE.U32 (left to itself ptxas splits the 64-bit address into LEA + IADD3.X per corner)
+__device__ __forceinline__ const uint2* entry_ptr(const uint2* base, uint32_t idx)
+{
+    uint64_t p;
+    asm("mad.wide.u32 %0, %1, 8, %2;" : "=l"(p) : "r"(idx), "l"(reinterpret_cast<uint64_t>(base)));
+    return reinterpret_cast<const uint2*>(p);
+}
+
 // Levels [4q, 4q+4) of both fields -> one 16-byte k-group of each feature tile.
 // KIND 0: generic addressing, 1: dense (fast), 2: hashed power-of-two (fast).
 template <int KIND, int SAVE, bool L0SMEM = false>
@@ -226,22 +234,28 @@ __device__ __forceinline__ void encode_group(const RenderArgs& a, const RenderSm
 #pragma unroll
     for (int ll = 0; ll < 4; ++ll) {
         const int l = 4 * q + ll;
-        Corner8 c;
-        if constexpr (KIND == 0) level_corners(a.lt, l, x, y, z, c);
-        else if constexpr (KIND == 1) level_corners_fast<false>(a.lt, l, x, y, z, c);
-        else level_corners_fast<true>(a.lt, l, x, y, z, c);
-        uint2 v[8];
-        if (KIND == 1 && L0SMEM && l == 0) {
+        uint2 v[8]; float w[8];
+        if constexpr (KIND == 0) {
+            Corner8 c; level_corners(a.lt, l, x, y, z, c);
 #pragma unroll
-            for (int kk = 0; kk < 8; ++kk) v[kk] = sm.l0[c.idx[kk]];           // offset of level 0 is 0
+            for (int kk = 0; kk < 8; ++kk) { v[kk] = __ldg(a.table + c.idx[kk]); w[kk] = c.w[kk]; }
         } else {
+            // level-local indices: the level offset goes into the pointer once, not into each of the 8 indices
+            uint32_t idx[8];
+            level_corners_rel<KIND == 2>(a.lt, l, x, y, z, idx, w);
+            if (KIND == 1 && L0SMEM && l == 0) {
 #pragma unroll
-            for (int kk = 0; kk < 8; ++kk) v[kk] = __ldg(a.table + c.idx[kk]);
+                for (int kk = 0; kk < 8; ++kk) v[kk] = sm.l0[idx[kk]];           // offset of level 0 is 0
+            } else {
+                const uint2* const tl = a.table + a.lt.offset[l];
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) v[kk] = __ldg(entry_ptr(tl, idx[kk]));
+            }
         }
         uint32_t vg[8], va[8];
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) { vg[kk] = v[kk].x; va[kk] = v[kk].y; }
-        pg[ll] = blend8_half(c.w, vg); pa[ll] = blend8_half(c.w, va);
+        pg[ll] = blend8_half(w, vg); pa[ll] = blend8_half(w, va);
     }
     *reinterpret_cast<uint4*>(sm.sAg + (q * TILE + tid) * 16) = make_uint4(pg[0], pg[1], pg[2], pg[3]);
     *reinterpret_cast<uint4*>(sm.sAa + (q * TILE + tid) * 16) = make_uint4(pa[0], pa[1], pa[2], pa[3]);
@@ -294,7 +308,7 @@ __device__ __forceinline__ void eval_fields(const RenderArgs& a, const RenderSme
     }
 
     // density: ReLU hidden -> 64-long dot -> fp16 logit -> exp     (ngp_nerf.py:141-150)
-    float og[1] = {0.f};
+    float2 og[1] = {make_float2(0.f, 0.f)};
 #pragma unroll
     for (int c = 0; c < 2; ++c) {                          // unrolled: the constant-bank offsets must be immediates
         float v[32]; uint32_t hp[16];
@@ -303,7 +317,7 @@ __device__ __forceinline__ void eval_fields(const RenderArgs& a, const RenderSme
         if constexpr (SAVE == 1) { if (srow != ~0ull) store_chunk_global(a.s_h1 + srow * 8, c, hp); }
         if (c == 0) out_dots_const<1, 0, 0>(hp, og); else out_dots_const<1, 0, 1>(hp, og);
     }
-    sigma = selector ? expf(finish_output(og[0], 0)) : 0.f;
+    sigma = selector ? expf(finish_output(out_sum(og[0]), 0)) : 0.f;
 
     // colour hidden 1 -> H tile (aliases the feature tiles: both layer-1 MMAs are complete)
 #pragma unroll 1
@@ -328,7 +342,7 @@ __device__ __forceinline__ void eval_fields(const RenderArgs& a, const RenderSme
     } else {
         __syncthreads();
     }
-    float oa[3] = {0.f, 0.f, 0.f};
+    float2 oa[3] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
         float v[32]; uint32_t hp[16];
@@ -337,9 +351,9 @@ __device__ __forceinline__ void eval_fields(const RenderArgs& a, const RenderSme
         if constexpr (SAVE == 2) { if (srow != ~0ull) store_chunk_global(a.s_h2 + srow * 8, c, hp); }
         if (c == 0) out_dots_const<3, HID, 0>(hp, oa); else out_dots_const<3, HID, 1>(hp, oa);
     }
-    cr = selector ? finish_output(oa[0], 1) : 0.f;      // ngp_nerf.py:156-161
-    cg = selector ? finish_output(oa[1], 1) : 0.f;
-    cb = selector ? finish_output(oa[2], 1) : 0.f;
+    cr = selector ? finish_output(out_sum(oa[0]), 1) : 0.f;      // ngp_nerf.py:156-161
+    cg = selector ? finish_output(out_sum(oa[1]), 1) : 0.f;
+    cb = selector ? finish_output(out_sum(oa[2]), 1) : 0.f;
 }
 
 template <bool PANO, bool SIMT>

@@ -66,6 +66,8 @@ def test_fast_addressing_equals_generic_where_admitted(log2_t, base, scale, seed
         a = hh.level_corners(pcfg, level, x, fast=False)
         b = hh.level_corners(pcfg, level, x, fast=True, n_dense=n_dense)
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), level
+        r = hh.level_corners(pcfg, level, x, fast="rel", n_dense=n_dense)           # level-local indices + offset
+        assert np.array_equal(a[0], r[0]) and np.array_equal(a[1], r[1]), level
 
 
 def test_perf_grid_is_admitted_with_four_dense_levels():
@@ -74,9 +76,15 @@ def test_perf_grid_is_admitted_with_four_dense_levels():
     assert hh.level_corners(pcfg, 0, x[:1], fast=True, n_dense=4)[2]
     assert not hh.level_corners(pcfg, 0, x[:1], fast=True, n_dense=3)[2]
     assert not hh.level_corners(GridConfig(16, 2, 18, 16, 1.4472692012786865, "Smoothstep"), 0, x[:1], fast=True, n_dense=4)[2]
+    # the far faces / corner of the box are where a dense level's `% size` wrap triggers: level_corners_rel guards its
+    # eight per-corner wraps with one comparison per level
+    faces = np.array([[1, 1, 1], [1, .5, 1], [.3, 1, 1], [1, 1, .2], [0, 0, 0], [1, 0, 0], [0, 1, 1], [.999999, .999999, 1]], np.float32)
+    x = np.concatenate([x, faces])
     for level in range(16):
         a, b = hh.level_corners(pcfg, level, x, fast=False), hh.level_corners(pcfg, level, x, fast=True)
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        r = hh.level_corners(pcfg, level, x, fast="rel")
+        assert np.array_equal(a[0], r[0]) and np.array_equal(a[1], r[1]), level
 
 
 def test_vector_atomic_scatter_pairs_equal_plain_scatter():
