@@ -34,7 +34,7 @@ int main(int argc, char** argv)
     uint64_t n_geo = 0, n_app = 0, n_entries = 0;
     CHECK_PERF(perf_network_param_count(&grid, &geo, &n_geo));
     CHECK_PERF(perf_network_param_count(&grid, &app, &n_app));
-    CHECK_PERF(perf_grid_describe(&grid, NULL, &n_entries));
+    CHECK_PERF(perf_packed_table_entries(&grid, &n_entries));     /* entries of the packed gather table (grid + cell-major dense levels) */
     if (perf_device_arch() != 100) fprintf(stderr, "warning: built for sm_100a, device reports %d\n", perf_device_arch());
 
     const int H = 512, W = 1024, S = 128;

@@ -87,10 +87,15 @@ int perf_network_param_count(const perf_grid_cfg* grid, const perf_mlp_cfg* mlp,
 int perf_params_to_half(const float* d_params, void* d_params_half, uint64_t n, void* stream);
 
 /* Interleave the two fp16 grid tables into one {geo.f0,geo.f1,app.f0,app.f1} table so one
- * 8-byte gather serves both fields.  d_*_params_half: full fp16 params of each network. */
+ * 8-byte gather serves both fields.  d_*_params_half: full fp16 params of each network.
+ * Layout of d_packed (8-byte entries, 16-byte aligned buffer): entries [0, n_entries) in parameter order,
+ * followed by a cell-major copy of the leading dense levels (up to four; for each, res^3 cells x the 8 corner
+ * entries of the cell = one 64-byte record per cell) which the fused field kernels read with four 16-byte
+ * loads per sample and level.  perf_packed_table_entries gives the total entry count to allocate. */
+int perf_packed_table_entries(const perf_grid_cfg* cfg, uint64_t* h_entries);
 int perf_pack_tables(const perf_grid_cfg* grid, const perf_mlp_cfg* geo_mlp, const perf_mlp_cfg* app_mlp,
                      const void* d_geo_params_half, const void* d_app_params_half,
-                     void* d_packed /* n_entries * 8 bytes */, void* stream);
+                     void* d_packed /* perf_packed_table_entries() * 8 bytes */, void* stream);
 
 /* Equirect rays for image rows [row0,row0+rows) of an H x W panorama; h_pose: row-major 4x4
  * camera-to-world.  d_rays_o/d_rays_d: [rows*W,3] fp32.
@@ -173,7 +178,7 @@ int perf_accumulate_along_rays(const float* d_weights, const float* d_values, in
  * fixed-S sampler; NeRFScene.render, nerf.py:74-99). */
 typedef struct perf_render_args {
     perf_grid_cfg grid;           /* both fields use the same grid config (ngp_nerf.py:96-134) */
-    const void*   d_packed_table; /* from perf_pack_tables                                      */
+    const void*   d_packed_table; /* from perf_pack_tables (perf_packed_table_entries() * 8 bytes) */
     const void*   d_geo_mlp_half; /* fp16 MLP matrices of the density net (3072 values)         */
     const void*   d_app_mlp_half; /* fp16 MLP matrices of the colour net  (7168 values)         */
     float         aabb[6];        /* min xyz, max xyz (nerf.py:35)                              */

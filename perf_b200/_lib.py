@@ -59,6 +59,7 @@ SIGNATURES = {
     "perf_grid_describe": (i32, [P(GridCfg), P(Level), P(u64)]),
     "perf_network_param_count": (i32, [P(GridCfg), P(MlpCfg), P(u64)]),
     "perf_params_to_half": (i32, [vp, vp, u64, vp]),
+    "perf_packed_table_entries": (i32, [P(GridCfg), P(u64)]),
     "perf_pack_tables": (i32, [P(GridCfg), P(MlpCfg), P(MlpCfg), vp, vp, vp, vp]),
     "perf_raygen_pano": (i32, [P(f32), i32, i32, i32, i32, vp, vp, vp]),
     "perf_raygen_pers": (i32, [P(f32), f32, i32, i32, vp, vp, vp]),

@@ -100,11 +100,26 @@ __global__ void params_to_half_kernel(const float* __restrict__ p, __half* __res
     }
 }
 
+struct PackCells {            // cell-major copies of the leading dense levels (common.cuh::PackedLayout)
+    uint32_t n_levels;
+    uint32_t res[PERF_CELL_LEVELS], size[PERF_CELL_LEVELS], offset[PERF_CELL_LEVELS];
+    uint64_t start[PERF_CELL_LEVELS + 1];     // first packed entry of each level's cells; [n_levels] = total
+};
 __global__ void pack_tables_kernel(const uint32_t* __restrict__ geo, const uint32_t* __restrict__ app,
-                                   uint2* __restrict__ out, uint64_t n)
+                                   uint2* __restrict__ out, uint64_t n, const PackCells pc, uint64_t total)
 {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = make_uint2(geo[i], app[i]);
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { out[i] = make_uint2(geo[i], app[i]); return; }
+    if (i >= total) return;
+    uint32_t l = 0;
+    while (l + 1 < pc.n_levels && i >= pc.start[l + 1]) ++l;
+    const uint64_t j = i - pc.start[l];
+    const uint32_t k = (uint32_t)(j & 7u), cell = (uint32_t)(j >> 3), res = pc.res[l];
+    const uint32_t gx = cell % res, gy = (cell / res) % res, gz = cell / (res * res);
+    uint32_t e = (gx + (k & 1u)) + res * ((gy + ((k >> 1) & 1u)) + res * (gz + (k >> 2)));
+    if (e >= pc.size[l]) e -= pc.size[l];                      // tcnn's `% size` of a dense level (e < 2 * size)
+    e += pc.offset[l];
+    out[i] = make_uint2(geo[e], app[e]);
 }
 
 // torch.linspace(start, end, steps)[i] in fp32 (ATen's symmetric formula), so that pixel centres
@@ -503,18 +518,33 @@ int perf_params_to_half(const float* d_params, void* d_params_half, uint64_t n, 
     return PERF_OK;
 }
 
+int perf_packed_table_entries(const perf_grid_cfg* cfg, uint64_t* h_entries)
+{
+    PERF_CHECK_ARG(h_entries != nullptr, "NULL pointer");
+    LevelTable lt; uint64_t ne = 0;
+    int rc = build_level_table(cfg, &lt, &ne); if (rc) return rc;
+    *h_entries = packed_layout(lt, ne).total_entries;
+    return PERF_OK;
+}
+
 int perf_pack_tables(const perf_grid_cfg* grid, const perf_mlp_cfg* geo_mlp, const perf_mlp_cfg* app_mlp,
                      const void* d_geo_params_half, const void* d_app_params_half, void* d_packed, void* stream)
 {
     PERF_CHECK_ARG(d_geo_params_half && d_app_params_half && d_packed, "NULL pointer");
     uint64_t ne = 0, ng = 0, na = 0;
-    int rc = build_level_table(grid, nullptr, &ne); if (rc) return rc;
+    LevelTable lt;
+    int rc = build_level_table(grid, &lt, &ne); if (rc) return rc;
     rc = mlp_param_count(geo_mlp, &ng); if (rc) return rc;
     rc = mlp_param_count(app_mlp, &na); if (rc) return rc;
     const uint32_t* geo = reinterpret_cast<const uint32_t*>((const __half*)d_geo_params_half + ng);
     const uint32_t* app = reinterpret_cast<const uint32_t*>((const __half*)d_app_params_half + na);
-    PERF_CHECK_ARG(((uintptr_t)geo % 4 == 0) && ((uintptr_t)app % 4 == 0) && ((uintptr_t)d_packed % 8 == 0), "misaligned tables");
-    pack_tables_kernel<<<blocks_for(ne, 256), 256, 0, S(stream)>>>(geo, app, (uint2*)d_packed, ne);
+    PERF_CHECK_ARG(((uintptr_t)geo % 4 == 0) && ((uintptr_t)app % 4 == 0) && ((uintptr_t)d_packed % 16 == 0), "misaligned tables (d_packed: 16-byte aligned)");
+    const PackedLayout pl = packed_layout(lt, ne);
+    PackCells pc; memset(&pc, 0, sizeof(pc));
+    pc.n_levels = pl.n_cell_levels;
+    for (uint32_t l = 0; l < pl.n_cell_levels; ++l) { pc.res[l] = lt.res[l]; pc.size[l] = lt.size[l]; pc.offset[l] = lt.offset[l]; pc.start[l] = pl.cell_start[l]; }
+    pc.start[pl.n_cell_levels] = pl.total_entries;
+    pack_tables_kernel<<<blocks_for(pl.total_entries, 256), 256, 0, S(stream)>>>(geo, app, (uint2*)d_packed, ne, pc, pl.total_entries);
     PERF_LAUNCH_CHECK();
     return PERF_OK;
 }

@@ -31,6 +31,31 @@ struct LevelTable {
     uint32_t smoothstep;
 };
 int build_level_table(const perf_grid_cfg* cfg, LevelTable* out, uint64_t* n_entries);
+
+// Layout of the packed gather table (perf_pack_tables): entries [0, n_entries) in parameter order, then a CELL-MAJOR copy
+// of the leading dense levels -- for level l, res_l^3 cells x 8 corners x 8 bytes, cell (gx,gy,gz) at gx + res (gy + res gz),
+// corner k (bit0 = x, bit1 = y, bit2 = z) holding entry ((gx+kx) + res (gy+ky) + res^2 (gz+kz)) % size of that level.
+// The fused field kernels read a dense level as ONE 64-byte record per sample (4 x LDG.128, one address, no wrap test)
+// instead of eight 8-byte gathers.  cell_start[l]: first entry (8-byte units) of level l's cells.
+constexpr uint32_t PERF_CELL_LEVELS = 4;                 // PeRF's grid: levels 0..3 are dense
+constexpr uint64_t PERF_CELL_CAP = 1ull << 20;           // at most 2^20 cells (64 MB) are ever duplicated
+struct PackedLayout {
+    uint32_t n_cell_levels;                              // leading dense levels with a cell-major copy (<= PERF_CELL_LEVELS)
+    uint64_t cell_start[PERF_CELL_LEVELS];
+    uint64_t total_entries;                              // n_entries + 8 * cells
+};
+inline PackedLayout packed_layout(const LevelTable& lt, uint64_t n_entries)
+{
+    PackedLayout pl; pl.n_cell_levels = 0; pl.total_entries = n_entries;
+    uint64_t cells = 0;
+    for (uint32_t l = 0; l < lt.n_levels && l < PERF_CELL_LEVELS; ++l) {
+        if ((lt.hashed_mask >> l) & 1u) break;
+        const uint64_t c = (uint64_t)lt.res[l] * lt.res[l] * lt.res[l];
+        if (cells + c > PERF_CELL_CAP) break;
+        pl.cell_start[l] = pl.total_entries; pl.total_entries += 8 * c; cells += c; pl.n_cell_levels = l + 1;
+    }
+    return pl;
+}
 int mlp_param_count(const perf_mlp_cfg* mlp, uint64_t* count);
 int check_mlp(const perf_mlp_cfg* mlp);
 
@@ -189,6 +214,23 @@ __host__ __device__ __forceinline__ void level_corners_rel(const LevelTable& lt,
         }
     }
 }
+// Dense level of the fused field kernels: cell index into the cell-major copy (PackedLayout) + the eight weights of
+// level_corners_fast().  Coordinates in [0,1] => gx, gy, gz <= res - 1, i.e. cell < res^3.
+__host__ __device__ __forceinline__ uint32_t level_cell_dense(const LevelTable& lt, int l, float x, float y, float z, float (&w)[8])
+{
+    const float scale = lt.scale[l];
+    const uint32_t res = lt.res[l];
+    const float px = fmaf(scale, x, 0.5f), py = fmaf(scale, y, 0.5f), pz = fmaf(scale, z, 0.5f);
+    const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+    const uint32_t gx = (uint32_t)(int)fx, gy = (uint32_t)(int)fy, gz = (uint32_t)(int)fz;
+    const float wx = px - fx, wy = py - fy, wz = pz - fz;
+    const float ox = 1.0f - wx, oy = 1.0f - wy, oz = 1.0f - wz;
+    const float wxy[4] = {PERF_FMUL_RN(ox, oy), PERF_FMUL_RN(wx, oy), PERF_FMUL_RN(ox, wy), PERF_FMUL_RN(wx, wy)};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[k] = PERF_FMUL_RN(wxy[k & 3], (k & 4) ? wz : oz);
+    return gx + res * (gy + res * gz);
+}
+
 // host-side precondition of the fast path: `n_dense` leading dense levels, every other level
 // hashed with a power-of-two size, Linear interpolation
 inline bool fast_addressing_ok(const LevelTable& lt, uint32_t n_dense)

@@ -17,6 +17,7 @@ namespace perf {
 struct RenderArgs {
     LevelTable    lt;
     const uint2*  table;        // {geo half2, app half2} per entry
+    const uint4*  cells[PERF_CELL_LEVELS];   // cell-major copies of the dense levels inside the same buffer (common.cuh::PackedLayout)
     const __half* geo_w;        // W1 [64,32] | Wout [16,64]
     const __half* app_w;        // W1 [64,32] | W2 [64,64] | Wout [16,64]
     float         aabb_min[3], aabb_ext[3];
@@ -239,18 +240,29 @@ __device__ __forceinline__ void encode_group(const RenderArgs& a, const RenderSm
             Corner8 c; level_corners(a.lt, l, x, y, z, c);
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) { v[kk] = __ldg(a.table + c.idx[kk]); w[kk] = c.w[kk]; }
-        } else {
-            // level-local indices: the level offset goes into the pointer once, not into each of the 8 indices
-            uint32_t idx[8];
-            level_corners_rel<KIND == 2>(a.lt, l, x, y, z, idx, w);
-            if (KIND == 1 && L0SMEM && l == 0) {
+        } else if constexpr (KIND == 1) {
+            if (L0SMEM && l == 0) {                // measured variant: level 0 (entry-major, offset 0) resident in shared memory
+                uint32_t idx[8];
+                level_corners_rel<false>(a.lt, l, x, y, z, idx, w);
 #pragma unroll
-                for (int kk = 0; kk < 8; ++kk) v[kk] = sm.l0[idx[kk]];           // offset of level 0 is 0
+                for (int kk = 0; kk < 8; ++kk) v[kk] = sm.l0[idx[kk]];
             } else {
-                const uint2* const tl = a.table + a.lt.offset[l];
+                // dense level: ONE 64-byte cell record (all 8 corners of both fields), 4 x LDG.128 from one address
+                const uint32_t cell = level_cell_dense(a.lt, l, x, y, z, w);
+                const uint4* const cp = a.cells[l] + 4ull * cell;
 #pragma unroll
-                for (int kk = 0; kk < 8; ++kk) v[kk] = __ldg(entry_ptr(tl, idx[kk]));
+                for (int j = 0; j < 4; ++j) {
+                    const uint4 c2 = __ldg(cp + j);
+                    v[2 * j] = make_uint2(c2.x, c2.y); v[2 * j + 1] = make_uint2(c2.z, c2.w);
+                }
             }
+        } else {
+            // hashed level, level-local indices: the level offset goes into the pointer once, not into each of the 8 indices
+            uint32_t idx[8];
+            level_corners_rel<true>(a.lt, l, x, y, z, idx, w);
+            const uint2* const tl = a.table + a.lt.offset[l];
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) v[kk] = __ldg(entry_ptr(tl, idx[kk]));
         }
         uint32_t vg[8], va[8];
 #pragma unroll
@@ -803,10 +815,13 @@ static int launch_render(const perf_render_args* args, RenderArgs& a, bool pano,
     PERF_CHECK_ARG(args->d_rgb && args->d_distance, "NULL output");
     PERF_CHECK_ARG(args->n_samples >= 1 && args->n_samples <= 4096, "n_samples=%u not in [1,4096]", args->n_samples);
     PERF_CHECK_ARG(args->far > args->near, "far <= near");
-    PERF_CHECK_ARG((uintptr_t)args->d_packed_table % 8 == 0 && (uintptr_t)args->d_geo_mlp_half % 16 == 0 && (uintptr_t)args->d_app_mlp_half % 16 == 0, "misaligned table / weights");
-    int rc = build_level_table(&args->grid, &a.lt, nullptr); if (rc) return rc;
+    PERF_CHECK_ARG((uintptr_t)args->d_packed_table % 16 == 0 && (uintptr_t)args->d_geo_mlp_half % 16 == 0 && (uintptr_t)args->d_app_mlp_half % 16 == 0, "misaligned table / weights");
+    uint64_t n_entries = 0;
+    int rc = build_level_table(&args->grid, &a.lt, &n_entries); if (rc) return rc;
     PERF_CHECK_SUP(args->grid.n_levels == 16, "fused renderer needs n_levels == 16 (got %u)", args->grid.n_levels);
     a.table = (const uint2*)args->d_packed_table;
+    const PackedLayout pl = packed_layout(a.lt, n_entries);
+    for (uint32_t l = 0; l < pl.n_cell_levels; ++l) a.cells[l] = reinterpret_cast<const uint4*>(a.table + pl.cell_start[l]);
     a.geo_w = (const __half*)args->d_geo_mlp_half; a.app_w = (const __half*)args->d_app_mlp_half;
     for (int i = 0; i < 3; ++i) { a.aabb_min[i] = args->aabb[i]; a.aabb_ext[i] = args->aabb[3 + i] - args->aabb[i]; }
     a.S = args->n_samples; a.near = args->near; a.far = args->far;
@@ -833,7 +848,7 @@ static int launch_render(const perf_render_args* args, RenderArgs& a, bool pano,
         if (attr_dev != dev_) { PERF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_TOTAL)); \
             attr_dev = dev_; } \
         k<<<grid, TILE, RS_TOTAL, stream>>>(a); } while (0)
-    const bool fast = fast_addressing_ok(a.lt, 4) && (args->flags & PERF_FLAG_GENERIC_ADDR) == 0;   // PeRF's grid: 4 dense + 12 hashed levels
+    const bool fast = fast_addressing_ok(a.lt, 4) && pl.n_cell_levels == 4 && (args->flags & PERF_FLAG_GENERIC_ADDR) == 0;   // PeRF's grid: 4 dense + 12 hashed levels
     if (save != 0) {
         PERF_CHECK_SUP(!pano && !simt && !scan, "training forward runs on the ray-marching tensor-core kernel only");
         if (fast) { if (save == 1) PERF_RENDER_LAUNCH(render_march_kernel<false, false, 4, 1>); else PERF_RENDER_LAUNCH(render_march_kernel<false, false, 4, 2>); }
@@ -925,9 +940,13 @@ int perf_fields_packed(const perf_render_args* args, const float* d_rays_o, cons
     PERF_CHECK_ARG(args->d_packed_table && args->d_geo_mlp_half && args->d_app_mlp_half, "NULL table / weights");
     PERF_CHECK_ARG(((uintptr_t)d_feat | (uintptr_t)d_h1 | (uintptr_t)d_h2) % 16 == 0 && (uintptr_t)d_rgb_half4 % 8 == 0, "misaligned buffer");
     RenderArgs a; memset(&a, 0, sizeof(a));
-    int rc = build_level_table(&args->grid, &a.lt, nullptr); if (rc) return rc;
+    uint64_t n_entries = 0;
+    int rc = build_level_table(&args->grid, &a.lt, &n_entries); if (rc) return rc;
     PERF_CHECK_SUP(args->grid.n_levels == 16, "fused field kernel needs n_levels == 16 (got %u)", args->grid.n_levels);
     a.table = (const uint2*)args->d_packed_table;
+    PERF_CHECK_ARG((uintptr_t)args->d_packed_table % 16 == 0, "misaligned table");
+    const PackedLayout pl = packed_layout(a.lt, n_entries);
+    for (uint32_t l = 0; l < pl.n_cell_levels; ++l) a.cells[l] = reinterpret_cast<const uint4*>(a.table + pl.cell_start[l]);
     a.geo_w = (const __half*)args->d_geo_mlp_half; a.app_w = (const __half*)args->d_app_mlp_half;
     for (int i = 0; i < 3; ++i) { a.aabb_min[i] = args->aabb[i]; a.aabb_ext[i] = args->aabb[3 + i] - args->aabb[i]; }
     a.rays_o = d_rays_o; a.rays_d = d_rays_d;
@@ -938,7 +957,7 @@ int perf_fields_packed(const perf_render_args* args, const float* d_rays_o, cons
     rc = prepare_weights(a, st); if (rc) return rc;
     const uint64_t n_tiles = (N + TILE - 1) / TILE;
     const unsigned grid = (unsigned)(n_tiles < (uint64_t)num_sms() * 4 ? n_tiles : (uint64_t)num_sms() * 4);
-    const bool fast = fast_addressing_ok(a.lt, 4) && (args->flags & PERF_FLAG_GENERIC_ADDR) == 0;
+    const bool fast = fast_addressing_ok(a.lt, 4) && pl.n_cell_levels == 4 && (args->flags & PERF_FLAG_GENERIC_ADDR) == 0;
 #define PERF_PACKED_LAUNCH(...) do { \
         auto k = __VA_ARGS__; \
         static thread_local int attr_dev = -1; int dev_ = 0; PERF_CUDA(cudaGetDevice(&dev_)); \

@@ -67,13 +67,31 @@ def params_to_half(params: torch.Tensor, out: Optional[torch.Tensor] = None) -> 
     return out
 
 
+_PACKED_ROWS = {}
+
+
+def packed_table_entries(grid: GridConfig = PERF_GRID) -> int:
+    """Rows of the packed gather table of a grid (entries + cell-major dense levels): perf_packed_table_entries."""
+    key = (grid.n_levels, grid.n_features_per_level, grid.log2_hashmap_size, grid.base_resolution, grid.per_level_scale, grid.interpolation)
+    n = _PACKED_ROWS.get(key)
+    if n is None:
+        v = C.c_uint64(0)
+        _call(_L().perf_packed_table_entries, grid.c(), C.byref(v))
+        n = _PACKED_ROWS[key] = int(v.value)
+    return n
+
+
 def pack_tables(geo_half: torch.Tensor, app_half: torch.Tensor, grid: GridConfig = PERF_GRID,
                 geo_mlp: MLPConfig = GEO_MLP, app_mlp: MLPConfig = APP_MLP,
                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Interleaved {geo.f0, geo.f1, app.f0, app.f1} fp16 table [n_entries, 4]."""
+    """Interleaved {geo.f0, geo.f1, app.f0, app.f1} fp16 table [packed_table_entries(grid), 4]: the first n_entries rows in
+    parameter order, then the cell-major copy of the dense levels (include/perfb200.h::perf_pack_tables)."""
     geo_half, app_half = _chk(geo_half, torch.float16, "geo_half"), _chk(app_half, torch.float16, "app_half")
+    n_rows = packed_table_entries(grid)
     if out is None:
-        out = torch.empty(grid.n_entries, 4, dtype=torch.float16, device=geo_half.device)
+        out = torch.empty(n_rows, 4, dtype=torch.float16, device=geo_half.device)
+    if out.shape[0] != n_rows or out.dtype != torch.float16 or not out.is_contiguous():
+        raise ValueError(f"pack_tables: out must be a contiguous fp16 [{n_rows}, 4] tensor, got {tuple(out.shape)} {out.dtype}")
     with torch.cuda.device(geo_half.device):
         _call(_L().perf_pack_tables, grid.c(), geo_mlp.c(), app_mlp.c(), _p(geo_half), _p(app_half), _p(out), _stream())
     return out

@@ -21,6 +21,11 @@ int perf_host_level_corners(const perf_grid_cfg* cfg, int level, int mode, uint3
     for (uint64_t i = 0; i < N; ++i) {
         Corner8 c;
         if (mode == 0) level_corners(lt, level, x01[3 * i], x01[3 * i + 1], x01[3 * i + 2], c);
+        else if (mode == 3) {                      // dense level of the fused field kernels: cell index (returned in idx[0]) + weights
+            if (hashed) return PERF_EINVAL;
+            const uint32_t cell = level_cell_dense(lt, level, x01[3 * i], x01[3 * i + 1], x01[3 * i + 2], c.w);
+            for (int k = 0; k < 8; ++k) c.idx[k] = cell;
+        }
         else if (mode == 2) {                      // level-local variant of the fused field kernels: offset added back here
             uint32_t ri[8];
             if (hashed) level_corners_rel<true>(lt, level, x01[3 * i], x01[3 * i + 1], x01[3 * i + 2], ri, c.w);

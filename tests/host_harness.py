@@ -66,10 +66,11 @@ def bwd_bwd_input(grid_cfg, table_half, x01, dfeat, ddx):
 
 def level_corners(grid_cfg, level: int, x01: np.ndarray, fast, n_dense: int = 4):
     """(idx [N,8] uint32, w [N,8] f32, fast_ok) from level_corners (fast=False), level_corners_fast (True) or the
-    level-local level_corners_rel of the fused field kernels with the level offset added back (fast="rel")."""
+    level-local level_corners_rel of the fused field kernels with the level offset added back (fast="rel"); fast="cell":
+    level_cell_dense -- the cell index of a dense level in every column of idx, and the weights."""
     n = x01.shape[0]
     idx, w, ok = np.zeros((n, 8), np.uint32), np.zeros((n, 8), np.float32), C.c_int(0)
-    rc = lib().perf_host_level_corners(C.byref(grid_cfg.c()), int(level), 2 if fast == "rel" else int(bool(fast)), C.c_uint32(n_dense), _p(x01), C.c_uint64(n),
+    rc = lib().perf_host_level_corners(C.byref(grid_cfg.c()), int(level), {"rel": 2, "cell": 3}.get(fast, int(bool(fast))) if isinstance(fast, str) else int(bool(fast)), C.c_uint32(n_dense), _p(x01), C.c_uint64(n),
                                        _p(idx), _p(w), C.byref(ok))
     assert rc == 0, rc
     return idx, w, bool(ok.value)

@@ -85,6 +85,18 @@ def test_perf_grid_is_admitted_with_four_dense_levels():
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
         r = hh.level_corners(pcfg, level, x, fast="rel")
         assert np.array_equal(a[0], r[0]) and np.array_equal(a[1], r[1]), level
+        if level < 4:
+            # dense level read through its cell-major copy: cell (gx,gy,gz) -> the pack kernel's corner rule gives the same
+            # eight entries as the generic addressing, with the same weights
+            lv = level_table(OGrid(n_levels=16, log2_hashmap_size=18, base_resolution=16, per_level_scale=1.4472692012786865))[level]
+            cidx, cw, _ = hh.level_corners(pcfg, level, x, fast="cell")
+            cell = cidx[:, 0].astype(np.int64)
+            res = lv.resolution
+            assert cell.max() < res ** 3
+            gx, gy, gz = cell % res, (cell // res) % res, cell // (res * res)
+            k = np.arange(8)
+            e = (gx[:, None] + (k & 1)) + res * ((gy[:, None] + ((k >> 1) & 1)) + res * (gz[:, None] + (k >> 2)))
+            assert np.array_equal(e % lv.size + lv.offset, a[0].astype(np.int64)) and np.array_equal(cw, a[1]), level
 
 
 def test_vector_atomic_scatter_pairs_equal_plain_scatter():

@@ -189,8 +189,25 @@ def test_params_to_half_and_pack(ops):
     gh, ah = ops.params_to_half(geo.cuda()), ops.params_to_half(app.cuda())
     assert torch.equal(gh.cpu(), geo.half()) and torch.equal(ah.cpu(), app.half())
     packed = ops.pack_tables(gh, ah).cpu()
-    assert torch.equal(packed[:, :2], geo.half()[GEO_MLP.n_params:].view(-1, 2))
-    assert torch.equal(packed[:, 2:], app.half()[APP_MLP.n_params:].view(-1, 2))
+    gt, at = geo.half()[GEO_MLP.n_params:].view(-1, 2), app.half()[APP_MLP.n_params:].view(-1, 2)
+    assert torch.equal(packed[:n_e, :2], gt) and torch.equal(packed[:n_e, 2:], at)
+    # cell-major copy of the four dense levels behind the entries: cell (gx,gy,gz), corner k -> entry
+    # ((gx+kx) + res (gy+ky) + res^2 (gz+kz)) % size of that level (include/perfb200.h::perf_pack_tables)
+    from oracle.hashgrid import GridConfig as OGrid, level_table
+    lv = level_table(OGrid(n_levels=16, log2_hashmap_size=18, base_resolution=16, per_level_scale=PERF_GRID.per_level_scale))
+    start = n_e
+    for l in range(4):
+        assert not lv[l].hashed
+        res, size, off = lv[l].resolution, lv[l].size, lv[l].offset
+        c = torch.arange(res ** 3)
+        gx, gy, gz = c % res, (c // res) % res, c // (res * res)
+        k = torch.arange(8)
+        e = (gx[:, None] + (k & 1)) + res * ((gy[:, None] + ((k >> 1) & 1)) + res * (gz[:, None] + (k >> 2)))
+        e = (e % size + off).reshape(-1)
+        blk = packed[start:start + 8 * res ** 3]
+        assert torch.equal(blk[:, :2], gt[e]) and torch.equal(blk[:, 2:], at[e]), l
+        start += 8 * res ** 3
+    assert start == packed.shape[0] == ops.packed_table_entries()
 
 
 def test_hashgrid_bwd_rays_matches_oracle(ops):
