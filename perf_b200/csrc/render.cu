@@ -25,6 +25,7 @@ struct RenderArgs {
     uint32_t      rays_per_unit, tiles_per_unit;
     float         near, far;
     uint32_t      training;
+    uint32_t      div_generic;  // 1: an aabb extent whose significand is all ones -> div_uniform() falls back to the IEEE division
     const float*  jitter;       // [R] or null
     const float*  bg_noise;     // [R,4] or null
     float*        rgb;          // [R,3]
@@ -68,6 +69,12 @@ constexpr int RS_CARRY = RS_TAILS + 2 * 4 * 8 * 4;  // [2 parities][8] floats
 constexpr int RS_BAR   = RS_CARRY + 2 * 8 * 4;
 constexpr int RS_BARW  = RS_BAR + 16;               // mbarrier of the weight bulk copy
 constexpr int RS_TOTAL = RS_BARW + 16;
+// measurement hook (tools/ab_lib.py, profiles/r02_render_variants.md): extra, unused dynamic shared memory per CTA of the
+// march kernels, i.e. what a second activation tile would cost in L1 capacity (4 CTAs/SM: 136 KB -> 200 KB of shared memory)
+#ifndef PERF_RS_PAD
+#define PERF_RS_PAD 0
+#endif
+constexpr int RS_LAUNCH = RS_TOTAL + PERF_RS_PAD;
 constexpr int W_IMG_BYTES = W32_BYTES + W32_BYTES + W64_BYTES;       // 16 KB: W1 density | W1 colour | W2 colour
 static_assert(RS_W1A == RS_W1G + W32_BYTES && RS_W2A == RS_W1A + W32_BYTES, "the three weight images are one contiguous block");
 // experiment (PERF_FLAG_L0_SMEM): level 0 of the packed table (16^3 entries x 8 B = 32 KB) resident in shared memory,
@@ -128,6 +135,24 @@ __device__ __forceinline__ void out_dots_const(const uint32_t (&p)[16], float2 (
         for (int o = 0; o < NOUT; ++o)
             ffma2(acc[o], f, make_float2(c_wout[BASE + o * HID + 32 * C + 2 * j], c_wout[BASE + o * HID + 32 * C + 2 * j + 1]));
     }
+}
+
+// (p - lo) / ext, correctly rounded, for a divisor that is the same for every sample of the launch: with r = RN(1 / ext)
+// computed once, q = RN(n r), q' = RN(q + RN(n - q ext) r) is the correctly rounded quotient (Markstein: the remainder is
+// exact in one FMA; holds unless the significand of ext is all ones, which the host checks) -- 3 dependent FMA-pipe
+// instructions per coordinate instead of the ~10 of the generic IEEE division (MUFU.RCP, refinement, range check).
+#ifndef PERF_OPT_DIV
+#define PERF_OPT_DIV 1
+#endif
+__device__ __forceinline__ float div_uniform(float n, float ext, float r, bool generic)
+{
+#if PERF_OPT_DIV
+    if (generic) return __fdiv_rn(n, ext);                // uniform branch; never taken for PeRF's [-1,1]^3 box
+    const float q = __fmul_rn(n, r);
+    return __fmaf_rn(__fmaf_rn(-q, ext, n), r, q);
+#else
+    (void)r; (void)generic; return __fdiv_rn(n, ext);
+#endif
 }
 
 __device__ __forceinline__ float linspace_val_r(int i, int n)
@@ -555,6 +580,7 @@ __global__ void __launch_bounds__(TILE, L0SMEM ? 3 : 4) render_march_kernel(cons
 
     const uint32_t S = a.S;
     const float step = __fdiv_rn(__fsub_rn(a.far, a.near), (float)S);
+    const float rext0 = __frcp_rn(a.aabb_ext[0]), rext1 = __frcp_rn(a.aabb_ext[1]), rext2 = __frcp_rn(a.aabb_ext[2]);
     // PANO, or explicit rays that form a row-major image of width a.W (perf_render_args.image_width):
     // tiles are 16x8 pixel patches; otherwise 128 consecutive rays
     const bool patch = PANO || a.W > 0;
@@ -637,9 +663,9 @@ __global__ void __launch_bounds__(TILE, L0SMEM ? 3 : 4) render_march_kernel(cons
             const float px = __fadd_rn(ox, __fmul_rn(dx, tsum) * 0.5f);
             const float py = __fadd_rn(oy, __fmul_rn(dy, tsum) * 0.5f);
             const float pz = __fadd_rn(oz, __fmul_rn(dz, tsum) * 0.5f);
-            const float x = __fdiv_rn(__fsub_rn(px, a.aabb_min[0]), a.aabb_ext[0]);
-            const float y = __fdiv_rn(__fsub_rn(py, a.aabb_min[1]), a.aabb_ext[1]);
-            const float z = __fdiv_rn(__fsub_rn(pz, a.aabb_min[2]), a.aabb_ext[2]);
+            const float x = div_uniform(__fsub_rn(px, a.aabb_min[0]), a.aabb_ext[0], rext0, a.div_generic != 0u);
+            const float y = div_uniform(__fsub_rn(py, a.aabb_min[1]), a.aabb_ext[1], rext1, a.div_generic != 0u);
+            const float z = div_uniform(__fsub_rn(pz, a.aabb_min[2]), a.aabb_ext[2], rext2, a.div_generic != 0u);
             const bool selector = live && x > 0.f && x < 1.f && y > 0.f && y < 1.f && z > 0.f && z < 1.f;
 
             float sigma, cr, cg, cb;
@@ -825,6 +851,10 @@ static int launch_render(const perf_render_args* args, RenderArgs& a, bool pano,
     a.geo_w = (const __half*)args->d_geo_mlp_half; a.app_w = (const __half*)args->d_app_mlp_half;
     for (int i = 0; i < 3; ++i) { a.aabb_min[i] = args->aabb[i]; a.aabb_ext[i] = args->aabb[3 + i] - args->aabb[i]; }
     a.S = args->n_samples; a.near = args->near; a.far = args->far;
+    for (int i = 0; i < 3; ++i) {
+        uint32_t bits; memcpy(&bits, &a.aabb_ext[i], 4);
+        if ((bits & 0x7FFFFFu) == 0x7FFFFFu || !(a.aabb_ext[i] > 1e-30f && a.aabb_ext[i] < 1e30f)) a.div_generic = 1u;
+    }
     a.training = (args->flags & PERF_FLAG_TRAINING) ? 1u : 0u;
     a.jitter = args->d_jitter; a.bg_noise = args->d_bg_noise;
     a.rgb = args->d_rgb; a.distance = args->d_distance; a.opacity = args->d_opacity;
@@ -845,9 +875,9 @@ static int launch_render(const perf_render_args* args, RenderArgs& a, bool pano,
 #define PERF_RENDER_LAUNCH(...) do { \
         auto k = __VA_ARGS__; \
         static thread_local int attr_dev = -1; int dev_ = 0; PERF_CUDA(cudaGetDevice(&dev_)); \
-        if (attr_dev != dev_) { PERF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_TOTAL)); \
+        if (attr_dev != dev_) { PERF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_LAUNCH)); \
             attr_dev = dev_; } \
-        k<<<grid, TILE, RS_TOTAL, stream>>>(a); } while (0)
+        k<<<grid, TILE, RS_LAUNCH, stream>>>(a); } while (0)
     const bool fast = fast_addressing_ok(a.lt, 4) && pl.n_cell_levels == 4 && (args->flags & PERF_FLAG_GENERIC_ADDR) == 0;   // PeRF's grid: 4 dense + 12 hashed levels
     if (save != 0) {
         PERF_CHECK_SUP(!pano && !simt && !scan, "training forward runs on the ray-marching tensor-core kernel only");
