@@ -251,6 +251,36 @@ __device__ __forceinline__ const uint2* entry_ptr(const uint2* base, uint32_t id
     return reinterpret_cast<const uint2*>(p);
 }
 
+// L1 eviction hints of the table gathers.  The fine hashed levels stream through L1 (a ray leaves a fine cell with every
+// step) while the dense / coarse levels are re-read from one sample to the next: 0 = default, 1 = L1::evict_first,
+// 2 = L1::no_allocate, 3 = L1::evict_last.  (Measured: tools/ab_lib.py, profiles/r02_render_variants.md.)
+#ifndef PERF_L1_HASHED
+#define PERF_L1_HASHED 0
+#endif
+#ifndef PERF_L1_DENSE
+#define PERF_L1_DENSE 0
+#endif
+template <int HINT>
+__device__ __forceinline__ uint2 ldg_entry(const uint2* p)
+{
+    if constexpr (HINT == 0) return __ldg(p);
+    uint2 v;
+    if constexpr (HINT == 1) asm("ld.global.nc.L1::evict_first.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    if constexpr (HINT == 2) asm("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    if constexpr (HINT == 3) asm("ld.global.nc.L1::evict_last.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+template <int HINT>
+__device__ __forceinline__ uint4 ldg_cell(const uint4* p)
+{
+    if constexpr (HINT == 0) return __ldg(p);
+    uint4 v;
+    if constexpr (HINT == 1) asm("ld.global.nc.L1::evict_first.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    if constexpr (HINT == 2) asm("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    if constexpr (HINT == 3) asm("ld.global.nc.L1::evict_last.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
 // Levels [4q, 4q+4) of both fields -> one 16-byte k-group of each feature tile.
 // KIND 0: generic addressing, 1: dense (fast), 2: hashed power-of-two (fast).
 template <int KIND, int SAVE, bool L0SMEM = false>
@@ -277,7 +307,7 @@ __device__ __forceinline__ void encode_group(const RenderArgs& a, const RenderSm
                 const uint4* const cp = a.cells[l] + 4ull * cell;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const uint4 c2 = __ldg(cp + j);
+                    const uint4 c2 = ldg_cell<PERF_L1_DENSE>(cp + j);
                     v[2 * j] = make_uint2(c2.x, c2.y); v[2 * j + 1] = make_uint2(c2.z, c2.w);
                 }
             }
@@ -287,7 +317,7 @@ __device__ __forceinline__ void encode_group(const RenderArgs& a, const RenderSm
             level_corners_rel<true>(a.lt, l, x, y, z, idx, w);
             const uint2* const tl = a.table + a.lt.offset[l];
 #pragma unroll
-            for (int kk = 0; kk < 8; ++kk) v[kk] = __ldg(entry_ptr(tl, idx[kk]));
+            for (int kk = 0; kk < 8; ++kk) v[kk] = ldg_entry<PERF_L1_HASHED>(entry_ptr(tl, idx[kk]));
         }
         uint32_t vg[8], va[8];
 #pragma unroll
