@@ -268,7 +268,8 @@ int perf_hashgrid_bwd_rays(const perf_grid_cfg* cfg, const float* aabb6, const f
 /* The fixed-S training step's MLP backward WITH the fine-level grid scatter in its epilogue: perf_mlp_bwd on the R x S
  * sample-major rows (row = k * R + ray) of perf_train_forward; the thread that owns a row issues the reductions of levels
  * [8, 16) into d_dtable itself (positions recomputed from the rays as in perf_hashgrid_bwd_rays) and writes only the coarse
- * half (columns [0, 16)) of d_dfeat [N, 32].  Follow with perf_hashgrid_bwd_rays_coarse for levels [0, 8).  Together they
+ * half of the feature gradient into d_dfeat (capacity >= 16 N floats) as eight LEVEL-MAJOR planes, plane l = float2 [N]
+ * (what the march kernel reads coalesced).  Follow with perf_hashgrid_bwd_rays_coarse for levels [0, 8).  Together they
  * replace perf_mlp_bwd + perf_hashgrid_bwd_rays; the fine half of dfeat never reaches HBM and the L2-reduction-bound
  * scatter overlaps the latency-bound MMA phases. */
 int perf_mlp_bwd_scatter(const perf_mlp_cfg* mlp, const void* d_weights_half, const void* d_feat, const void* d_h1, const void* d_h2,

@@ -408,9 +408,11 @@ __global__ void __launch_bounds__(128) mlp_bwd_kernel(const MlpBwdArgs a_in, con
             if constexpr (FUSE) {
                 const uint64_t row = tile * TILE + t;
                 if (row < a.N) {
-                    float4* dst = reinterpret_cast<float4*>(a.dfeat + row * 32);          // coarse half only: levels 0-7 for the march kernel
+                    // coarse half only, as LEVEL-MAJOR planes for the march kernel (plane l = float2 [N]): a warp of that
+                    // kernel reads one level of 32 neighbouring rays -- 256 contiguous bytes here, 32 sectors in [N, 32] rows
+                    float2* const planes = reinterpret_cast<float2*>(a.dfeat);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    for (int l = 0; l < 8; ++l) planes[(uint64_t)l * a.N + row] = make_float2(v[2 * l], v[2 * l + 1]);
                     scatter_fine_levels(sc, row, v);
                 }
             } else {

@@ -217,6 +217,7 @@ struct GridBwdRaysArgs {
     const float *rays_o, *rays_d, *jitter;
     uint64_t R; uint32_t S; float near, far;
     const float* dfeat; float2* dtable;
+    uint64_t plane_rows;        // 0: dfeat is [N, 2 n_levels] rows; N > 0: level-major planes, plane l = float2 [N] (perf_mlp_bwd_scatter's output)
 };
 
 // One (row, level) of the fine-level scatter.  __host__ __device__ like the other per-thread bodies of this file:
@@ -317,7 +318,8 @@ __host__ __device__ __forceinline__ void bwd_march_ray_level(const GridBwdRaysAr
     };
 #pragma unroll 2
     for (uint32_t ks = k_lo; ks < k_hi; ++ks) {
-        const float2 g = *reinterpret_cast<const float2*>(a.dfeat + ((uint64_t)ks * a.R + ray) * stride + 2 * l);
+        const float2 g = a.plane_rows ? reinterpret_cast<const float2*>(a.dfeat)[(uint64_t)l * a.plane_rows + (uint64_t)ks * a.R + ray]
+                                      : *reinterpret_cast<const float2*>(a.dfeat + ((uint64_t)ks * a.R + ray) * stride + 2 * l);
         if (g.x == 0.f && g.y == 0.f) continue;
         const float ts = PERF_FADD_RN(a.near, PERF_FMUL_RN(PERF_FADD_RN((float)ks, jit), step));
         const float te = PERF_FADD_RN(a.near, PERF_FMUL_RN(PERF_FADD_RN((float)(ks + 1), jit), step));
@@ -608,7 +610,7 @@ int perf_hashgrid_bwd_rays(const perf_grid_cfg* cfg, const float* aabb6, const f
 }
 
 /* The coarse levels [0, 8) only (run-merging march kernel): the companion of perf_mlp_bwd_scatter, whose epilogue has already
- * issued the fine levels' reductions.  d_dfeat rows keep the [N, 32] stride; only columns [0, 16) are read. */
+ * issued the fine levels' reductions.  d_dfeat: the eight level-major planes (float2 [N] each) that kernel wrote. */
 int perf_hashgrid_bwd_rays_coarse(const perf_grid_cfg* cfg, const float* aabb6, const float* d_rays_o, const float* d_rays_d,
                                   const float* d_jitter, uint64_t R, uint32_t n_samples, float near, float far,
                                   const float* d_dfeat, float* d_dtable, void* stream)
@@ -616,6 +618,8 @@ int perf_hashgrid_bwd_rays_coarse(const perf_grid_cfg* cfg, const float* aabb6, 
     GridBwdRaysArgs a, b; uint32_t n_agg = 0;
     int rc = setup_bwd_rays(cfg, aabb6, d_rays_o, d_rays_d, d_jitter, R, n_samples, near, far, d_dfeat, d_dtable, a, b, n_agg); if (rc) return rc;
     if (R * (uint64_t)n_samples == 0) return PERF_OK;
+    PERF_CHECK_SUP(a.lt.n_levels == 16 && n_agg == 8, "the fused scatter pair needs 16 levels (8 coarse planes)");
+    a.plane_rows = R * (uint64_t)n_samples;
     unsigned pieces = 1;
     while (pieces < 8 && (uint64_t)R * n_agg * pieces < (uint64_t)num_sms() * 2048 && n_samples / (pieces * 2) >= 16) pieces *= 2;
     dim3 g_agg((unsigned)((R + 127) / 128), n_agg, pieces);
