@@ -25,6 +25,7 @@ struct RenderArgs {
     uint32_t      rays_per_unit, tiles_per_unit;
     float         near, far;
     uint32_t      training;
+    uint32_t      tile_mul;     // image-shaped work: tile = (i * tile_mul) % n_tiles (a bijection, gcd(tile_mul, n_tiles) == 1); 0 / 1 = row-major
     uint32_t      div_generic;  // 1: an aabb extent whose significand is all ones -> div_uniform() falls back to the IEEE division
     const float*  jitter;       // [R] or null
     const float*  bg_noise;     // [R,4] or null
@@ -621,7 +622,11 @@ __global__ void __launch_bounds__(TILE, L0SMEM ? 3 : 4) render_march_kernel(cons
     const uint32_t my_seg = (uint32_t)tid / rpt;
     const uint64_t n_tiles = patch ? (uint64_t)tiles_x * (uint64_t)((rows + PATCH_H - 1) / PATCH_H) : (a.R + rpt - 1) / rpt;
 
-    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (uint64_t work = blockIdx.x; work < n_tiles; work += gridDim.x) {
+        // Image-shaped work is dealt out in a scattered order: the tiles in flight at any moment (4 per SM) are spread over
+        // the whole image instead of forming one band of neighbouring tiles that all pull the same table lines through the
+        // same L2 slices at the same time (measured: profiles/r02_render_variants.md).
+        const uint64_t tile = (patch && a.tile_mul > 1u) ? (work * a.tile_mul) % n_tiles : work;
         // ---- this thread's ray
         uint64_t ray; bool valid;
         float ox = 0.f, oy = 0.f, oz = 0.f, dx = 1.f, dy = 0.f, dz = 0.f, jit = 0.f;
@@ -823,6 +828,7 @@ __global__ void __launch_bounds__(TILE, 4) packed_fields_kernel(const __grid_con
     uint64_t N = p.N;
     if (p.n_dev) { const int64_t nd = *p.n_dev; N = nd < 0 ? 0 : ((uint64_t)nd < N ? (uint64_t)nd : N); }      // graph-replayable count
     const uint64_t n_tiles = (N + TILE - 1) / TILE;
+    const float rext0 = __frcp_rn(a.aabb_ext[0]), rext1 = __frcp_rn(a.aabb_ext[1]), rext2 = __frcp_rn(a.aabb_ext[2]);
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint64_t n = tile * TILE + tid;
         const bool valid = n < N;
@@ -833,9 +839,9 @@ __global__ void __launch_bounds__(TILE, 4) packed_fields_kernel(const __grid_con
             const float px = __fadd_rn(a.rays_o[3 * ray], __fmul_rn(a.rays_d[3 * ray], tsum) * 0.5f);
             const float py = __fadd_rn(a.rays_o[3 * ray + 1], __fmul_rn(a.rays_d[3 * ray + 1], tsum) * 0.5f);
             const float pz = __fadd_rn(a.rays_o[3 * ray + 2], __fmul_rn(a.rays_d[3 * ray + 2], tsum) * 0.5f);
-            x = __fdiv_rn(__fsub_rn(px, a.aabb_min[0]), a.aabb_ext[0]);
-            y = __fdiv_rn(__fsub_rn(py, a.aabb_min[1]), a.aabb_ext[1]);
-            z = __fdiv_rn(__fsub_rn(pz, a.aabb_min[2]), a.aabb_ext[2]);
+            x = div_uniform(__fsub_rn(px, a.aabb_min[0]), a.aabb_ext[0], rext0, a.div_generic != 0u);
+            y = div_uniform(__fsub_rn(py, a.aabb_min[1]), a.aabb_ext[1], rext1, a.div_generic != 0u);
+            z = div_uniform(__fsub_rn(pz, a.aabb_min[2]), a.aabb_ext[2], rext2, a.div_generic != 0u);
         }
         const bool selector = valid && x > 0.f && x < 1.f && y > 0.f && y < 1.f && z > 0.f && z < 1.f;
         float sigma, cr, cg, cb;
@@ -863,6 +869,16 @@ static int prepare_weights(const RenderArgs& a, cudaStream_t stream)
     return PERF_OK;
 }
 
+// div_uniform()'s precondition: no box extent with an all-ones significand (Markstein's exception) or out of the normal range
+static void set_div_mode(RenderArgs& a)
+{
+    a.div_generic = 0u;
+    for (int i = 0; i < 3; ++i) {
+        uint32_t bits; memcpy(&bits, &a.aabb_ext[i], 4);
+        if ((bits & 0x7FFFFFu) == 0x7FFFFFu || !(a.aabb_ext[i] > 1e-30f && a.aabb_ext[i] < 1e30f)) a.div_generic = 1u;
+    }
+}
+
 static uint32_t gcd_u32(uint32_t a, uint32_t b) { while (b) { uint32_t t = a % b; a = b; b = t; } return a; }
 
 static int launch_render(const perf_render_args* args, RenderArgs& a, bool pano, cudaStream_t stream, int save = 0)
@@ -881,10 +897,7 @@ static int launch_render(const perf_render_args* args, RenderArgs& a, bool pano,
     a.geo_w = (const __half*)args->d_geo_mlp_half; a.app_w = (const __half*)args->d_app_mlp_half;
     for (int i = 0; i < 3; ++i) { a.aabb_min[i] = args->aabb[i]; a.aabb_ext[i] = args->aabb[3 + i] - args->aabb[i]; }
     a.S = args->n_samples; a.near = args->near; a.far = args->far;
-    for (int i = 0; i < 3; ++i) {
-        uint32_t bits; memcpy(&bits, &a.aabb_ext[i], 4);
-        if ((bits & 0x7FFFFFu) == 0x7FFFFFu || !(a.aabb_ext[i] > 1e-30f && a.aabb_ext[i] < 1e30f)) a.div_generic = 1u;
-    }
+    set_div_mode(a);
     a.training = (args->flags & PERF_FLAG_TRAINING) ? 1u : 0u;
     a.jitter = args->d_jitter; a.bg_noise = args->d_bg_noise;
     a.rgb = args->d_rgb; a.distance = args->d_distance; a.opacity = args->d_opacity;
@@ -894,6 +907,9 @@ static int launch_render(const perf_render_args* args, RenderArgs& a, bool pano,
     const bool simt = (args->flags & PERF_FLAG_SIMT_MLP) != 0;
     const bool scan = (args->flags & PERF_FLAG_SCAN_KERNEL) != 0;
     uint64_t n_work;
+#ifndef PERF_TILE_SCATTER
+#define PERF_TILE_SCATTER 1
+#endif
     if (scan) n_work = (a.R + a.rays_per_unit - 1) / a.rays_per_unit;
     else if (pano || a.W > 0) n_work = (uint64_t)((a.W + PATCH_W - 1) / PATCH_W) * (uint64_t)(((int)(a.R / (uint64_t)a.W) + PATCH_H - 1) / PATCH_H);
     else {
@@ -901,6 +917,13 @@ static int launch_render(const perf_render_args* args, RenderArgs& a, bool pano,
         n_work = (a.R + rpt - 1) / rpt;
     }
     const unsigned grid = (unsigned)(n_work < (uint64_t)num_sms() * 4 ? n_work : (uint64_t)num_sms() * 4);
+    a.tile_mul = 0;
+    if (PERF_TILE_SCATTER && !scan && (pano || a.W > 0) && n_work > grid && n_work < (1ull << 31)) {
+        // golden-ratio stride, made coprime with the tile count: consecutive work items land far apart, evenly spread
+        uint32_t m = (uint32_t)((double)n_work * 0.6180339887498949) | 1u;
+        while (m > 1u && gcd_u32(m, (uint32_t)n_work) != 1u) m += 2u;
+        a.tile_mul = m % (uint32_t)n_work;
+    }
     rc = prepare_weights(a, stream); if (rc) return rc;     // constant-bank output weights + operand images (c_wout, g_wimg)
 #define PERF_RENDER_LAUNCH(...) do { \
         auto k = __VA_ARGS__; \
@@ -1009,6 +1032,7 @@ int perf_fields_packed(const perf_render_args* args, const float* d_rays_o, cons
     for (uint32_t l = 0; l < pl.n_cell_levels; ++l) a.cells[l] = reinterpret_cast<const uint4*>(a.table + pl.cell_start[l]);
     a.geo_w = (const __half*)args->d_geo_mlp_half; a.app_w = (const __half*)args->d_app_mlp_half;
     for (int i = 0; i < 3; ++i) { a.aabb_min[i] = args->aabb[i]; a.aabb_ext[i] = args->aabb[3 + i] - args->aabb[i]; }
+    set_div_mode(a);
     a.rays_o = d_rays_o; a.rays_d = d_rays_d;
     a.s_feat = (uint4*)d_feat; a.s_h1 = (uint4*)d_h1; a.s_h2 = (uint4*)d_h2;
     if (N == 0) return PERF_OK;
