@@ -102,24 +102,41 @@ __global__ void params_to_half_kernel(const float* __restrict__ p, __half* __res
 
 struct PackCells {            // cell-major copies of the leading dense levels (common.cuh::PackedLayout)
     uint32_t n_levels;
-    uint32_t res[PERF_CELL_LEVELS], size[PERF_CELL_LEVELS], offset[PERF_CELL_LEVELS];
-    uint64_t start[PERF_CELL_LEVELS + 1];     // first packed entry of each level's cells; [n_levels] = total
+    uint32_t res[PERF_CELL_LEVELS], size[PERF_CELL_LEVELS], offset[PERF_CELL_LEVELS], cells[PERF_CELL_LEVELS];
+    uint64_t start[PERF_CELL_LEVELS];         // first packed entry of each level's cells
 };
-__global__ void pack_tables_kernel(const uint32_t* __restrict__ geo, const uint32_t* __restrict__ app,
-                                   uint2* __restrict__ out, uint64_t n, const PackCells pc, uint64_t total)
+// Threads [0, n/2): two entries each (8-byte loads from both tables, one 16-byte store).  Threads behind them: one CELL each
+// -- two integer divisions, then the cell's four x-neighbour pairs as 16-byte stores (64 contiguous bytes per thread).
+// Runs in front of every training step's forward (the tables changed): ~64 MB of traffic.
+__global__ void __launch_bounds__(256) pack_tables_kernel(const uint32_t* __restrict__ geo, const uint32_t* __restrict__ app,
+                                                          uint2* __restrict__ out, uint64_t n, const PackCells pc)
 {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { out[i] = make_uint2(geo[i], app[i]); return; }
-    if (i >= total) return;
-    uint32_t l = 0;
-    while (l + 1 < pc.n_levels && i >= pc.start[l + 1]) ++l;
-    const uint64_t j = i - pc.start[l];
-    const uint32_t k = (uint32_t)(j & 7u), cell = (uint32_t)(j >> 3), res = pc.res[l];
-    const uint32_t gx = cell % res, gy = (cell / res) % res, gz = cell / (res * res);
-    uint32_t e = (gx + (k & 1u)) + res * ((gy + ((k >> 1) & 1u)) + res * (gz + (k >> 2)));
-    if (e >= pc.size[l]) e -= pc.size[l];                      // tcnn's `% size` of a dense level (e < 2 * size)
-    e += pc.offset[l];
-    out[i] = make_uint2(geo[e], app[e]);
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n / 2) {
+        const uint2 g = reinterpret_cast<const uint2*>(geo)[t], a = reinterpret_cast<const uint2*>(app)[t];
+        reinterpret_cast<uint4*>(out)[t] = make_uint4(g.x, a.x, g.y, a.y);
+        return;
+    }
+    uint64_t c = t - n / 2;
+    int l = -1;
+#pragma unroll
+    for (int i = 0; i < (int)PERF_CELL_LEVELS; ++i) {              // constant indices: pc stays in the constant bank
+        if (l < 0 && i < (int)pc.n_levels) { if (c < pc.cells[i]) l = i; else c -= pc.cells[i]; }
+    }
+    if (l < 0) return;
+    uint32_t res = 0, size = 0, off = 0; uint64_t start = 0;
+#pragma unroll
+    for (int i = 0; i < (int)PERF_CELL_LEVELS; ++i) if (i == l) { res = pc.res[i]; size = pc.size[i]; off = pc.offset[i]; start = pc.start[i]; }
+    const uint32_t cell = (uint32_t)c;
+    const uint32_t gz = cell / (res * res), rem = cell - gz * res * res, gy = rem / res, gx = rem - gy * res;
+    uint4* dst = reinterpret_cast<uint4*>(out + start + 8ull * cell);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {                                  // q = ky + 2 kz; the pair = corners (kx = 0, 1)
+        uint32_t e0 = gx + res * ((gy + (q & 1)) + res * (gz + (q >> 1))), e1 = e0 + 1u;
+        if (e0 >= size) e0 -= size;                                // tcnn's `% size` of a dense level (e < 2 * size)
+        if (e1 >= size) e1 -= size;
+        dst[q] = make_uint4(geo[off + e0], app[off + e0], geo[off + e1], app[off + e1]);
+    }
 }
 
 // torch.linspace(start, end, steps)[i] in fp32 (ATen's symmetric formula), so that pixel centres
@@ -538,13 +555,16 @@ int perf_pack_tables(const perf_grid_cfg* grid, const perf_mlp_cfg* geo_mlp, con
     rc = mlp_param_count(app_mlp, &na); if (rc) return rc;
     const uint32_t* geo = reinterpret_cast<const uint32_t*>((const __half*)d_geo_params_half + ng);
     const uint32_t* app = reinterpret_cast<const uint32_t*>((const __half*)d_app_params_half + na);
-    PERF_CHECK_ARG(((uintptr_t)geo % 4 == 0) && ((uintptr_t)app % 4 == 0) && ((uintptr_t)d_packed % 16 == 0), "misaligned tables (d_packed: 16-byte aligned)");
+    PERF_CHECK_ARG(((uintptr_t)geo % 8 == 0) && ((uintptr_t)app % 8 == 0) && ((uintptr_t)d_packed % 16 == 0) && ne % 2 == 0, "misaligned tables (grids 8-byte, d_packed 16-byte aligned)");
     const PackedLayout pl = packed_layout(lt, ne);
     PackCells pc; memset(&pc, 0, sizeof(pc));
     pc.n_levels = pl.n_cell_levels;
-    for (uint32_t l = 0; l < pl.n_cell_levels; ++l) { pc.res[l] = lt.res[l]; pc.size[l] = lt.size[l]; pc.offset[l] = lt.offset[l]; pc.start[l] = pl.cell_start[l]; }
-    pc.start[pl.n_cell_levels] = pl.total_entries;
-    pack_tables_kernel<<<blocks_for(pl.total_entries, 256), 256, 0, S(stream)>>>(geo, app, (uint2*)d_packed, ne, pc, pl.total_entries);
+    uint64_t n_cells = 0;
+    for (uint32_t l = 0; l < pl.n_cell_levels; ++l) {
+        pc.res[l] = lt.res[l]; pc.size[l] = lt.size[l]; pc.offset[l] = lt.offset[l]; pc.start[l] = pl.cell_start[l];
+        pc.cells[l] = lt.res[l] * lt.res[l] * lt.res[l]; n_cells += pc.cells[l];
+    }
+    pack_tables_kernel<<<blocks_for(ne / 2 + n_cells, 256), 256, 0, S(stream)>>>(geo, app, (uint2*)d_packed, ne, pc);
     PERF_LAUNCH_CHECK();
     return PERF_OK;
 }
