@@ -41,7 +41,7 @@ def workload_config(n_gpus):
                         f"(density 32-64-1, colour 32-64-64-3), fixed-S sampler",
             "H": H, "W": W, "samples_per_ray": S, "rays": H * W, "samples_per_step": H * W * S,
             "parallelism": f"rows tiled over {n_gpus} GPU(s), no collective",
-            "l2": "flushed between timed steps (256 MiB write); tables (26.6 MB) are re-fetched every step"}
+            "l2": "flushed between timed steps (256 MiB write); the packed gather table (37.8 MB) is re-fetched every step"}
 
 
 def make_field(device):
@@ -616,7 +616,7 @@ def run_ours(args, rank, world, local_rank):
             "roofline": {"bound": "hbm", "kernel": "perf::render_march_kernel<PANO=true,SIMT=false,NDENSE=4>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_sample": ALG_BYTES_PER_SAMPLE, **physical,
-                         "note": "tables (26.6 MB fp16) are L2-resident: DRAM traffic is far below algorithmic bytes, see profiles/"}}
+                         "note": "the packed table (37.8 MB fp16: 26.6 MB of entries + 11.2 MB cell-major dense levels) is L2-resident: DRAM traffic is far below algorithmic bytes, see profiles/"}}
     if cpu_v is not None:
         # parity of THIS run's kernel against the CPU restatement on the very rays the baseline timed
         # (the metric's second half: "PSNR delta vs reference")
