@@ -1,6 +1,7 @@
 // render.cu -- the fused per-ray megakernel: ray-gen -> fixed-S sampling -> hash-grid encode of
-// BOTH fields (one 8-byte gather per corner from the interleaved table) -> density MLP and
-// colour MLP on tcgen05 -> alpha composite with warp-shuffle segmented scans along the ray.
+// BOTH fields (hashed levels: one 8-byte gather per corner from the interleaved table; dense levels:
+// one 64-byte cell record) -> density MLP and colour MLP on tcgen05 -> alpha composite (a running
+// sum per thread in render_march_kernel, warp-shuffle segmented scans in the legacy render_kernel).
 // Nothing per-sample ever touches HBM: inputs are the pose (or [R,3] rays) and the tables,
 // outputs are 16-20 B per ray.
 //
