@@ -4,6 +4,7 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include <math.h>
+#include <string.h>
 #include "../../include/perfb200.h"
 
 namespace perf {
@@ -301,6 +302,31 @@ __device__ __forceinline__ uint32_t blend8_half(const float (&w)[8], const uint3
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc = __hfma2(__float2half2_rn(w[k]), *reinterpret_cast<const __half2*>(&v[k]), acc);
     return *reinterpret_cast<uint32_t*>(&acc);
+}
+
+// (p - lo) / ext, correctly rounded, for a divisor that is the same for every sample of the launch: with r = RN(1 / ext)
+// computed once, q = RN(n r), q' = RN(q + RN(n - q ext) r) is the correctly rounded quotient (Markstein: the remainder is
+// exact in one FMA; holds unless the significand of ext is all ones, which the host checks with div_uniform_ok) -- 3
+// dependent FMA-pipe instructions per coordinate instead of the ~10 of the generic IEEE division (MUFU.RCP, refinement,
+// range check).  __host__ __device__: tests/test_addressing_host.py compares the sequence with the IEEE division on the CPU.
+#ifndef PERF_OPT_DIV
+#define PERF_OPT_DIV 1
+#endif
+__host__ __device__ __forceinline__ float div_uniform(float n, float ext, float r, bool generic)
+{
+#if PERF_OPT_DIV
+    if (generic) return PERF_FDIV_RN(n, ext);             // uniform branch; never taken for PeRF's [-1,1]^3 box
+    const float q = PERF_FMUL_RN(n, r);
+    return fmaf(fmaf(-q, ext, n), r, q);
+#else
+    (void)r; (void)generic; return PERF_FDIV_RN(n, ext);
+#endif
+}
+// host-side precondition of the 3-FMA path: a normal-range extent whose significand is not all ones
+inline bool div_uniform_ok(float ext)
+{
+    uint32_t bits; memcpy(&bits, &ext, 4);
+    return (bits & 0x7FFFFFu) != 0x7FFFFFu && ext > 1e-30f && ext < 1e30f;
 }
 
 // ---------------------------------------------------------------- device: tcgen05 / mbarrier PTX

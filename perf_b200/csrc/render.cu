@@ -139,24 +139,6 @@ __device__ __forceinline__ void out_dots_const(const uint32_t (&p)[16], float2 (
     }
 }
 
-// (p - lo) / ext, correctly rounded, for a divisor that is the same for every sample of the launch: with r = RN(1 / ext)
-// computed once, q = RN(n r), q' = RN(q + RN(n - q ext) r) is the correctly rounded quotient (Markstein: the remainder is
-// exact in one FMA; holds unless the significand of ext is all ones, which the host checks) -- 3 dependent FMA-pipe
-// instructions per coordinate instead of the ~10 of the generic IEEE division (MUFU.RCP, refinement, range check).
-#ifndef PERF_OPT_DIV
-#define PERF_OPT_DIV 1
-#endif
-__device__ __forceinline__ float div_uniform(float n, float ext, float r, bool generic)
-{
-#if PERF_OPT_DIV
-    if (generic) return __fdiv_rn(n, ext);                // uniform branch; never taken for PeRF's [-1,1]^3 box
-    const float q = __fmul_rn(n, r);
-    return __fmaf_rn(__fmaf_rn(-q, ext, n), r, q);
-#else
-    (void)r; (void)generic; return __fdiv_rn(n, ext);
-#endif
-}
-
 __device__ __forceinline__ float linspace_val_r(int i, int n)
 {
     const float start = (float)(0.5 / (double)n), end = (float)(1.0 - 0.5 / (double)n);
@@ -874,10 +856,7 @@ static int prepare_weights(const RenderArgs& a, cudaStream_t stream)
 static void set_div_mode(RenderArgs& a)
 {
     a.div_generic = 0u;
-    for (int i = 0; i < 3; ++i) {
-        uint32_t bits; memcpy(&bits, &a.aabb_ext[i], 4);
-        if ((bits & 0x7FFFFFu) == 0x7FFFFFu || !(a.aabb_ext[i] > 1e-30f && a.aabb_ext[i] < 1e30f)) a.div_generic = 1u;
-    }
+    for (int i = 0; i < 3; ++i) if (!div_uniform_ok(a.aabb_ext[i])) a.div_generic = 1u;
 }
 
 static uint32_t gcd_u32(uint32_t a, uint32_t b) { while (b) { uint32_t t = a % b; a = b; b = t; } return a; }

@@ -39,6 +39,17 @@ int perf_host_level_corners(const perf_grid_cfg* cfg, int level, int mode, uint3
     return PERF_OK;
 }
 
+// div_uniform (common.cuh): out[i] = n[i] / ext by the 3-FMA sequence (or the IEEE division when the extent is not admitted);
+// *ok = div_uniform_ok(ext)
+int perf_host_div_uniform(const float* n, uint64_t N, float ext, float* out, int* ok)
+{
+    const bool admitted = div_uniform_ok(ext);
+    if (ok) *ok = admitted ? 1 : 0;
+    const float r = 1.0f / ext;                            // the correctly rounded reciprocal (device: __frcp_rn)
+    for (uint64_t i = 0; i < N; ++i) out[i] = div_uniform(n[i], ext, r, !admitted);
+    return PERF_OK;
+}
+
 // scatter8<V4> over N rows of (idx[8], v[8] float2) into dtable (float2 entries, 16-byte aligned for v4 != 0)
 int perf_host_scatter8(int v4, const uint32_t* idx, const float* v, uint64_t N, float* dtable)
 {

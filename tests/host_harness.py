@@ -76,6 +76,15 @@ def level_corners(grid_cfg, level: int, x01: np.ndarray, fast, n_dense: int = 4)
     return idx, w, bool(ok.value)
 
 
+def div_uniform(n: np.ndarray, ext: float):
+    """(n / ext by common.cuh::div_uniform [N] f32, admitted): the launch-uniform division of the field kernels."""
+    n = np.ascontiguousarray(n, np.float32)
+    out, ok = np.zeros_like(n), C.c_int(0)
+    rc = lib().perf_host_div_uniform(_p(n), C.c_uint64(n.size), C.c_float(ext), _p(out), C.byref(ok))
+    assert rc == 0, rc
+    return out, bool(ok.value)
+
+
 def scatter8(idx: np.ndarray, v: np.ndarray, n_entries: int, v4: bool) -> np.ndarray:
     """scatter8<V4> of common.cuh: idx [N,8] uint32, v [N,8,2] f32 -> dtable [n_entries,2] f32."""
     raw = np.zeros(2 * n_entries + 4, np.float32)

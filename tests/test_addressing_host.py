@@ -129,3 +129,22 @@ def test_vector_atomic_scatter_pairs_equal_plain_scatter():
         a, b = hh.scatter8(idx, val, pcfg.n_entries, v4=False), hh.scatter8(idx, val, pcfg.n_entries, v4=True)
         np.testing.assert_allclose(a, b, atol=1e-6)
         assert abs(float(b[:, 0].sum()) - len(x)) < 1e-2          # the 8 weights of a sample sum to 1
+
+
+def test_uniform_extent_division_is_the_ieee_division():
+    """render.cu normalises positions with (p - lo) / (hi - lo) (`ngp_nerf.py:137-140`).  The kernels divide by the launch-
+    uniform extent with q = n r, q' = fma(fma(-q, ext, n), r, q), r = RN(1 / ext): bit-equal to the IEEE quotient for every
+    admitted extent; an extent whose significand is all ones is not admitted and takes the IEEE division."""
+    rng = np.random.default_rng(5)
+    for ext in (2.0, 1.0, 1.8, 2.1, 2.3, 0.1, 3.0, 5.123, 1.0000001, 123.456, 7e-3):
+        e = np.float32(ext)
+        pos = ((rng.random(400_000) * 2 - 1) * 4 * float(e)).astype(np.float32)                     # positions around the box
+        bits = (rng.integers(0, 1 << 23, 400_000, dtype=np.uint32) | (rng.integers(100, 156, 400_000, dtype=np.uint32) << 23)
+                | (rng.integers(0, 2, 400_000, dtype=np.uint32) << 31)).view(np.float32)              # any normal numerator
+        n = np.concatenate([pos, bits, np.float32([0.0, e, -e, np.nextafter(e, np.float32(0)), 1e-30])])
+        got, ok = hh.div_uniform(n, float(e))
+        assert ok
+        assert np.array_equal(got.view(np.uint32), (n / e).astype(np.float32).view(np.uint32)), ext
+    allones = np.uint32(0x3FFFFFFF).view(np.float32)                                                 # 1.9999999
+    got, ok = hh.div_uniform(np.float32([0.3, -1.7, 1.9999999]), float(allones))
+    assert not ok and np.array_equal(got, np.float32([0.3, -1.7, 1.9999999]) / allones)
